@@ -1,0 +1,63 @@
+"""TEST INFRASTRUCTURE ONLY: runs the unmodified reference (oracle/_ref/ref_demod).
+
+One subprocess per stream: the reference keeps function-static filter state
+(icao_filter.c:151) that cannot be reset in-process.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+from readsb_protobuf_b200 import build as _build
+from readsb_protobuf_b200.results import DemodResult, read_result_file
+
+HERE = Path(__file__).resolve().parent
+
+
+def binary() -> Path | None:
+    """Path of ref_demod; built from /root/reference when that exists, else a prebuilt copy."""
+    return _build.ensure_ref()
+
+
+def available() -> bool:
+    return binary() is not None
+
+
+def run_file(path, fmt: str = "uc8", nfix: int = 1, threshold: int = 58, block_samples: int | None = None,
+             max_samples: int | None = None, repeat: int = 1, mag_out=None) -> DemodResult:
+    exe = binary()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/ref_demod is not built and /root/reference is absent")
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "ref.res")
+        cmd = [str(exe), "--in", str(path), "--out", out, "--format", fmt, "--nfix", str(nfix),
+               "--threshold", str(threshold), "--repeat", str(repeat)]
+        if block_samples:
+            cmd += ["--block", str(block_samples)]
+        if max_samples is not None:
+            cmd += ["--max-samples", str(max_samples)]
+        if mag_out:
+            cmd += ["--mag-out", str(mag_out)]
+        subprocess.run(cmd, check=True, capture_output=True)
+        return read_result_file(out)
+
+
+def run(iq: np.ndarray, fmt: str = "uc8", **kw) -> DemodResult:
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "in.bin")
+        np.ascontiguousarray(iq).view(np.uint8).tofile(path)
+        return run_file(path, fmt, **kw)
+
+
+def magnitudes(iq: np.ndarray, fmt: str = "uc8") -> np.ndarray:
+    """The reference converter's u16 magnitudes for the whole stream."""
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "in.bin")
+        mag = os.path.join(td, "mag.bin")
+        np.ascontiguousarray(iq).view(np.uint8).tofile(path)
+        run_file(path, fmt, mag_out=mag)
+        return np.fromfile(mag, dtype=np.uint16)
