@@ -1,0 +1,751 @@
+// cabi.cu -- the C ABI of include/readsb_b200.h: context, device buffers, launch sequence.
+//
+// A process call is: (H2D) -> K1 scan/slice/CRC -> K2 classify -> D2H of the survivors ->
+// host resolve (resolver.cc).  There is no CPU implementation of the kernels; without a usable
+// sm_100 device every entry point returns B200_ERR_CUDA.
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "device_types.h"
+#include "host_tables.h"
+#include "kernels.cuh"
+#include "readsb_b200.h"
+#include "resolver.h"
+
+using namespace b200;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess)
+            cap = n;
+        return e;
+    }
+    void release() {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess)
+            cap = n;
+        return e;
+    }
+    void release() {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+struct b200_demod {
+    b200_demod_config cfg;
+    int bytes_per_sample = 2;
+    int sm_count = 0;
+    int scan_grid = 0;
+    std::unique_ptr<CrcTables> crc;
+    std::unique_ptr<Resolver> resolver;
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+    // tables
+    DevBuf<uint16_t> d_lut;
+    DevBuf<ErrorInfo> d_tab_short, d_tab_long;
+    DevBuf<uint32_t> d_bitmap;
+    std::vector<uint16_t> h_lut;
+
+    // stream state
+    DevBuf<uint8_t> d_head, d_head_tmp;
+    uint32_t head_valid = 0;
+    uint64_t first_sample = 0;
+    bool finished = false;
+
+    // span buffers
+    DevBuf<uint8_t> d_iq;
+    DevBuf<uint32_t> d_cand, d_dead;
+    DevBuf<PhaseRec> d_recs;
+    DevBuf<TileDesc> d_tiles;
+    DevBuf<TileOut> d_tiles_out;
+    DevBuf<LivePos> d_live;
+    DevBuf<LiveRec> d_liverecs;
+    DevBuf<ScanCounters> d_counters;
+    DevBuf<unsigned long long> d_sums_u64;
+    DevBuf<double> d_sums_f64;
+    DevBuf<BlockDead> d_block_dead;
+    DevBuf<uint8_t> d_dbg_masks;
+    DevBuf<uint16_t> d_mag;
+    DevBuf<uint8_t> d_frames;
+    DevBuf<uint32_t> d_syn;
+    DevBuf<int8_t> d_err, d_bits;
+
+    PinnedBuf<ScanCounters> h_counters;
+    PinnedBuf<TileOut> h_tiles_out;
+    PinnedBuf<uint32_t> h_dead;
+    PinnedBuf<LivePos> h_live;
+    PinnedBuf<LiveRec> h_liverecs;
+    PinnedBuf<unsigned long long> h_sums_u64;
+    PinnedBuf<double> h_sums_f64;
+    PinnedBuf<BlockDead> h_block_dead;
+
+    // results of the last call
+    std::vector<b200_message> msgs;
+    std::vector<b200_block_info> blocks;
+    b200_timing timing;
+
+    ~b200_demod() {
+        cudaSetDevice(cfg.device);
+        d_lut.release(); d_tab_short.release(); d_tab_long.release(); d_bitmap.release();
+        d_head.release(); d_head_tmp.release(); d_iq.release(); d_cand.release(); d_dead.release();
+        d_recs.release(); d_tiles.release(); d_tiles_out.release(); d_live.release(); d_liverecs.release();
+        d_counters.release(); d_sums_u64.release(); d_sums_f64.release(); d_block_dead.release();
+        d_dbg_masks.release(); d_mag.release(); d_frames.release(); d_syn.release(); d_err.release(); d_bits.release();
+        h_counters.release(); h_tiles_out.release(); h_dead.release(); h_live.release(); h_liverecs.release();
+        h_sums_u64.release(); h_sums_f64.release(); h_block_dead.release();
+        for (auto &e : ev)
+            if (e)
+                cudaEventDestroy(e);
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+};
+
+extern "C" const char *b200_last_error(void) {
+    return g_last_error.c_str();
+}
+
+static int ensure_span_buffers(b200_demod *d, uint64_t nsamples, size_t cand_cap, size_t rec_cap, size_t live_cap,
+                               size_t liverec_cap) {
+    const size_t ntiles = (size_t) ((nsamples + kTile - 1) / kTile);
+    const size_t nblocks = (size_t) (nsamples / d->cfg.block_samples + 2);
+    CUDA_TRY(d->d_cand.ensure(cand_cap));
+    CUDA_TRY(d->d_dead.ensure(cand_cap));
+    CUDA_TRY(d->d_recs.ensure(rec_cap));
+    CUDA_TRY(d->d_live.ensure(live_cap));
+    CUDA_TRY(d->d_liverecs.ensure(liverec_cap));
+    CUDA_TRY(d->d_tiles.ensure(ntiles + 1));
+    CUDA_TRY(d->d_tiles_out.ensure(ntiles + 1));
+    CUDA_TRY(d->d_counters.ensure(1));
+    CUDA_TRY(d->d_sums_u64.ensure(2 * nblocks));
+    CUDA_TRY(d->d_sums_f64.ensure(2 * nblocks));
+    CUDA_TRY(d->d_block_dead.ensure(nblocks));
+    CUDA_TRY(d->h_counters.ensure(1));
+    CUDA_TRY(d->h_tiles_out.ensure(ntiles + 1));
+    CUDA_TRY(d->h_sums_u64.ensure(2 * nblocks));
+    CUDA_TRY(d->h_sums_f64.ensure(2 * nblocks));
+    CUDA_TRY(d->h_block_dead.ensure(nblocks));
+    return B200_OK;
+}
+
+extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out) {
+    if (!cfg || !out)
+        return fail(B200_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != B200_ABI_VERSION)
+        return fail(B200_ERR_ARG, "abi_version %d != %d", cfg->abi_version, B200_ABI_VERSION);
+    if (cfg->input_format < B200_INPUT_UC8 || cfg->input_format > B200_INPUT_SC16Q11)
+        return fail(B200_ERR_ARG, "no suitable converter for format=%d", cfg->input_format); // convert.c:460-464
+    if (cfg->nfix_crc < 0 || cfg->nfix_crc > 2)
+        return fail(B200_ERR_ARG, "nfix_crc must be 0, 1 or 2");
+    if (cfg->preamble_threshold < 1 || cfg->preamble_threshold > 6000)
+        return fail(B200_ERR_ARG, "preamble_threshold out of range");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(B200_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(B200_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(B200_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", cfg->device, prop.major,
+                    prop.minor);
+
+    std::unique_ptr<b200_demod> d(new (std::nothrow) b200_demod());
+    if (!d)
+        return fail(B200_ERR_NOMEM, "out of memory");
+    d->cfg = *cfg;
+    if (d->cfg.block_samples == 0)
+        d->cfg.block_samples = B200_DEFAULT_BLOCK_SAMPLES;
+    if (d->cfg.block_samples % 8 != 0)
+        return fail(B200_ERR_ARG, "block_samples must be a multiple of 8");
+    if (d->cfg.max_span_samples == 0)
+        d->cfg.max_span_samples = 64ull << 20;
+    if (d->cfg.max_span_samples > 0xfff00000ull)
+        return fail(B200_ERR_ARG, "max_span_samples must stay below 2^32 - 2^20");
+    d->bytes_per_sample = (cfg->input_format == B200_INPUT_UC8) ? 2 : 4;
+    d->sm_count = prop.multiProcessorCount;
+    memset(&d->timing, 0, sizeof(d->timing));
+
+    d->crc.reset(new CrcTables(cfg->nfix_crc));
+    d->resolver.reset(new Resolver(d->crc.get(), cfg->startup_time_ms));
+
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    for (auto &ev : d->ev)
+        CUDA_TRY(cudaEventCreate(&ev));
+    CUDA_TRY(scan_configure());
+    CUDA_TRY(upload_constants(d->crc->bit_syndromes()));
+
+    d->h_lut.resize(65536);
+    build_uc8_table(d->h_lut.data());
+    CUDA_TRY(d->d_lut.ensure(65536));
+    CUDA_TRY(cudaMemcpy(d->d_lut.p, d->h_lut.data(), 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+
+    const auto &ts = d->crc->short_table();
+    const auto &tl = d->crc->long_table();
+    CUDA_TRY(d->d_tab_short.ensure(ts.size() + 1));
+    CUDA_TRY(d->d_tab_long.ensure(tl.size() + 1));
+    if (!ts.empty())
+        CUDA_TRY(cudaMemcpy(d->d_tab_short.p, ts.data(), ts.size() * sizeof(ErrorInfo), cudaMemcpyHostToDevice));
+    if (!tl.empty())
+        CUDA_TRY(cudaMemcpy(d->d_tab_long.p, tl.data(), tl.size() * sizeof(ErrorInfo), cudaMemcpyHostToDevice));
+
+    CUDA_TRY(d->d_bitmap.ensure((1u << 24) / 32));
+    CUDA_TRY(cudaMemset(d->d_bitmap.p, 0, (1u << 24) / 8));
+    CUDA_TRY(d->d_head.ensure((size_t) kHead * 4));
+    CUDA_TRY(d->d_head_tmp.ensure((size_t) kHead * 4));
+    CUDA_TRY(cudaMemset(d->d_head.p, 0, (size_t) kHead * 4));
+
+    // one persistent CTA per SM (the uc8 table takes most of an SM's shared memory)
+    d->scan_grid = d->sm_count;
+    *out = d.release();
+    return B200_OK;
+}
+
+extern "C" void b200_demod_destroy(b200_demod *d) {
+    delete d;
+}
+
+extern "C" int b200_demod_reset(b200_demod *d) {
+    if (!d)
+        return fail(B200_ERR_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(d->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    CUDA_TRY(cudaMemset(d->d_bitmap.p, 0, (1u << 24) / 8));
+    CUDA_TRY(cudaMemset(d->d_head.p, 0, (size_t) kHead * 4));
+    d->head_valid = 0;
+    d->first_sample = 0;
+    d->finished = false;
+    d->resolver->reset();
+    d->msgs.clear();
+    d->blocks.clear();
+    memset(&d->timing, 0, sizeof(d->timing));
+    return B200_OK;
+}
+
+static ScanArgs make_scan_args(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t head_valid) {
+    ScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.iq = d_iq;
+    a.head = d->d_head.p;
+    a.head_valid = head_valid;
+    a.format = (uint32_t) d->cfg.input_format;
+    a.nsamples = nsamples;
+    a.threshold = d->cfg.preamble_threshold;
+    a.block_samples = d->cfg.block_samples;
+    a.ntiles = (uint32_t) ((nsamples + kTile - 1) / kTile);
+    a.lut = d->d_lut.p;
+    a.tab_short = d->d_tab_short.p;
+    a.tab_long = d->d_tab_long.p;
+    a.n_short = (int32_t) d->crc->short_table().size();
+    a.n_long = (int32_t) d->crc->long_table().size();
+    a.addr_bitmap = d->d_bitmap.p;
+    a.cand = d->d_cand.p;
+    a.recs = d->d_recs.p;
+    a.tiles = d->d_tiles.p;
+    a.cand_cap = (uint32_t) std::min<size_t>(d->d_cand.cap, 0xffffffffu);
+    a.rec_cap = (uint32_t) std::min<size_t>(d->d_recs.cap, 0xffffffffu);
+    a.counters = d->d_counters.p;
+    a.block_sums_u64 = d->d_sums_u64.p;
+    a.block_sums_f64 = d->d_sums_f64.p;
+    a.dbg_masks = nullptr;
+    return a;
+}
+
+static int zero_span_outputs(b200_demod *d, uint64_t nsamples, cudaStream_t s) {
+    const size_t nblocks = (size_t) (nsamples / d->cfg.block_samples + 2);
+    CUDA_TRY(cudaMemsetAsync(d->d_counters.p, 0, sizeof(ScanCounters), s));
+    CUDA_TRY(cudaMemsetAsync(d->d_sums_u64.p, 0, 2 * nblocks * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(d->d_sums_f64.p, 0, 2 * nblocks * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(d->d_block_dead.p, 0, nblocks * sizeof(BlockDead), s));
+    return B200_OK;
+}
+
+// after a span: head <- last kHead samples of (head ++ span)
+static int carry_head(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, cudaStream_t s) {
+    const size_t bps = (size_t) d->bytes_per_sample;
+    if (nsamples >= (uint64_t) kHead) {
+        CUDA_TRY(cudaMemcpyAsync(d->d_head.p, d_iq + (nsamples - kHead) * bps, kHead * bps, cudaMemcpyDeviceToDevice, s));
+        d->head_valid = kHead;
+    } else if (nsamples > 0) {
+        const size_t keep = kHead - (size_t) nsamples;
+        CUDA_TRY(cudaMemcpyAsync(d->d_head_tmp.p, d->d_head.p + nsamples * bps, keep * bps, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d->d_head.p, d->d_head_tmp.p, keep * bps, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d->d_head.p + keep * bps, d_iq, nsamples * bps, cudaMemcpyDeviceToDevice, s));
+        d->head_valid = (uint32_t) std::min<uint64_t>(kHead, d->head_valid + nsamples);
+    }
+    return B200_OK;
+}
+
+static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t flags, cudaStream_t s, bool timed_h2d) {
+    const bool final_span = (flags & B200_FLAG_FINAL) != 0;
+    const uint32_t B = d->cfg.block_samples;
+    const double t_start = now_ms();
+
+    size_t cand_cap = std::max<size_t>(d->d_cand.cap, (size_t) (nsamples / 24 + 4096));
+    size_t rec_cap = std::max<size_t>(d->d_recs.cap, (size_t) (nsamples / 64 + 4096));
+    size_t live_cap = std::max<size_t>(d->d_live.cap, (size_t) (nsamples / 128 + 4096));
+    size_t liverec_cap = std::max<size_t>(d->d_liverecs.cap, (size_t) (nsamples / 64 + 4096));
+    const uint32_t ntiles = (uint32_t) ((nsamples + kTile - 1) / kTile);
+    const size_t nblocks = (size_t) (nsamples / B + (final_span ? 1 : 0));
+    uint32_t launches = 0;
+
+    ScanCounters cnt;
+    memset(&cnt, 0, sizeof(cnt));
+    for (int attempt = 0;; ++attempt) {
+        int rc = ensure_span_buffers(d, nsamples, cand_cap, rec_cap, live_cap, liverec_cap);
+        if (rc != B200_OK)
+            return rc;
+        rc = zero_span_outputs(d, nsamples, s);
+        if (rc != B200_OK)
+            return rc;
+
+        ScanArgs sa = make_scan_args(d, d_iq, nsamples, d->head_valid);
+        CUDA_TRY(cudaEventRecord(d->ev[1], s));
+        CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
+        CUDA_TRY(cudaEventRecord(d->ev[2], s));
+
+        ClassifyArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.iq = d_iq;
+        ca.head = d->d_head.p;
+        ca.head_valid = d->head_valid;
+        ca.format = sa.format;
+        ca.nsamples = nsamples;
+        ca.block_samples = B;
+        ca.ntiles = ntiles;
+        ca.lut = d->d_lut.p;
+        ca.tab_short = sa.tab_short;
+        ca.tab_long = sa.tab_long;
+        ca.n_short = sa.n_short;
+        ca.n_long = sa.n_long;
+        ca.addr_bitmap = d->d_bitmap.p;
+        ca.cand = d->d_cand.p;
+        ca.recs = d->d_recs.p;
+        ca.tiles = d->d_tiles.p;
+        ca.dead = d->d_dead.p;
+        ca.live = d->d_live.p;
+        ca.liverecs = d->d_liverecs.p;
+        ca.tiles_out = d->d_tiles_out.p;
+        ca.dead_cap = (uint32_t) std::min<size_t>(d->d_dead.cap, 0xffffffffu);
+        ca.live_cap = (uint32_t) std::min<size_t>(d->d_live.cap, 0xffffffffu);
+        ca.liverec_cap = (uint32_t) std::min<size_t>(d->d_liverecs.cap, 0xffffffffu);
+        ca.counters = d->d_counters.p;
+        ca.block_dead = d->d_block_dead.p;
+        // K2 looks at K1's overflow flag itself and does nothing when K1 did not fit
+        CUDA_TRY(launch_classify(ca, s));
+        launches += ntiles ? 2 : 0;
+        CUDA_TRY(cudaEventRecord(d->ev[3], s));
+        CUDA_TRY(cudaMemcpyAsync(d->h_counters.p, d->d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+        if (ntiles)
+            CUDA_TRY(cudaMemcpyAsync(d->h_tiles_out.p, d->d_tiles_out.p, ntiles * sizeof(TileOut), cudaMemcpyDeviceToHost, s));
+        if (nblocks) {
+            CUDA_TRY(cudaMemcpyAsync(d->h_sums_u64.p, d->d_sums_u64.p, 2 * nblocks * sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(d->h_sums_f64.p, d->d_sums_f64.p, 2 * nblocks * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(d->h_block_dead.p, d->d_block_dead.p, nblocks * sizeof(BlockDead), cudaMemcpyDeviceToHost, s));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+        cnt = *d->h_counters.p;
+        if (!cnt.overflow)
+            break;
+        if (attempt >= 3)
+            return fail(B200_ERR_CAPACITY, "candidate buffers overflowed after %d attempts (flags 0x%x)", attempt + 1, cnt.overflow);
+        // grow to what the kernels asked for (their counters keep counting past the capacity)
+        cand_cap = std::max<size_t>(cand_cap, (size_t) cnt.n_cand + (size_t) cnt.n_cand / 8 + 4096);
+        rec_cap = std::max<size_t>(rec_cap, (size_t) cnt.n_rec + (size_t) cnt.n_rec / 8 + 4096);
+        if (cnt.overflow & 0x1cu) {
+            live_cap = std::max<size_t>(live_cap, (size_t) cnt.n_live + (size_t) cnt.n_live / 8 + 4096);
+            liverec_cap = std::max<size_t>(liverec_cap, (size_t) cnt.n_liverec + (size_t) cnt.n_liverec / 8 + 4096);
+        } else {
+            // K2 did not run: size its lists from K1's counts so that the retry cannot fail there
+            live_cap = std::max<size_t>(live_cap, cand_cap);
+            liverec_cap = std::max<size_t>(liverec_cap, rec_cap);
+        }
+    }
+
+    // survivors back to the host
+    CUDA_TRY(d->h_dead.ensure(std::max<size_t>((size_t) cnt.n_dead, 1)));
+    CUDA_TRY(d->h_live.ensure(std::max<size_t>((size_t) cnt.n_live, 1)));
+    CUDA_TRY(d->h_liverecs.ensure(std::max<size_t>((size_t) cnt.n_liverec, 1)));
+    if (cnt.n_dead)
+        CUDA_TRY(cudaMemcpyAsync(d->h_dead.p, d->d_dead.p, (size_t) cnt.n_dead * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (cnt.n_live)
+        CUDA_TRY(cudaMemcpyAsync(d->h_live.p, d->d_live.p, (size_t) cnt.n_live * sizeof(LivePos), cudaMemcpyDeviceToHost, s));
+    if (cnt.n_liverec)
+        CUDA_TRY(cudaMemcpyAsync(d->h_liverecs.p, d->d_liverecs.p, (size_t) cnt.n_liverec * sizeof(LiveRec), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(d->ev[4], s));
+    {
+        int rc = carry_head(d, d_iq, nsamples, s);
+        if (rc != B200_OK)
+            return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+
+    // host: the order-dependent tail
+    const double t_res0 = now_ms();
+    SpanView v;
+    v.nsamples = nsamples;
+    v.first_sample = d->first_sample;
+    v.block_samples = B;
+    v.final_span = final_span;
+    v.format = (uint32_t) d->cfg.input_format;
+    v.ntiles = ntiles;
+    v.tiles = d->h_tiles_out.p;
+    v.dead = d->h_dead.p;
+    v.live = d->h_live.p;
+    v.liverecs = d->h_liverecs.p;
+    v.block_dead = d->h_block_dead.p;
+    v.block_sums_u64 = d->h_sums_u64.p;
+    v.block_sums_f64 = d->h_sums_f64.p;
+    d->msgs.clear();
+    d->blocks.clear();
+    d->resolver->resolve(v, d->msgs, d->blocks);
+    const double t_res1 = now_ms();
+
+    d->first_sample += nsamples;
+    if (final_span)
+        d->finished = true;
+
+    b200_timing &t = d->timing;
+    memset(&t, 0, sizeof(t));
+    if (timed_h2d)
+        cudaEventElapsedTime(&t.h2d_ms, d->ev[0], d->ev[1]);
+    cudaEventElapsedTime(&t.scan_ms, d->ev[1], d->ev[2]);
+    cudaEventElapsedTime(&t.classify_ms, d->ev[2], d->ev[3]);
+    cudaEventElapsedTime(&t.d2h_ms, d->ev[3], d->ev[4]);
+    t.resolve_ms = (float) (t_res1 - t_res0);
+    t.total_ms = (float) (now_ms() - t_start);
+    t.n_candidates = cnt.n_cand;
+    t.n_phase_records = cnt.n_rec;
+    t.n_live = cnt.n_live;
+    t.scan_launches = launches;
+    return B200_OK;
+}
+
+static int check_span(b200_demod *d, const void *iq, uint64_t nsamples, uint32_t flags) {
+    if (!d)
+        return fail(B200_ERR_ARG, "null context");
+    if (!iq && nsamples)
+        return fail(B200_ERR_ARG, "null sample buffer");
+    if (d->finished)
+        return fail(B200_ERR_STATE, "the stream already ended (B200_FLAG_FINAL); call b200_demod_reset");
+    if (nsamples > d->cfg.max_span_samples)
+        return fail(B200_ERR_CAPACITY, "span of %llu samples exceeds max_span_samples %llu", (unsigned long long) nsamples,
+                    (unsigned long long) d->cfg.max_span_samples);
+    if (!(flags & B200_FLAG_FINAL) && nsamples % d->cfg.block_samples != 0)
+        return fail(B200_ERR_ARG, "a non-final span must hold whole blocks of %u samples", d->cfg.block_samples);
+    return B200_OK;
+}
+
+extern "C" int b200_demod_process(b200_demod *d, const void *iq, uint64_t nsamples, uint32_t flags) {
+    int rc = check_span(d, iq, nsamples, flags);
+    if (rc != B200_OK)
+        return rc;
+    CUDA_TRY(cudaSetDevice(d->cfg.device));
+    const size_t bytes = (size_t) nsamples * d->bytes_per_sample;
+    CUDA_TRY(d->d_iq.ensure(bytes + 256));
+    const double t0 = now_ms();
+    CUDA_TRY(cudaEventRecord(d->ev[0], d->stream));
+    if (bytes)
+        CUDA_TRY(cudaMemcpyAsync(d->d_iq.p, iq, bytes, cudaMemcpyHostToDevice, d->stream));
+    rc = run_span(d, d->d_iq.p, nsamples, flags, d->stream, true);
+    if (rc == B200_OK)
+        d->timing.total_ms = (float) (now_ms() - t0);
+    return rc;
+}
+
+extern "C" int b200_demod_process_device(b200_demod *d, const void *d_iq, uint64_t nsamples, uint32_t flags, void *cuda_stream) {
+    int rc = check_span(d, d_iq, nsamples, flags);
+    if (rc != B200_OK)
+        return rc;
+    if ((uintptr_t) d_iq & 15u)
+        return fail(B200_ERR_ARG, "device span must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(d->cfg.device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
+    return run_span(d, (const uint8_t *) d_iq, nsamples, flags, s, false);
+}
+
+extern "C" uint64_t b200_demod_message_count(const b200_demod *d) {
+    return d ? d->msgs.size() : 0;
+}
+
+extern "C" const b200_message *b200_demod_messages(const b200_demod *d) {
+    return d ? d->msgs.data() : nullptr;
+}
+
+extern "C" uint64_t b200_demod_block_count(const b200_demod *d) {
+    return d ? d->blocks.size() : 0;
+}
+
+extern "C" const b200_block_info *b200_demod_blocks(const b200_demod *d) {
+    return d ? d->blocks.data() : nullptr;
+}
+
+extern "C" int b200_demod_get_stats(const b200_demod *d, b200_demod_stats *out) {
+    if (!d || !out)
+        return fail(B200_ERR_ARG, "null argument");
+    *out = d->resolver->stats();
+    // reserved[0]: kernel/host CRC disagreements (must stay 0)
+    out->reserved[0] = (double) d->resolver->gpu_host_mismatches();
+    return B200_OK;
+}
+
+extern "C" int b200_demod_get_timing(const b200_demod *d, b200_timing *out) {
+    if (!d || !out)
+        return fail(B200_ERR_ARG, "null argument");
+    *out = d->timing;
+    return B200_OK;
+}
+
+extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsamples, int mode, void *cuda_stream, float *ms_out,
+                                uint64_t *n_candidates_out) {
+    if (!d || !d_iq)
+        return fail(B200_ERR_ARG, "null argument");
+    if ((uintptr_t) d_iq & 15u)
+        return fail(B200_ERR_ARG, "device span must be 16-byte aligned");
+    if (nsamples > d->cfg.max_span_samples)
+        return fail(B200_ERR_CAPACITY, "span exceeds max_span_samples");
+    CUDA_TRY(cudaSetDevice(d->cfg.device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
+    int rc = ensure_span_buffers(d, nsamples, std::max<size_t>(d->d_cand.cap, (size_t) (nsamples / 24 + 4096)),
+                                 std::max<size_t>(d->d_recs.cap, (size_t) (nsamples / 64 + 4096)),
+                                 std::max<size_t>(d->d_live.cap, 4096), std::max<size_t>(d->d_liverecs.cap, 4096));
+    if (rc != B200_OK)
+        return rc;
+    rc = zero_span_outputs(d, nsamples, s);
+    if (rc != B200_OK)
+        return rc;
+    ScanArgs sa = make_scan_args(d, (const uint8_t *) d_iq, nsamples, 0);
+    CUDA_TRY(cudaEventRecord(d->ev[1], s));
+    CUDA_TRY(launch_scan(sa, mode ? 1 : 0, d->scan_grid, s));
+    CUDA_TRY(cudaEventRecord(d->ev[2], s));
+    CUDA_TRY(cudaMemcpyAsync(d->h_counters.p, d->d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]));
+    if (ms_out)
+        *ms_out = ms;
+    if (n_candidates_out)
+        *n_candidates_out = d->h_counters.p->n_cand;
+    return B200_OK;
+}
+
+extern "C" int b200_convert(b200_demod *d, const void *iq, uint32_t nsamples, uint16_t *mag, double *mean_level, double *mean_power) {
+    if (!d || (!iq && nsamples) || (!mag && nsamples))
+        return fail(B200_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(d->cfg.device));
+    const size_t bytes = (size_t) nsamples * d->bytes_per_sample;
+    CUDA_TRY(d->d_frames.ensure(bytes + 16));
+    CUDA_TRY(d->d_mag.ensure((size_t) nsamples + 8));
+    CUDA_TRY(d->d_sums_u64.ensure(4));
+    CUDA_TRY(d->d_sums_f64.ensure(4));
+    cudaStream_t s = d->stream;
+    CUDA_TRY(cudaMemsetAsync(d->d_sums_u64.p, 0, 2 * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(d->d_sums_f64.p, 0, 2 * sizeof(double), s));
+    if (bytes)
+        CUDA_TRY(cudaMemcpyAsync(d->d_frames.p, iq, bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_convert(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, d->d_lut.p, d->d_mag.p, d->d_sums_u64.p,
+                            d->d_sums_f64.p, s));
+    unsigned long long su[2] = {0, 0};
+    double sf[2] = {0, 0};
+    if (nsamples)
+        CUDA_TRY(cudaMemcpyAsync(mag, d->d_mag.p, (size_t) nsamples * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(su, d->d_sums_u64.p, sizeof(su), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(sf, d->d_sums_f64.p, sizeof(sf), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (d->cfg.input_format == B200_INPUT_UC8) {
+        if (mean_level)
+            *mean_level = su[0] / 65536.0 / nsamples; // convert.c:105
+        if (mean_power)
+            *mean_power = su[1] / 65535.0 / 65535.0 / nsamples; // convert.c:109
+    } else {
+        if (mean_level)
+            *mean_level = (double) ((float) sf[0] / (float) nsamples); // convert.c:246-252
+        if (mean_power)
+            *mean_power = (double) ((float) sf[1] / (float) nsamples);
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_uc8_table(b200_demod *d, uint16_t *table65536) {
+    if (!d || !table65536)
+        return fail(B200_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(d->cfg.device));
+    // what the kernels actually read, not the host copy
+    CUDA_TRY(cudaMemcpy(table65536, d->d_lut.p, 65536 * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples, uint8_t *try_masks, b200_phase_record *records,
+                               uint64_t record_cap, uint64_t *n_records) {
+    if (!d || (!iq && nsamples))
+        return fail(B200_ERR_ARG, "null argument");
+    if (nsamples > d->cfg.max_span_samples)
+        return fail(B200_ERR_CAPACITY, "span exceeds max_span_samples");
+    CUDA_TRY(cudaSetDevice(d->cfg.device));
+    cudaStream_t s = d->stream;
+    const size_t bytes = (size_t) nsamples * d->bytes_per_sample;
+    CUDA_TRY(d->d_iq.ensure(bytes + 256));
+    CUDA_TRY(d->d_dbg_masks.ensure((size_t) nsamples + 16));
+    // generous: every position a candidate with five records
+    int rc = ensure_span_buffers(d, nsamples, std::max<size_t>(d->d_cand.cap, (size_t) nsamples + 4096),
+                                 std::max<size_t>(d->d_recs.cap, (size_t) nsamples * 5 + 4096), std::max<size_t>(d->d_live.cap, 4096),
+                                 std::max<size_t>(d->d_liverecs.cap, 4096));
+    if (rc != B200_OK)
+        return rc;
+    rc = zero_span_outputs(d, nsamples, s);
+    if (rc != B200_OK)
+        return rc;
+    if (bytes)
+        CUDA_TRY(cudaMemcpyAsync(d->d_iq.p, iq, bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(d->d_dbg_masks.p, 0, (size_t) nsamples + 16, s));
+    ScanArgs sa = make_scan_args(d, d->d_iq.p, nsamples, 0);
+    sa.dbg_masks = d->d_dbg_masks.p;
+    CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
+    CUDA_TRY(cudaMemcpyAsync(d->h_counters.p, d->d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (d->h_counters.p->overflow)
+        return fail(B200_ERR_CAPACITY, "debug scan overflowed its buffers");
+    if (try_masks && nsamples)
+        CUDA_TRY(cudaMemcpy(try_masks, d->d_dbg_masks.p, (size_t) nsamples, cudaMemcpyDeviceToHost));
+    const uint32_t ntiles = sa.ntiles;
+    std::vector<TileDesc> tiles(ntiles);
+    if (ntiles)
+        CUDA_TRY(cudaMemcpy(tiles.data(), d->d_tiles.p, ntiles * sizeof(TileDesc), cudaMemcpyDeviceToHost));
+    uint64_t total = 0;
+    std::vector<PhaseRec> tmp;
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        const TileDesc &td = tiles[t];
+        if (!td.nrec)
+            continue;
+        tmp.resize(td.nrec);
+        CUDA_TRY(cudaMemcpy(tmp.data(), d->d_recs.p + td.rec_off, td.nrec * sizeof(PhaseRec), cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < td.nrec; ++i) {
+            if (records && total < record_cap) {
+                b200_phase_record &o = records[total];
+                o.position = tmp[i].pos;
+                o.crc = tmp[i].w0 & 0xffffffu;
+                o.key = tmp[i].w1 & 0xffffffu;
+                o.phase = (uint8_t) ((tmp[i].w1 >> 24) & 15u);
+                o.kind = (uint8_t) ((tmp[i].w0 >> 24) & 7u);
+                o.errors = (uint8_t) ((tmp[i].w0 >> 28) & 3u);
+                o.reserved = 0;
+            }
+            ++total;
+        }
+    }
+    if (n_records)
+        *n_records = total;
+    return B200_OK;
+}
+
+extern "C" int b200_crc_batch(b200_demod *d, const uint8_t *frames14, uint32_t n, uint32_t *syndromes, int8_t *errors, int8_t *bits2) {
+    if (!d || (!frames14 && n) || !syndromes || !errors || !bits2)
+        return fail(B200_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(d->cfg.device));
+    cudaStream_t s = d->stream;
+    CUDA_TRY(d->d_frames.ensure((size_t) n * 14 + 16));
+    CUDA_TRY(d->d_syn.ensure((size_t) n + 1));
+    CUDA_TRY(d->d_err.ensure((size_t) n + 1));
+    CUDA_TRY(d->d_bits.ensure((size_t) 2 * n + 2));
+    if (n == 0)
+        return B200_OK;
+    CUDA_TRY(cudaMemcpyAsync(d->d_frames.p, frames14, (size_t) n * 14, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_crc_batch(d->d_frames.p, n, d->d_tab_short.p, (int) d->crc->short_table().size(), d->d_tab_long.p,
+                              (int) d->crc->long_table().size(), d->d_syn.p, d->d_err.p, d->d_bits.p, s));
+    CUDA_TRY(cudaMemcpyAsync(syndromes, d->d_syn.p, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(errors, d->d_err.p, (size_t) n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(bits2, d->d_bits.p, (size_t) 2 * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return B200_OK;
+}
+
+extern "C" int b200_error_table(b200_demod *d, int bits, b200_errorinfo *out, int cap) {
+    if (!d || (bits != 56 && bits != 112))
+        return fail(B200_ERR_ARG, "bits must be 56 or 112");
+    const auto &t = (bits == 56) ? d->crc->short_table() : d->crc->long_table();
+    for (size_t i = 0; i < t.size() && (int) i < cap && out; ++i) {
+        out[i].syndrome = t[i].syndrome;
+        out[i].errors = t[i].errors;
+        out[i].bit[0] = t[i].bit[0];
+        out[i].bit[1] = t[i].bit[1];
+        out[i].padding = 0;
+    }
+    return (int) t.size();
+}

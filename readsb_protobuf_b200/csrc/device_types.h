@@ -1,0 +1,96 @@
+// device_types.h -- records exchanged between the kernels and the host resolver.
+#pragma once
+
+#include <stdint.h>
+
+namespace b200 {
+
+// ---- geometry ---------------------------------------------------------------------------
+constexpr int kOverlap = 326;      // Modes.trailing_samples at 2.4 MS/s (readsb.c:198)
+constexpr int kHead = 328;         // samples carried in front of a span: kOverlap rounded up to 16 bytes
+constexpr int kTile = 8192;        // scan positions per tile
+constexpr int kTileHalo = 336;     // extra samples a tile converts: kHead in front + 8 behind
+constexpr int kTileSamples = kTile + kTileHalo;
+constexpr int kScanThreads = 512;
+constexpr int kPosPerThread = kTile / kScanThreads; // 16
+constexpr int kMaxCand = 1024;     // candidates one slice round can hold
+constexpr int kMaxItems = kMaxCand * 5;
+constexpr int kSlowRounds = kTile / kMaxCand; // 8: a round of kMaxCand positions can never overflow
+
+// ---- scoring classes of a sliced frame that does not score -2 outright ------------------
+// (the filter-independent half of scoreModesMessage, mode_s.c:311-409)
+enum : uint32_t {
+    kKindBad = 0,     // -2 whatever the ICAO filter holds
+    kKindAP = 1,      // DF0/4/5/16/24: filter(crc) ? 1000 : -1
+    kKindAPCommB = 2, // DF20/21:       filter(crc) ? 1000 : -2
+    kKindDF11 = 3,    // all-call reply, syndrome (ignoring IID) clean or 1-bit repairable
+    kKindES = 4,      // DF17/18, syndrome clean or repairable
+};
+
+// K1 -> K2: one per (candidate position, phase) whose class is not kKindBad.  16 bytes.
+struct PhaseRec {
+    uint32_t pos;  // scan position within the span
+    uint32_t w0;   // crc[23:0] | kind[26:24] | errors[29:28]
+    uint32_t w1;   // key[23:0] (address the score depends on) | phase[27:24]
+    uint32_t cand; // global candidate index
+};
+
+// K1 per tile
+struct TileDesc {
+    uint32_t cand_off, ncand;
+    uint32_t rec_off, nrec;
+};
+
+// candidate entry (K1): pos_in_tile[12:0] | trymask[17:13] | nonbad[20:18]
+// dead entry (K2):      pos_in_tile[12:0] | trymask[17:13] | unknown_icao[18]
+
+// K2 per tile
+struct TileOut {
+    uint32_t dead_off, ndead;
+    uint32_t live_off, nlive;
+    uint32_t liverec_off, nliverec;
+};
+
+// K2 -> host: a position the resolver must look at.  8 bytes.
+struct LivePos {
+    uint32_t pos;  // scan position within the span
+    uint32_t info; // trymask[4:0] | nrec[10:8] | first live record (relative to the tile's liverec_off) [31:16]
+};
+
+// K2 -> host: a sliced frame of a live position.  48 bytes.
+struct LiveRec {
+    uint32_t pos;
+    uint32_t w0;    // as PhaseRec
+    uint32_t w1;
+    uint32_t errbits; // bit0[7:0] | bit1[15:8] (0xff = none)
+    uint64_t power; // sum of m^2 over the frame's 134/268 samples (demod_2400.c:393-396)
+    uint8_t msg[14];
+    uint8_t pad[2];
+};
+
+// per mag_buf counters of positions that can never be accepted (K2)
+struct BlockDead {
+    uint32_t preambles;
+    uint32_t rejected_bad;
+    uint32_t rejected_unknown;
+    uint32_t phase[5];
+};
+
+struct ScanCounters {
+    unsigned long long n_cand;
+    unsigned long long n_rec;
+    unsigned long long n_dead;
+    unsigned long long n_live;
+    unsigned long long n_liverec;
+    unsigned int overflow; // bit0 cand, bit1 rec, bit2 dead, bit3 live, bit4 liverec
+    unsigned int slow_tiles;
+};
+
+struct ErrorInfo { // struct errorinfo, crc.h:32-37
+    uint32_t syndrome;
+    int32_t errors;
+    int8_t bit[2];
+    uint16_t padding;
+};
+
+} // namespace b200

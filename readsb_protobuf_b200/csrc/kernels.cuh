@@ -1,0 +1,82 @@
+// kernels.cuh -- launch interface of the sm_100a kernels (kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+
+namespace b200 {
+
+struct ScanArgs {
+    // input
+    const uint8_t *iq;    // new samples of the span, 16-byte aligned
+    const uint8_t *head;  // kHead samples carried from the previous span, 16-byte aligned
+    uint32_t head_valid;  // how many of them are real (0 at stream start: magnitude 0, fifo.c:47)
+    uint32_t format;      // B200_INPUT_*
+    uint64_t nsamples;    // new samples == scan positions of the span
+    int32_t threshold;    // Modes.preambleThreshold
+    uint32_t block_samples;
+    uint32_t ntiles;
+    // tables
+    const uint16_t *lut;  // uc8 magnitude table (65536 entries)
+    const ErrorInfo *tab_short;
+    const ErrorInfo *tab_long;
+    int32_t n_short, n_long;
+    uint32_t *addr_bitmap; // 2^24 bits: every address icaoFilterAdd could ever see
+    // output
+    uint32_t *cand;
+    PhaseRec *recs;
+    TileDesc *tiles;
+    uint32_t cand_cap, rec_cap;
+    ScanCounters *counters;
+    unsigned long long *block_sums_u64; // [nblocks][2]: sum mag, sum mag^2 (table formats)
+    double *block_sums_f64;             // [nblocks][2]: sum mag, sum magsq (float formats)
+    uint8_t *dbg_masks;                 // optional: try mask per scan position
+};
+
+struct ClassifyArgs {
+    const uint8_t *iq;
+    const uint8_t *head;
+    uint32_t head_valid;
+    uint32_t format;
+    uint64_t nsamples;
+    uint32_t block_samples;
+    uint32_t ntiles;
+    const uint16_t *lut;
+    const ErrorInfo *tab_short;
+    const ErrorInfo *tab_long;
+    int32_t n_short, n_long;
+    const uint32_t *addr_bitmap;
+    const uint32_t *cand;
+    const PhaseRec *recs;
+    const TileDesc *tiles;
+    // output
+    uint32_t *dead;
+    LivePos *live;
+    LiveRec *liverecs;
+    TileOut *tiles_out;
+    uint32_t dead_cap, live_cap, liverec_cap;
+    ScanCounters *counters;
+    BlockDead *block_dead; // [nblocks]
+};
+
+// dynamic shared memory the scan kernel needs for a format
+size_t scan_smem_bytes(uint32_t format);
+cudaError_t scan_configure();
+// mode 0: magnitude + preamble scan only (candidates counted); 1: + slice + CRC + records
+cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
+cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream);
+
+// IQ -> u16 magnitudes materialised in global memory (+ sums into sums_u64[2] / sums_f64[2])
+cudaError_t launch_convert(const uint8_t *iq, uint32_t format, uint32_t nsamples, const uint16_t *lut,
+                           uint16_t *mag, unsigned long long *sums_u64, double *sums_f64, cudaStream_t stream);
+
+// frames14[n][14] -> syndrome, errors (-1 = uncorrectable), bits[n][2]
+cudaError_t launch_crc_batch(const uint8_t *frames14, uint32_t n, const ErrorInfo *tab_short, int n_short,
+                             const ErrorInfo *tab_long, int n_long, uint32_t *syndromes, int8_t *errors,
+                             int8_t *bits2, cudaStream_t stream);
+
+cudaError_t upload_constants(const uint32_t *bit_syndromes112);
+
+} // namespace b200

@@ -1,0 +1,391 @@
+// resolver.cc -- see resolver.h.
+#include "resolver.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+// ICAO filter (icao_filter.c)
+// ------------------------------------------------------------------------------------------
+
+uint32_t IcaoFilter::hash(uint32_t a) {
+    // icao_filter.c:44-65: Jenkins one-at-a-time over the three address bytes, low byte first
+    uint32_t h = 0;
+    for (int shift = 0; shift < 24; shift += 8) {
+        h += (a >> shift) & 0xffu;
+        h += h << 10;
+        h ^= h >> 6;
+    }
+    h += h << 3;
+    h ^= h >> 11;
+    h += h << 15;
+    return h & (kSize - 1);
+}
+
+void IcaoFilter::reset() {
+    memset(a_, 0xff, sizeof(a_));
+    memset(b_, 0xff, sizeof(b_));
+    active_ = a_;
+    next_flip_ = 0;
+}
+
+void IcaoFilter::add(uint32_t addr) {
+    // the address itself ...
+    uint32_t h0 = hash(addr), h = h0;
+    bool full = false;
+    while (active_[h] != kEmpty && active_[h] != addr) {
+        h = (h + 1) & (kSize - 1);
+        if (h == h0) {
+            full = true;
+            break;
+        }
+    }
+    if (full)
+        return; // icao_filter.c:78-81: a full table drops the address (and skips the second insert)
+    if (active_[h] == kEmpty)
+        active_[h] = addr;
+    // ... and once more on the chain of its low 16 bits (Data/Parity lookups, icao_filter.c:87-96)
+    const uint32_t low = addr & 0x00ffffu;
+    h0 = h = hash(low);
+    while (active_[h] != kEmpty && (active_[h] & 0x00ffffu) != low) {
+        h = (h + 1) & (kSize - 1);
+        if (h == h0)
+            return;
+    }
+    if (active_[h] == kEmpty)
+        active_[h] = addr;
+}
+
+bool IcaoFilter::probe(const uint32_t *t, uint32_t addr) {
+    uint32_t h0 = hash(addr), h = h0;
+    while (t[h] != kEmpty && t[h] != addr) {
+        h = (h + 1) & (kSize - 1);
+        if (h == h0)
+            break;
+    }
+    return t[h] == addr;
+}
+
+bool IcaoFilter::test(uint32_t addr) const {
+    return probe(a_, addr) || probe(b_, addr);
+}
+
+void IcaoFilter::expire(uint64_t now_ms) {
+    if (now_ms < next_flip_)
+        return;
+    uint32_t *other = (active_ == a_) ? b_ : a_;
+    memset(other, 0xff, sizeof(a_));
+    active_ = other;
+    next_flip_ = now_ms + 60000; // MODES_ICAO_FILTER_TTL, icao_filter.c:30
+}
+
+void IcaoFilter::collect(std::vector<uint32_t> &out) const {
+    for (uint32_t i = 0; i < kSize; ++i) {
+        if (a_[i] != kEmpty)
+            out.push_back(a_[i]);
+        if (b_[i] != kEmpty)
+            out.push_back(b_[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// scoring and the CRC-dependent part of decode
+// ------------------------------------------------------------------------------------------
+
+void Resolver::reset() {
+    filter_.reset();
+    memset(&stats_, 0, sizeof(stats_));
+    ifile_now_ = 0;
+    mismatches_ = 0;
+}
+
+// scoreModesMessage (mode_s.c:311-409) for a frame K1 already classified
+int Resolver::score(const LiveRec &r) const {
+    const uint32_t crc = r.w0 & 0xffffffu, kind = (r.w0 >> 24) & 7u, errors = (r.w0 >> 28) & 3u;
+    const uint32_t key = r.w1 & 0xffffffu;
+    switch (kind) {
+        case kKindAP: // mode_s.c:343
+            return filter_.test(crc) ? 1000 : -1;
+        case kKindAPCommB: // mode_s.c:393-403
+            return filter_.test(crc) ? 1000 : -2;
+        case kKindDF11: { // mode_s.c:364-374
+            const bool known = filter_.test(key);
+            if ((crc & 0x7fu) == 0)
+                return (known ? 1600 : 750) / (int) (errors + 1);
+            return known ? 1000 / (int) (errors + 1) : -1;
+        }
+        case kKindES: // mode_s.c:386-389
+            return (filter_.test(key) ? 1800 : 1400) / (int) (errors + 1);
+        default:
+            return -2;
+    }
+}
+
+static inline uint32_t aa_field(const uint8_t *msg) { // getbits(msg, 9, 32)
+    return ((uint32_t) msg[1] << 16) | ((uint32_t) msg[2] << 8) | (uint32_t) msg[3];
+}
+
+// The part of decodeModesMessage that can reject the frame or touches the filter
+// (mode_s.c:424-555, 560-562, 717-726).  CRC and repair are recomputed on the host from the
+// sliced bytes; a disagreement with the kernel's values is counted, never hidden.
+int Resolver::decode(const LiveRec &r, b200_message &mm) {
+    memcpy(mm.msg, r.msg, 14);
+    memcpy(mm.verbatim, r.msg, 14);
+    uint8_t *msg = mm.msg;
+    static const uint8_t zeros[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (!memcmp(msg, zeros, 7))
+        return -2;
+    mm.msgtype = msg[0] >> 3;
+    mm.msgbits = (mm.msgtype & 0x10) ? 112 : 56;
+    mm.crc = crc_->checksum(msg, mm.msgbits);
+    mm.correctedbits = 0;
+    mm.addr = 0;
+    if (mm.crc != (r.w0 & 0xffffffu))
+        ++mismatches_;
+    uint32_t iid = 0;
+
+    switch (mm.msgtype) {
+        case 0: case 4: case 5: case 16:
+        case 24: case 25: case 26: case 27: case 28: case 29: case 30: case 31:
+            if (!filter_.test(mm.crc))
+                return -1;
+            mm.addr = mm.crc;
+            break;
+        case 11: {
+            iid = mm.crc & 0x7fu;
+            if (mm.crc & 0xffff80u) {
+                const ErrorInfo *ei = crc_->diagnose(mm.crc & 0xffff80u, mm.msgbits);
+                if (!ei || ei->errors > 1)
+                    return -2;
+                mm.correctedbits = (uint8_t) ei->errors;
+                CrcTables::fix(msg, ei);
+                if (!filter_.test(aa_field(msg)))
+                    return -1;
+            }
+            break;
+        }
+        case 17: case 18: {
+            if (mm.crc != 0) {
+                const ErrorInfo *ei = crc_->diagnose(mm.crc, mm.msgbits);
+                if (!ei)
+                    return -2;
+                const uint32_t addr1 = aa_field(msg);
+                mm.correctedbits = (uint8_t) ei->errors;
+                CrcTables::fix(msg, ei);
+                const uint32_t addr2 = aa_field(msg);
+                if (addr1 != addr2 && !filter_.test(addr2))
+                    return -1;
+            }
+            break;
+        }
+        case 20: case 21:
+            if (!filter_.test(mm.crc))
+                return -1;
+            mm.addr = mm.crc;
+            break;
+        default:
+            return -2;
+    }
+    if (mm.msgtype == 11 || mm.msgtype == 17 || mm.msgtype == 18)
+        mm.addr = aa_field(msg);
+    if (((r.w0 >> 28) & 3u) != mm.correctedbits && mm.msgtype != 11)
+        ++mismatches_;
+    // the only place addresses enter the filter
+    if (!mm.correctedbits && (mm.msgtype == 17 || (mm.msgtype == 11 && iid == 0)))
+        filter_.add(mm.addr);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// the walk
+// ------------------------------------------------------------------------------------------
+
+namespace {
+
+struct DeadCount {
+    uint32_t preambles = 0, bad = 0, unknown = 0, phase[5] = {0, 0, 0, 0, 0};
+};
+
+// dead positions in (lo, hi] that a skip-ahead hides (they are in the per-block totals K2 made)
+void count_dead(const SpanView &v, uint64_t lo, uint64_t hi, DeadCount &dc) {
+    if (hi <= lo)
+        return;
+    const uint32_t t0 = (uint32_t) ((lo + 1) / kTile), t1 = (uint32_t) (hi / kTile);
+    for (uint32_t t = t0; t <= t1 && t < v.ntiles; ++t) {
+        const TileOut &to = v.tiles[t];
+        const uint32_t *d = v.dead + to.dead_off, *dend = d + to.ndead;
+        const uint64_t base = (uint64_t) t * kTile;
+        const uint32_t rel_lo = (lo + 1 > base) ? (uint32_t) (lo + 1 - base) : 0; // first position counted
+        const uint32_t *it = std::lower_bound(d, dend, rel_lo, [](uint32_t e, uint32_t x) { return (e & 0x1fffu) < x; });
+        for (; it != dend; ++it) {
+            const uint64_t p = base + (*it & 0x1fffu);
+            if (p > hi)
+                break;
+            const uint32_t tm = (*it >> 13) & 31u;
+            ++dc.preambles;
+            if ((*it >> 18) & 1u)
+                ++dc.unknown;
+            else
+                ++dc.bad;
+            for (int k = 0; k < 5; ++k)
+                dc.phase[k] += (tm >> k) & 1u;
+        }
+    }
+}
+
+} // namespace
+
+void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::vector<b200_block_info> &blocks) {
+    const uint64_t n = v.nsamples, B = v.block_samples;
+    // ifileRun: full blocks, then (at end of stream) one short block, which is empty when the stream
+    // length is a multiple of the block size (sdr_ifile.c:192-216)
+    const uint64_t nfull = n / B;
+    const uint64_t nblocks = nfull + (v.final_span ? 1 : 0);
+
+    uint32_t tile = 0, live_i = 0; // cursor over live positions
+    auto next_live = [&](const LivePos *&lp, const TileOut *&to) -> bool {
+        while (tile < v.ntiles) {
+            to = &v.tiles[tile];
+            if (live_i < to->nlive) {
+                lp = &v.live[to->live_off + live_i];
+                return true;
+            }
+            ++tile;
+            live_i = 0;
+        }
+        return false;
+    };
+
+    for (uint64_t k = 0; k < nblocks; ++k) {
+        const uint64_t b0 = k * B, b1 = std::min(n, b0 + B), nk = b1 - b0;
+        const uint64_t sample_counter = v.first_sample + b0;
+        // sdr_ifile.c:187-190
+        const uint64_t sampleTimestamp = (uint64_t) ((double) sample_counter * 12e6 / 2400000.0);
+        const uint64_t sysTimestamp = sampleTimestamp / 12000U + startup_;
+
+        // converter outputs of the block (convert.c:104-110 / 246-252)
+        b200_block_info bi;
+        if (v.format == B200_INPUT_UC8) {
+            const unsigned long long sl = v.block_sums_u64[2 * k], sp = v.block_sums_u64[2 * k + 1];
+            bi.mean_level = sl / 65536.0 / (unsigned) nk; // sic: 65536
+            bi.mean_power = sp / 65535.0 / 65535.0 / (unsigned) nk;
+        } else {
+            bi.mean_level = (double) ((float) v.block_sums_f64[2 * k] / (float) (unsigned) nk);
+            bi.mean_power = (double) ((float) v.block_sums_f64[2 * k + 1] / (float) (unsigned) nk);
+        }
+        blocks.push_back(bi);
+
+        ifile_now_ = sysTimestamp; // demod_2400.c:253-255
+        uint64_t sum_scaled_signal_power = 0;
+        DeadCount hidden;
+        bool skipping = false;
+        uint64_t skip_until = 0; // positions <= skip_until are skipped while `skipping`
+
+        const LivePos *lp;
+        const TileOut *to;
+        while (next_live(lp, to) && lp->pos < b1) {
+            const uint64_t p = lp->pos;
+            ++live_i;
+            if (skipping && p <= skip_until)
+                continue;
+            const uint32_t trymask = lp->info & 31u, nrec = (lp->info >> 8) & 7u;
+            const LiveRec *recs = v.liverecs + to->liverec_off + (lp->info >> 16);
+
+            // score_phase for every tried phase, in order (demod_2400.c:183-229, 306-330)
+            int bestscore = -42, bestphase = -1;
+            const LiveRec *best = nullptr;
+            uint32_t ri = 0;
+            for (int ph = 4; ph <= 8; ++ph) {
+                if (!((trymask >> (ph - 4)) & 1u))
+                    continue;
+                stats_.demod_preamblePhase[ph - 4]++;
+                int sc = -2;
+                const LiveRec *rec = nullptr;
+                if (ri < nrec && (int) ((recs[ri].w1 >> 24) & 15u) == ph) {
+                    rec = &recs[ri++];
+                    sc = score(*rec);
+                }
+                if (sc > bestscore) {
+                    bestscore = sc;
+                    bestphase = ph;
+                    best = rec;
+                }
+            }
+            stats_.demod_preambles++; // demod_2400.c:339
+            if (bestscore < 0) {      // demod_2400.c:342-348
+                if (bestscore == -1)
+                    stats_.demod_rejected_unknown_icao++;
+                else
+                    stats_.demod_rejected_bad++;
+                continue;
+            }
+
+            b200_message mm;
+            memset(&mm, 0, sizeof(mm));
+            const uint64_t j = p - b0;
+            mm.timestampMsg = sampleTimestamp + j * 5 + (8 + 56) * 12 + (uint64_t) bestphase; // demod_2400.c:358
+            mm.sysTimestampMsg = sysTimestamp + (mm.timestampMsg - sampleTimestamp) / 12000U; // :361
+            ifile_now_ = mm.sysTimestampMsg;                                                   // :364-366
+            mm.score = bestscore;
+            mm.bestphase = (uint8_t) bestphase;
+
+            const int result = decode(*best, mm); // demod_2400.c:372
+            if (result < 0) {
+                if (result == -1)
+                    stats_.demod_rejected_unknown_icao++;
+                else
+                    stats_.demod_rejected_bad++;
+                continue;
+            }
+            stats_.demod_accepted[mm.correctedbits]++;
+            stats_.demod_bestPhase[bestphase - 4]++;
+
+            // demod_2400.c:387-408
+            const int msglen = (best->msg[0] & 0x80) ? 112 : 56; // :350, from the uncorrected DF
+            const int signal_len = msglen * 12 / 5;
+            const uint64_t scaled = best->power;
+            const double signal_power = scaled / 65535.0 / 65535.0;
+            mm.signalLevel = signal_power / signal_len;
+            stats_.signal_power_sum += signal_power;
+            stats_.signal_power_count += (uint64_t) signal_len;
+            sum_scaled_signal_power += scaled;
+            if (mm.signalLevel > stats_.peak_signal_power)
+                stats_.peak_signal_power = mm.signalLevel;
+            if (mm.signalLevel > 0.50119)
+                stats_.strong_signal_count++;
+
+            // demod_2400.c:416: skip the frame body; the for loop ends at the block boundary
+            skipping = true;
+            skip_until = std::min<uint64_t>(p + (uint64_t) signal_len, b1 - 1);
+            count_dead(v, p, skip_until, hidden);
+
+            stats_.messages_total++; // useModesMessage, mode_s.c:2149
+            memset(mm.msg + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
+            memset(mm.verbatim + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
+            msgs.push_back(mm);
+        }
+
+        // positions no message can come from: K2's per-block totals minus what skip-ahead hid
+        if (nk) {
+            const BlockDead &bd = v.block_dead[k];
+            stats_.demod_preambles += bd.preambles - hidden.preambles;
+            stats_.demod_rejected_bad += bd.rejected_bad - hidden.bad;
+            stats_.demod_rejected_unknown_icao += bd.rejected_unknown - hidden.unknown;
+            for (int q = 0; q < 5; ++q)
+                stats_.demod_preamblePhase[q] += bd.phase[q] - hidden.phase[q];
+        }
+
+        // demod_2400.c:423-427
+        const double sum_signal_power = sum_scaled_signal_power / 65535.0 / 65535.0;
+        stats_.noise_power_sum += (bi.mean_power * (uint32_t) nk - sum_signal_power);
+        stats_.noise_power_count += nk;
+        stats_.samples_processed += kOverlap + nk; // readsb.c:835
+
+        filter_.expire(ifile_now_); // readsb.c:331
+    }
+}
+
+} // namespace b200

@@ -1,0 +1,77 @@
+// resolver.h -- the order-dependent tail of demodulate2400 on the host.
+//
+// The kernels decide everything that does not depend on what was decoded before.  What is left
+// is the part of the reference loop whose outcome depends on earlier messages of the same
+// stream: the ICAO filter (icao_filter.c), best-phase pick (demod_2400.c:218-228), decode-time
+// rejects (mode_s.c:445-555), skip-ahead (demod_2400.c:416) and the statistics that follow
+// from them.  It walks only the positions K2 marked live.
+#pragma once
+
+#include <stdint.h>
+
+#include <vector>
+
+#include "device_types.h"
+#include "host_tables.h"
+#include "readsb_b200.h"
+
+namespace b200 {
+
+// icao_filter.c: two open-addressed tables, flipped every 60 s of stream time
+class IcaoFilter {
+  public:
+    IcaoFilter() { reset(); }
+    void reset();
+    void add(uint32_t addr);          // icaoFilterAdd, icao_filter.c:73-97
+    bool test(uint32_t addr) const;   // icaoFilterTest, icao_filter.c:99-122
+    void expire(uint64_t now_ms);     // icaoFilterExpire, icao_filter.c:150-164
+    // every address currently stored (for seeding the device-side address set)
+    void collect(std::vector<uint32_t> &out) const;
+
+  private:
+    static constexpr uint32_t kSize = 8192, kEmpty = 0xffffffffu;
+    static uint32_t hash(uint32_t a);
+    static bool probe(const uint32_t *t, uint32_t addr);
+    uint32_t a_[kSize], b_[kSize];
+    uint32_t *active_;
+    uint64_t next_flip_;
+};
+
+struct SpanView {
+    uint64_t nsamples;        // new samples == scan positions of the span
+    uint64_t first_sample;    // stream sample index of the span's first new sample
+    uint32_t block_samples;
+    bool final_span;
+    uint32_t format;
+    uint32_t ntiles;
+    const TileOut *tiles;
+    const uint32_t *dead;
+    const LivePos *live;
+    const LiveRec *liverecs;
+    const BlockDead *block_dead;               // [nblocks]
+    const unsigned long long *block_sums_u64;  // [nblocks][2]
+    const double *block_sums_f64;              // [nblocks][2]
+};
+
+class Resolver {
+  public:
+    Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), startup_(startup_time_ms) { reset(); }
+    void reset();
+    // Appends the span's messages and block infos; updates the running statistics.
+    void resolve(const SpanView &v, std::vector<b200_message> &msgs, std::vector<b200_block_info> &blocks);
+    const b200_demod_stats &stats() const { return stats_; }
+    const IcaoFilter &filter() const { return filter_; }
+    uint64_t gpu_host_mismatches() const { return mismatches_; }
+
+  private:
+    int score(const LiveRec &r) const;
+    int decode(const LiveRec &r, b200_message &mm);
+    const CrcTables *crc_;
+    uint64_t startup_;
+    IcaoFilter filter_;
+    b200_demod_stats stats_;
+    uint64_t ifile_now_;
+    uint64_t mismatches_;
+};
+
+} // namespace b200
