@@ -202,6 +202,21 @@ typedef struct b200_errorinfo {
 #pragma pack(pop)
 int b200_error_table(b200_demod *d, int bits, b200_errorinfo *out, int cap);
 
+/* ---- host-only helpers (no device needed): the tables and the filter the resolver uses ---- */
+
+/* sizeof of the packed ABI structs: 0 b200_message, 1 b200_demod_stats, 2 b200_block_info,
+ * 3 b200_timing, 4 b200_phase_record, 5 b200_errorinfo, 6 b200_demod_config */
+int b200_abi_sizeof(int which);
+/* modesChecksum (crc.c:67-82) on the host */
+uint32_t b200_host_checksum(const uint8_t *msg, int bits);
+/* prepareErrorTable (crc.c:184-354) on the host for nfix in 0..2; returns the entry count */
+int b200_host_error_table(int nfix, int bits, b200_errorinfo *out, int cap);
+/* init_uc8_lookup (convert.c:35-61) on the host */
+void b200_host_uc8_table(uint16_t *table65536);
+/* icao_filter.c:73-164 driven step by step: ops[i] = 0 add, 1 test, 2 expire(arg = now ms);
+ * results[i] = test outcome (0/1), else 0 */
+int b200_host_filter_script(const uint8_t *ops, const uint64_t *args, uint32_t n, uint8_t *results);
+
 #ifdef __cplusplus
 }
 #endif

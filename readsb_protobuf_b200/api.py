@@ -36,7 +36,8 @@ EXPORTED_SYMBOLS = (
     "b200_demod_process", "b200_demod_process_device", "b200_demod_message_count", "b200_demod_messages",
     "b200_demod_block_count", "b200_demod_blocks", "b200_demod_get_stats", "b200_demod_get_timing",
     "b200_scan_device", "b200_convert", "b200_uc8_table", "b200_debug_scan", "b200_crc_batch",
-    "b200_error_table",
+    "b200_error_table", "b200_abi_sizeof", "b200_host_checksum", "b200_host_error_table", "b200_host_uc8_table",
+    "b200_host_filter_script",
 )
 
 
@@ -115,8 +116,45 @@ def load():
     L.b200_crc_batch.argtypes = [vp, vp, u32, vp, vp, vp]
     L.b200_error_table.restype = i32
     L.b200_error_table.argtypes = [vp, i32, vp, i32]
+    L.b200_abi_sizeof.restype = i32
+    L.b200_abi_sizeof.argtypes = [i32]
+    L.b200_host_checksum.restype = u32
+    L.b200_host_checksum.argtypes = [vp, i32]
+    L.b200_host_error_table.restype = i32
+    L.b200_host_error_table.argtypes = [i32, i32, vp, i32]
+    L.b200_host_uc8_table.restype = None
+    L.b200_host_uc8_table.argtypes = [vp]
+    L.b200_host_filter_script.restype = i32
+    L.b200_host_filter_script.argtypes = [vp, vp, u32, vp]
     _lib = L
     return L
+
+
+def host_checksum(msg: bytes) -> int:
+    buf = (ctypes.c_uint8 * len(msg)).from_buffer_copy(msg)
+    return int(load().b200_host_checksum(buf, len(msg) * 8))
+
+
+def host_error_table(nfix: int, bits: int) -> np.ndarray:
+    L = load()
+    n = L.b200_host_error_table(nfix, bits, None, 0)
+    t = np.zeros(max(n, 1), dtype=ERRORINFO_DTYPE)
+    L.b200_host_error_table(nfix, bits, t.ctypes.data, n)
+    return t[:n]
+
+
+def host_uc8_table() -> np.ndarray:
+    t = np.empty(65536, dtype=np.uint16)
+    load().b200_host_uc8_table(t.ctypes.data)
+    return t
+
+
+def host_filter_script(ops, args) -> np.ndarray:
+    ops = np.ascontiguousarray(ops, dtype=np.uint8)
+    args = np.ascontiguousarray(args, dtype=np.uint64)
+    res = np.zeros(len(ops), dtype=np.uint8)
+    _check(load().b200_host_filter_script(ops.ctypes.data, args.ctypes.data, len(ops), res.ctypes.data))
+    return res
 
 
 def _check(rc: int):

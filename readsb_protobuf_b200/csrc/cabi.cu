@@ -266,10 +266,11 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
         CUDA_TRY(cudaMemcpy(d->d_tab_long.p, tl.data(), tl.size() * sizeof(ErrorInfo), cudaMemcpyHostToDevice));
 
     CUDA_TRY(d->d_bitmap.ensure((1u << 24) / 32));
-    CUDA_TRY(cudaMemset(d->d_bitmap.p, 0, (1u << 24) / 8));
+    CUDA_TRY(cudaMemsetAsync(d->d_bitmap.p, 0, (1u << 24) / 8, d->stream));
     CUDA_TRY(d->d_head.ensure((size_t) kHead * 4));
     CUDA_TRY(d->d_head_tmp.ensure((size_t) kHead * 4));
-    CUDA_TRY(cudaMemset(d->d_head.p, 0, (size_t) kHead * 4));
+    CUDA_TRY(cudaMemsetAsync(d->d_head.p, 0, (size_t) kHead * 4, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
 
     // one persistent CTA per SM (the uc8 table takes most of an SM's shared memory)
     d->scan_grid = d->sm_count;
@@ -285,9 +286,9 @@ extern "C" int b200_demod_reset(b200_demod *d) {
     if (!d)
         return fail(B200_ERR_ARG, "null context");
     CUDA_TRY(cudaSetDevice(d->cfg.device));
+    CUDA_TRY(cudaMemsetAsync(d->d_bitmap.p, 0, (1u << 24) / 8, d->stream));
+    CUDA_TRY(cudaMemsetAsync(d->d_head.p, 0, (size_t) kHead * 4, d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
-    CUDA_TRY(cudaMemset(d->d_bitmap.p, 0, (1u << 24) / 8));
-    CUDA_TRY(cudaMemset(d->d_head.p, 0, (size_t) kHead * 4));
     d->head_valid = 0;
     d->first_sample = 0;
     d->finished = false;
@@ -748,4 +749,59 @@ extern "C" int b200_error_table(b200_demod *d, int bits, b200_errorinfo *out, in
         out[i].padding = 0;
     }
     return (int) t.size();
+}
+
+// ---- host-only helpers ----
+
+extern "C" int b200_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int) sizeof(b200_message);
+        case 1: return (int) sizeof(b200_demod_stats);
+        case 2: return (int) sizeof(b200_block_info);
+        case 3: return (int) sizeof(b200_timing);
+        case 4: return (int) sizeof(b200_phase_record);
+        case 5: return (int) sizeof(b200_errorinfo);
+        case 6: return (int) sizeof(b200_demod_config);
+        default: return -1;
+    }
+}
+
+extern "C" uint32_t b200_host_checksum(const uint8_t *msg, int bits) {
+    static const CrcTables tables(0);
+    return tables.checksum(msg, bits);
+}
+
+extern "C" int b200_host_error_table(int nfix, int bits, b200_errorinfo *out, int cap) {
+    if (nfix < 0 || nfix > 2 || (bits != 56 && bits != 112))
+        return fail(B200_ERR_ARG, "bad nfix/bits");
+    CrcTables tables(nfix);
+    const auto &t = (bits == 56) ? tables.short_table() : tables.long_table();
+    for (size_t i = 0; i < t.size() && (int) i < cap && out; ++i) {
+        out[i].syndrome = t[i].syndrome;
+        out[i].errors = t[i].errors;
+        out[i].bit[0] = t[i].bit[0];
+        out[i].bit[1] = t[i].bit[1];
+        out[i].padding = 0;
+    }
+    return (int) t.size();
+}
+
+extern "C" void b200_host_uc8_table(uint16_t *table65536) {
+    build_uc8_table(table65536);
+}
+
+extern "C" int b200_host_filter_script(const uint8_t *ops, const uint64_t *args, uint32_t n, uint8_t *results) {
+    if (!ops || !args || !results)
+        return fail(B200_ERR_ARG, "null argument");
+    std::unique_ptr<IcaoFilter> f(new IcaoFilter());
+    for (uint32_t i = 0; i < n; ++i) {
+        results[i] = 0;
+        switch (ops[i]) {
+            case 0: f->add((uint32_t) args[i]); break;
+            case 1: results[i] = f->test((uint32_t) args[i]) ? 1 : 0; break;
+            case 2: f->expire(args[i]); break;
+            default: return fail(B200_ERR_ARG, "bad filter op");
+        }
+    }
+    return B200_OK;
 }

@@ -1,0 +1,88 @@
+"""Regenerates tests/golden/*: run in the build container, where /root/reference exists.
+
+The reference's own tests hold no vector for this path, so the golden
+results here are OUTPUTS OF THE UNMODIFIED REFERENCE (oracle/_ref/ref_demod, built by
+oracle/Makefile from /root/reference) on small seeded IQ streams.  Each fixture is
+    <name>.npz : iq (raw little-endian IQ bytes), msgs / stats / blocks (reference results),
+                 meta (JSON: format, flags, generator config, sha256 of the IQ)
+Small enough to commit; they travel to the GPU box, where /root/reference does not exist.
+
+    python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref  # noqa: E402
+from readsb_protobuf_b200 import synth  # noqa: E402
+
+# name -> (generator config, demodulator flags)
+FIXTURES = {
+    "uc8_fix1": (synth.SynthConfig(seed=101, nsamples=200_000, fmt="uc8", frames_per_s=3000, frac_biterror=0.2),
+                 dict(nfix=1, threshold=58, block_samples=131072)),
+    "uc8_fix2_aggressive": (synth.SynthConfig(seed=102, nsamples=150_000, fmt="uc8", frames_per_s=4000, frac_biterror=0.4),
+                            dict(nfix=2, threshold=58, block_samples=131072)),
+    "uc8_nofix_thr75": (synth.SynthConfig(seed=103, nsamples=150_000, fmt="uc8", frames_per_s=3000, frac_biterror=0.2),
+                        dict(nfix=0, threshold=75, block_samples=131072)),
+    # stream length an exact multiple of the block: the reference then demodulates an empty
+    # final block whose mean power is 0/0 (convert.c:108-110, demod_2400.c:425)
+    "uc8_whole_blocks": (synth.SynthConfig(seed=104, nsamples=3 * 32768, fmt="uc8", frames_per_s=3000),
+                         dict(nfix=1, threshold=58, block_samples=32768)),
+    "sc16": (synth.SynthConfig(seed=105, nsamples=120_000, fmt="sc16", frames_per_s=3000, frac_biterror=0.2),
+             dict(nfix=1, threshold=58, block_samples=131072)),
+    "sc16q11": (synth.SynthConfig(seed=106, nsamples=120_000, fmt="sc16q11", frames_per_s=3000, frac_biterror=0.2),
+                dict(nfix=1, threshold=58, block_samples=131072)),
+}
+
+# the one known-answer frame in the reference tree (comment at net_io.c:1645)
+KAT_FRAME_HEX = "8D4B969699155600E87406F5B69F"
+
+
+def render_single_frame(frame: bytes, start_tick: int, nsamples: int, amp: float = 0.5) -> np.ndarray:
+    """Noise-free uc8 rendering of one frame on the 12 MHz grid (same envelope as synth_iq.c)."""
+    ticks = np.zeros(96 + len(frame) * 8 * 12 + 16, dtype=np.float64)
+    for p in (0, 12, 42, 54):
+        ticks[p:p + 6] = 1
+    for i in range(len(frame) * 8):
+        bit = (frame[i >> 3] >> (7 - (i & 7))) & 1
+        o = 96 + 12 * i + (0 if bit else 6)
+        ticks[o:o + 6] = 1
+    env = np.zeros(nsamples * 5 + len(ticks) + 8)
+    env[start_tick:start_tick + len(ticks)] = ticks
+    mag = env[: nsamples * 5].reshape(nsamples, 5).mean(axis=1) * amp
+    i = np.clip(np.rint(mag * 127.5 + 127.5), 0, 255).astype(np.uint8)
+    q = np.full(nsamples, 128, dtype=np.uint8)
+    return np.stack([i, q], axis=1).reshape(-1)
+
+
+def main():
+    assert ref.available(), "needs /root/reference (or a prebuilt oracle/_ref)"
+    for name, (cfg, flags) in FIXTURES.items():
+        iq, frames = synth.generate(cfg)
+        res = ref.run(iq, cfg.fmt, **flags)
+        meta = dict(fmt=cfg.fmt, flags=flags, generator=cfg.__dict__, sha256=synth.sha256(iq), n_frames=len(frames),
+                    source="oracle/_ref/ref_demod (unmodified reference objects)")
+        np.savez_compressed(HERE / f"{name}.npz", iq=iq, msgs=res.msgs, stats=np.array([res.stats]), blocks=res.blocks,
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        print(f"{name}: {len(frames)} frames, {len(res.msgs)} reference messages, {iq.nbytes} IQ bytes")
+
+    frame = bytes.fromhex(KAT_FRAME_HEX)
+    iq = np.concatenate([render_single_frame(frame, 100003, 24000), render_single_frame(frame, 20001, 8000)])
+    res = ref.run(iq, "uc8")
+    meta = dict(fmt="uc8", flags=dict(nfix=1, threshold=58, block_samples=131072), frame=KAT_FRAME_HEX,
+                sha256=synth.sha256(iq), source="oracle/_ref/ref_demod; frame from the comment at net_io.c:1645")
+    np.savez_compressed(HERE / "kat_frame.npz", iq=iq, msgs=res.msgs, stats=np.array([res.stats]), blocks=res.blocks,
+                        meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+    print("kat_frame:", [(int(m["timestampMsg"]), bytes(m["msg"]).hex(), int(m["score"])) for m in res.msgs])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,270 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the goldens.
+
+Bar: bit-exact for everything integer (message bytes, CRC, corrected bits, score, 12 MHz and ms
+timestamps, every demod counter, the uc8 block sums) and for signalLevel (an integer sum divided
+twice; north_star allows 1e-5).  The float-path converters (sc16 / sc16q11) produce bit-exact
+magnitudes; their per-block mean_level / mean_power are sequential float32 sums in the reference
+(convert.c:228,241-242) and are compared to 2e-4 relative (the reference's own accumulation
+error), as is the noise_power_sum derived from them.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, load_golden
+from oracle import port, ref
+from readsb_protobuf_b200 import api, results, synth
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_SUM_RTOL = 2e-4  # only for sc16 / sc16q11 block means and noise_power_sum
+
+
+def rtol_for(fmt):
+    return 0.0 if fmt == "uc8" else FLOAT_SUM_RTOL
+
+
+def run_gpu(iq, fmt="uc8", span_samples=None, **flags):
+    with api.Demodulator(fmt=fmt, **flags) as d:
+        got = d.run(iq, span_samples=span_samples)
+        assert d.crc_mismatches() == 0
+    return got
+
+
+def assert_parity(got, want, fmt):
+    diffs = results.compare_results(got, want, float_rtol=rtol_for(fmt), signal_atol=0.0)
+    assert diffs == [], diffs
+
+
+# ------------------------------------------------------------------------------------------
+# whole path
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_matches_reference_golden(name):
+    iq, want, meta = load_golden(name)
+    got = run_gpu(iq, meta["fmt"], **meta["flags"])
+    assert len(got.msgs) == len(want.msgs) > 0
+    assert_parity(got, want, meta["fmt"])
+
+
+CASES = [
+    dict(cfg=synth.SynthConfig(seed=1, nsamples=2_400_000, frames_per_s=200)),  # BASELINE configs[0]
+    dict(cfg=synth.SynthConfig(seed=51, nsamples=3_000_000, frames_per_s=5000, frac_biterror=0.2)),  # dense, configs[3] shape
+    dict(cfg=synth.SynthConfig(seed=52, nsamples=1_500_000, fmt="sc16", frames_per_s=2000, frac_biterror=0.2)),
+    dict(cfg=synth.SynthConfig(seed=53, nsamples=1_500_000, fmt="sc16q11", frames_per_s=2000, frac_biterror=0.2)),
+    dict(cfg=synth.SynthConfig(seed=54, nsamples=1_000_000, frames_per_s=5000, frac_biterror=0.5), nfix=2),
+    dict(cfg=synth.SynthConfig(seed=55, nsamples=1_000_000, frames_per_s=5000, frac_biterror=0.5), nfix=0),
+    dict(cfg=synth.SynthConfig(seed=56, nsamples=1_000_003, frames_per_s=3000, frac_biterror=0.3), block_samples=50000),
+    dict(cfg=synth.SynthConfig(seed=57, nsamples=700_000, frames_per_s=3000), threshold=40),
+    dict(cfg=synth.SynthConfig(seed=58, nsamples=700_000, frames_per_s=3000), threshold=120),
+    dict(cfg=synth.SynthConfig(seed=59, nsamples=700_000, frames_per_s=3000), threshold=400),
+    dict(cfg=synth.SynthConfig(seed=60, nsamples=4 * 131072, frames_per_s=3000)),  # whole blocks: empty final block
+    dict(cfg=synth.SynthConfig(seed=61, nsamples=900_000, frames_per_s=8000, noise_sigma=0.1, amp_max=1.4)),  # clipping, overlaps
+    dict(cfg=synth.SynthConfig(seed=62, nsamples=600_000, frames_per_s=2000, noise_sigma=0.001)),  # near silence
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c['cfg'].fmt}-s{c['cfg'].seed}")
+def test_matches_oracle(case):
+    case = dict(case)
+    cfg = case.pop("cfg")
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, cfg.fmt, **case)
+    got = run_gpu(iq, cfg.fmt, **case)
+    assert_parity(got, want, cfg.fmt)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 18, 19, 100, 325, 326, 327, 328, 329, 600, 8191, 8192, 8193, 8520, 16384 + 5])
+def test_ragged_and_empty_inputs(n):
+    cfg = synth.SynthConfig(seed=70 + n % 13, nsamples=max(n, 1), frames_per_s=20000, noise_sigma=0.05)
+    iq = synth.generate(cfg)[0][: 2 * n]
+    want = port.run(iq, "uc8")
+    got = run_gpu(iq, "uc8")
+    assert_parity(got, want, "uc8")
+
+
+def test_span_split_is_invisible():
+    """Feeding the stream span by span (overlap carry, filter state, counters) equals one shot."""
+    cfg = synth.SynthConfig(seed=81, nsamples=2_000_000, frames_per_s=5000, frac_biterror=0.2)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "uc8")
+    for span in (131072, 131072 * 4):
+        assert_parity(run_gpu(iq, "uc8", span_samples=span), want, "uc8")
+    # small blocks, spans shorter than the 326-sample overlap history
+    want = port.run(iq[:200_000], "uc8", block_samples=256)
+    assert_parity(run_gpu(iq[:200_000], "uc8", span_samples=256, block_samples=256), want, "uc8")
+
+
+def test_icao_filter_flips_across_minutes():
+    """> 120 s of stream so that addresses age out (icao_filter.c:150-164) -- sparse, to stay fast."""
+    cfg = synth.SynthConfig(seed=82, nsamples=int(130 * 2.4e6), frames_per_s=20, n_icao=5, noise_sigma=0.004)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "uc8")
+    got = run_gpu(iq, "uc8", max_span_samples=cfg.nsamples + 1024)
+    assert len(want.msgs) > 500
+    assert_parity(got, want, "uc8")
+
+
+def test_adversarial_candidate_density():
+    """A pulse train that makes most positions preamble candidates: exercises K1's slow rounds and the
+    grow-and-retry of the candidate buffers."""
+    n = 300_000
+    pattern = np.array([200, 128, 128, 128, 140, 128, 140, 128, 140, 250, 250], dtype=np.uint8)  # ~27 % of positions
+    i = np.tile(pattern, n // len(pattern) + 1)[:n]
+    i[100_000:200_000] = 128  # a quiet stretch in the middle: fast and slow tiles in one span
+    q = np.full(n, 128, dtype=np.uint8)
+    iq = np.stack([i, q], axis=1).reshape(-1)
+    want = port.run(iq, "uc8")
+    assert int(want.stats["demod_preambles"]) > n // 8
+    assert_parity(run_gpu(iq, "uc8"), want, "uc8")
+
+
+def test_device_resident_input_equals_host_input():
+    import torch
+    cfg = synth.SynthConfig(seed=83, nsamples=1_200_000, frames_per_s=4000, frac_biterror=0.2)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "uc8")
+    dev = torch.from_numpy(iq).cuda()
+    with api.Demodulator() as d:
+        r = d.process_device(dev.data_ptr(), cfg.nsamples, final=True, stream=torch.cuda.current_stream().cuda_stream)
+        st = d.stats().copy()
+        t = r.timing
+    st["convert_cpu_s"] = st["demod_cpu_s"] = 0
+    got = results.DemodResult(r.msgs, st, r.blocks, cfg.nsamples)
+    assert_parity(got, want, "uc8")
+    assert t["scan_launches"] == 2 and t["scan_ms"] > 0 and t["n_candidates"] > 0
+
+
+@pytest.mark.skipif(not ref.available(), reason="prebuilt oracle/_ref not present")
+def test_full_size_stream_matches_the_reference_itself():
+    """BASELINE configs[1] at full size (60 s, 144 M samples) against the unmodified reference."""
+    cfg = synth.baseline_config(1)
+    iq, frames = synth.generate(cfg)
+    want = ref.run(iq, "uc8")
+    got = run_gpu(iq, "uc8", max_span_samples=cfg.nsamples + 1024)
+    assert len(want.msgs) > 0.7 * len(frames)
+    assert_parity(got, want, "uc8")
+    # size-independent property: span-by-span equals one shot (checksum of checksums)
+    again = run_gpu(iq, "uc8", span_samples=131072 * 64)
+    assert np.bitwise_xor.reduce(again.msgs["crc"] ^ again.msgs["timestampMsg"].astype(np.uint32)) == \
+        np.bitwise_xor.reduce(got.msgs["crc"] ^ got.msgs["timestampMsg"].astype(np.uint32))
+    assert_parity(again, want, "uc8")
+
+
+# ------------------------------------------------------------------------------------------
+# kernel-level parity
+# ------------------------------------------------------------------------------------------
+
+def test_uc8_table_exhaustive():
+    with api.Demodulator() as d:
+        assert np.array_equal(d.uc8_table(), port.uc8_table())
+
+
+@pytest.mark.parametrize("fmt", ["uc8", "sc16", "sc16q11"])
+def test_converter_bit_exact(fmt):
+    rng = np.random.default_rng(9)
+    n = 300_001
+    if fmt == "uc8":
+        iq = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+        iq[:512] = np.repeat(np.array([0, 255, 127, 128], dtype=np.uint8), 128)  # corners / centre
+    else:
+        full = 32767 if fmt == "sc16" else 2047
+        v = rng.integers(-full - 1, full + 1, 2 * n).astype("<i2")
+        v[:8] = [full, full, -full - 1, -full - 1, 0, 0, full, 0]  # clamp at 1.0, zero
+        iq = v.view(np.uint8)
+    with api.Demodulator(fmt=fmt) as d:
+        mag, ml, mp = d.convert(iq)
+    want, wl, wp = port.convert(iq, fmt)
+    assert np.array_equal(mag, want)
+    if fmt == "uc8":
+        assert ml == wl and mp == wp
+    else:
+        assert ml == pytest.approx(wl, rel=FLOAT_SUM_RTOL) and mp == pytest.approx(wp, rel=FLOAT_SUM_RTOL)
+
+
+def test_try_masks_and_phase_records():
+    """K1's per-position try mask and its (position, phase) class records against the oracle's
+    preamble test, slicer and CRC on every candidate."""
+    cfg = synth.SynthConfig(seed=84, nsamples=400_000, frames_per_s=5000, frac_biterror=0.3)
+    iq, _ = synth.generate(cfg)
+    with api.Demodulator() as d:
+        masks, recs = d.debug_scan(iq)
+        tab_short, tab_long = d.error_table(56), d.error_table(112)
+    mag, _, _ = port.convert(iq, "uc8")
+    m = np.concatenate([np.zeros(326, np.uint16), mag, np.zeros(64, np.uint16)])  # stream start: zero overlap
+    want_masks = port.try_masks(m[: cfg.nsamples + 18])
+    assert np.array_equal(masks, want_masks[: cfg.nsamples])
+    assert 0.002 < (masks != 0).mean() < 0.1
+
+    short_syn = {int(e["syndrome"]): e for e in tab_short}
+    long_syn = {int(e["syndrome"]): e for e in tab_long}
+    got = {(int(r["position"]), int(r["phase"])): r for r in recs}
+    assert len(got) == len(recs)
+    n_expected = 0
+    for j in np.nonzero(masks)[0]:
+        for ph in range(4, 9):
+            if not (masks[j] >> (ph - 4)) & 1:
+                continue
+            b0 = port.slice_bytes(m, int(j), ph, 1)[0]
+            df = b0 >> 3
+            nbytes = 7 if df in (0, 4, 5, 11) else 14 if df in (16, 17, 18, 20, 21, 24) else 0
+            kind, key, errors = 0, None, 0
+            if nbytes:
+                msg = port.slice_bytes(m, int(j), ph, nbytes)
+                crc = port.checksum(msg)
+                aa = int.from_bytes(msg[1:4], "big")
+                if any(msg):
+                    if df in (0, 4, 5, 16, 24):
+                        kind, key = api.KIND_AP, crc
+                    elif df in (20, 21):
+                        kind, key = api.KIND_AP_COMMB, crc
+                    else:
+                        syn = crc & 0xFFFF80 if df == 11 else crc
+                        tab = short_syn if df == 11 else long_syn
+                        e = None if syn == 0 else tab.get(syn)
+                        if syn == 0 or (e is not None and (df != 11 or e["errors"] <= 1)):
+                            kind = api.KIND_DF11 if df == 11 else api.KIND_ES
+                            errors = 0 if syn == 0 else int(e["errors"])
+                            key = aa
+                            for b in ([] if syn == 0 else [int(x) for x in e["bit"][:errors]]):
+                                if 8 <= b <= 31:
+                                    key ^= 1 << (31 - b)
+            if kind:
+                n_expected += 1
+                r = got.get((int(j), ph))
+                assert r is not None, (j, ph)
+                assert (int(r["crc"]), int(r["kind"]), int(r["key"]), int(r["errors"])) == (crc, kind, key, errors)
+    assert n_expected == len(recs) > 100
+
+
+@pytest.mark.parametrize("nfix", [0, 1, 2])
+def test_crc_batch_and_tables(nfix):
+    rng = np.random.default_rng(10 + nfix)
+    with api.Demodulator(nfix=nfix) as d:
+        for bits in (56, 112):
+            a, b = d.error_table(bits), port.error_table(nfix, bits)
+            assert all(np.array_equal(a[f], b[f]) for f in ("syndrome", "errors", "bit"))
+        frames = rng.integers(0, 256, (4000, 14), dtype=np.uint8)
+        # plant valid frames with 0, 1 and 2 flipped bits
+        for i in range(0, 3000):
+            nb = 14 if frames[i, 0] & 0x80 else 7
+            crc = port.checksum(bytes(frames[i, :nb - 3]) + b"\0\0\0")
+            frames[i, nb - 3:nb] = [crc >> 16, (crc >> 8) & 255, crc & 255]
+            for _ in range(i % 3):
+                bit = int(rng.integers(5, nb * 8))
+                frames[i, bit >> 3] ^= 0x80 >> (bit & 7)
+        syn, err, bits2 = d.crc_batch(frames)
+    tabs = {56: {int(e["syndrome"]): e for e in port.error_table(nfix, 56)},
+            112: {int(e["syndrome"]): e for e in port.error_table(nfix, 112)}}
+    for i in range(len(frames)):
+        nb = 14 if frames[i, 0] & 0x80 else 7
+        want = port.checksum(bytes(frames[i, :nb]))
+        assert int(syn[i]) == want
+        if want == 0:
+            assert err[i] == 0
+        else:
+            e = tabs[nb * 8].get(want)
+            assert err[i] == (-1 if e is None else e["errors"])
+            if e is not None:
+                assert list(bits2[i]) == list(e["bit"])
+    assert (err[:3000:3] == 0).all()

@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library loads without a GPU, exports what include/readsb_b200.h declares, fails
+loudly when asked to compute, and its host-side tables / filter equal the oracle's."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import port
+from readsb_protobuf_b200 import api, results
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "readsb_b200.h").read_text()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    L = api.load()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/readsb_b200.h but not exported"
+    assert declared == set(api.EXPORTED_SYMBOLS)
+
+
+def test_abi_struct_sizes_match_python_mirrors():
+    L = api.load()
+    assert L.b200_abi_sizeof(0) == results.MSG_DTYPE.itemsize == 68
+    assert L.b200_abi_sizeof(1) == results.STATS_DTYPE.itemsize == 136
+    assert L.b200_abi_sizeof(2) == results.BLOCK_DTYPE.itemsize == 16
+    assert L.b200_abi_sizeof(3) == ctypes.sizeof(api.Timing)
+    assert L.b200_abi_sizeof(4) == api.PHASE_RECORD_DTYPE.itemsize
+    assert L.b200_abi_sizeof(5) == api.ERRORINFO_DTYPE.itemsize == 12  # struct errorinfo, crc.h:32-37
+    assert L.b200_abi_sizeof(6) == ctypes.sizeof(api._Config)
+
+
+def test_no_cpu_fallback():
+    """Without a usable B200 the product must refuse, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.B200Error) as e:
+        api.Demodulator()
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_bad_configuration_is_rejected():
+    L = api.load()
+    h = ctypes.c_void_p()
+    for bad in (api._Config(99, 0, 0, 1, 58, 0, 0, 0), api._Config(1, 0, 7, 1, 58, 0, 0, 0),
+                api._Config(1, 0, 0, 5, 58, 0, 0, 0), api._Config(1, 0, 0, 1, 0, 0, 0, 0)):
+        assert L.b200_demod_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+        assert not h.value
+    assert L.b200_demod_create(None, ctypes.byref(h)) == -1
+
+
+def test_host_crc_tables_equal_oracle():
+    rng = np.random.default_rng(3)
+    for bits in (56, 112):
+        for _ in range(300):
+            m = rng.integers(0, 256, bits // 8, dtype=np.uint8).tobytes()
+            assert api.host_checksum(m) == port.checksum(m)
+    for nfix in (0, 1, 2):
+        for bits in (56, 112):
+            a, b = api.host_error_table(nfix, bits), port.error_table(nfix, bits)
+            assert len(a) == len(b)
+            for f in ("syndrome", "errors", "bit"):
+                assert np.array_equal(a[f], b[f]), (nfix, bits, f)
+
+
+def test_host_uc8_table_equals_oracle():
+    assert np.array_equal(api.host_uc8_table(), port.uc8_table())
+
+
+def test_host_icao_filter_semantics():
+    # icao_filter.c: membership lasts from the add until the second flip after it
+    add, test, expire = 0, 1, 2
+    ops = [test, add, test, expire, test, expire, test, expire, test,  # expire(0) flips at once (next_flip = 0)
+           add, expire, test, expire, test]
+    args = [0x4B9696, 0x4B9696, 0x4B9696, 0, 0x4B9696, 59_999, 0x4B9696, 60_000, 0x4B9696,
+            0xABCDEF, 60_001, 0xABCDEF, 120_000, 0xABCDEF]
+    res = api.host_filter_script(ops, args)
+    assert list(res[[0, 2, 4, 6, 8, 11, 13]]) == [0, 1, 1, 1, 0, 1, 1]
+    # the low-16-bit alias (icao_filter.c:87-96) is stored but never matches a full-address test
+    res = api.host_filter_script([add, test, test], [0x123456, 0x003456, 0x123456])
+    assert list(res[1:]) == [0, 1]
+    # a full table drops further addresses instead of looping (icao_filter.c:78-81)
+    n = 5000
+    ops = [add] * n + [test] * n
+    addrs = [0x100000 + 7 * i for i in range(n)]
+    res = api.host_filter_script(ops, addrs + addrs)
+    assert 4000 <= int(res[n:].sum()) < n

@@ -1,0 +1,123 @@
+"""CPU: the oracle (C restatement) against the reference-generated goldens, the reference's own
+known answers, and -- where /root/reference is mounted -- the live reference binary."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, load_golden
+from oracle import port, ref
+from readsb_protobuf_b200 import results, synth
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_port_matches_reference_golden(name):
+    iq, want, meta = load_golden(name)
+    assert hashlib.sha256(iq.tobytes()).hexdigest() == meta["sha256"]
+    got = port.run(iq, meta["fmt"], **meta["flags"])
+    assert len(want.msgs) > 0
+    # bit-exact everywhere, float sums included (same operations in the same order)
+    assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
+
+
+def test_known_answer_frame():
+    # the only Mode S frame quoted in the reference tree (net_io.c:1645): DF17, CRC 0;
+    # first sight scores 1400, second sight 1800 (mode_s.c:288-289)
+    iq, want, meta = load_golden("kat_frame")
+    got = port.run(iq, "uc8")
+    assert [bytes(m["msg"]).hex().upper() for m in got.msgs] == [meta["frame"], meta["frame"]]
+    assert [int(m["score"]) for m in got.msgs] == [1400, 1800]
+    assert [int(m["crc"]) for m in got.msgs] == [0, 0]
+    # the frame starts at tick 100003; the reference reports 0x19000 (+326*5 bias)
+    assert int(got.msgs[0]["timestampMsg"]) == 0x19000
+    assert port.checksum(bytes.fromhex(meta["frame"])) == 0
+
+
+def test_crc_known_answers():
+    # crc.c:59-64 / SURVEY.md 8a: first and last single-bit syndromes
+    assert port.lib().mo_single_bit_syndrome(0) == 0x3935EA
+    assert port.lib().mo_single_bit_syndrome(111) == 0x000001
+    # table sizes printed by the reference's own `crctests` (crc.c -DCRCDEBUG)
+    assert len(port.error_table(1, 56)) == 51 and len(port.error_table(1, 112)) == 107
+    assert len(port.error_table(2, 56)) == 1326 and len(port.error_table(2, 112)) == 3831
+    assert len(port.error_table(0, 112)) == 0
+    # every entry regenerates its own syndrome (the check crc.c:309-333 performs)
+    for nfix, bits in ((1, 56), (1, 112), (2, 56), (2, 112)):
+        t = port.error_table(nfix, bits)
+        assert np.all(np.diff(t["syndrome"].astype(np.int64)) > 0)
+        for e in t[:: max(1, len(t) // 97)]:
+            msg = bytearray(bits // 8)
+            for b in (int(x) for x in e["bit"][: int(e["errors"])]):
+                assert 5 <= b < bits
+                msg[b >> 3] ^= 0x80 >> (b & 7)
+            assert port.checksum(bytes(msg)) == e["syndrome"]
+
+
+def test_checksum_is_linear():
+    rng = np.random.default_rng(5)
+    for bits in (56, 112):
+        for _ in range(200):
+            m = rng.integers(0, 256, bits // 8, dtype=np.uint8)
+            x = 0
+            for b in range(bits):
+                if (m[b >> 3] >> (7 - (b & 7))) & 1:
+                    x ^= port.lib().mo_single_bit_syndrome(b + 112 - bits)
+            assert x == port.checksum(m.tobytes())
+
+
+def test_uc8_table_known_answers():
+    t = port.uc8_table().reshape(256, 256)
+    # SURVEY.md section 7.2 probes of the reference table
+    assert t[0, 0] == 65535 and t[127, 127] == 363 and t[128, 128] == 363 and t[255, 128] == 65535
+    assert t.min() == 363
+    assert np.array_equal(t, t[::-1, :]) and np.array_equal(t, t[:, ::-1]) and np.array_equal(t, t.T)
+    grid = t.astype(np.float64)
+    assert abs(grid.mean() / 65536.0 - 0.740231129) < 1e-9
+    assert abs((grid ** 2).mean() / 65535.0 ** 2 - 0.610363797) < 1e-9
+
+
+@pytest.mark.skipif(not ref.available(), reason="reference binary not built (no /root/reference here)")
+@pytest.mark.parametrize("case", [
+    dict(cfg=synth.SynthConfig(seed=21, nsamples=700_000, frames_per_s=4000, frac_biterror=0.3)),
+    dict(cfg=synth.SynthConfig(seed=22, nsamples=500_000, fmt="sc16", frames_per_s=3000, frac_biterror=0.2)),
+    dict(cfg=synth.SynthConfig(seed=23, nsamples=500_000, fmt="sc16q11", frames_per_s=3000, frac_biterror=0.2)),
+    dict(cfg=synth.SynthConfig(seed=24, nsamples=400_000, frames_per_s=5000, frac_biterror=0.5), nfix=2),
+    dict(cfg=synth.SynthConfig(seed=25, nsamples=400_000, frames_per_s=5000, frac_biterror=0.5), nfix=0),
+    dict(cfg=synth.SynthConfig(seed=26, nsamples=300_003, frames_per_s=5000), block_samples=50000, threshold=40),
+    dict(cfg=synth.SynthConfig(seed=27, nsamples=4 * 65536, frames_per_s=5000), block_samples=65536),
+    dict(cfg=synth.SynthConfig(seed=28, nsamples=100, frames_per_s=0)),
+    dict(cfg=synth.SynthConfig(seed=29, nsamples=0, frames_per_s=0)),
+])
+def test_port_matches_live_reference(case):
+    case = dict(case)
+    cfg = case.pop("cfg")
+    iq, _ = synth.generate(cfg)
+    got = port.run(iq, cfg.fmt, **case)
+    want = ref.run(iq, cfg.fmt, **case)
+    assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
+
+
+@pytest.mark.skipif(not ref.available(), reason="reference binary not built (no /root/reference here)")
+def test_port_converter_matches_live_reference():
+    for fmt in ("uc8", "sc16", "sc16q11"):
+        cfg = synth.SynthConfig(seed=31, nsamples=140_000, fmt=fmt, frames_per_s=3000, amp_max=1.5)
+        iq, _ = synth.generate(cfg)
+        want = ref.magnitudes(iq, fmt)
+        bps = 2 if fmt == "uc8" else 4
+        got = np.concatenate([port.convert(iq[o * bps: (o + 131072) * bps], fmt)[0] for o in range(0, cfg.nsamples, 131072)])
+        assert np.array_equal(got, want)
+
+
+def test_generator_is_deterministic_and_chunk_invariant():
+    cfg = synth.SynthConfig(seed=7, nsamples=300_000, frames_per_s=2000)
+    frames = synth.plan(cfg)
+    whole = synth.render(cfg, frames)
+    parts = np.concatenate([synth.render(cfg, frames, first=a, count=b - a)
+                            for a, b in ((0, 1000), (1000, 70_001), (70_001, 300_000))])
+    assert np.array_equal(whole, parts)
+    assert np.array_equal(whole, synth.render(cfg, synth.plan(cfg)))
+    # every planted frame has a valid parity field for its type
+    for f in frames[:200]:
+        msg = bytes(f["msg"][: f["nbytes"]])
+        if f["errbit"] < 0 and f["df"] in (11, 17):
+            assert port.checksum(msg) == 0
