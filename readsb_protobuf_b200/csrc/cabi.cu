@@ -128,6 +128,7 @@ struct b200_demod {
     DevBuf<uint32_t> d_cand, d_dead;
     DevBuf<PhaseRec> d_recs;
     DevBuf<TileDesc> d_tiles;
+    DevBuf<uint32_t> d_tile_off;
     DevBuf<TileOut> d_tiles_out;
     DevBuf<LivePos> d_live;
     DevBuf<LiveRec> d_liverecs;
@@ -159,7 +160,7 @@ struct b200_demod {
         cudaSetDevice(cfg.device);
         d_lut.release(); d_tab_short.release(); d_tab_long.release(); d_bitmap.release();
         d_head.release(); d_head_tmp.release(); d_iq.release(); d_cand.release(); d_dead.release();
-        d_recs.release(); d_tiles.release(); d_tiles_out.release(); d_live.release(); d_liverecs.release();
+        d_recs.release(); d_tiles.release(); d_tile_off.release(); d_tiles_out.release(); d_live.release(); d_liverecs.release();
         d_counters.release(); d_sums_u64.release(); d_sums_f64.release(); d_block_dead.release();
         d_dbg_masks.release(); d_mag.release(); d_frames.release(); d_syn.release(); d_err.release(); d_bits.release();
         h_counters.release(); h_tiles_out.release(); h_dead.release(); h_live.release(); h_liverecs.release();
@@ -176,13 +177,13 @@ extern "C" const char *b200_last_error(void) {
     return g_last_error.c_str();
 }
 
-static int ensure_span_buffers(b200_demod *d, uint64_t nsamples, size_t cand_cap, size_t rec_cap, size_t live_cap,
-                               size_t liverec_cap) {
-    const size_t ntiles = (size_t) ((nsamples + kTile - 1) / kTile);
+static int ensure_span_buffers(b200_demod *d, uint64_t nsamples, size_t cand_total, size_t rec_total, size_t dead_cap,
+                               size_t live_cap, size_t liverec_cap) {
+    const size_t ntiles = tiles_for(nsamples);
     const size_t nblocks = (size_t) (nsamples / d->cfg.block_samples + 2);
-    CUDA_TRY(d->d_cand.ensure(cand_cap));
-    CUDA_TRY(d->d_dead.ensure(cand_cap));
-    CUDA_TRY(d->d_recs.ensure(rec_cap));
+    CUDA_TRY(d->d_cand.ensure(cand_total + 1));
+    CUDA_TRY(d->d_recs.ensure(rec_total + 1));
+    CUDA_TRY(d->d_dead.ensure(dead_cap));
     CUDA_TRY(d->d_live.ensure(live_cap));
     CUDA_TRY(d->d_liverecs.ensure(liverec_cap));
     CUDA_TRY(d->d_tiles.ensure(ntiles + 1));
@@ -299,7 +300,8 @@ extern "C" int b200_demod_reset(b200_demod *d) {
     return B200_OK;
 }
 
-static ScanArgs make_scan_args(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t head_valid) {
+static ScanArgs make_scan_args(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t head_valid, uint32_t cand_slab,
+                               uint32_t rec_slab, const uint32_t *tile_off) {
     ScanArgs a;
     memset(&a, 0, sizeof(a));
     a.iq = d_iq;
@@ -309,7 +311,7 @@ static ScanArgs make_scan_args(b200_demod *d, const uint8_t *d_iq, uint64_t nsam
     a.nsamples = nsamples;
     a.threshold = d->cfg.preamble_threshold;
     a.block_samples = d->cfg.block_samples;
-    a.ntiles = (uint32_t) ((nsamples + kTile - 1) / kTile);
+    a.ntiles = tiles_for(nsamples);
     a.lut = d->d_lut.p;
     a.tab_short = d->d_tab_short.p;
     a.tab_long = d->d_tab_long.p;
@@ -319,8 +321,9 @@ static ScanArgs make_scan_args(b200_demod *d, const uint8_t *d_iq, uint64_t nsam
     a.cand = d->d_cand.p;
     a.recs = d->d_recs.p;
     a.tiles = d->d_tiles.p;
-    a.cand_cap = (uint32_t) std::min<size_t>(d->d_cand.cap, 0xffffffffu);
-    a.rec_cap = (uint32_t) std::min<size_t>(d->d_recs.cap, 0xffffffffu);
+    a.cand_slab = cand_slab;
+    a.rec_slab = rec_slab;
+    a.tile_off = tile_off;
     a.counters = d->d_counters.p;
     a.block_sums_u64 = d->d_sums_u64.p;
     a.block_sums_f64 = d->d_sums_f64.p;
@@ -353,30 +356,35 @@ static int carry_head(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, cud
     return B200_OK;
 }
 
+// per-tile slabs K1 writes into on the first attempt: ~6x the candidate / record density of noise at
+// the default threshold; a span that needs more is run again with slabs placed exactly
+static const uint32_t kCandSlab = 640, kRecSlab = 448;
+
 static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t flags, cudaStream_t s, bool timed_h2d) {
     const bool final_span = (flags & B200_FLAG_FINAL) != 0;
     const uint32_t B = d->cfg.block_samples;
     const double t_start = now_ms();
 
-    size_t cand_cap = std::max<size_t>(d->d_cand.cap, (size_t) (nsamples / 24 + 4096));
-    size_t rec_cap = std::max<size_t>(d->d_recs.cap, (size_t) (nsamples / 64 + 4096));
+    const uint32_t ntiles = tiles_for(nsamples);
+    size_t cand_total = (size_t) ntiles * kCandSlab, rec_total = (size_t) ntiles * kRecSlab;
+    size_t dead_cap = std::max<size_t>(d->d_dead.cap, (size_t) (nsamples / 24 + 4096));
     size_t live_cap = std::max<size_t>(d->d_live.cap, (size_t) (nsamples / 128 + 4096));
     size_t liverec_cap = std::max<size_t>(d->d_liverecs.cap, (size_t) (nsamples / 64 + 4096));
-    const uint32_t ntiles = (uint32_t) ((nsamples + kTile - 1) / kTile);
     const size_t nblocks = (size_t) (nsamples / B + (final_span ? 1 : 0));
     uint32_t launches = 0;
+    bool exact = false;
 
     ScanCounters cnt;
     memset(&cnt, 0, sizeof(cnt));
     for (int attempt = 0;; ++attempt) {
-        int rc = ensure_span_buffers(d, nsamples, cand_cap, rec_cap, live_cap, liverec_cap);
+        int rc = ensure_span_buffers(d, nsamples, cand_total, rec_total, dead_cap, live_cap, liverec_cap);
         if (rc != B200_OK)
             return rc;
         rc = zero_span_outputs(d, nsamples, s);
         if (rc != B200_OK)
             return rc;
 
-        ScanArgs sa = make_scan_args(d, d_iq, nsamples, d->head_valid);
+        ScanArgs sa = make_scan_args(d, d_iq, nsamples, d->head_valid, kCandSlab, kRecSlab, exact ? d->d_tile_off.p : nullptr);
         CUDA_TRY(cudaEventRecord(d->ev[1], s));
         CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
         CUDA_TRY(cudaEventRecord(d->ev[2], s));
@@ -427,16 +435,36 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
             break;
         if (attempt >= 3)
             return fail(B200_ERR_CAPACITY, "candidate buffers overflowed after %d attempts (flags 0x%x)", attempt + 1, cnt.overflow);
-        // grow to what the kernels asked for (their counters keep counting past the capacity)
-        cand_cap = std::max<size_t>(cand_cap, (size_t) cnt.n_cand + (size_t) cnt.n_cand / 8 + 4096);
-        rec_cap = std::max<size_t>(rec_cap, (size_t) cnt.n_rec + (size_t) cnt.n_rec / 8 + 4096);
-        if (cnt.overflow & 0x1cu) {
-            live_cap = std::max<size_t>(live_cap, (size_t) cnt.n_live + (size_t) cnt.n_live / 8 + 4096);
-            liverec_cap = std::max<size_t>(liverec_cap, (size_t) cnt.n_liverec + (size_t) cnt.n_liverec / 8 + 4096);
-        } else {
+        if (cnt.overflow & 3u) {
+            // a tile outgrew its slab: every tile reported its true counts, place the slabs exactly
+            std::vector<TileDesc> tiles(ntiles);
+            CUDA_TRY(cudaMemcpy(tiles.data(), d->d_tiles.p, ntiles * sizeof(TileDesc), cudaMemcpyDeviceToHost));
+            std::vector<uint32_t> off(2 * ((size_t) ntiles + 1));
+            uint64_t co = 0, ro = 0;
+            for (uint32_t t = 0; t < ntiles; ++t) {
+                off[2 * t] = (uint32_t) co;
+                off[2 * t + 1] = (uint32_t) ro;
+                co += tiles[t].ncand;
+                ro += tiles[t].nrec;
+            }
+            off[2 * (size_t) ntiles] = (uint32_t) co;
+            off[2 * (size_t) ntiles + 1] = (uint32_t) ro;
+            if (co > 0xfffffff0ull || ro > 0xfffffff0ull)
+                return fail(B200_ERR_CAPACITY, "span too dense for 32-bit record indices; use shorter spans");
+            CUDA_TRY(d->d_tile_off.ensure(off.size()));
+            CUDA_TRY(cudaMemcpy(d->d_tile_off.p, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            cand_total = std::max<size_t>((size_t) co, 1);
+            rec_total = std::max<size_t>((size_t) ro, 1);
+            exact = true;
             // K2 did not run: size its lists from K1's counts so that the retry cannot fail there
-            live_cap = std::max<size_t>(live_cap, cand_cap);
-            liverec_cap = std::max<size_t>(liverec_cap, rec_cap);
+            dead_cap = std::max<size_t>(dead_cap, cand_total);
+            live_cap = std::max<size_t>(live_cap, cand_total);
+            liverec_cap = std::max<size_t>(liverec_cap, rec_total);
+        } else {
+            // K2's lists were too small; its counters kept counting past the capacity
+            dead_cap = std::max<size_t>(dead_cap, (size_t) cnt.n_dead + 4096);
+            live_cap = std::max<size_t>(live_cap, (size_t) cnt.n_live + 4096);
+            liverec_cap = std::max<size_t>(liverec_cap, (size_t) cnt.n_liverec + 4096);
         }
     }
 
@@ -584,15 +612,15 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
         return fail(B200_ERR_CAPACITY, "span exceeds max_span_samples");
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
-    int rc = ensure_span_buffers(d, nsamples, std::max<size_t>(d->d_cand.cap, (size_t) (nsamples / 24 + 4096)),
-                                 std::max<size_t>(d->d_recs.cap, (size_t) (nsamples / 64 + 4096)),
+    const size_t nt = tiles_for(nsamples);
+    int rc = ensure_span_buffers(d, nsamples, nt * kCandSlab, nt * kRecSlab, std::max<size_t>(d->d_dead.cap, 4096),
                                  std::max<size_t>(d->d_live.cap, 4096), std::max<size_t>(d->d_liverecs.cap, 4096));
     if (rc != B200_OK)
         return rc;
     rc = zero_span_outputs(d, nsamples, s);
     if (rc != B200_OK)
         return rc;
-    ScanArgs sa = make_scan_args(d, (const uint8_t *) d_iq, nsamples, 0);
+    ScanArgs sa = make_scan_args(d, (const uint8_t *) d_iq, nsamples, 0, kCandSlab, kRecSlab, nullptr);
     CUDA_TRY(cudaEventRecord(d->ev[1], s));
     CUDA_TRY(launch_scan(sa, mode ? 1 : 0, d->scan_grid, s));
     CUDA_TRY(cudaEventRecord(d->ev[2], s));
@@ -665,9 +693,10 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
     CUDA_TRY(d->d_iq.ensure(bytes + 256));
     CUDA_TRY(d->d_dbg_masks.ensure((size_t) nsamples + 16));
     // generous: every position a candidate with five records
-    int rc = ensure_span_buffers(d, nsamples, std::max<size_t>(d->d_cand.cap, (size_t) nsamples + 4096),
-                                 std::max<size_t>(d->d_recs.cap, (size_t) nsamples * 5 + 4096), std::max<size_t>(d->d_live.cap, 4096),
-                                 std::max<size_t>(d->d_liverecs.cap, 4096));
+    // slabs that can hold every position of a tile as a candidate with five records
+    const size_t nt = tiles_for(nsamples);
+    int rc = ensure_span_buffers(d, nsamples, nt * kTile, nt * kTile * 5, std::max<size_t>(d->d_dead.cap, 4096),
+                                 std::max<size_t>(d->d_live.cap, 4096), std::max<size_t>(d->d_liverecs.cap, 4096));
     if (rc != B200_OK)
         return rc;
     rc = zero_span_outputs(d, nsamples, s);
@@ -676,7 +705,7 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
     if (bytes)
         CUDA_TRY(cudaMemcpyAsync(d->d_iq.p, iq, bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(d->d_dbg_masks.p, 0, (size_t) nsamples + 16, s));
-    ScanArgs sa = make_scan_args(d, d->d_iq.p, nsamples, 0);
+    ScanArgs sa = make_scan_args(d, d->d_iq.p, nsamples, 0, kTile, kTile * 5, nullptr);
     sa.dbg_masks = d->d_dbg_masks.p;
     CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
     CUDA_TRY(cudaMemcpyAsync(d->h_counters.p, d->d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));

@@ -6,16 +6,28 @@
 namespace b200 {
 
 // ---- geometry ---------------------------------------------------------------------------
-constexpr int kOverlap = 326;      // Modes.trailing_samples at 2.4 MS/s (readsb.c:198)
-constexpr int kHead = 328;         // samples carried in front of a span: kOverlap rounded up to 16 bytes
-constexpr int kTile = 8192;        // scan positions per tile
-constexpr int kTileHalo = 336;     // extra samples a tile converts: kHead in front + 8 behind
-constexpr int kTileSamples = kTile + kTileHalo;
-constexpr int kScanThreads = 512;
-constexpr int kPosPerThread = kTile / kScanThreads; // 16
-constexpr int kMaxCand = 1024;     // candidates one slice round can hold
-constexpr int kMaxItems = kMaxCand * 5;
-constexpr int kSlowRounds = kTile / kMaxCand; // 8: a round of kMaxCand positions can never overflow
+constexpr int kOverlap = 326;  // Modes.trailing_samples at 2.4 MS/s (readsb.c:198)
+constexpr int kHead = 328;     // samples carried in front of a span: kOverlap rounded up to 16 bytes
+constexpr int kPosShift = kHead - kOverlap; // 2
+
+// A tile (K1 "segment") is kTile consecutive scan positions whose preamble windows start at a
+// 16-byte aligned sample: tile t covers positions [t*kTile - kPosShift, (t+1)*kTile - kPosShift),
+// i.e. window-start samples [t*kTile - kHead, (t+1)*kTile - kHead) relative to the span's first
+// new sample.  It also owns the block sums of exactly those samples.
+constexpr int kTile = 8192;
+constexpr int kStep = 512;                 // samples one warp converts per step (16 per lane)
+constexpr int kLanePos = kStep / 32;       // 16 scan positions per lane per step
+constexpr int kScanSteps = kTile / kStep;  // 16 steps of window starts
+constexpr int kLookahead = 296;            // samples past the last window start a slice can touch (290) rounded to 8
+constexpr int kScanWarps = 15;             // warps per CTA (shared memory: 128 KiB table + 6 KiB per warp)
+constexpr int kScanThreads = kScanWarps * 32;
+constexpr int kWarpBuf = 3 * kStep;        // u32 magnitudes per warp: two chunks + a mirror of the even one
+constexpr int kItemCap = 64;               // (position, phase) items a warp queues before slicing them
+
+inline uint32_t tiles_for(uint64_t nsamples) {
+    // every position < nsamples and every sample < nsamples must fall into a tile
+    return nsamples ? (uint32_t) ((nsamples + kHead - 1) / kTile + 1) : 0;
+}
 
 // ---- scoring classes of a sliced frame that does not score -2 outright ------------------
 // (the filter-independent half of scoreModesMessage, mode_s.c:311-409)
@@ -32,16 +44,16 @@ struct PhaseRec {
     uint32_t pos;  // scan position within the span
     uint32_t w0;   // crc[23:0] | kind[26:24] | errors[29:28]
     uint32_t w1;   // key[23:0] (address the score depends on) | phase[27:24]
-    uint32_t cand; // global candidate index
+    uint32_t pad;
 };
 
-// K1 per tile
+// K1 per tile: where the tile's candidate entries and class records are, and how many
 struct TileDesc {
     uint32_t cand_off, ncand;
     uint32_t rec_off, nrec;
 };
 
-// candidate entry (K1): pos_in_tile[12:0] | trymask[17:13] | nonbad[20:18]
+// candidate entry (K1): pos_in_tile[12:0] | trymask[17:13]
 // dead entry (K2):      pos_in_tile[12:0] | trymask[17:13] | unknown_icao[18]
 
 // K2 per tile
@@ -83,7 +95,7 @@ struct ScanCounters {
     unsigned long long n_live;
     unsigned long long n_liverec;
     unsigned int overflow; // bit0 cand, bit1 rec, bit2 dead, bit3 live, bit4 liverec
-    unsigned int slow_tiles;
+    unsigned int next_tile; // K1 work queue
 };
 
 struct ErrorInfo { // struct errorinfo, crc.h:32-37

@@ -240,89 +240,57 @@ __device__ __forceinline__ void warp_slice_frame(const uint16_t *m, int try_phas
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: scan kernel
+// K1: scan kernel -- warp-autonomous streaming
+//
+// A warp owns a tile (kTile scan positions) at a time, taken from a global work queue, and
+// streams through it in steps of kStep samples with no block-wide synchronisation at all:
+//   convert   16 samples per lane (uint4 loads prefetched one step ahead, 64 K-entry magnitude
+//             table in shared memory for uc8, IEEE float path for sc16) -> warp-private buffer,
+//             block sums of the samples the tile owns
+//   scan      one step behind: 16 positions per lane, 36-sample register window, pre-check +
+//             the three preamble correlators -> three 16-bit maps per lane
+//   slice     candidates -> (position, phase) items; 8 lanes per item, 4 items per pass, one bit
+//             of every byte per lane, ballot = 4 message bytes; CRC syndrome by XOR of single-bit
+//             syndromes; syndrome-table lookup; class record into the tile's slab
 // ------------------------------------------------------------------------------------------
-
-struct ScanSmem {
-    // layout computed by scan_smem_layout()
-    uint16_t *lut;    // 65536 (uc8 only)
-    uint16_t *mag;    // kTileSamples (+8 pad)
-    uint32_t *cand;   // kMaxCand
-    uint16_t *itemoff; // kMaxCand
-    uint32_t *items;  // kMaxItems
-    uint2 *res;       // kMaxItems
-    uint32_t *syn;    // 112
-    int (*coef)[4];   // 5
-    int *warp;        // 32
-    unsigned long long *red; // 64
-};
-
-constexpr size_t kSmemMagBytes = (kTileSamples + 8) * sizeof(uint16_t);
-constexpr size_t kSmemCommon = kSmemMagBytes + kMaxCand * 4 + kMaxCand * 2 + kMaxItems * 4 + kMaxItems * 8 +
-                               112 * 4 + 5 * 4 * 4 + 32 * 4 + 64 * 8 + 64;
-
-size_t scan_smem_bytes(uint32_t format) {
-    return kSmemCommon + (format == 0 ? 65536 * sizeof(uint16_t) : 0);
-}
-
-__device__ __forceinline__ ScanSmem scan_smem_layout(unsigned char *base, bool with_lut) {
-    ScanSmem s;
-    size_t o = 0;
-    s.lut = reinterpret_cast<uint16_t *>(base);
-    if (with_lut)
-        o += 65536 * sizeof(uint16_t);
-    s.mag = reinterpret_cast<uint16_t *>(base + o);
-    o += kSmemMagBytes;
-    s.res = reinterpret_cast<uint2 *>(base + o);
-    o += kMaxItems * 8;
-    s.red = reinterpret_cast<unsigned long long *>(base + o);
-    o += 64 * 8;
-    s.cand = reinterpret_cast<uint32_t *>(base + o);
-    o += kMaxCand * 4;
-    s.items = reinterpret_cast<uint32_t *>(base + o);
-    o += kMaxItems * 4;
-    s.syn = reinterpret_cast<uint32_t *>(base + o);
-    o += 112 * 4;
-    s.coef = reinterpret_cast<int(*)[4]>(base + o);
-    o += 5 * 4 * 4;
-    s.warp = reinterpret_cast<int *>(base + o);
-    o += 32 * 4;
-    s.itemoff = reinterpret_cast<uint16_t *>(base + o);
-    return s;
-}
 
 template <int FORMAT>
 struct Fmt;
 template <>
-struct Fmt<0> { // uc8: 2 bytes per sample, 8 samples per 16-byte chunk
-    static constexpr int kBytes = 2, kChunkSamples = 8;
+struct Fmt<0> { // uc8: 2 bytes per sample, 8 samples per 16-byte unit
+    static constexpr int kBytes = 2, kUnitSamples = 8;
 };
 template <>
 struct Fmt<1> { // sc16
-    static constexpr int kBytes = 4, kChunkSamples = 4;
+    static constexpr int kBytes = 4, kUnitSamples = 4;
 };
 template <>
 struct Fmt<2> { // sc16q11
-    static constexpr int kBytes = 4, kChunkSamples = 4;
+    static constexpr int kBytes = 4, kUnitSamples = 4;
 };
 
-// Load the 16-byte chunk holding samples [s, s + kChunkSamples) of the span (s relative to the first
-// new sample; negative = carried head).  lo/hi = the valid sample range inside the chunk.
+constexpr size_t kSmemLut = 65536 * sizeof(uint16_t);
+constexpr size_t kSmemWarp = kWarpBuf * sizeof(uint32_t) + 3 * kItemCap * sizeof(uint16_t);
+constexpr size_t kSmemTail = 112 * sizeof(uint32_t) + 5 * sizeof(int4);
+
+size_t scan_smem_bytes(uint32_t format) {
+    return (format == 0 ? kSmemLut : 0) + kScanWarps * kSmemWarp + kSmemTail;
+}
+
+// Load the 16-byte unit holding samples [s, s + kUnitSamples) of the span (s relative to the first
+// new sample; negative = carried head).  lo/hi = the valid sample range inside the unit.
 template <int FORMAT>
-__device__ __forceinline__ uint4 load_chunk(const ScanArgs &a, long long s, int &lo, int &hi) {
-    constexpr int CS = Fmt<FORMAT>::kChunkSamples, BPS = Fmt<FORMAT>::kBytes;
+__device__ __forceinline__ uint4 load_unit(const ScanArgs &a, long long s, int &lo, int &hi) {
+    constexpr int US = Fmt<FORMAT>::kUnitSamples, BPS = Fmt<FORMAT>::kBytes;
     const long long n = (long long) a.nsamples;
-    long long first_valid = -(long long) a.head_valid;
-    long long l = first_valid - s, h = n - s;
-    lo = l < 0 ? 0 : (l > CS ? CS : (int) l);
-    hi = h > CS ? CS : (h < 0 ? 0 : (int) h);
-    uint4 v = make_uint4(0, 0, 0, 0);
+    const long long l = -(long long) a.head_valid - s, h = n - s;
+    lo = l < 0 ? 0 : (l > US ? US : (int) l);
+    hi = h > US ? US : (h < 0 ? 0 : (int) h);
     if (hi <= lo)
-        return v;
-    if (s < 0) { // carried head: always fully addressable
+        return make_uint4(0, 0, 0, 0);
+    if (s < 0) // carried head: always fully addressable
         return ldg_stream(reinterpret_cast<const uint4 *>(a.head + (s + kHead) * BPS));
-    }
-    if (hi == CS)
+    if (hi == US)
         return ldg_stream(reinterpret_cast<const uint4 *>(a.iq + s * BPS));
     // ragged end of the span: never read past the caller's buffer
     uint32_t w[4] = {0, 0, 0, 0};
@@ -332,383 +300,465 @@ __device__ __forceinline__ uint4 load_chunk(const ScanArgs &a, long long s, int 
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// One PPM bit decision on the warp buffer (u32 magnitudes); see slice_bit() for the closed form.
+__device__ __forceinline__ bool slice_bit_u32(const uint32_t *m, int t, const int4 *coef) {
+    const int s = (t * 52429) >> 18; // t / 5 for 0 <= t < 43690
+    const int r = t - 5 * s;
+    const int4 c = coef[r];
+    const uint32_t *p = m + 19 + s;
+    const int v = c.x * (int) p[0] + c.y * (int) p[1] + c.z * (int) p[2] + c.w * (int) p[3];
+    return v > 0;
+}
+
+struct WarpCtx {
+    const uint32_t *buf;   // window-start base of the chunk being scanned
+    const uint32_t *syn;   // 112 single-bit syndromes (shared)
+    const int4 *coef;      // 5 correlators (shared)
+    uint16_t *items, *lng, *sht;
+    long long chunk_pos0;  // scan position of window start 0 of the chunk
+    uint32_t tile_pos0;    // first position of the tile (may be "negative": stored as int)
+    // tile output cursors
+    uint32_t *cand_out;
+    PhaseRec *rec_out;
+    uint32_t cand_cap, rec_cap, ncand, nrec;
+};
+
+// stage 2: 4 frames per pass, 8 lanes per frame, lane l decides bit l of every byte
+template <int NBYTES>
+__device__ __forceinline__ void slice_pass(const ScanArgs &a, WarpCtx &cx, const uint16_t *list, int first, int count) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
+    const bool active = first + g < count;
+    const uint32_t item = list[active ? first + g : first];
+    const uint32_t pic = item & 511u; // position in chunk
+    const int ph = (int) ((item >> 9) & 7u) + 4;
+    const uint32_t *m = cx.buf + pic;
+    uint32_t w[4] = {0, 0, 0, 0};
+    uint32_t x = 0;
+    int t = ph + 12 * l;
+#pragma unroll
+    for (int k = 0; k < NBYTES; ++k, t += 96) {
+        const bool bit = slice_bit_u32(m, t, cx.coef);
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        w[k >> 2] |= ((bal >> (8 * g)) & 0xffu) << (8 * (k & 3)); // frame bit b -> bit b%32 of w[b/32]
+        if (bit)
+            x ^= cx.syn[8 * k + l + (112 - 8 * NBYTES)]; // crc.c:143: short frames use the tail of the list
+    }
+    x ^= __shfl_xor_sync(0xffffffffu, x, 1);
+    x ^= __shfl_xor_sync(0xffffffffu, x, 2);
+    x ^= __shfl_xor_sync(0xffffffffu, x, 4);
+    const uint32_t syn = x;
+    const uint32_t head32 = __brev(w[0]); // frame bits 0..31, MSB first
+    const uint32_t df = head32 >> 27, aa = head32 & 0xffffffu;
+    const FrameClass fc = classify_frame(df, aa, syn, (w[0] | w[1] | w[2] | w[3]) == 0, a.tab_short, a.n_short, a.tab_long, a.n_long);
+    const bool has = active && l == 0 && fc.kind != kKindBad;
+    const uint32_t mask = __ballot_sync(0xffffffffu, has);
+    if (has) {
+        const uint32_t slot = cx.nrec + __popc(mask & ((1u << lane) - 1u));
+        if (slot < cx.rec_cap) {
+            PhaseRec pr;
+            pr.pos = (uint32_t) (cx.chunk_pos0 + pic);
+            pr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
+            pr.w1 = fc.key | ((uint32_t) ph << 24);
+            pr.pad = 0;
+            *reinterpret_cast<uint4 *>(&cx.rec_out[slot]) = *reinterpret_cast<const uint4 *>(&pr);
+        }
+        // mode_s.c:717-726: only a clean DF17, or a clean DF11 with IID 0, can ever be added to the
+        // ICAO filter; remember every such address of the stream
+        if (syn == 0 && (df == 17 || df == 11))
+            atomicOr(&a.addr_bitmap[aa >> 5], 1u << (aa & 31u));
+    }
+    cx.nrec += __popc(mask);
+}
+
+// stage 1 + 2 for the queued items of the chunk
+__device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, int &nitems) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
+    __syncwarp();
+    int nl = 0, ns = 0;
+    for (int it = 0; it < nitems; it += 4) {
+        // first byte of 4 items -> DF -> frame length (demod_2400.c:188-205)
+        const bool active = it + g < nitems;
+        const uint32_t item = cx.items[active ? it + g : it];
+        const uint32_t *m = cx.buf + (item & 511u);
+        const int ph = (int) ((item >> 9) & 7u) + 4;
+        const bool bit = slice_bit_u32(m, ph + 12 * l, cx.coef);
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (it + q < nitems) { // uniform
+                const uint32_t df = __brev((bal >> (8 * q)) & 0x1fu) >> 27;
+                const int nb = frame_bytes_for_df(df);
+                const uint32_t its = cx.items[it + q];
+                if (nb == 14) {
+                    if (lane == 0)
+                        cx.lng[nl] = (uint16_t) its;
+                    ++nl;
+                } else if (nb == 7) {
+                    if (lane == 0)
+                        cx.sht[ns] = (uint16_t) its;
+                    ++ns;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int it = 0; it < nl; it += 4)
+        slice_pass<14>(a, cx, cx.lng, it, nl);
+    for (int it = 0; it < ns; it += 4)
+        slice_pass<7>(a, cx, cx.sht, it, ns);
+    __syncwarp();
+    nitems = 0;
+}
+
 template <int FORMAT, bool SLICE>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const ScanSmem sm = scan_smem_layout(smem_raw, FORMAT == 0);
-    constexpr int CS = Fmt<FORMAT>::kChunkSamples;
-    constexpr int kChunks = kTileSamples / CS;
-    constexpr int kChunksPerThread = (kChunks + kScanThreads - 1) / kScanThreads;
+    constexpr int US = Fmt<FORMAT>::kUnitSamples;
+    constexpr int UNITS = kLanePos / US; // 16-byte units per lane per step
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inv_scale = (FORMAT == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f);
 
-    // one-time staging of the tables
+    // shared memory carve-up
+    unsigned char *sp = smem_raw;
+    const uint16_t *s_lut = reinterpret_cast<const uint16_t *>(sp);
+    if (FORMAT == 0)
+        sp += kSmemLut;
+    uint32_t *s_buf = reinterpret_cast<uint32_t *>(sp + (size_t) warp * kWarpBuf * sizeof(uint32_t));
+    sp += (size_t) kScanWarps * kWarpBuf * sizeof(uint32_t);
+    uint16_t *s_lists = reinterpret_cast<uint16_t *>(sp) + (size_t) warp * 3 * kItemCap;
+    sp += (size_t) kScanWarps * 3 * kItemCap * sizeof(uint16_t);
+    uint32_t *s_syn = reinterpret_cast<uint32_t *>(sp);
+    sp += 112 * sizeof(uint32_t);
+    int4 *s_coef = reinterpret_cast<int4 *>(sp);
+
+    // one-time staging of the tables (the only block-wide barrier of the kernel)
     if (FORMAT == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.lut);
-        uint4 *dst = reinterpret_cast<uint4 *>(sm.lut);
-        for (int i = tid; i < 65536 * 2 / 16; i += kScanThreads)
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+        for (int i = tid; i < (int) (kSmemLut / 16); i += kScanThreads)
             dst[i] = __ldg(src + i);
     }
     if (tid < 112)
-        sm.syn[tid] = c_bit_syndrome[tid];
-    if (tid < 20)
-        (&sm.coef[0][0])[tid] = (&c_slice_coef[0][0])[tid];
+        s_syn[tid] = c_bit_syndrome[tid];
+    if (tid < 5)
+        s_coef[tid] = make_int4(c_slice_coef[tid][0], c_slice_coef[tid][1], c_slice_coef[tid][2], c_slice_coef[tid][3]);
     __syncthreads();
 
     const long long n = (long long) a.nsamples;
-    uint4 pre[kChunksPerThread];
-    int pre_lo[kChunksPerThread], pre_hi[kChunksPerThread];
+    const long long B = (long long) a.block_samples;
+    const int thr = a.threshold;
 
-    auto prefetch = [&](uint32_t tile) {
-        const long long s0 = (long long) tile * kTile - kHead;
-#pragma unroll
-        for (int k = 0; k < kChunksPerThread; ++k) {
-            int c = tid + k * kScanThreads;
-            pre_lo[k] = pre_hi[k] = 0;
-            pre[k] = make_uint4(0, 0, 0, 0);
-            if (c < kChunks)
-                pre[k] = load_chunk<FORMAT>(a, s0 + (long long) c * CS, pre_lo[k], pre_hi[k]);
+    WarpCtx cx;
+    cx.syn = s_syn;
+    cx.coef = s_coef;
+    cx.items = s_lists;
+    cx.lng = s_lists + kItemCap;
+    cx.sht = s_lists + 2 * kItemCap;
+
+    for (;;) {
+        // ---- next tile from the work queue ----
+        uint32_t tile = 0;
+        if (lane == 0)
+            tile = atomicAdd(&a.counters->next_tile, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.ntiles)
+            break;
+
+        const long long c0 = (long long) tile * kTile - kHead; // first window-start sample of the tile
+        uint32_t cand_off, rec_off;
+        if (a.tile_off) {
+            cand_off = a.tile_off[2 * tile];
+            rec_off = a.tile_off[2 * tile + 1];
+            cx.cand_cap = a.tile_off[2 * tile + 2] - cand_off;
+            cx.rec_cap = a.tile_off[2 * tile + 3] - rec_off;
+        } else {
+            cand_off = tile * a.cand_slab;
+            rec_off = tile * a.rec_slab;
+            cx.cand_cap = a.cand_slab;
+            cx.rec_cap = a.rec_slab;
         }
-    };
+        cx.cand_out = a.cand + cand_off;
+        cx.rec_out = a.recs + rec_off;
+        cx.ncand = cx.nrec = 0;
+        int nitems = 0;
+        uint32_t ncand_lane = 0; // scan-only mode: candidates seen by this lane
 
-    uint32_t tile = blockIdx.x;
-    if (tile < a.ntiles)
-        prefetch(tile);
-
-    for (; tile < a.ntiles; tile += gridDim.x) {
-        const long long p0 = (long long) tile * kTile;
-
-        // ---------------- phase A: IQ -> magnitudes of the tile, block sums ----------------
+        // block sums of the samples this tile owns: [c0, c0 + kTile) within [0, n)
         unsigned long long sum_level = 0, sum_power = 0;
         double fsum_level = 0, fsum_power = 0;
-        const uint32_t kb0 = (uint32_t) (p0 / a.block_samples);
-        const bool one_block = ((long long) (kb0 + 1) * a.block_samples >= p0 + kTile);
-#pragma unroll
-        for (int k = 0; k < kChunksPerThread; ++k) {
-            int c = tid + k * kScanThreads;
-            if (c >= kChunks)
-                continue;
-            const uint4 raw = pre[k];
-            const int lo = pre_lo[k], hi = pre_hi[k];
-            uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
-            uint32_t m[CS];
-            unsigned long long cl = 0, cp = 0;
-            double fl = 0, fp = 0;
+        long long blk = (c0 > 0 ? c0 : 0) / B, next_bound = (blk + 1) * B;
+        auto flush_sums = [&]() {
             if (FORMAT == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    m[2 * j] = sm.lut[words[j] & 0xffffu];
-                    m[2 * j + 1] = sm.lut[words[j] >> 16];
-                }
-#pragma unroll
-                for (int j = 0; j < CS; ++j) {
-                    if (j < lo || j >= hi)
-                        m[j] = 0;
-                    cl += m[j];
-                    cp += (unsigned long long) m[j] * m[j];
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < CS; ++j) {
-                    float magsq, mag;
-                    m[j] = mag_sc16_word(words[j], inv_scale, magsq, mag);
-                    if (j < lo || j >= hi) {
-                        m[j] = 0;
-                    } else {
-                        fl += (double) mag;
-                        fp += (double) magsq;
-                    }
-                }
-            }
-            if (CS == 8) {
-                uint4 packed = make_uint4(m[0] | (m[1] << 16), m[2] | (m[3] << 16), m[4 % CS] | (m[5 % CS] << 16),
-                                          m[6 % CS] | (m[7 % CS] << 16));
-                *reinterpret_cast<uint4 *>(sm.mag + c * CS) = packed;
-            } else {
-                uint2 packed = make_uint2(m[0] | (m[1] << 16), m[2] | (m[3] << 16));
-                *reinterpret_cast<uint2 *>(sm.mag + c * CS) = packed;
-            }
-            // this tile owns the sums of samples [p0, p0 + kTile)
-            const int q = c * CS;
-            if (q >= kHead && q < kHead + kTile) {
-                if (one_block) {
-                    sum_level += cl;
-                    sum_power += cp;
-                    fsum_level += fl;
-                    fsum_power += fp;
-                } else if (hi > lo) {
-                    const uint32_t kb = (uint32_t) ((p0 + q - kHead) / a.block_samples);
-                    if (FORMAT == 0) {
-                        atomicAdd(&a.block_sums_u64[2 * kb], cl);
-                        atomicAdd(&a.block_sums_u64[2 * kb + 1], cp);
-                    } else {
-                        atomicAdd(&a.block_sums_f64[2 * kb], fl);
-                        atomicAdd(&a.block_sums_f64[2 * kb + 1], fp);
-                    }
-                }
-            }
-        }
-        if (one_block) {
-            if (FORMAT == 0) {
-                sum_level = warp_sum_u64(sum_level);
-                sum_power = warp_sum_u64(sum_power);
-                if (lane == 0) {
-                    sm.red[2 * warp] = sum_level;
-                    sm.red[2 * warp + 1] = sum_power;
-                }
-            } else {
-                fsum_level = warp_sum_f64(fsum_level);
-                fsum_power = warp_sum_f64(fsum_power);
-                if (lane == 0) {
-                    reinterpret_cast<double *>(sm.red)[2 * warp] = fsum_level;
-                    reinterpret_cast<double *>(sm.red)[2 * warp + 1] = fsum_power;
-                }
-            }
-        }
-
-        // next tile's IQ is requested now and consumed after this tile's scan/slice work
-        if (tile + gridDim.x < a.ntiles)
-            prefetch(tile + gridDim.x);
-
-        __syncthreads();
-        if (one_block && warp == 0) {
-            constexpr int NW = kScanThreads / 32;
-            if (FORMAT == 0) {
-                unsigned long long l = (lane < NW) ? sm.red[2 * lane] : 0, p = (lane < NW) ? sm.red[2 * lane + 1] : 0;
-                l = warp_sum_u64(l);
-                p = warp_sum_u64(p);
+                const unsigned long long l = warp_sum_u64(sum_level), p = warp_sum_u64(sum_power);
                 if (lane == 0 && (l | p)) {
-                    atomicAdd(&a.block_sums_u64[2 * kb0], l);
-                    atomicAdd(&a.block_sums_u64[2 * kb0 + 1], p);
+                    atomicAdd(&a.block_sums_u64[2 * blk], l);
+                    atomicAdd(&a.block_sums_u64[2 * blk + 1], p);
                 }
             } else {
-                const double *red = reinterpret_cast<const double *>(sm.red);
-                double l = (lane < NW) ? red[2 * lane] : 0, p = (lane < NW) ? red[2 * lane + 1] : 0;
-                l = warp_sum_f64(l);
-                p = warp_sum_f64(p);
-                if (lane == 0) {
-                    atomicAdd(&a.block_sums_f64[2 * kb0], l);
-                    atomicAdd(&a.block_sums_f64[2 * kb0 + 1], p);
+                const double l = warp_sum_f64(fsum_level), p = warp_sum_f64(fsum_power);
+                if (lane == 0 && (l != 0 || p != 0)) {
+                    atomicAdd(&a.block_sums_f64[2 * blk], l);
+                    atomicAdd(&a.block_sums_f64[2 * blk + 1], p);
                 }
             }
-        }
+            sum_level = sum_power = 0;
+            fsum_level = fsum_power = 0;
+        };
 
-        // ---------------- phase B: preamble scan, kPosPerThread positions per thread ----------------
-        // position i of the tile has its window at mag[i + 2 ...] (mag[0] is sample p0 - kHead,
-        // the window of position p starts kOverlap samples before sample p)
-        uint32_t masks[kPosPerThread]; // 5-bit try masks
-        int ncand_mine = 0;
-        {
-            const int i0 = tid * kPosPerThread;
-            uint32_t w[kPosPerThread + 18];
+        // the tile's last chunk only feeds the slicer's look-ahead; the stream's last tile also
+        // converts whatever is left of the span, for the block sums
+        uint4 pre[UNITS];
+        auto prefetch = [&](int k) {
+            const long long ls = c0 + (long long) k * kStep + lane * kLanePos;
 #pragma unroll
-            for (int x = 0; x < kPosPerThread + 18; ++x)
-                w[x] = sm.mag[i0 + 2 + x];
-            const int thr = a.threshold;
-#pragma unroll
-            for (int i = 0; i < kPosPerThread; ++i) {
-                const uint32_t *pa = &w[i];
-                uint32_t mask = 0;
-                // demod_2400.c:276
-                if (pa[1] > pa[7] && pa[12] > pa[14] && pa[12] > pa[15]) {
-                    // demod_2400.c:281-292
-                    int base_noise = (int) (pa[5] + pa[8] + pa[16] + pa[17] + pa[18]);
-                    int ref_level = (base_noise * thr) >> 5;
-                    // demod_2400.c:298-301
-                    int diff_2_3 = (int) pa[2] - (int) pa[3];
-                    int sum_1_4 = (int) pa[1] + (int) pa[4];
-                    int diff_10_11 = (int) pa[10] - (int) pa[11];
-                    int common3456 = sum_1_4 - diff_2_3 + (int) pa[9] + (int) pa[12];
-                    if (common3456 - diff_10_11 >= ref_level) // :306-312 -> phases 4, 5
-                        mask |= 0x03;
-                    if (common3456 + diff_10_11 >= ref_level) // :316-322 -> phases 6, 7
-                        mask |= 0x0c;
-                    if (sum_1_4 + 2 * diff_2_3 + diff_10_11 + (int) pa[12] >= ref_level) // :327-330 -> phase 8
-                        mask |= 0x10;
-                }
-                if (p0 + i0 + i >= n)
-                    mask = 0;
-                masks[i] = mask;
-                ncand_mine += (mask != 0);
-                if (a.dbg_masks && p0 + i0 + i < n)
-                    a.dbg_masks[p0 + i0 + i] = (uint8_t) mask;
+            for (int u = 0; u < UNITS; ++u) {
+                int lo, hi;
+                pre[u] = load_unit<FORMAT>(a, ls + u * US, lo, hi);
             }
-        }
+        };
+        prefetch(0);
 
-        int ncand_tile;
-        int my_off = block_exclusive_scan(ncand_mine, sm.warp, ncand_tile);
-
-        if (!SLICE) {
-            if (tid == 0 && ncand_tile)
-                atomicAdd(&a.counters->n_cand, (unsigned long long) ncand_tile);
-            __syncthreads();
-            continue;
-        }
-
-        // ---------------- phases C/D in rounds that cannot overflow the shared lists ----------------
-        const int nrounds = (ncand_tile <= kMaxCand) ? 1 : kSlowRounds;
-        if (tid == 0 && nrounds > 1)
-            atomicAdd(&a.counters->slow_tiles, 1u);
-        uint32_t tile_cand_off = 0, tile_rec_off = 0, tile_ncand = 0, tile_nrec = 0;
-        bool tile_ovf = false;
-
-        for (int round = 0; round < nrounds; ++round) {
-            int ncand = ncand_tile, off = my_off;
-            bool mine = true;
-            if (nrounds > 1) {
-                // round r takes the kMaxCand positions [r*kMaxCand, (r+1)*kMaxCand)
-                mine = (tid * kPosPerThread) / kMaxCand == round;
-                off = block_exclusive_scan(mine ? ncand_mine : 0, sm.warp, ncand);
-            }
-            if (mine) {
+        for (int k = 0; k <= kScanSteps; ++k) {
+            const long long cs = c0 + (long long) k * kStep; // first sample of chunk k
+            const long long ls = cs + lane * kLanePos;        // this lane's first sample
+            // ---------------- convert chunk k ----------------
+            uint32_t m[kLanePos];
+            unsigned long long cl[UNITS], cp[UNITS];
+            double fl[UNITS], fp[UNITS];
 #pragma unroll
-                for (int i = 0; i < kPosPerThread; ++i)
-                    if (masks[i])
-                        sm.cand[off++] = (uint32_t) (tid * kPosPerThread + i) | (masks[i] << 13);
-            }
-            __syncthreads();
-
-            // ---- C1: first byte of every tried phase -> DF -> frame length (demod_2400.c:188-205) ----
-            int nitems = 0;
-            for (int cb = 0; cb < ncand; cb += kScanThreads) { // uniform trip count
-                const int c = cb + tid;
-                uint32_t my_items[5];
-                int my_n = 0;
-                if (c < ncand) {
-                    const uint32_t e = sm.cand[c];
-                    const uint16_t *m = sm.mag + (e & 0x1fffu) + 2;
-                    const uint32_t tm = (e >> 13) & 31u;
+            for (int u = 0; u < UNITS; ++u) {
+                const uint32_t words[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
+                cl[u] = cp[u] = 0;
+                fl[u] = fp[u] = 0;
+                float fmag[US], fmagsq[US];
+                if (FORMAT == 0) {
 #pragma unroll
-                    for (int ph = 0; ph < 5; ++ph) {
-                        if (!((tm >> ph) & 1u))
-                            continue;
-                        uint32_t byte0 = 0;
-#pragma unroll
-                        for (int b = 0; b < 8; ++b)
-                            byte0 = (byte0 << 1) | (slice_bit(m, ph + 4, b, sm.coef) ? 1u : 0u);
-                        int nb = frame_bytes_for_df(byte0 >> 3);
-                        if (nb)
-                            my_items[my_n++] = (uint32_t) c | ((uint32_t) ph << 10) | ((nb == 14) ? (1u << 13) : 0u);
+                    for (int j = 0; j < 4; ++j) {
+                        m[u * US + 2 * j] = s_lut[words[j] & 0xffffu];
+                        m[u * US + 2 * j + 1] = s_lut[words[j] >> 16];
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < US; ++j)
+                        m[u * US + j] = mag_sc16_word(words[j % 4], inv_scale, fmagsq[j], fmag[j]);
                 }
-                int tot;
-                int ioff = block_exclusive_scan(my_n, sm.warp, tot);
-                if (c < ncand)
-                    sm.itemoff[c] = (uint16_t) (nitems + ioff);
-                for (int k = 0; k < my_n; ++k)
-                    sm.items[nitems + ioff + k] = my_items[k];
-                nitems += tot;
-            }
-            __syncthreads();
-
-            // ---- C2: one warp per (candidate, phase): slice, CRC, class ----
-            for (int it = warp; it < nitems; it += kScanThreads / 32) {
-                const uint32_t item = sm.items[it];
-                const uint32_t e = sm.cand[item & 1023u];
-                const uint16_t *m = sm.mag + (e & 0x1fffu) + 2;
-                const int ph = (int) ((item >> 10) & 7u) + 4;
-                const int nbits = (item & (1u << 13)) ? 112 : 56;
-                uint32_t w[4], syn;
-                warp_slice_frame(m, ph, nbits, sm.coef, sm.syn, w, syn);
-                const uint32_t head32 = __brev(w[0]); // frame bits 0..31, MSB first
-                const FrameClass fc = classify_frame(head32 >> 27, head32 & 0xffffffu, syn, (w[0] | w[1] | w[2] | w[3]) == 0,
-                                                     a.tab_short, a.n_short, a.tab_long, a.n_long);
-                if (lane == 0) {
-                    sm.res[it] = make_uint2(syn | (fc.kind << 24) | (fc.errors << 28), fc.key | ((uint32_t) ph << 24));
-                    // mode_s.c:717-726: only a clean DF17, or a clean DF11 with IID 0, can ever be
-                    // added to the ICAO filter; remember every such address of the stream
-                    const uint32_t df = head32 >> 27;
-                    if (fc.kind != kKindBad && syn == 0 && (df == 17 || df == 11)) {
-                        const uint32_t aa = head32 & 0xffffffu;
-                        atomicOr(&a.addr_bitmap[aa >> 5], 1u << (aa & 31u));
+                // samples outside the stream have magnitude 0 (fifo.c:47) and are not summed
+                const long long us = ls + u * US;
+                if (us < -(long long) a.head_valid || us + US > n) {
+                    const long long l = -(long long) a.head_valid - us, h = n - us;
+#pragma unroll
+                    for (int j = 0; j < US; ++j)
+                        if (j < l || j >= h) {
+                            m[u * US + j] = 0;
+                            if (FORMAT != 0)
+                                fmag[j] = fmagsq[j] = 0;
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < US; ++j) {
+                    if (FORMAT == 0) {
+                        cl[u] += m[u * US + j];
+                        cp[u] += (unsigned long long) m[u * US + j] * m[u * US + j];
+                    } else {
+                        fl[u] += (double) fmag[j];
+                        fp[u] += (double) fmagsq[j];
                     }
                 }
             }
-            __syncthreads();
+            // request the next chunk now; it is consumed one iteration later
+            if (k < kScanSteps)
+                prefetch(k + 1);
 
-            // ---- D: ordered write-out of candidate entries and class records ----
-            int nrec = 0;
+            // store: chunk k lives in slot k&1; even chunks are mirrored behind slot 1 so that a reader
+            // starting in either slot sees the following chunk contiguously
             {
-                // count the records first (items are ordered by candidate, then phase)
-                int mine_n = 0;
-                for (int it = tid; it < nitems; it += kScanThreads)
-                    mine_n += ((sm.res[it].x >> 24) & 7u) != kKindBad;
-                block_exclusive_scan(mine_n, sm.warp, nrec);
-                // The tile's entries and records must be contiguous for K2.  A one-round tile reserves
-                // exactly what it has; a slow tile reserves its worst case (5 records per candidate)
-                // once, in round 0, and fills it round after round.
-                if (round == 0) {
-                    if (tid == 0) {
-                        const unsigned long long want_c = (unsigned long long) ncand_tile;
-                        const unsigned long long want_r = (nrounds == 1) ? (unsigned long long) nrec : 5ull * want_c;
-                        unsigned long long co = atomicAdd(&a.counters->n_cand, want_c);
-                        unsigned long long ro = atomicAdd(&a.counters->n_rec, want_r);
-                        unsigned int ovf = 0;
-                        if (co + want_c > a.cand_cap)
-                            ovf |= 1u;
-                        if (ro + want_r > a.rec_cap)
-                            ovf |= 2u;
-                        if (ovf)
-                            atomicOr(&a.counters->overflow, ovf);
-                        sm.warp[20] = (int) (uint32_t) co;
-                        sm.warp[21] = (int) (uint32_t) ro;
-                        sm.warp[22] = (int) ovf;
-                    }
-                    __syncthreads();
-                    tile_cand_off = (uint32_t) sm.warp[20];
-                    tile_rec_off = (uint32_t) sm.warp[21];
-                    tile_ovf = sm.warp[22] != 0;
+                uint4 *dst = reinterpret_cast<uint4 *>(s_buf + (k & 1) * kStep + lane * kLanePos);
+#pragma unroll
+                for (int q = 0; q < kLanePos / 4; ++q)
+                    dst[q] = make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+                if (!(k & 1)) {
+                    uint4 *mir = reinterpret_cast<uint4 *>(s_buf + 2 * kStep + lane * kLanePos);
+#pragma unroll
+                    for (int q = 0; q < kLanePos / 4; ++q)
+                        mir[q] = make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
                 }
-                const uint32_t cand_base = tile_cand_off + tile_ncand;
-                const uint32_t rec_base = tile_rec_off + tile_nrec;
-                tile_ncand += (uint32_t) ncand;
-                tile_nrec += (uint32_t) nrec;
+            }
 
-                if (!tile_ovf) {
-                    // records: ordered compaction over the item list, kScanThreads items at a time
-                    int done = 0;
-                    for (int ib = 0; ib < nitems; ib += kScanThreads) {
-                        const int it = ib + tid;
-                        uint2 r = make_uint2(0, 0);
-                        bool keep = false;
-                        if (it < nitems) {
-                            r = sm.res[it];
-                            keep = ((r.x >> 24) & 7u) != kKindBad;
-                        }
-                        int tot;
-                        int o = block_exclusive_scan(keep ? 1 : 0, sm.warp, tot);
-                        if (keep) {
-                            const uint32_t c = sm.items[it] & 1023u;
-                            PhaseRec pr;
-                            pr.pos = (uint32_t) (p0 + (sm.cand[c] & 0x1fffu));
-                            pr.w0 = r.x;
-                            pr.w1 = r.y;
-                            pr.cand = cand_base + c;
-                            a.recs[rec_base + done + o] = pr;
-                        }
-                        done += tot;
+            // block sums: chunks 0..kScanSteps-1 are owned by this tile (samples < 0 belong to the
+            // previous span and were masked to zero above, which is harmless: they add nothing)
+            if (k < kScanSteps) {
+                const long long own_lo = cs > 0 ? cs : 0, own_hi = (cs + kStep < n) ? cs + kStep : n;
+                if (own_hi > own_lo) {
+                    if (own_lo >= next_bound) {
+                        flush_sums();
+                        blk = own_lo / B;
+                        next_bound = (blk + 1) * B;
                     }
-                    // candidate entries, with the count of records each owns
-                    for (int c = tid; c < ncand; c += kScanThreads) {
-                        const int i0 = sm.itemoff[c];
-                        const int i1 = (c + 1 < ncand) ? sm.itemoff[c + 1] : nitems;
-                        uint32_t nonbad = 0;
-                        for (int it = i0; it < i1; ++it)
-                            nonbad += ((sm.res[it].x >> 24) & 7u) != kKindBad;
-                        a.cand[cand_base + c] = sm.cand[c] | (nonbad << 18);
+                    if (own_hi <= next_bound) {
+#pragma unroll
+                        for (int u = 0; u < UNITS; ++u) {
+                            if (ls + u * US >= 0) { // head samples are not this span's
+                                sum_level += cl[u];
+                                sum_power += cp[u];
+                                fsum_level += fl[u];
+                                fsum_power += fp[u];
+                            }
+                        }
+                    } else {
+                        // a mag_buf boundary inside the chunk: every 16-byte unit lies on one side of it
+                        flush_sums();
+#pragma unroll
+                        for (int u = 0; u < UNITS; ++u) {
+                            const long long us = ls + u * US;
+                            if (us >= 0 && us < n) {
+                                const long long kb = us / B;
+                                if (FORMAT == 0) {
+                                    if (cl[u] | cp[u]) {
+                                        atomicAdd(&a.block_sums_u64[2 * kb], cl[u]);
+                                        atomicAdd(&a.block_sums_u64[2 * kb + 1], cp[u]);
+                                    }
+                                } else {
+                                    atomicAdd(&a.block_sums_f64[2 * kb], fl[u]);
+                                    atomicAdd(&a.block_sums_f64[2 * kb + 1], fp[u]);
+                                }
+                            }
+                        }
+                        blk = own_hi / B;
+                        next_bound = (blk + 1) * B;
                     }
                 }
             }
-            __syncthreads();
-        }
+            __syncwarp();
 
-        if (tid == 0) {
-            TileDesc td;
-            td.cand_off = tile_cand_off;
-            td.ncand = tile_ncand;
-            td.rec_off = tile_rec_off;
-            td.nrec = tile_nrec;
-            a.tiles[tile] = td;
+            // ---------------- scan chunk k-1 (its look-ahead, chunk k, is now in the buffer) ----------------
+            if (k >= 1) {
+                const int j = k - 1;
+                const uint32_t *base = s_buf + (j & 1) * kStep; // window start 0 of chunk j
+                const long long pos0 = c0 + (long long) j * kStep + kOverlap; // its scan position
+                const long long lp0 = pos0 + lane * kLanePos;
+                // positions of this lane that exist: 0 <= p < n
+                int vlo = (lp0 < 0) ? (int) (-lp0 > kLanePos ? kLanePos : -lp0) : 0;
+                long long vh = n - lp0;
+                int vhi = vh > kLanePos ? kLanePos : (vh < 0 ? 0 : (int) vh);
+                const uint32_t vmask = (vhi > vlo) ? (((1u << vhi) - 1u) & ~((1u << vlo) - 1u)) : 0u;
+
+                uint32_t b45 = 0, b67 = 0, b8 = 0;
+                if (__any_sync(0xffffffffu, vmask != 0)) {
+                    uint32_t w[kLanePos + 20];
+                    {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(base + lane * kLanePos);
+#pragma unroll
+                        for (int q = 0; q < (kLanePos + 20) / 4; ++q) {
+                            const uint4 v = src[q];
+                            w[4 * q] = v.x;
+                            w[4 * q + 1] = v.y;
+                            w[4 * q + 2] = v.z;
+                            w[4 * q + 3] = v.w;
+                        }
+                    }
+                    // shared partial sums of the three correlators (demod_2400.c:298-330):
+                    //   Q[x] = m[x] + m[x+3], D[x] = m[x] - m[x+1], T[x] = m[x] + m[x+1] + m[x+2]
+                    int Q[kLanePos + 9], D[kLanePos + 11], T[kLanePos];
+#pragma unroll
+                    for (int x2 = 1; x2 < kLanePos + 9; ++x2)
+                        Q[x2] = (int) (w[x2] + w[x2 + 3]);
+#pragma unroll
+                    for (int x2 = 2; x2 < kLanePos + 11; ++x2)
+                        D[x2] = (int) w[x2] - (int) w[x2 + 1];
+#pragma unroll
+                    for (int i = 0; i < kLanePos; ++i)
+                        T[i] = (int) (w[i + 16] + w[i + 17] + w[i + 18]);
+#pragma unroll
+                    for (int i = 0; i < kLanePos; ++i) {
+                        // demod_2400.c:276
+                        const bool pre_ok = w[i + 1] > w[i + 7] && w[i + 12] > w[i + 14] && w[i + 12] > w[i + 15];
+                        // demod_2400.c:281-292: base_noise = pa[5] + pa[8] + pa[16] + pa[17] + pa[18]
+                        const int ref_level = ((Q[i + 5] + T[i]) * thr) >> 5;
+                        // common3456 = pa[1] + pa[4] - (pa[2] - pa[3]) + pa[9] + pa[12]
+                        const int v = Q[i + 1] - D[i + 2] + Q[i + 9] - ref_level;
+                        const int d10 = D[i + 10];
+                        const bool t45 = v >= d10;                                  // :306 common3456 - diff_10_11 >= ref
+                        const bool t67 = v + d10 >= 0;                              // :316 common3456 + diff_10_11 >= ref
+                        const bool t8 = v + d10 + 3 * D[i + 2] - (int) w[i + 9] >= 0; // :327 sum_1_4 + 2 diff_2_3 + diff_10_11 + pa[12] >= ref
+                        b45 |= (pre_ok && t45) ? (1u << i) : 0u;
+                        b67 |= (pre_ok && t67) ? (1u << i) : 0u;
+                        b8 |= (pre_ok && t8) ? (1u << i) : 0u;
+                    }
+                    b45 &= vmask;
+                    b67 &= vmask;
+                    b8 &= vmask;
+                }
+
+                if (a.dbg_masks) {
+                    for (int i = 0; i < kLanePos; ++i)
+                        if ((vmask >> i) & 1u)
+                            a.dbg_masks[lp0 + i] = (uint8_t) ((((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u));
+                }
+
+                const uint32_t any = b45 | b67 | b8;
+                if (!SLICE) {
+                    ncand_lane += __popc(any);
+                } else {
+                    uint32_t lanes = __ballot_sync(0xffffffffu, any != 0);
+                    cx.buf = base;
+                    cx.chunk_pos0 = pos0;
+                    while (lanes) {
+                        const int L = __ffs(lanes) - 1;
+                        lanes &= lanes - 1;
+                        const uint32_t a45 = __shfl_sync(0xffffffffu, b45, L);
+                        const uint32_t a67 = __shfl_sync(0xffffffffu, b67, L);
+                        const uint32_t a8 = __shfl_sync(0xffffffffu, b8, L);
+                        uint32_t u = a45 | a67 | a8;
+                        while (u) {
+                            const int i = __ffs(u) - 1;
+                            u &= u - 1;
+                            const uint32_t tm = (((a45 >> i) & 1u) * 3u) | (((a67 >> i) & 1u) * 12u) | (((a8 >> i) & 1u) * 16u);
+                            const uint32_t pic = (uint32_t) (L * kLanePos + i);
+                            if (lane == 0) {
+                                if (cx.ncand < cx.cand_cap)
+                                    cx.cand_out[cx.ncand] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
+#pragma unroll
+                                for (int ph = 0; ph < 5; ++ph)
+                                    if ((tm >> ph) & 1u)
+                                        cx.items[nitems + __popc(tm & ((1u << ph) - 1u))] = (uint16_t) (pic | ((uint32_t) ph << 9));
+                            }
+                            ++cx.ncand;
+                            nitems += __popc(tm);
+                            if (nitems > kItemCap - 5)
+                                process_items(a, cx, nitems);
+                        }
+                    }
+                    if (nitems)
+                        process_items(a, cx, nitems);
+                }
+                __syncwarp();
+            }
+        }
+        flush_sums();
+
+        // ---- tile descriptor ----
+        if (!SLICE) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                ncand_lane += __shfl_xor_sync(0xffffffffu, ncand_lane, o);
+            cx.ncand = ncand_lane;
+        }
+        if (lane == 0) {
+            if (SLICE) {
+                TileDesc td;
+                td.cand_off = cand_off;
+                td.ncand = cx.ncand;
+                td.rec_off = rec_off;
+                td.nrec = cx.nrec;
+                a.tiles[tile] = td;
+                unsigned int ovf = (cx.ncand > cx.cand_cap ? 1u : 0u) | (cx.nrec > cx.rec_cap ? 2u : 0u);
+                if (ovf)
+                    atomicOr(&a.counters->overflow, ovf);
+                if (cx.nrec)
+                    atomicAdd(&a.counters->n_rec, (unsigned long long) cx.nrec);
+            }
+            if (cx.ncand)
+                atomicAdd(&a.counters->n_cand, (unsigned long long) cx.ncand);
         }
     }
 }
@@ -727,8 +777,9 @@ cudaError_t scan_configure() {
 cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stream) {
     if (a.ntiles == 0)
         return cudaSuccess;
-    if (grid > (int) a.ntiles)
-        grid = (int) a.ntiles;
+    const int max_useful = (int) ((a.ntiles + kScanWarps - 1) / kScanWarps);
+    if (grid > max_useful)
+        grid = max_useful;
     const size_t smem = scan_smem_bytes(a.format);
 #define LAUNCH(F)                                                              \
     if (mode)                                                                  \
@@ -746,11 +797,12 @@ cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stre
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: classify kernel -- one CTA per tile
+// K2: classify kernel -- one CTA per tile, position-indexed so that K1's output order is free
 // ------------------------------------------------------------------------------------------
 
 constexpr int kClassifyThreads = 256;
 constexpr int kFrameSamples = 296; // samples a frame's slice + power can touch: m[0..290]
+constexpr int kPosPerThread2 = kTile / kClassifyThreads; // 32
 
 __device__ __forceinline__ bool bitmap_test(const uint32_t *__restrict__ bm, uint32_t addr) {
     return (__ldg(&bm[(addr & 0xffffffu) >> 5]) >> (addr & 31u)) & 1u;
@@ -770,19 +822,22 @@ __device__ __forceinline__ bool record_is_live(uint32_t w0, uint32_t w1, const u
 __device__ __forceinline__ uint32_t sample_mag(const ClassifyArgs &a, long long s) {
     if (s < -(long long) a.head_valid || s >= (long long) a.nsamples)
         return 0;
-    const uint8_t *base = (s < 0) ? a.head + (s + kHead) * (a.format == 0 ? 2 : 4) : a.iq + s * (a.format == 0 ? 2 : 4);
+    const int bps = (a.format == 0) ? 2 : 4;
+    const uint8_t *base = (s < 0) ? a.head + (s + kHead) * bps : a.iq + s * bps;
     if (a.format == 0) {
-        uint32_t idx = (uint32_t) base[0] | ((uint32_t) base[1] << 8);
+        const uint32_t idx = (uint32_t) base[0] | ((uint32_t) base[1] << 8);
         return __ldg(&a.lut[idx]);
     }
-    uint32_t w = *reinterpret_cast<const uint32_t *>(base);
+    const uint32_t w = *reinterpret_cast<const uint32_t *>(base);
     float magsq, mag;
     return mag_sc16_word(w, (a.format == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f), magsq, mag);
 }
 
 __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const ClassifyArgs a) {
-    __shared__ __align__(4) uint8_t s_flags[kTile]; // per candidate of the tile: bit0 live, bit1 has a -1 phase
-    __shared__ uint16_t s_slot[kTile];               // first live-record slot of a live candidate
+    // per position of the tile
+    __shared__ __align__(16) uint8_t s_info[kTile]; // trymask[4:0] | live[5] | has a -1 phase[6]
+    __shared__ __align__(16) uint8_t s_nb[kTile];   // which phases own a class record
+    __shared__ uint16_t s_slot[kTile];              // first live-record slot of a live position
     __shared__ int s_warp[40];
     __shared__ uint32_t s_syn[112];
     __shared__ int s_coef[5][4];
@@ -792,9 +847,9 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
     if (a.counters->overflow & 3u)
-        return; // K1 ran out of room: the host grows the buffers and runs the span again
+        return; // K1 ran out of room: the host places the slabs exactly and runs the span again
     const TileDesc td = a.tiles[tile];
-    const long long p0 = (long long) tile * kTile;
+    const long long p0 = (long long) tile * kTile - kPosShift; // position of tile-local index 0
 
     if (tid < 112)
         s_syn[tid] = c_bit_syndrome[tid];
@@ -802,44 +857,56 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
         (&s_coef[0][0])[tid] = (&c_slice_coef[0][0])[tid];
     if (tid < 8)
         s_bd[tid] = 0;
-    for (uint32_t c = tid; c < td.ncand; c += kClassifyThreads)
-        s_flags[c] = 0;
+    for (int i = tid; i < kTile / 16; i += kClassifyThreads) {
+        reinterpret_cast<uint4 *>(s_info)[i] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4 *>(s_nb)[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
 
-    // ---- pass 1: which candidates have a phase that can still score >= 0, which have a -1 phase ----
+    // ---- pass 1: candidates -> try masks by position ----
+    for (uint32_t c = tid; c < td.ncand; c += kClassifyThreads) {
+        const uint32_t e = a.cand[td.cand_off + c];
+        s_info[e & 0x1fffu] = (uint8_t) ((e >> 13) & 31u);
+    }
+    __syncthreads();
+
+    // ---- pass 2: class records -> can the position still be accepted, does it hold a -1 phase ----
     for (uint32_t r = tid; r < td.nrec; r += kClassifyThreads) {
         const PhaseRec pr = a.recs[td.rec_off + r];
         const uint32_t kind = (pr.w0 >> 24) & 7u;
+        const uint32_t pl = (uint32_t) ((long long) pr.pos - p0);
+        const uint32_t ph = (pr.w1 >> 24) & 15u;
         const bool live = record_is_live(pr.w0, pr.w1, a.addr_bitmap);
-        uint32_t f = live ? 1u : 0u;
+        uint32_t f = live ? 32u : 0u;
         // static score of a phase whose address can never be in the filter:
         // AP -> -1, DF11 with IID != 0 -> -1, Comm-B -> -2 (mode_s.c:343,373,403)
         if (!live && (kind == kKindAP || kind == kKindDF11))
-            f |= 2u;
-        if (f) {
-            const uint32_t c = pr.cand - td.cand_off;
-            // byte-wide atomic OR through the containing word
-            atomicOr(reinterpret_cast<unsigned int *>(s_flags) + (c >> 2), f << (8 * (c & 3)));
-        }
+            f |= 64u;
+        if (f)
+            atomicOr(reinterpret_cast<unsigned int *>(s_info) + (pl >> 2), f << (8 * (pl & 3)));
+        atomicOr(reinterpret_cast<unsigned int *>(s_nb) + (pl >> 2), (1u << (ph - 4)) << (8 * (pl & 3)));
     }
     __syncthreads();
 
-    // ---- pass 2: ordered dead list / live position list ----
-    // count first so that one thread can reserve the tile's output ranges
+    // ---- pass 3: ordered dead list / live position list; thread t owns 32 consecutive positions ----
+    const int i0 = tid * kPosPerThread2;
     int n_dead_mine = 0, n_live_mine = 0, n_liverec_mine = 0;
-    for (uint32_t c = tid; c < td.ncand; c += kClassifyThreads) {
-        const uint32_t e = a.cand[td.cand_off + c];
-        if (s_flags[c] & 1u) {
-            ++n_live_mine;
-            n_liverec_mine += (int) ((e >> 18) & 7u);
-        } else {
-            ++n_dead_mine;
+#pragma unroll 4
+    for (int i = 0; i < kPosPerThread2; ++i) {
+        const uint32_t inf = s_info[i0 + i];
+        if (inf & 31u) {
+            if (inf & 32u) {
+                ++n_live_mine;
+                n_liverec_mine += __popc((uint32_t) s_nb[i0 + i]);
+            } else {
+                ++n_dead_mine;
+            }
         }
     }
     int n_dead, n_live, n_liverec;
-    block_exclusive_scan(n_dead_mine, s_warp, n_dead);
-    block_exclusive_scan(n_live_mine, s_warp, n_live);
-    block_exclusive_scan(n_liverec_mine, s_warp, n_liverec);
+    const int od = block_exclusive_scan(n_dead_mine, s_warp, n_dead);
+    const int ol = block_exclusive_scan(n_live_mine, s_warp, n_live);
+    const int orr = block_exclusive_scan(n_liverec_mine, s_warp, n_liverec);
     if (tid == 0) {
         unsigned long long d_off = atomicAdd(&a.counters->n_dead, (unsigned long long) n_dead);
         unsigned long long l_off = atomicAdd(&a.counters->n_live, (unsigned long long) n_live);
@@ -871,87 +938,78 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
     if (s_warp[36])
         return; // the host grows the buffers and runs the span again
 
-    const uint32_t kb0 = (uint32_t) (p0 / a.block_samples);
-    const bool one_block = ((long long) (kb0 + 1) * a.block_samples >= p0 + kTile);
-    uint32_t bd_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-
-    int dead_done = 0, live_done = 0, liverec_done = 0;
-    for (uint32_t cb = 0; cb < td.ncand; cb += kClassifyThreads) { // uniform trip count
-        const uint32_t c = cb + tid;
-        bool is_dead = false, is_live = false;
-        uint32_t e = 0, nonbad = 0;
-        if (c < td.ncand) {
-            e = a.cand[td.cand_off + c];
-            nonbad = (e >> 18) & 7u;
-            is_live = (s_flags[c] & 1u) != 0;
-            is_dead = !is_live;
-        }
-        int tot_d, tot_l, tot_r;
-        const int od = block_exclusive_scan(is_dead ? 1 : 0, s_warp, tot_d);
-        const int ol = block_exclusive_scan(is_live ? 1 : 0, s_warp, tot_l);
-        const int orr = block_exclusive_scan(is_live ? (int) nonbad : 0, s_warp, tot_r);
-        if (is_dead) {
-            const uint32_t unknown = (s_flags[c] >> 1) & 1u;
-            a.dead[dead_off + dead_done + od] = (e & 0x3ffffu) | (unknown << 18);
-            // what demodulate2400 counts for a position whose best score is negative
-            // (demod_2400.c:184,339-347), provided no accepted frame skips over it
-            const uint32_t tm = (e >> 13) & 31u;
-            uint32_t bd[8] = {1u, unknown ? 0u : 1u, unknown, tm & 1u, (tm >> 1) & 1u, (tm >> 2) & 1u, (tm >> 3) & 1u, (tm >> 4) & 1u};
-            if (one_block) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    bd_local[k] += bd[k];
+    {
+        const long long B = (long long) a.block_samples;
+        const long long first_pos = p0 < 0 ? 0 : p0;
+        const uint32_t kb0 = (uint32_t) (first_pos / B);
+        const bool one_block = ((long long) (kb0 + 1) * B >= p0 + kTile);
+        uint32_t bd_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int d = od, l = ol, r = orr;
+        for (int i = 0; i < kPosPerThread2; ++i) {
+            const uint32_t inf = s_info[i0 + i];
+            const uint32_t tm = inf & 31u;
+            if (!tm)
+                continue;
+            const uint32_t pl = (uint32_t) (i0 + i);
+            if (inf & 32u) {
+                const uint32_t nrec = (uint32_t) __popc((uint32_t) s_nb[pl]);
+                LivePos lp;
+                lp.pos = (uint32_t) (p0 + pl);
+                lp.info = tm | (nrec << 8) | ((uint32_t) r << 16);
+                a.live[live_off + l] = lp;
+                s_slot[pl] = (uint16_t) r;
+                ++l;
+                r += (int) nrec;
             } else {
-                const uint32_t kb = (uint32_t) ((p0 + (e & 0x1fffu)) / a.block_samples);
-                uint32_t *dst = reinterpret_cast<uint32_t *>(&a.block_dead[kb]);
+                const uint32_t unknown = (inf >> 6) & 1u;
+                a.dead[dead_off + d] = pl | (tm << 13) | (unknown << 18);
+                ++d;
+                // what demodulate2400 counts for a position whose best score is negative
+                // (demod_2400.c:184,339-347), provided no accepted frame skips over it
+                const uint32_t bd[8] = {1u, unknown ? 0u : 1u, unknown, tm & 1u, (tm >> 1) & 1u, (tm >> 2) & 1u, (tm >> 3) & 1u, (tm >> 4) & 1u};
+                if (one_block) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (bd[k])
-                        atomicAdd(&dst[k], bd[k]);
+                    for (int q = 0; q < 8; ++q)
+                        bd_local[q] += bd[q];
+                } else {
+                    const uint32_t kb = (uint32_t) ((p0 + pl) / B);
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(&a.block_dead[kb]);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (bd[q])
+                            atomicAdd(&dst[q], bd[q]);
+                }
             }
         }
-        if (is_live) {
-            LivePos lp;
-            lp.pos = (uint32_t) (p0 + (e & 0x1fffu));
-            lp.info = ((e >> 13) & 31u) | (nonbad << 8) | ((uint32_t) (liverec_done + orr) << 16);
-            a.live[live_off + live_done + ol] = lp;
-            s_slot[c] = (uint16_t) (liverec_done + orr);
-        }
-        dead_done += tot_d;
-        live_done += tot_l;
-        liverec_done += tot_r;
-    }
-    if (one_block) {
+        if (one_block) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint32_t v = bd_local[k];
+            for (int q = 0; q < 8; ++q) {
+                uint32_t v = bd_local[q];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && v)
-                atomicAdd(&s_bd[k], v);
+                for (int o = 16; o > 0; o >>= 1)
+                    v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && v)
+                    atomicAdd(&s_bd[q], v);
+            }
+            __syncthreads();
+            if (tid < 8 && s_bd[tid])
+                atomicAdd(reinterpret_cast<uint32_t *>(&a.block_dead[kb0]) + tid, s_bd[tid]);
         }
-        __syncthreads();
-        if (tid < 8 && s_bd[tid])
-            atomicAdd(reinterpret_cast<uint32_t *>(&a.block_dead[kb0]) + tid, s_bd[tid]);
     }
     if (n_liverec == 0)
         return;
-
-    // ---- pass 3: records of live positions, in (position, phase) order: re-slice + signal power ----
-    // the tile's records are ordered by candidate then phase; a live position owns consecutive slots
     __syncthreads();
 
+    // ---- pass 4: class records of live positions: re-slice the frame, signal power ----
+    // a live position owns consecutive output slots, one per recorded phase in phase order
     for (uint32_t r = warp; r < td.nrec; r += kClassifyThreads / 32) {
         const PhaseRec pr = a.recs[td.rec_off + r];
-        const uint32_t c = pr.cand - td.cand_off;
-        if (!(s_flags[c] & 1u))
+        const uint32_t pl = (uint32_t) ((long long) pr.pos - p0);
+        if (!(s_info[pl] & 32u))
             continue;
-        // slot: first record slot of the position + rank of this record among the position's records
-        uint32_t rank = 0;
-        for (uint32_t q = r; q > 0 && a.recs[td.rec_off + q - 1].cand == pr.cand; --q)
-            ++rank;
-        const uint32_t slot = liverec_off + s_slot[c] + rank;
+        const int ph = (int) ((pr.w1 >> 24) & 15u);
+        const uint32_t rank = (uint32_t) __popc((uint32_t) s_nb[pl] & ((1u << (ph - 4)) - 1u));
+        const uint32_t slot = liverec_off + s_slot[pl] + rank;
 
         // magnitudes the frame touches: window position pos -> samples pos - kOverlap ...
         uint16_t *fm = s_frame[warp];
@@ -960,7 +1018,6 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
             fm[x] = (uint16_t) sample_mag(a, s_first + x);
         __syncwarp();
 
-        const int ph = (int) ((pr.w1 >> 24) & 15u);
         uint32_t w[4], syn;
         // DF from the first five bits decides the length (demod_2400.c:193-205)
         uint32_t df = 0;

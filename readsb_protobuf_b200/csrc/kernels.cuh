@@ -24,11 +24,15 @@ struct ScanArgs {
     const ErrorInfo *tab_long;
     int32_t n_short, n_long;
     uint32_t *addr_bitmap; // 2^24 bits: every address icaoFilterAdd could ever see
-    // output
+    // output: every tile writes into its own slab of the two arrays
     uint32_t *cand;
     PhaseRec *recs;
     TileDesc *tiles;
-    uint32_t cand_cap, rec_cap;
+    // slab placement: tile t owns cand[t*cand_slab ...) / recs[t*rec_slab ...), or, when tile_off is
+    // given (the exact-fit retry), cand[tile_off[2t] .. ) and recs[tile_off[2t+1] ..) with the caps
+    // taken from the next tile's offsets
+    uint32_t cand_slab, rec_slab;
+    const uint32_t *tile_off; // [2 * (ntiles + 1)] or nullptr
     ScanCounters *counters;
     unsigned long long *block_sums_u64; // [nblocks][2]: sum mag, sum mag^2 (table formats)
     double *block_sums_f64;             // [nblocks][2]: sum mag, sum magsq (float formats)

@@ -213,15 +213,17 @@ struct DeadCount {
 void count_dead(const SpanView &v, uint64_t lo, uint64_t hi, DeadCount &dc) {
     if (hi <= lo)
         return;
-    const uint32_t t0 = (uint32_t) ((lo + 1) / kTile), t1 = (uint32_t) (hi / kTile);
+    // tile t covers positions [t*kTile - kPosShift, (t+1)*kTile - kPosShift)
+    const uint32_t t0 = (uint32_t) ((lo + 1 + kPosShift) / kTile), t1 = (uint32_t) ((hi + kPosShift) / kTile);
     for (uint32_t t = t0; t <= t1 && t < v.ntiles; ++t) {
         const TileOut &to = v.tiles[t];
         const uint32_t *d = v.dead + to.dead_off, *dend = d + to.ndead;
-        const uint64_t base = (uint64_t) t * kTile;
-        const uint32_t rel_lo = (lo + 1 > base) ? (uint32_t) (lo + 1 - base) : 0; // first position counted
+        const int64_t base = (int64_t) t * kTile - kPosShift;
+        const int64_t first = (int64_t) lo + 1 - base; // first tile-local index counted
+        const uint32_t rel_lo = first > 0 ? (uint32_t) first : 0;
         const uint32_t *it = std::lower_bound(d, dend, rel_lo, [](uint32_t e, uint32_t x) { return (e & 0x1fffu) < x; });
         for (; it != dend; ++it) {
-            const uint64_t p = base + (*it & 0x1fffu);
+            const uint64_t p = (uint64_t) (base + (int64_t) (*it & 0x1fffu));
             if (p > hi)
                 break;
             const uint32_t tm = (*it >> 13) & 31u;
