@@ -19,9 +19,15 @@ constexpr int kStep = 512;                 // samples one warp converts per step
 constexpr int kLanePos = kStep / 32;       // 16 scan positions per lane per step
 constexpr int kScanSteps = kTile / kStep;  // 16 steps of window starts
 constexpr int kLookahead = 296;            // samples past the last window start a slice can touch (290) rounded to 8
-constexpr int kScanWarps = 15;             // warps per CTA (shared memory: 128 KiB table + 6 KiB per warp)
+constexpr int kScanWarps = 16;             // warps per CTA (shared memory: 128 KiB table + 5.4 KiB per warp)
 constexpr int kScanThreads = kScanWarps * 32;
-constexpr int kWarpBuf = 3 * kStep;        // u32 magnitudes per warp: two chunks + a mirror of the even one
+// Warp buffer: a ring of two chunks of u32 magnitudes, one row per lane.  A row is the lane's 16
+// magnitudes followed by a copy of the next row's first 4: the 80-byte row stride makes every
+// 128-bit access of a quarter warp hit 8 distinct 16-byte bank groups, and the copy lets the slicer
+// read 4 consecutive magnitudes from any start without crossing a row.
+constexpr int kRowWords = kLanePos + 4;     // 20
+constexpr int kRows = 64;                   // 2 chunks x 32 lanes
+constexpr int kWarpBuf = kRows * kRowWords; // u32 words per warp (5120 bytes)
 constexpr int kItemCap = 64;               // (position, phase) items a warp queues before slicing them
 
 inline uint32_t tiles_for(uint64_t nsamples) {

@@ -300,48 +300,54 @@ __device__ __forceinline__ uint4 load_unit(const ScanArgs &a, long long s, int &
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// One PPM bit decision on the warp buffer (u32 magnitudes); see slice_bit() for the closed form.
-__device__ __forceinline__ bool slice_bit_u32(const uint32_t *m, int t, const int4 *coef) {
+// One PPM bit decision on the warp buffer (u32 magnitudes, padded rows); see slice_bit() for the
+// closed form.  x = window start of the frame as a sample offset from the chunk's first row.
+__device__ __forceinline__ bool slice_bit_u32(const uint32_t *buf, int row0, int x, int t, const int4 *coef) {
     const int s = (t * 52429) >> 18; // t / 5 for 0 <= t < 43690
     const int r = t - 5 * s;
     const int4 c = coef[r];
-    const uint32_t *p = m + 19 + s;
+    const int x0 = x + 19 + s;
+    const uint32_t *p = buf + ((row0 + (x0 >> 4)) & (kRows - 1)) * kRowWords + (x0 & 15);
     const int v = c.x * (int) p[0] + c.y * (int) p[1] + c.z * (int) p[2] + c.w * (int) p[3];
     return v > 0;
 }
 
 struct WarpCtx {
-    const uint32_t *buf;   // window-start base of the chunk being scanned
+    const uint32_t *buf;   // the warp's magnitude rows
+    int row0;              // first row of the chunk being scanned
     const uint32_t *syn;   // 112 single-bit syndromes (shared)
     const int4 *coef;      // 5 correlators (shared)
-    uint16_t *items, *lng, *sht;
+    uint16_t *items, *valid;
     long long chunk_pos0;  // scan position of window start 0 of the chunk
-    uint32_t tile_pos0;    // first position of the tile (may be "negative": stored as int)
     // tile output cursors
     uint32_t *cand_out;
     PhaseRec *rec_out;
     uint32_t cand_cap, rec_cap, ncand, nrec;
 };
 
-// stage 2: 4 frames per pass, 8 lanes per frame, lane l decides bit l of every byte
-template <int NBYTES>
+// stage 2: up to 4 frames per pass, 8 lanes per frame, lane l decides bit l of every byte.
+// list entries: position in chunk [8:0] | phase - 4 [11:9] | long frame [12]
 __device__ __forceinline__ void slice_pass(const ScanArgs &a, WarpCtx &cx, const uint16_t *list, int first, int count) {
     const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
     const bool active = first + g < count;
     const uint32_t item = list[active ? first + g : first];
     const uint32_t pic = item & 511u; // position in chunk
     const int ph = (int) ((item >> 9) & 7u) + 4;
-    const uint32_t *m = cx.buf + pic;
+    const bool is_long = (item >> 12) & 1u;
+    const int off = is_long ? 0 : 56; // crc.c:143: short frames use the tail of the syndrome list
+    const bool any_long = __any_sync(0xffffffffu, active && is_long);
     uint32_t w[4] = {0, 0, 0, 0};
     uint32_t x = 0;
     int t = ph + 12 * l;
 #pragma unroll
-    for (int k = 0; k < NBYTES; ++k, t += 96) {
-        const bool bit = slice_bit_u32(m, t, cx.coef);
+    for (int k = 0; k < 14; ++k, t += 96) {
+        if (k == 7 && !any_long)
+            break;
+        const bool bit = slice_bit_u32(cx.buf, cx.row0, (int) pic, t, cx.coef) && (is_long || k < 7);
         const uint32_t bal = __ballot_sync(0xffffffffu, bit);
         w[k >> 2] |= ((bal >> (8 * g)) & 0xffu) << (8 * (k & 3)); // frame bit b -> bit b%32 of w[b/32]
         if (bit)
-            x ^= cx.syn[8 * k + l + (112 - 8 * NBYTES)]; // crc.c:143: short frames use the tail of the list
+            x ^= cx.syn[8 * k + l + off];
     }
     x ^= __shfl_xor_sync(0xffffffffu, x, 1);
     x ^= __shfl_xor_sync(0xffffffffu, x, 2);
@@ -372,51 +378,392 @@ __device__ __forceinline__ void slice_pass(const ScanArgs &a, WarpCtx &cx, const
 
 // stage 1 + 2 for the queued items of the chunk
 __device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, int &nitems) {
-    const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
+    const int lane = threadIdx.x & 31;
     __syncwarp();
-    int nl = 0, ns = 0;
-    for (int it = 0; it < nitems; it += 4) {
-        // first byte of 4 items -> DF -> frame length (demod_2400.c:188-205)
-        const bool active = it + g < nitems;
-        const uint32_t item = cx.items[active ? it + g : it];
-        const uint32_t *m = cx.buf + (item & 511u);
+    // stage 1: one lane per item slices the five DF bits -> frame length (demod_2400.c:188-205)
+    int nvalid = 0;
+    for (int it = 0; it < nitems; it += 32) {
+        const bool active = it + lane < nitems;
+        const uint32_t item = cx.items[active ? it + lane : it];
         const int ph = (int) ((item >> 9) & 7u) + 4;
-        const bool bit = slice_bit_u32(m, ph + 12 * l, cx.coef);
-        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        uint32_t df = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (it + q < nitems) { // uniform
-                const uint32_t df = __brev((bal >> (8 * q)) & 0x1fu) >> 27;
-                const int nb = frame_bytes_for_df(df);
-                const uint32_t its = cx.items[it + q];
-                if (nb == 14) {
-                    if (lane == 0)
-                        cx.lng[nl] = (uint16_t) its;
-                    ++nl;
-                } else if (nb == 7) {
-                    if (lane == 0)
-                        cx.sht[ns] = (uint16_t) its;
-                    ++ns;
+        for (int b = 0; b < 5; ++b)
+            df = (df << 1) | (slice_bit_u32(cx.buf, cx.row0, (int) (item & 511u), ph + 12 * b, cx.coef) ? 1u : 0u);
+        const int nb = active ? frame_bytes_for_df(df) : 0;
+        const uint32_t vm = __ballot_sync(0xffffffffu, nb != 0);
+        if (nb)
+            cx.valid[nvalid + __popc(vm & ((1u << lane) - 1u))] = (uint16_t) (item | (nb == 14 ? (1u << 12) : 0u));
+        nvalid += __popc(vm);
+    }
+    __syncwarp();
+    for (int it = 0; it < nvalid; it += 4)
+        slice_pass(a, cx, cx.valid, it, nvalid);
+    __syncwarp();
+    nitems = 0;
+}
+
+// uc8 table index with the shared-memory bank swizzle applied to both samples of a word:
+// entry i lives at i ^ (((i >> 8) & 31) << 1), so that samples with equal I but different Q
+// (receiver noise sits in a few codes around 127) do not collide on one bank
+__device__ __forceinline__ uint32_t swizzle_pair(uint32_t w) {
+    return w ^ ((w >> 7) & 0x003e003eu);
+}
+
+template <int FORMAT, bool SLICE, bool EDGE>
+__device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, const uint32_t tile, const uint16_t *s_lut, uint32_t *s_buf) {
+    constexpr int US = Fmt<FORMAT>::kUnitSamples, BPS = Fmt<FORMAT>::kBytes;
+    constexpr int UNITS = kLanePos / US; // 16-byte units per lane per step
+    const int lane = threadIdx.x & 31;
+    const float inv_scale = (FORMAT == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f);
+    const long long n = (long long) a.nsamples;
+    const long long B = (long long) a.block_samples;
+    const int thr = a.threshold;
+
+    const long long c0 = (long long) tile * kTile - kHead; // first window-start sample of the tile
+    uint32_t cand_off, rec_off;
+    if (a.tile_off) {
+        cand_off = a.tile_off[2 * tile];
+        rec_off = a.tile_off[2 * tile + 1];
+        cx.cand_cap = a.tile_off[2 * tile + 2] - cand_off;
+        cx.rec_cap = a.tile_off[2 * tile + 3] - rec_off;
+    } else {
+        cand_off = tile * a.cand_slab;
+        rec_off = tile * a.rec_slab;
+        cx.cand_cap = a.cand_slab;
+        cx.rec_cap = a.rec_slab;
+    }
+    cx.cand_out = a.cand + cand_off;
+    cx.rec_out = a.recs + rec_off;
+    cx.ncand = cx.nrec = 0;
+    int nitems = 0;
+    uint32_t ncand_lane = 0; // scan-only mode: candidates seen by this lane
+
+    // block sums of the samples this tile owns: [c0, c0 + kTile) within [0, n)
+    unsigned long long sum_level = 0, sum_power = 0;
+    double fsum_level = 0, fsum_power = 0;
+    long long blk = (c0 > 0 ? c0 : 0) / B, next_bound = (blk + 1) * B;
+    auto flush_sums = [&]() {
+        if (FORMAT == 0) {
+            const unsigned long long l = warp_sum_u64(sum_level), p = warp_sum_u64(sum_power);
+            if (lane == 0 && (l | p)) {
+                atomicAdd(&a.block_sums_u64[2 * blk], l);
+                atomicAdd(&a.block_sums_u64[2 * blk + 1], p);
+            }
+        } else {
+            const double l = warp_sum_f64(fsum_level), p = warp_sum_f64(fsum_power);
+            if (lane == 0 && (l != 0 || p != 0)) {
+                atomicAdd(&a.block_sums_f64[2 * blk], l);
+                atomicAdd(&a.block_sums_f64[2 * blk + 1], p);
+            }
+        }
+        sum_level = sum_power = 0;
+        fsum_level = fsum_power = 0;
+    };
+
+    uint4 pre[UNITS];
+    // interior tiles: every sample of the tile's 17 chunks is a new sample of the span
+    const uint4 *gp = reinterpret_cast<const uint4 *>(a.iq + (c0 + lane * kLanePos) * BPS);
+    auto prefetch = [&](int k) {
+        if (EDGE) {
+            const long long ls = c0 + (long long) k * kStep + lane * kLanePos;
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u) {
+                int lo, hi;
+                pre[u] = load_unit<FORMAT>(a, ls + u * US, lo, hi);
+            }
+        } else {
+            const uint4 *p = gp + (size_t) k * (kStep * BPS / 16);
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u)
+                pre[u] = ldg_stream(p + u);
+        }
+    };
+    prefetch(0);
+
+    for (int k = 0; k <= kScanSteps; ++k) {
+        const long long cs = c0 + (long long) k * kStep; // first sample of chunk k
+        const long long ls = cs + lane * kLanePos;        // this lane's first sample
+        // ---------------- convert chunk k ----------------
+        uint32_t m[kLanePos];
+        float fmag[kLanePos], fmagsq[kLanePos];
+        if (FORMAT == 0) {
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u) {
+                const uint32_t words[4] = {swizzle_pair(pre[u].x), swizzle_pair(pre[u].y), swizzle_pair(pre[u].z), swizzle_pair(pre[u].w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    m[u * US + 2 * j] = s_lut[words[j] & 0xffffu];
+                    m[u * US + 2 * j + 1] = s_lut[words[j] >> 16];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u) {
+                const uint32_t words[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
+#pragma unroll
+                for (int j = 0; j < US; ++j)
+                    m[u * US + j] = mag_sc16_word(words[j % 4], inv_scale, fmagsq[u * US + j], fmag[u * US + j]);
+            }
+        }
+        if (EDGE) {
+            // samples outside the stream have magnitude 0 (fifo.c:47) and are not summed
+            const long long l = -(long long) a.head_valid - ls, h = n - ls;
+            if (l > 0 || h < kLanePos) {
+#pragma unroll
+                for (int j = 0; j < kLanePos; ++j)
+                    if (j < l || j >= h) {
+                        m[j] = 0;
+                        if (FORMAT != 0)
+                            fmag[j] = fmagsq[j] = 0;
+                    }
+            }
+        }
+        // request the next chunk now; it is consumed one iteration later
+        if (k < kScanSteps)
+            prefetch(k + 1);
+
+        // store: chunk k occupies rows (k&1)*32 + lane; the first four magnitudes are also copied into
+        // the pad of the previous row
+        {
+            const int row = (k & 1) * 32 + lane;
+            uint4 *dst = reinterpret_cast<uint4 *>(s_buf + row * kRowWords);
+#pragma unroll
+            for (int q = 0; q < kLanePos / 4; ++q)
+                dst[q] = make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+            uint4 *pad = reinterpret_cast<uint4 *>(s_buf + ((row - 1) & (kRows - 1)) * kRowWords + kLanePos);
+            *pad = make_uint4(m[0], m[1], m[2], m[3]);
+        }
+
+        // block sums: chunks 0..kScanSteps-1 are owned by this tile
+        if (k < kScanSteps) {
+            const long long own_lo = cs > 0 ? cs : 0, own_hi = (cs + kStep < n) ? cs + kStep : n;
+            if (!EDGE || own_hi > own_lo) {
+                if (own_lo >= next_bound) {
+                    flush_sums();
+                    blk = own_lo / B;
+                    next_bound = (blk + 1) * B;
+                }
+                if (own_hi <= next_bound) {
+                    if (!EDGE || ls >= 0) { // head samples are not this span's (a lane never straddles 0: kHead % 16 == 8 is
+                                            // handled below for the one lane that does)
+                        if (FORMAT == 0) {
+                            uint32_t s32 = 0;
+                            unsigned long long p64 = 0;
+#pragma unroll
+                            for (int j = 0; j < kLanePos; ++j) {
+                                s32 += m[j];
+                                p64 += (unsigned long long) m[j] * m[j];
+                            }
+                            sum_level += s32;
+                            sum_power += p64;
+                        } else {
+                            float fl = 0, fp = 0;
+#pragma unroll
+                            for (int j = 0; j < kLanePos; ++j) {
+                                fl += fmag[j];
+                                fp += fmagsq[j];
+                            }
+                            fsum_level += (double) fl;
+                            fsum_power += (double) fp;
+                        }
+                    } else if (ls + kLanePos > 0) {
+                        // the lane whose 16 samples straddle the start of the span: only samples >= 0
+#pragma unroll
+                        for (int j = 0; j < kLanePos; ++j)
+                            if (ls + j >= 0) {
+                                if (FORMAT == 0) {
+                                    sum_level += m[j];
+                                    sum_power += (unsigned long long) m[j] * m[j];
+                                } else {
+                                    fsum_level += (double) fmag[j];
+                                    fsum_power += (double) fmagsq[j];
+                                }
+                            }
+                    }
+                } else {
+                    // a mag_buf boundary inside the chunk: every 16-byte unit lies on one side of it
+                    flush_sums();
+#pragma unroll
+                    for (int u = 0; u < UNITS; ++u) {
+                        const long long us = ls + u * US;
+                        if (us >= 0 && us < n) {
+                            const long long kb = us / B;
+                            if (FORMAT == 0) {
+                                unsigned long long cl = 0, cp = 0;
+#pragma unroll
+                                for (int j = 0; j < US; ++j) {
+                                    cl += m[u * US + j];
+                                    cp += (unsigned long long) m[u * US + j] * m[u * US + j];
+                                }
+                                if (cl | cp) {
+                                    atomicAdd(&a.block_sums_u64[2 * kb], cl);
+                                    atomicAdd(&a.block_sums_u64[2 * kb + 1], cp);
+                                }
+                            } else {
+                                double fl = 0, fp = 0;
+#pragma unroll
+                                for (int j = 0; j < US; ++j) {
+                                    fl += (double) fmag[u * US + j];
+                                    fp += (double) fmagsq[u * US + j];
+                                }
+                                atomicAdd(&a.block_sums_f64[2 * kb], fl);
+                                atomicAdd(&a.block_sums_f64[2 * kb + 1], fp);
+                            }
+                        }
+                    }
+                    blk = own_hi / B;
+                    next_bound = (blk + 1) * B;
                 }
             }
         }
+        __syncwarp();
+
+        // ---------------- scan chunk k-1 (its look-ahead, chunk k, is now in the buffer) ----------------
+        if (k >= 1) {
+            const int j = k - 1;
+            const int row0 = (j & 1) * 32; // first row of chunk j
+            const long long pos0 = c0 + (long long) j * kStep + kOverlap; // its scan position
+            const long long lp0 = pos0 + lane * kLanePos;
+            uint32_t vmask = 0xffffu;
+            if (EDGE) {
+                // positions of this lane that exist: 0 <= p < n
+                const int vlo = (lp0 < 0) ? (int) (-lp0 > kLanePos ? kLanePos : -lp0) : 0;
+                const long long vh = n - lp0;
+                const int vhi = vh > kLanePos ? kLanePos : (vh < 0 ? 0 : (int) vh);
+                vmask = (vhi > vlo) ? (((1u << vhi) - 1u) & ~((1u << vlo) - 1u)) : 0u;
+            }
+
+            uint32_t b45 = 0, b67 = 0, b8 = 0;
+            if (!EDGE || __any_sync(0xffffffffu, vmask != 0)) {
+                uint32_t w[kLanePos + 20];
+                {
+                    // 36 consecutive magnitudes: this lane's row, the next row, 4 of the one after
+                    const uint4 *ra = reinterpret_cast<const uint4 *>(s_buf + (row0 + lane) * kRowWords);
+                    const uint4 *rb = reinterpret_cast<const uint4 *>(s_buf + ((row0 + lane + 1) & (kRows - 1)) * kRowWords);
+                    const uint4 *rc = reinterpret_cast<const uint4 *>(s_buf + ((row0 + lane + 2) & (kRows - 1)) * kRowWords);
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const uint4 v = (q < 4) ? ra[q] : (q < 8 ? rb[q - 4] : rc[0]);
+                        w[4 * q] = v.x;
+                        w[4 * q + 1] = v.y;
+                        w[4 * q + 2] = v.z;
+                        w[4 * q + 3] = v.w;
+                    }
+                }
+                // shared partial sums of the three correlators (demod_2400.c:298-330):
+                //   Q[x] = m[x] + m[x+3], D[x] = m[x] - m[x+1], T[x] = m[x] + m[x+1] + m[x+2]
+                int Q[kLanePos + 9], D[kLanePos + 11], T[kLanePos];
+#pragma unroll
+                for (int x2 = 1; x2 < kLanePos + 9; ++x2)
+                    Q[x2] = (int) (w[x2] + w[x2 + 3]);
+#pragma unroll
+                for (int x2 = 2; x2 < kLanePos + 11; ++x2)
+                    D[x2] = (int) w[x2] - (int) w[x2 + 1];
+#pragma unroll
+                for (int i = 0; i < kLanePos; ++i)
+                    T[i] = (int) (w[i + 16] + w[i + 17] + w[i + 18]);
+#pragma unroll
+                for (int i = 0; i < kLanePos; ++i) {
+                    // demod_2400.c:276
+                    const bool pre_ok = w[i + 1] > w[i + 7] && w[i + 12] > w[i + 14] && w[i + 12] > w[i + 15];
+                    // demod_2400.c:281-292: base_noise = pa[5] + pa[8] + pa[16] + pa[17] + pa[18]
+                    const int ref_level = ((Q[i + 5] + T[i]) * thr) >> 5;
+                    // common3456 = pa[1] + pa[4] - (pa[2] - pa[3]) + pa[9] + pa[12]
+                    const int v = Q[i + 1] - D[i + 2] + Q[i + 9] - ref_level;
+                    const int d10 = D[i + 10];
+                    const bool t45 = v >= d10;                                  // :306 common3456 - diff_10_11 >= ref
+                    const bool t67 = v + d10 >= 0;                              // :316 common3456 + diff_10_11 >= ref
+                    const bool t8 = v + d10 + 3 * D[i + 2] - (int) w[i + 9] >= 0; // :327 sum_1_4 + 2 diff_2_3 + diff_10_11 + pa[12] >= ref
+                    b45 |= (pre_ok && t45) ? (1u << i) : 0u;
+                    b67 |= (pre_ok && t67) ? (1u << i) : 0u;
+                    b8 |= (pre_ok && t8) ? (1u << i) : 0u;
+                }
+                if (EDGE) {
+                    b45 &= vmask;
+                    b67 &= vmask;
+                    b8 &= vmask;
+                }
+            }
+
+            if (a.dbg_masks) {
+                for (int i = 0; i < kLanePos; ++i)
+                    if ((vmask >> i) & 1u)
+                        a.dbg_masks[lp0 + i] = (uint8_t) ((((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u));
+            }
+
+            const uint32_t any = b45 | b67 | b8;
+            if (!SLICE) {
+                ncand_lane += __popc(any);
+            } else {
+                uint32_t lanes = __ballot_sync(0xffffffffu, any != 0);
+                cx.buf = s_buf;
+                cx.row0 = row0;
+                cx.chunk_pos0 = pos0;
+                while (lanes) {
+                    const int L = __ffs(lanes) - 1;
+                    lanes &= lanes - 1;
+                    const uint32_t a45 = __shfl_sync(0xffffffffu, b45, L);
+                    const uint32_t a67 = __shfl_sync(0xffffffffu, b67, L);
+                    const uint32_t a8 = __shfl_sync(0xffffffffu, b8, L);
+                    uint32_t u = a45 | a67 | a8;
+                    while (u) {
+                        const int i = __ffs(u) - 1;
+                        u &= u - 1;
+                        const uint32_t tm = (((a45 >> i) & 1u) * 3u) | (((a67 >> i) & 1u) * 12u) | (((a8 >> i) & 1u) * 16u);
+                        const uint32_t pic = (uint32_t) (L * kLanePos + i);
+                        if (lane == 0) {
+                            if (cx.ncand < cx.cand_cap)
+                                cx.cand_out[cx.ncand] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
+#pragma unroll
+                            for (int ph = 0; ph < 5; ++ph)
+                                if ((tm >> ph) & 1u)
+                                    cx.items[nitems + __popc(tm & ((1u << ph) - 1u))] = (uint16_t) (pic | ((uint32_t) ph << 9));
+                        }
+                        ++cx.ncand;
+                        nitems += __popc(tm);
+                        if (nitems > kItemCap - 5)
+                            process_items(a, cx, nitems);
+                    }
+                }
+                if (nitems)
+                    process_items(a, cx, nitems);
+            }
+            __syncwarp();
+        }
     }
-    __syncwarp();
-    for (int it = 0; it < nl; it += 4)
-        slice_pass<14>(a, cx, cx.lng, it, nl);
-    for (int it = 0; it < ns; it += 4)
-        slice_pass<7>(a, cx, cx.sht, it, ns);
-    __syncwarp();
-    nitems = 0;
+    flush_sums();
+
+    // ---- tile descriptor ----
+    if (!SLICE) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            ncand_lane += __shfl_xor_sync(0xffffffffu, ncand_lane, o);
+        cx.ncand = ncand_lane;
+    }
+    if (lane == 0) {
+        if (SLICE) {
+            TileDesc td;
+            td.cand_off = cand_off;
+            td.ncand = cx.ncand;
+            td.rec_off = rec_off;
+            td.nrec = cx.nrec;
+            a.tiles[tile] = td;
+            unsigned int ovf = (cx.ncand > cx.cand_cap ? 1u : 0u) | (cx.nrec > cx.rec_cap ? 2u : 0u);
+            if (ovf)
+                atomicOr(&a.counters->overflow, ovf);
+            if (cx.nrec)
+                atomicAdd(&a.counters->n_rec, (unsigned long long) cx.nrec);
+        }
+        if (cx.ncand)
+            atomicAdd(&a.counters->n_cand, (unsigned long long) cx.ncand);
+    }
 }
 
 template <int FORMAT, bool SLICE>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int US = Fmt<FORMAT>::kUnitSamples;
-    constexpr int UNITS = kLanePos / US; // 16-byte units per lane per step
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float inv_scale = (FORMAT == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f);
 
     // shared memory carve-up
     unsigned char *sp = smem_raw;
@@ -431,12 +778,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     sp += 112 * sizeof(uint32_t);
     int4 *s_coef = reinterpret_cast<int4 *>(sp);
 
-    // one-time staging of the tables (the only block-wide barrier of the kernel)
+    // one-time staging of the tables (the only block-wide barrier of the kernel); the magnitude
+    // table is stored bank-swizzled: 32-bit word j of row Q goes to word j ^ (Q & 31)
     if (FORMAT == 0) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.lut);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
-        for (int i = tid; i < (int) (kSmemLut / 16); i += kScanThreads)
-            dst[i] = __ldg(src + i);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.lut);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smem_raw);
+        for (int i = tid; i < 65536 / 2; i += kScanThreads) {
+            const int row = i >> 7;
+            dst[i ^ (row & 31)] = __ldg(src + i);
+        }
     }
     if (tid < 112)
         s_syn[tid] = c_bit_syndrome[tid];
@@ -444,17 +794,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         s_coef[tid] = make_int4(c_slice_coef[tid][0], c_slice_coef[tid][1], c_slice_coef[tid][2], c_slice_coef[tid][3]);
     __syncthreads();
 
-    const long long n = (long long) a.nsamples;
-    const long long B = (long long) a.block_samples;
-    const int thr = a.threshold;
-
     WarpCtx cx;
     cx.syn = s_syn;
     cx.coef = s_coef;
     cx.items = s_lists;
-    cx.lng = s_lists + kItemCap;
-    cx.sht = s_lists + 2 * kItemCap;
+    cx.valid = s_lists + kItemCap;
 
+    const long long n = (long long) a.nsamples;
     for (;;) {
         // ---- next tile from the work queue ----
         uint32_t tile = 0;
@@ -463,303 +809,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= a.ntiles)
             break;
-
-        const long long c0 = (long long) tile * kTile - kHead; // first window-start sample of the tile
-        uint32_t cand_off, rec_off;
-        if (a.tile_off) {
-            cand_off = a.tile_off[2 * tile];
-            rec_off = a.tile_off[2 * tile + 1];
-            cx.cand_cap = a.tile_off[2 * tile + 2] - cand_off;
-            cx.rec_cap = a.tile_off[2 * tile + 3] - rec_off;
-        } else {
-            cand_off = tile * a.cand_slab;
-            rec_off = tile * a.rec_slab;
-            cx.cand_cap = a.cand_slab;
-            cx.rec_cap = a.rec_slab;
-        }
-        cx.cand_out = a.cand + cand_off;
-        cx.rec_out = a.recs + rec_off;
-        cx.ncand = cx.nrec = 0;
-        int nitems = 0;
-        uint32_t ncand_lane = 0; // scan-only mode: candidates seen by this lane
-
-        // block sums of the samples this tile owns: [c0, c0 + kTile) within [0, n)
-        unsigned long long sum_level = 0, sum_power = 0;
-        double fsum_level = 0, fsum_power = 0;
-        long long blk = (c0 > 0 ? c0 : 0) / B, next_bound = (blk + 1) * B;
-        auto flush_sums = [&]() {
-            if (FORMAT == 0) {
-                const unsigned long long l = warp_sum_u64(sum_level), p = warp_sum_u64(sum_power);
-                if (lane == 0 && (l | p)) {
-                    atomicAdd(&a.block_sums_u64[2 * blk], l);
-                    atomicAdd(&a.block_sums_u64[2 * blk + 1], p);
-                }
-            } else {
-                const double l = warp_sum_f64(fsum_level), p = warp_sum_f64(fsum_power);
-                if (lane == 0 && (l != 0 || p != 0)) {
-                    atomicAdd(&a.block_sums_f64[2 * blk], l);
-                    atomicAdd(&a.block_sums_f64[2 * blk + 1], p);
-                }
-            }
-            sum_level = sum_power = 0;
-            fsum_level = fsum_power = 0;
-        };
-
-        // the tile's last chunk only feeds the slicer's look-ahead; the stream's last tile also
-        // converts whatever is left of the span, for the block sums
-        uint4 pre[UNITS];
-        auto prefetch = [&](int k) {
-            const long long ls = c0 + (long long) k * kStep + lane * kLanePos;
-#pragma unroll
-            for (int u = 0; u < UNITS; ++u) {
-                int lo, hi;
-                pre[u] = load_unit<FORMAT>(a, ls + u * US, lo, hi);
-            }
-        };
-        prefetch(0);
-
-        for (int k = 0; k <= kScanSteps; ++k) {
-            const long long cs = c0 + (long long) k * kStep; // first sample of chunk k
-            const long long ls = cs + lane * kLanePos;        // this lane's first sample
-            // ---------------- convert chunk k ----------------
-            uint32_t m[kLanePos];
-            unsigned long long cl[UNITS], cp[UNITS];
-            double fl[UNITS], fp[UNITS];
-#pragma unroll
-            for (int u = 0; u < UNITS; ++u) {
-                const uint32_t words[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
-                cl[u] = cp[u] = 0;
-                fl[u] = fp[u] = 0;
-                float fmag[US], fmagsq[US];
-                if (FORMAT == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        m[u * US + 2 * j] = s_lut[words[j] & 0xffffu];
-                        m[u * US + 2 * j + 1] = s_lut[words[j] >> 16];
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < US; ++j)
-                        m[u * US + j] = mag_sc16_word(words[j % 4], inv_scale, fmagsq[j], fmag[j]);
-                }
-                // samples outside the stream have magnitude 0 (fifo.c:47) and are not summed
-                const long long us = ls + u * US;
-                if (us < -(long long) a.head_valid || us + US > n) {
-                    const long long l = -(long long) a.head_valid - us, h = n - us;
-#pragma unroll
-                    for (int j = 0; j < US; ++j)
-                        if (j < l || j >= h) {
-                            m[u * US + j] = 0;
-                            if (FORMAT != 0)
-                                fmag[j] = fmagsq[j] = 0;
-                        }
-                }
-#pragma unroll
-                for (int j = 0; j < US; ++j) {
-                    if (FORMAT == 0) {
-                        cl[u] += m[u * US + j];
-                        cp[u] += (unsigned long long) m[u * US + j] * m[u * US + j];
-                    } else {
-                        fl[u] += (double) fmag[j];
-                        fp[u] += (double) fmagsq[j];
-                    }
-                }
-            }
-            // request the next chunk now; it is consumed one iteration later
-            if (k < kScanSteps)
-                prefetch(k + 1);
-
-            // store: chunk k lives in slot k&1; even chunks are mirrored behind slot 1 so that a reader
-            // starting in either slot sees the following chunk contiguously
-            {
-                uint4 *dst = reinterpret_cast<uint4 *>(s_buf + (k & 1) * kStep + lane * kLanePos);
-#pragma unroll
-                for (int q = 0; q < kLanePos / 4; ++q)
-                    dst[q] = make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-                if (!(k & 1)) {
-                    uint4 *mir = reinterpret_cast<uint4 *>(s_buf + 2 * kStep + lane * kLanePos);
-#pragma unroll
-                    for (int q = 0; q < kLanePos / 4; ++q)
-                        mir[q] = make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-                }
-            }
-
-            // block sums: chunks 0..kScanSteps-1 are owned by this tile (samples < 0 belong to the
-            // previous span and were masked to zero above, which is harmless: they add nothing)
-            if (k < kScanSteps) {
-                const long long own_lo = cs > 0 ? cs : 0, own_hi = (cs + kStep < n) ? cs + kStep : n;
-                if (own_hi > own_lo) {
-                    if (own_lo >= next_bound) {
-                        flush_sums();
-                        blk = own_lo / B;
-                        next_bound = (blk + 1) * B;
-                    }
-                    if (own_hi <= next_bound) {
-#pragma unroll
-                        for (int u = 0; u < UNITS; ++u) {
-                            if (ls + u * US >= 0) { // head samples are not this span's
-                                sum_level += cl[u];
-                                sum_power += cp[u];
-                                fsum_level += fl[u];
-                                fsum_power += fp[u];
-                            }
-                        }
-                    } else {
-                        // a mag_buf boundary inside the chunk: every 16-byte unit lies on one side of it
-                        flush_sums();
-#pragma unroll
-                        for (int u = 0; u < UNITS; ++u) {
-                            const long long us = ls + u * US;
-                            if (us >= 0 && us < n) {
-                                const long long kb = us / B;
-                                if (FORMAT == 0) {
-                                    if (cl[u] | cp[u]) {
-                                        atomicAdd(&a.block_sums_u64[2 * kb], cl[u]);
-                                        atomicAdd(&a.block_sums_u64[2 * kb + 1], cp[u]);
-                                    }
-                                } else {
-                                    atomicAdd(&a.block_sums_f64[2 * kb], fl[u]);
-                                    atomicAdd(&a.block_sums_f64[2 * kb + 1], fp[u]);
-                                }
-                            }
-                        }
-                        blk = own_hi / B;
-                        next_bound = (blk + 1) * B;
-                    }
-                }
-            }
-            __syncwarp();
-
-            // ---------------- scan chunk k-1 (its look-ahead, chunk k, is now in the buffer) ----------------
-            if (k >= 1) {
-                const int j = k - 1;
-                const uint32_t *base = s_buf + (j & 1) * kStep; // window start 0 of chunk j
-                const long long pos0 = c0 + (long long) j * kStep + kOverlap; // its scan position
-                const long long lp0 = pos0 + lane * kLanePos;
-                // positions of this lane that exist: 0 <= p < n
-                int vlo = (lp0 < 0) ? (int) (-lp0 > kLanePos ? kLanePos : -lp0) : 0;
-                long long vh = n - lp0;
-                int vhi = vh > kLanePos ? kLanePos : (vh < 0 ? 0 : (int) vh);
-                const uint32_t vmask = (vhi > vlo) ? (((1u << vhi) - 1u) & ~((1u << vlo) - 1u)) : 0u;
-
-                uint32_t b45 = 0, b67 = 0, b8 = 0;
-                if (__any_sync(0xffffffffu, vmask != 0)) {
-                    uint32_t w[kLanePos + 20];
-                    {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(base + lane * kLanePos);
-#pragma unroll
-                        for (int q = 0; q < (kLanePos + 20) / 4; ++q) {
-                            const uint4 v = src[q];
-                            w[4 * q] = v.x;
-                            w[4 * q + 1] = v.y;
-                            w[4 * q + 2] = v.z;
-                            w[4 * q + 3] = v.w;
-                        }
-                    }
-                    // shared partial sums of the three correlators (demod_2400.c:298-330):
-                    //   Q[x] = m[x] + m[x+3], D[x] = m[x] - m[x+1], T[x] = m[x] + m[x+1] + m[x+2]
-                    int Q[kLanePos + 9], D[kLanePos + 11], T[kLanePos];
-#pragma unroll
-                    for (int x2 = 1; x2 < kLanePos + 9; ++x2)
-                        Q[x2] = (int) (w[x2] + w[x2 + 3]);
-#pragma unroll
-                    for (int x2 = 2; x2 < kLanePos + 11; ++x2)
-                        D[x2] = (int) w[x2] - (int) w[x2 + 1];
-#pragma unroll
-                    for (int i = 0; i < kLanePos; ++i)
-                        T[i] = (int) (w[i + 16] + w[i + 17] + w[i + 18]);
-#pragma unroll
-                    for (int i = 0; i < kLanePos; ++i) {
-                        // demod_2400.c:276
-                        const bool pre_ok = w[i + 1] > w[i + 7] && w[i + 12] > w[i + 14] && w[i + 12] > w[i + 15];
-                        // demod_2400.c:281-292: base_noise = pa[5] + pa[8] + pa[16] + pa[17] + pa[18]
-                        const int ref_level = ((Q[i + 5] + T[i]) * thr) >> 5;
-                        // common3456 = pa[1] + pa[4] - (pa[2] - pa[3]) + pa[9] + pa[12]
-                        const int v = Q[i + 1] - D[i + 2] + Q[i + 9] - ref_level;
-                        const int d10 = D[i + 10];
-                        const bool t45 = v >= d10;                                  // :306 common3456 - diff_10_11 >= ref
-                        const bool t67 = v + d10 >= 0;                              // :316 common3456 + diff_10_11 >= ref
-                        const bool t8 = v + d10 + 3 * D[i + 2] - (int) w[i + 9] >= 0; // :327 sum_1_4 + 2 diff_2_3 + diff_10_11 + pa[12] >= ref
-                        b45 |= (pre_ok && t45) ? (1u << i) : 0u;
-                        b67 |= (pre_ok && t67) ? (1u << i) : 0u;
-                        b8 |= (pre_ok && t8) ? (1u << i) : 0u;
-                    }
-                    b45 &= vmask;
-                    b67 &= vmask;
-                    b8 &= vmask;
-                }
-
-                if (a.dbg_masks) {
-                    for (int i = 0; i < kLanePos; ++i)
-                        if ((vmask >> i) & 1u)
-                            a.dbg_masks[lp0 + i] = (uint8_t) ((((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u));
-                }
-
-                const uint32_t any = b45 | b67 | b8;
-                if (!SLICE) {
-                    ncand_lane += __popc(any);
-                } else {
-                    uint32_t lanes = __ballot_sync(0xffffffffu, any != 0);
-                    cx.buf = base;
-                    cx.chunk_pos0 = pos0;
-                    while (lanes) {
-                        const int L = __ffs(lanes) - 1;
-                        lanes &= lanes - 1;
-                        const uint32_t a45 = __shfl_sync(0xffffffffu, b45, L);
-                        const uint32_t a67 = __shfl_sync(0xffffffffu, b67, L);
-                        const uint32_t a8 = __shfl_sync(0xffffffffu, b8, L);
-                        uint32_t u = a45 | a67 | a8;
-                        while (u) {
-                            const int i = __ffs(u) - 1;
-                            u &= u - 1;
-                            const uint32_t tm = (((a45 >> i) & 1u) * 3u) | (((a67 >> i) & 1u) * 12u) | (((a8 >> i) & 1u) * 16u);
-                            const uint32_t pic = (uint32_t) (L * kLanePos + i);
-                            if (lane == 0) {
-                                if (cx.ncand < cx.cand_cap)
-                                    cx.cand_out[cx.ncand] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
-#pragma unroll
-                                for (int ph = 0; ph < 5; ++ph)
-                                    if ((tm >> ph) & 1u)
-                                        cx.items[nitems + __popc(tm & ((1u << ph) - 1u))] = (uint16_t) (pic | ((uint32_t) ph << 9));
-                            }
-                            ++cx.ncand;
-                            nitems += __popc(tm);
-                            if (nitems > kItemCap - 5)
-                                process_items(a, cx, nitems);
-                        }
-                    }
-                    if (nitems)
-                        process_items(a, cx, nitems);
-                }
-                __syncwarp();
-            }
-        }
-        flush_sums();
-
-        // ---- tile descriptor ----
-        if (!SLICE) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                ncand_lane += __shfl_xor_sync(0xffffffffu, ncand_lane, o);
-            cx.ncand = ncand_lane;
-        }
-        if (lane == 0) {
-            if (SLICE) {
-                TileDesc td;
-                td.cand_off = cand_off;
-                td.ncand = cx.ncand;
-                td.rec_off = rec_off;
-                td.nrec = cx.nrec;
-                a.tiles[tile] = td;
-                unsigned int ovf = (cx.ncand > cx.cand_cap ? 1u : 0u) | (cx.nrec > cx.rec_cap ? 2u : 0u);
-                if (ovf)
-                    atomicOr(&a.counters->overflow, ovf);
-                if (cx.nrec)
-                    atomicAdd(&a.counters->n_rec, (unsigned long long) cx.nrec);
-            }
-            if (cx.ncand)
-                atomicAdd(&a.counters->n_cand, (unsigned long long) cx.ncand);
-        }
+        // interior tile: all 17 chunks are new samples of the span and all positions exist
+        const long long c0 = (long long) tile * kTile - kHead;
+        const bool interior = c0 >= 0 && c0 + (long long) (kScanSteps + 1) * kStep <= n;
+        if (interior)
+            process_tile<FORMAT, SLICE, false>(a, cx, tile, s_lut, s_buf);
+        else
+            process_tile<FORMAT, SLICE, true>(a, cx, tile, s_lut, s_buf);
     }
 }
 
