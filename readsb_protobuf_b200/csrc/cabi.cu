@@ -1,8 +1,13 @@
 // cabi.cu -- the C ABI of include/readsb_b200.h: context, device buffers, launch sequence.
 //
-// A process call is: (H2D) -> K1 scan/slice/CRC -> K2 classify -> D2H of the survivors ->
-// host resolve (resolver.cc).  There is no CPU implementation of the kernels; without a usable
-// sm_100 device every entry point returns B200_ERR_CUDA.
+// A process call cuts the span into chunks of whole mag_bufs and runs them as a pipeline:
+//   copy stream : H2D of chunk i+1 ...................... (host-buffer entry only)
+//   exec stream : K1 scan/slice/CRC -> K2 classify -> counters/descriptors D2H of chunk i+1
+//   list stream : survivors of chunk i D2H
+//   host        : order-dependent resolve (resolver.cc) of chunk i
+// Chunks are exact: K2 of chunk i only needs the address set of chunks <= i, which is what the ICAO
+// filter can hold when the host resolves chunk i.  There is no CPU implementation of the kernels;
+// without a usable sm_100 device every entry point returns B200_ERR_CUDA.
 
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -98,6 +103,54 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// per-tile slabs K1 writes into on the first attempt: ~6x the candidate / record density of noise at
+// the default threshold; a chunk that needs more is run again with slabs placed exactly
+const uint32_t kCandSlab = 640, kRecSlab = 448;
+// samples per pipeline chunk (rounded to whole mag_bufs)
+const uint64_t kChunkTarget = 32ull << 20;
+
+// everything one in-flight chunk owns
+struct ChunkSet {
+    DevBuf<uint32_t> d_cand, d_dead, d_tile_off;
+    DevBuf<PhaseRec> d_recs;
+    DevBuf<TileDesc> d_tiles;
+    DevBuf<TileOut> d_tiles_out;
+    DevBuf<LivePos> d_live;
+    DevBuf<LiveRec> d_liverecs;
+    DevBuf<ScanCounters> d_counters;
+    DevBuf<unsigned long long> d_sums_u64;
+    DevBuf<double> d_sums_f64;
+    DevBuf<BlockDead> d_block_dead;
+    PinnedBuf<ScanCounters> h_counters;
+    PinnedBuf<TileOut> h_tiles_out;
+    PinnedBuf<uint32_t> h_dead;
+    PinnedBuf<LivePos> h_live;
+    PinnedBuf<LiveRec> h_liverecs;
+    PinnedBuf<unsigned long long> h_sums_u64;
+    PinnedBuf<double> h_sums_f64;
+    PinnedBuf<BlockDead> h_block_dead;
+    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr;
+
+    // what is in flight
+    uint64_t start = 0, nsamples = 0;
+    bool final_chunk = false;
+    uint32_t head_valid = 0;
+    const uint8_t *iq = nullptr, *head = nullptr;
+
+    void release() {
+        d_cand.release(); d_dead.release(); d_tile_off.release(); d_recs.release(); d_tiles.release();
+        d_tiles_out.release(); d_live.release(); d_liverecs.release(); d_counters.release();
+        d_sums_u64.release(); d_sums_f64.release(); d_block_dead.release();
+        h_counters.release(); h_tiles_out.release(); h_dead.release(); h_live.release(); h_liverecs.release();
+        h_sums_u64.release(); h_sums_f64.release(); h_block_dead.release();
+        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k2, &ev_small, &ev_lists})
+            if (*e) {
+                cudaEventDestroy(*e);
+                *e = nullptr;
+            }
+    }
+};
+
 } // namespace
 
 struct b200_demod {
@@ -108,8 +161,11 @@ struct b200_demod {
     std::unique_ptr<CrcTables> crc;
     std::unique_ptr<Resolver> resolver;
 
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream = nullptr;      // exec stream of the host-buffer entry
+    cudaStream_t copy_stream = nullptr; // H2D
+    cudaStream_t list_stream = nullptr; // survivor lists D2H
+    cudaEvent_t ev_h2d_begin = nullptr, ev_h2d_end = nullptr;
+    std::vector<cudaEvent_t> ev_chunk_h2d;
 
     // tables
     DevBuf<uint16_t> d_lut;
@@ -125,31 +181,14 @@ struct b200_demod {
 
     // span buffers
     DevBuf<uint8_t> d_iq;
-    DevBuf<uint32_t> d_cand, d_dead;
-    DevBuf<PhaseRec> d_recs;
-    DevBuf<TileDesc> d_tiles;
-    DevBuf<uint32_t> d_tile_off;
-    DevBuf<TileOut> d_tiles_out;
-    DevBuf<LivePos> d_live;
-    DevBuf<LiveRec> d_liverecs;
-    DevBuf<ScanCounters> d_counters;
-    DevBuf<unsigned long long> d_sums_u64;
-    DevBuf<double> d_sums_f64;
-    DevBuf<BlockDead> d_block_dead;
+    ChunkSet sets[2];
     DevBuf<uint8_t> d_dbg_masks;
     DevBuf<uint16_t> d_mag;
     DevBuf<uint8_t> d_frames;
     DevBuf<uint32_t> d_syn;
     DevBuf<int8_t> d_err, d_bits;
-
-    PinnedBuf<ScanCounters> h_counters;
-    PinnedBuf<TileOut> h_tiles_out;
-    PinnedBuf<uint32_t> h_dead;
-    PinnedBuf<LivePos> h_live;
-    PinnedBuf<LiveRec> h_liverecs;
-    PinnedBuf<unsigned long long> h_sums_u64;
-    PinnedBuf<double> h_sums_f64;
-    PinnedBuf<BlockDead> h_block_dead;
+    DevBuf<unsigned long long> d_csum_u64;
+    DevBuf<double> d_csum_f64;
 
     // results of the last call
     std::vector<b200_message> msgs;
@@ -159,17 +198,19 @@ struct b200_demod {
     ~b200_demod() {
         cudaSetDevice(cfg.device);
         d_lut.release(); d_tab_short.release(); d_tab_long.release(); d_bitmap.release();
-        d_head.release(); d_head_tmp.release(); d_iq.release(); d_cand.release(); d_dead.release();
-        d_recs.release(); d_tiles.release(); d_tile_off.release(); d_tiles_out.release(); d_live.release(); d_liverecs.release();
-        d_counters.release(); d_sums_u64.release(); d_sums_f64.release(); d_block_dead.release();
+        d_head.release(); d_head_tmp.release(); d_iq.release();
+        sets[0].release(); sets[1].release();
         d_dbg_masks.release(); d_mag.release(); d_frames.release(); d_syn.release(); d_err.release(); d_bits.release();
-        h_counters.release(); h_tiles_out.release(); h_dead.release(); h_live.release(); h_liverecs.release();
-        h_sums_u64.release(); h_sums_f64.release(); h_block_dead.release();
-        for (auto &e : ev)
-            if (e)
-                cudaEventDestroy(e);
-        if (stream)
-            cudaStreamDestroy(stream);
+        d_csum_u64.release(); d_csum_f64.release();
+        for (cudaEvent_t e : ev_chunk_h2d)
+            cudaEventDestroy(e);
+        if (ev_h2d_begin)
+            cudaEventDestroy(ev_h2d_begin);
+        if (ev_h2d_end)
+            cudaEventDestroy(ev_h2d_end);
+        for (cudaStream_t s : {stream, copy_stream, list_stream})
+            if (s)
+                cudaStreamDestroy(s);
     }
 };
 
@@ -177,26 +218,33 @@ extern "C" const char *b200_last_error(void) {
     return g_last_error.c_str();
 }
 
-static int ensure_span_buffers(b200_demod *d, uint64_t nsamples, size_t cand_total, size_t rec_total, size_t dead_cap,
-                               size_t live_cap, size_t liverec_cap) {
+static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, size_t cand_total, size_t rec_total, size_t dead_cap,
+                                size_t live_cap, size_t liverec_cap) {
     const size_t ntiles = tiles_for(nsamples);
     const size_t nblocks = (size_t) (nsamples / d->cfg.block_samples + 2);
-    CUDA_TRY(d->d_cand.ensure(cand_total + 1));
-    CUDA_TRY(d->d_recs.ensure(rec_total + 1));
-    CUDA_TRY(d->d_dead.ensure(dead_cap));
-    CUDA_TRY(d->d_live.ensure(live_cap));
-    CUDA_TRY(d->d_liverecs.ensure(liverec_cap));
-    CUDA_TRY(d->d_tiles.ensure(ntiles + 1));
-    CUDA_TRY(d->d_tiles_out.ensure(ntiles + 1));
-    CUDA_TRY(d->d_counters.ensure(1));
-    CUDA_TRY(d->d_sums_u64.ensure(2 * nblocks));
-    CUDA_TRY(d->d_sums_f64.ensure(2 * nblocks));
-    CUDA_TRY(d->d_block_dead.ensure(nblocks));
-    CUDA_TRY(d->h_counters.ensure(1));
-    CUDA_TRY(d->h_tiles_out.ensure(ntiles + 1));
-    CUDA_TRY(d->h_sums_u64.ensure(2 * nblocks));
-    CUDA_TRY(d->h_sums_f64.ensure(2 * nblocks));
-    CUDA_TRY(d->h_block_dead.ensure(nblocks));
+    CUDA_TRY(c.d_cand.ensure(cand_total + 1));
+    CUDA_TRY(c.d_recs.ensure(rec_total + 1));
+    CUDA_TRY(c.d_dead.ensure(dead_cap));
+    CUDA_TRY(c.d_live.ensure(live_cap));
+    CUDA_TRY(c.d_liverecs.ensure(liverec_cap));
+    CUDA_TRY(c.d_tiles.ensure(ntiles + 1));
+    CUDA_TRY(c.d_tiles_out.ensure(ntiles + 1));
+    CUDA_TRY(c.d_counters.ensure(1));
+    CUDA_TRY(c.d_sums_u64.ensure(2 * nblocks));
+    CUDA_TRY(c.d_sums_f64.ensure(2 * nblocks));
+    CUDA_TRY(c.d_block_dead.ensure(nblocks));
+    CUDA_TRY(c.h_counters.ensure(1));
+    CUDA_TRY(c.h_tiles_out.ensure(ntiles + 1));
+    CUDA_TRY(c.h_sums_u64.ensure(2 * nblocks));
+    CUDA_TRY(c.h_sums_f64.ensure(2 * nblocks));
+    CUDA_TRY(c.h_block_dead.ensure(nblocks));
+    if (!c.ev_begin) {
+        CUDA_TRY(cudaEventCreate(&c.ev_begin));
+        CUDA_TRY(cudaEventCreate(&c.ev_k1));
+        CUDA_TRY(cudaEventCreate(&c.ev_k2));
+        CUDA_TRY(cudaEventCreate(&c.ev_small));
+        CUDA_TRY(cudaEventCreate(&c.ev_lists));
+    }
     return B200_OK;
 }
 
@@ -237,8 +285,6 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
         return fail(B200_ERR_ARG, "block_samples must be a multiple of 8");
     if (d->cfg.max_span_samples == 0)
         d->cfg.max_span_samples = 64ull << 20;
-    if (d->cfg.max_span_samples > 0xfff00000ull)
-        return fail(B200_ERR_ARG, "max_span_samples must stay below 2^32 - 2^20");
     d->bytes_per_sample = (cfg->input_format == B200_INPUT_UC8) ? 2 : 4;
     d->sm_count = prop.multiProcessorCount;
     memset(&d->timing, 0, sizeof(d->timing));
@@ -247,8 +293,10 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     d->resolver.reset(new Resolver(d->crc.get(), cfg->startup_time_ms));
 
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-    for (auto &ev : d->ev)
-        CUDA_TRY(cudaEventCreate(&ev));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->list_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&d->ev_h2d_begin));
+    CUDA_TRY(cudaEventCreate(&d->ev_h2d_end));
     CUDA_TRY(scan_configure());
     CUDA_TRY(upload_constants(d->crc->bit_syndromes()));
 
@@ -300,12 +348,12 @@ extern "C" int b200_demod_reset(b200_demod *d) {
     return B200_OK;
 }
 
-static ScanArgs make_scan_args(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t head_valid, uint32_t cand_slab,
-                               uint32_t rec_slab, const uint32_t *tile_off) {
+static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, const uint8_t *d_head, uint64_t nsamples,
+                               uint32_t head_valid, uint32_t cand_slab, uint32_t rec_slab, const uint32_t *tile_off) {
     ScanArgs a;
     memset(&a, 0, sizeof(a));
     a.iq = d_iq;
-    a.head = d->d_head.p;
+    a.head = d_head;
     a.head_valid = head_valid;
     a.format = (uint32_t) d->cfg.input_format;
     a.nsamples = nsamples;
@@ -318,25 +366,25 @@ static ScanArgs make_scan_args(b200_demod *d, const uint8_t *d_iq, uint64_t nsam
     a.n_short = (int32_t) d->crc->short_table().size();
     a.n_long = (int32_t) d->crc->long_table().size();
     a.addr_bitmap = d->d_bitmap.p;
-    a.cand = d->d_cand.p;
-    a.recs = d->d_recs.p;
-    a.tiles = d->d_tiles.p;
+    a.cand = c.d_cand.p;
+    a.recs = c.d_recs.p;
+    a.tiles = c.d_tiles.p;
     a.cand_slab = cand_slab;
     a.rec_slab = rec_slab;
     a.tile_off = tile_off;
-    a.counters = d->d_counters.p;
-    a.block_sums_u64 = d->d_sums_u64.p;
-    a.block_sums_f64 = d->d_sums_f64.p;
+    a.counters = c.d_counters.p;
+    a.block_sums_u64 = c.d_sums_u64.p;
+    a.block_sums_f64 = c.d_sums_f64.p;
     a.dbg_masks = nullptr;
     return a;
 }
 
-static int zero_span_outputs(b200_demod *d, uint64_t nsamples, cudaStream_t s) {
+static int zero_chunk_outputs(b200_demod *d, ChunkSet &c, uint64_t nsamples, cudaStream_t s) {
     const size_t nblocks = (size_t) (nsamples / d->cfg.block_samples + 2);
-    CUDA_TRY(cudaMemsetAsync(d->d_counters.p, 0, sizeof(ScanCounters), s));
-    CUDA_TRY(cudaMemsetAsync(d->d_sums_u64.p, 0, 2 * nblocks * sizeof(unsigned long long), s));
-    CUDA_TRY(cudaMemsetAsync(d->d_sums_f64.p, 0, 2 * nblocks * sizeof(double), s));
-    CUDA_TRY(cudaMemsetAsync(d->d_block_dead.p, 0, nblocks * sizeof(BlockDead), s));
+    CUDA_TRY(cudaMemsetAsync(c.d_counters.p, 0, sizeof(ScanCounters), s));
+    CUDA_TRY(cudaMemsetAsync(c.d_sums_u64.p, 0, 2 * nblocks * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(c.d_sums_f64.p, 0, 2 * nblocks * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(c.d_block_dead.p, 0, nblocks * sizeof(BlockDead), s));
     return B200_OK;
 }
 
@@ -356,103 +404,107 @@ static int carry_head(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, cud
     return B200_OK;
 }
 
-// per-tile slabs K1 writes into on the first attempt: ~6x the candidate / record density of noise at
-// the default threshold; a span that needs more is run again with slabs placed exactly
-static const uint32_t kCandSlab = 640, kRecSlab = 448;
-
-static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t flags, cudaStream_t s, bool timed_h2d) {
-    const bool final_span = (flags & B200_FLAG_FINAL) != 0;
+// enqueue K1, K2 and the small D2H of a chunk on stream s
+static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, size_t cand_total, size_t rec_total, size_t dead_cap,
+                       size_t live_cap, size_t liverec_cap, uint32_t *launches) {
+    const uint64_t n = c.nsamples;
     const uint32_t B = d->cfg.block_samples;
-    const double t_start = now_ms();
+    int rc = ensure_chunk_buffers(d, c, n, cand_total, rec_total, dead_cap, live_cap, liverec_cap);
+    if (rc != B200_OK)
+        return rc;
+    rc = zero_chunk_outputs(d, c, n, s);
+    if (rc != B200_OK)
+        return rc;
+    const uint32_t ntiles = tiles_for(n);
+    const size_t nblocks = (size_t) (n / B + (c.final_chunk ? 1 : 0));
 
-    const uint32_t ntiles = tiles_for(nsamples);
-    size_t cand_total = (size_t) ntiles * kCandSlab, rec_total = (size_t) ntiles * kRecSlab;
-    size_t dead_cap = std::max<size_t>(d->d_dead.cap, (size_t) (nsamples / 24 + 4096));
-    size_t live_cap = std::max<size_t>(d->d_live.cap, (size_t) (nsamples / 128 + 4096));
-    size_t liverec_cap = std::max<size_t>(d->d_liverecs.cap, (size_t) (nsamples / 64 + 4096));
-    const size_t nblocks = (size_t) (nsamples / B + (final_span ? 1 : 0));
-    uint32_t launches = 0;
-    bool exact = false;
+    ScanArgs sa = make_scan_args(d, c, c.iq, c.head, n, c.head_valid, kCandSlab, kRecSlab, exact ? c.d_tile_off.p : nullptr);
+    CUDA_TRY(cudaEventRecord(c.ev_begin, s));
+    CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
+    CUDA_TRY(cudaEventRecord(c.ev_k1, s));
 
-    ScanCounters cnt;
-    memset(&cnt, 0, sizeof(cnt));
-    for (int attempt = 0;; ++attempt) {
-        int rc = ensure_span_buffers(d, nsamples, cand_total, rec_total, dead_cap, live_cap, liverec_cap);
-        if (rc != B200_OK)
-            return rc;
-        rc = zero_span_outputs(d, nsamples, s);
-        if (rc != B200_OK)
-            return rc;
+    ClassifyArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.iq = c.iq;
+    ca.head = c.head;
+    ca.head_valid = c.head_valid;
+    ca.format = sa.format;
+    ca.nsamples = n;
+    ca.block_samples = B;
+    ca.ntiles = ntiles;
+    ca.lut = d->d_lut.p;
+    ca.tab_short = sa.tab_short;
+    ca.tab_long = sa.tab_long;
+    ca.n_short = sa.n_short;
+    ca.n_long = sa.n_long;
+    ca.addr_bitmap = d->d_bitmap.p;
+    ca.cand = c.d_cand.p;
+    ca.recs = c.d_recs.p;
+    ca.tiles = c.d_tiles.p;
+    ca.dead = c.d_dead.p;
+    ca.live = c.d_live.p;
+    ca.liverecs = c.d_liverecs.p;
+    ca.tiles_out = c.d_tiles_out.p;
+    ca.dead_cap = (uint32_t) std::min<size_t>(c.d_dead.cap, 0xffffffffu);
+    ca.live_cap = (uint32_t) std::min<size_t>(c.d_live.cap, 0xffffffffu);
+    ca.liverec_cap = (uint32_t) std::min<size_t>(c.d_liverecs.cap, 0xffffffffu);
+    ca.counters = c.d_counters.p;
+    ca.block_dead = c.d_block_dead.p;
+    // K2 looks at K1's overflow flag itself and does nothing when K1 did not fit
+    CUDA_TRY(launch_classify(ca, s));
+    CUDA_TRY(cudaEventRecord(c.ev_k2, s));
+    if (launches)
+        *launches += ntiles ? 2 : 0;
+    CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+    if (ntiles)
+        CUDA_TRY(cudaMemcpyAsync(c.h_tiles_out.p, c.d_tiles_out.p, ntiles * sizeof(TileOut), cudaMemcpyDeviceToHost, s));
+    if (nblocks) {
+        CUDA_TRY(cudaMemcpyAsync(c.h_sums_u64.p, c.d_sums_u64.p, 2 * nblocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(c.h_sums_f64.p, c.d_sums_f64.p, 2 * nblocks * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(c.h_block_dead.p, c.d_block_dead.p, nblocks * sizeof(BlockDead), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaEventRecord(c.ev_small, s));
+    return B200_OK;
+}
 
-        ScanArgs sa = make_scan_args(d, d_iq, nsamples, d->head_valid, kCandSlab, kRecSlab, exact ? d->d_tile_off.p : nullptr);
-        CUDA_TRY(cudaEventRecord(d->ev[1], s));
-        CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
-        CUDA_TRY(cudaEventRecord(d->ev[2], s));
+// wait for a chunk's kernels, fetch its survivors, resolve it on the host
+static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t *launches, b200_timing &t) {
+    const uint64_t n = c.nsamples;
+    const uint32_t ntiles = tiles_for(n);
+    size_t dead_cap = c.d_dead.cap, live_cap = c.d_live.cap, liverec_cap = c.d_liverecs.cap;
 
-        ClassifyArgs ca;
-        memset(&ca, 0, sizeof(ca));
-        ca.iq = d_iq;
-        ca.head = d->d_head.p;
-        ca.head_valid = d->head_valid;
-        ca.format = sa.format;
-        ca.nsamples = nsamples;
-        ca.block_samples = B;
-        ca.ntiles = ntiles;
-        ca.lut = d->d_lut.p;
-        ca.tab_short = sa.tab_short;
-        ca.tab_long = sa.tab_long;
-        ca.n_short = sa.n_short;
-        ca.n_long = sa.n_long;
-        ca.addr_bitmap = d->d_bitmap.p;
-        ca.cand = d->d_cand.p;
-        ca.recs = d->d_recs.p;
-        ca.tiles = d->d_tiles.p;
-        ca.dead = d->d_dead.p;
-        ca.live = d->d_live.p;
-        ca.liverecs = d->d_liverecs.p;
-        ca.tiles_out = d->d_tiles_out.p;
-        ca.dead_cap = (uint32_t) std::min<size_t>(d->d_dead.cap, 0xffffffffu);
-        ca.live_cap = (uint32_t) std::min<size_t>(d->d_live.cap, 0xffffffffu);
-        ca.liverec_cap = (uint32_t) std::min<size_t>(d->d_liverecs.cap, 0xffffffffu);
-        ca.counters = d->d_counters.p;
-        ca.block_dead = d->d_block_dead.p;
-        // K2 looks at K1's overflow flag itself and does nothing when K1 did not fit
-        CUDA_TRY(launch_classify(ca, s));
-        launches += ntiles ? 2 : 0;
-        CUDA_TRY(cudaEventRecord(d->ev[3], s));
-        CUDA_TRY(cudaMemcpyAsync(d->h_counters.p, d->d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
-        if (ntiles)
-            CUDA_TRY(cudaMemcpyAsync(d->h_tiles_out.p, d->d_tiles_out.p, ntiles * sizeof(TileOut), cudaMemcpyDeviceToHost, s));
-        if (nblocks) {
-            CUDA_TRY(cudaMemcpyAsync(d->h_sums_u64.p, d->d_sums_u64.p, 2 * nblocks * sizeof(unsigned long long),
-                                     cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaMemcpyAsync(d->h_sums_f64.p, d->d_sums_f64.p, 2 * nblocks * sizeof(double), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaMemcpyAsync(d->h_block_dead.p, d->d_block_dead.p, nblocks * sizeof(BlockDead), cudaMemcpyDeviceToHost, s));
-        }
-        CUDA_TRY(cudaStreamSynchronize(s));
-        cnt = *d->h_counters.p;
-        if (!cnt.overflow)
-            break;
+    CUDA_TRY(cudaEventSynchronize(c.ev_small));
+    ScanCounters cnt = *c.h_counters.p;
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev_begin, c.ev_k1);
+        t.scan_ms += ms;
+        cudaEventElapsedTime(&ms, c.ev_k1, c.ev_k2);
+        t.classify_ms += ms;
+    }
+    for (int attempt = 0; cnt.overflow; ++attempt) {
         if (attempt >= 3)
             return fail(B200_ERR_CAPACITY, "candidate buffers overflowed after %d attempts (flags 0x%x)", attempt + 1, cnt.overflow);
+        bool exact = false;
+        size_t cand_total = (size_t) ntiles * kCandSlab, rec_total = (size_t) ntiles * kRecSlab;
         if (cnt.overflow & 3u) {
             // a tile outgrew its slab: every tile reported its true counts, place the slabs exactly
             std::vector<TileDesc> tiles(ntiles);
-            CUDA_TRY(cudaMemcpy(tiles.data(), d->d_tiles.p, ntiles * sizeof(TileDesc), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(tiles.data(), c.d_tiles.p, ntiles * sizeof(TileDesc), cudaMemcpyDeviceToHost));
             std::vector<uint32_t> off(2 * ((size_t) ntiles + 1));
             uint64_t co = 0, ro = 0;
-            for (uint32_t t = 0; t < ntiles; ++t) {
-                off[2 * t] = (uint32_t) co;
-                off[2 * t + 1] = (uint32_t) ro;
-                co += tiles[t].ncand;
-                ro += tiles[t].nrec;
+            for (uint32_t i = 0; i < ntiles; ++i) {
+                off[2 * i] = (uint32_t) co;
+                off[2 * i + 1] = (uint32_t) ro;
+                co += tiles[i].ncand;
+                ro += tiles[i].nrec;
             }
             off[2 * (size_t) ntiles] = (uint32_t) co;
             off[2 * (size_t) ntiles + 1] = (uint32_t) ro;
             if (co > 0xfffffff0ull || ro > 0xfffffff0ull)
-                return fail(B200_ERR_CAPACITY, "span too dense for 32-bit record indices; use shorter spans");
-            CUDA_TRY(d->d_tile_off.ensure(off.size()));
-            CUDA_TRY(cudaMemcpy(d->d_tile_off.p, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+                return fail(B200_ERR_CAPACITY, "chunk too dense for 32-bit record indices");
+            CUDA_TRY(c.d_tile_off.ensure(off.size()));
+            CUDA_TRY(cudaMemcpy(c.d_tile_off.p, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             cand_total = std::max<size_t>((size_t) co, 1);
             rec_total = std::max<size_t>((size_t) ro, 1);
             exact = true;
@@ -466,64 +518,142 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
             live_cap = std::max<size_t>(live_cap, (size_t) cnt.n_live + 4096);
             liverec_cap = std::max<size_t>(liverec_cap, (size_t) cnt.n_liverec + 4096);
         }
-    }
-
-    // survivors back to the host
-    CUDA_TRY(d->h_dead.ensure(std::max<size_t>((size_t) cnt.n_dead, 1)));
-    CUDA_TRY(d->h_live.ensure(std::max<size_t>((size_t) cnt.n_live, 1)));
-    CUDA_TRY(d->h_liverecs.ensure(std::max<size_t>((size_t) cnt.n_liverec, 1)));
-    if (cnt.n_dead)
-        CUDA_TRY(cudaMemcpyAsync(d->h_dead.p, d->d_dead.p, (size_t) cnt.n_dead * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (cnt.n_live)
-        CUDA_TRY(cudaMemcpyAsync(d->h_live.p, d->d_live.p, (size_t) cnt.n_live * sizeof(LivePos), cudaMemcpyDeviceToHost, s));
-    if (cnt.n_liverec)
-        CUDA_TRY(cudaMemcpyAsync(d->h_liverecs.p, d->d_liverecs.p, (size_t) cnt.n_liverec * sizeof(LiveRec), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaEventRecord(d->ev[4], s));
-    {
-        int rc = carry_head(d, d_iq, nsamples, s);
+        // the other chunk set may still be running on `exec`; this one is idle, so re-issuing is safe
+        int rc = issue_chunk(d, c, exec, exact, cand_total, rec_total, dead_cap, live_cap, liverec_cap, launches);
         if (rc != B200_OK)
             return rc;
+        CUDA_TRY(cudaEventSynchronize(c.ev_small));
+        cnt = *c.h_counters.p;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.ev_begin, c.ev_k1);
+        t.scan_ms += ms;
+        cudaEventElapsedTime(&ms, c.ev_k1, c.ev_k2);
+        t.classify_ms += ms;
     }
-    CUDA_TRY(cudaStreamSynchronize(s));
+
+    // survivors back to the host, on their own stream so that the next chunk's kernels are not in the way
+    const double t_d2h = now_ms();
+    CUDA_TRY(c.h_dead.ensure(std::max<size_t>((size_t) cnt.n_dead, 1)));
+    CUDA_TRY(c.h_live.ensure(std::max<size_t>((size_t) cnt.n_live, 1)));
+    CUDA_TRY(c.h_liverecs.ensure(std::max<size_t>((size_t) cnt.n_liverec, 1)));
+    cudaStream_t ls = d->list_stream;
+    if (cnt.n_dead)
+        CUDA_TRY(cudaMemcpyAsync(c.h_dead.p, c.d_dead.p, (size_t) cnt.n_dead * sizeof(uint32_t), cudaMemcpyDeviceToHost, ls));
+    if (cnt.n_live)
+        CUDA_TRY(cudaMemcpyAsync(c.h_live.p, c.d_live.p, (size_t) cnt.n_live * sizeof(LivePos), cudaMemcpyDeviceToHost, ls));
+    if (cnt.n_liverec)
+        CUDA_TRY(cudaMemcpyAsync(c.h_liverecs.p, c.d_liverecs.p, (size_t) cnt.n_liverec * sizeof(LiveRec), cudaMemcpyDeviceToHost, ls));
+    CUDA_TRY(cudaEventRecord(c.ev_lists, ls));
+    CUDA_TRY(cudaEventSynchronize(c.ev_lists));
+    t.d2h_ms += (float) (now_ms() - t_d2h);
 
     // host: the order-dependent tail
     const double t_res0 = now_ms();
     SpanView v;
-    v.nsamples = nsamples;
-    v.first_sample = d->first_sample;
-    v.block_samples = B;
-    v.final_span = final_span;
+    v.nsamples = n;
+    v.first_sample = d->first_sample + c.start;
+    v.block_samples = d->cfg.block_samples;
+    v.final_span = c.final_chunk;
     v.format = (uint32_t) d->cfg.input_format;
     v.ntiles = ntiles;
-    v.tiles = d->h_tiles_out.p;
-    v.dead = d->h_dead.p;
-    v.live = d->h_live.p;
-    v.liverecs = d->h_liverecs.p;
-    v.block_dead = d->h_block_dead.p;
-    v.block_sums_u64 = d->h_sums_u64.p;
-    v.block_sums_f64 = d->h_sums_f64.p;
+    v.tiles = c.h_tiles_out.p;
+    v.dead = c.h_dead.p;
+    v.live = c.h_live.p;
+    v.liverecs = c.h_liverecs.p;
+    v.block_dead = c.h_block_dead.p;
+    v.block_sums_u64 = c.h_sums_u64.p;
+    v.block_sums_f64 = c.h_sums_f64.p;
+    d->resolver->resolve(v, d->msgs, d->blocks);
+    t.resolve_ms += (float) (now_ms() - t_res0);
+    t.n_candidates += cnt.n_cand;
+    t.n_phase_records += cnt.n_rec;
+    t.n_live += cnt.n_live;
+    return B200_OK;
+}
+
+// The span is resident (or arriving, chunk by chunk, on the copy stream) at d_iq.
+static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t flags, cudaStream_t exec, const void *host_src) {
+    const bool final_span = (flags & B200_FLAG_FINAL) != 0;
+    const uint32_t B = d->cfg.block_samples;
+    const size_t bps = (size_t) d->bytes_per_sample;
+    const double t_start = now_ms();
+
+    const uint64_t chunk = std::max<uint64_t>(1, kChunkTarget / B) * B;
+    const uint64_t nchunks = nsamples ? (nsamples + chunk - 1) / chunk : 1;
+    b200_timing t;
+    memset(&t, 0, sizeof(t));
+    uint32_t launches = 0;
     d->msgs.clear();
     d->blocks.clear();
-    d->resolver->resolve(v, d->msgs, d->blocks);
-    const double t_res1 = now_ms();
+
+    // host-buffer entry: all chunk copies are queued up front on the copy stream
+    if (host_src) {
+        while (d->ev_chunk_h2d.size() < nchunks) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            d->ev_chunk_h2d.push_back(e);
+        }
+        CUDA_TRY(cudaEventRecord(d->ev_h2d_begin, d->copy_stream));
+        for (uint64_t i = 0; i < nchunks; ++i) {
+            const uint64_t s0 = i * chunk, s1 = std::min(nsamples, s0 + chunk);
+            if (s1 > s0)
+                CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t *>(d_iq) + s0 * bps, (const uint8_t *) host_src + s0 * bps, (s1 - s0) * bps,
+                                         cudaMemcpyHostToDevice, d->copy_stream));
+            CUDA_TRY(cudaEventRecord(d->ev_chunk_h2d[i], d->copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(d->ev_h2d_end, d->copy_stream));
+    }
+
+    auto setup = [&](uint64_t i) -> int {
+        ChunkSet &c = d->sets[i & 1];
+        c.start = std::min(nsamples, i * chunk);
+        c.nsamples = std::min(nsamples, c.start + chunk) - c.start;
+        c.final_chunk = final_span && (i + 1 == nchunks);
+        c.iq = d_iq + c.start * bps;
+        if (i == 0) {
+            c.head = d->d_head.p;
+            c.head_valid = d->head_valid;
+        } else {
+            c.head = c.iq - (size_t) kHead * bps; // the previous chunk's tail, contiguous in the span buffer
+            c.head_valid = kHead;
+        }
+        if (host_src)
+            CUDA_TRY(cudaStreamWaitEvent(exec, d->ev_chunk_h2d[i], 0));
+        const uint32_t ntiles = tiles_for(c.nsamples);
+        return issue_chunk(d, c, exec, false, (size_t) ntiles * kCandSlab, (size_t) ntiles * kRecSlab,
+                           std::max<size_t>(c.d_dead.cap, (size_t) (c.nsamples / 24 + 4096)),
+                           std::max<size_t>(c.d_live.cap, (size_t) (c.nsamples / 128 + 4096)),
+                           std::max<size_t>(c.d_liverecs.cap, (size_t) (c.nsamples / 64 + 4096)), &launches);
+    };
+
+    int rc = setup(0);
+    if (rc != B200_OK)
+        return rc;
+    for (uint64_t i = 0; i < nchunks; ++i) {
+        if (i + 1 < nchunks) {
+            rc = setup(i + 1); // the GPU works on chunk i+1 while the host resolves chunk i
+            if (rc != B200_OK)
+                return rc;
+        }
+        rc = finish_chunk(d, d->sets[i & 1], exec, &launches, t);
+        if (rc != B200_OK)
+            return rc;
+    }
+    rc = carry_head(d, d_iq, nsamples, exec);
+    if (rc != B200_OK)
+        return rc;
+    CUDA_TRY(cudaStreamSynchronize(exec));
 
     d->first_sample += nsamples;
     if (final_span)
         d->finished = true;
-
-    b200_timing &t = d->timing;
-    memset(&t, 0, sizeof(t));
-    if (timed_h2d)
-        cudaEventElapsedTime(&t.h2d_ms, d->ev[0], d->ev[1]);
-    cudaEventElapsedTime(&t.scan_ms, d->ev[1], d->ev[2]);
-    cudaEventElapsedTime(&t.classify_ms, d->ev[2], d->ev[3]);
-    cudaEventElapsedTime(&t.d2h_ms, d->ev[3], d->ev[4]);
-    t.resolve_ms = (float) (t_res1 - t_res0);
+    if (host_src) {
+        CUDA_TRY(cudaEventSynchronize(d->ev_h2d_end));
+        cudaEventElapsedTime(&t.h2d_ms, d->ev_h2d_begin, d->ev_h2d_end);
+    }
     t.total_ms = (float) (now_ms() - t_start);
-    t.n_candidates = cnt.n_cand;
-    t.n_phase_records = cnt.n_rec;
-    t.n_live = cnt.n_live;
     t.scan_launches = launches;
+    d->timing = t;
     return B200_OK;
 }
 
@@ -549,14 +679,7 @@ extern "C" int b200_demod_process(b200_demod *d, const void *iq, uint64_t nsampl
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     const size_t bytes = (size_t) nsamples * d->bytes_per_sample;
     CUDA_TRY(d->d_iq.ensure(bytes + 256));
-    const double t0 = now_ms();
-    CUDA_TRY(cudaEventRecord(d->ev[0], d->stream));
-    if (bytes)
-        CUDA_TRY(cudaMemcpyAsync(d->d_iq.p, iq, bytes, cudaMemcpyHostToDevice, d->stream));
-    rc = run_span(d, d->d_iq.p, nsamples, flags, d->stream, true);
-    if (rc == B200_OK)
-        d->timing.total_ms = (float) (now_ms() - t0);
-    return rc;
+    return run_span(d, d->d_iq.p, nsamples, flags, d->stream, nsamples ? iq : nullptr);
 }
 
 extern "C" int b200_demod_process_device(b200_demod *d, const void *d_iq, uint64_t nsamples, uint32_t flags, void *cuda_stream) {
@@ -567,7 +690,7 @@ extern "C" int b200_demod_process_device(b200_demod *d, const void *d_iq, uint64
         return fail(B200_ERR_ARG, "device span must be 16-byte aligned");
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
-    return run_span(d, (const uint8_t *) d_iq, nsamples, flags, s, false);
+    return run_span(d, (const uint8_t *) d_iq, nsamples, flags, s, nullptr);
 }
 
 extern "C" uint64_t b200_demod_message_count(const b200_demod *d) {
@@ -612,26 +735,27 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
         return fail(B200_ERR_CAPACITY, "span exceeds max_span_samples");
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
+    ChunkSet &c = d->sets[0];
     const size_t nt = tiles_for(nsamples);
-    int rc = ensure_span_buffers(d, nsamples, nt * kCandSlab, nt * kRecSlab, std::max<size_t>(d->d_dead.cap, 4096),
-                                 std::max<size_t>(d->d_live.cap, 4096), std::max<size_t>(d->d_liverecs.cap, 4096));
+    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kCandSlab, nt * kRecSlab, std::max<size_t>(c.d_dead.cap, 4096),
+                                  std::max<size_t>(c.d_live.cap, 4096), std::max<size_t>(c.d_liverecs.cap, 4096));
     if (rc != B200_OK)
         return rc;
-    rc = zero_span_outputs(d, nsamples, s);
+    rc = zero_chunk_outputs(d, c, nsamples, s);
     if (rc != B200_OK)
         return rc;
-    ScanArgs sa = make_scan_args(d, (const uint8_t *) d_iq, nsamples, 0, kCandSlab, kRecSlab, nullptr);
-    CUDA_TRY(cudaEventRecord(d->ev[1], s));
+    ScanArgs sa = make_scan_args(d, c, (const uint8_t *) d_iq, d->d_head.p, nsamples, 0, kCandSlab, kRecSlab, nullptr);
+    CUDA_TRY(cudaEventRecord(c.ev_begin, s));
     CUDA_TRY(launch_scan(sa, mode ? 1 : 0, d->scan_grid, s));
-    CUDA_TRY(cudaEventRecord(d->ev[2], s));
-    CUDA_TRY(cudaMemcpyAsync(d->h_counters.p, d->d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(c.ev_k1, s));
+    CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, d->ev[1], d->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&ms, c.ev_begin, c.ev_k1));
     if (ms_out)
         *ms_out = ms;
     if (n_candidates_out)
-        *n_candidates_out = d->h_counters.p->n_cand;
+        *n_candidates_out = c.h_counters.p->n_cand;
     return B200_OK;
 }
 
@@ -642,21 +766,21 @@ extern "C" int b200_convert(b200_demod *d, const void *iq, uint32_t nsamples, ui
     const size_t bytes = (size_t) nsamples * d->bytes_per_sample;
     CUDA_TRY(d->d_frames.ensure(bytes + 16));
     CUDA_TRY(d->d_mag.ensure((size_t) nsamples + 8));
-    CUDA_TRY(d->d_sums_u64.ensure(4));
-    CUDA_TRY(d->d_sums_f64.ensure(4));
+    CUDA_TRY(d->d_csum_u64.ensure(4));
+    CUDA_TRY(d->d_csum_f64.ensure(4));
     cudaStream_t s = d->stream;
-    CUDA_TRY(cudaMemsetAsync(d->d_sums_u64.p, 0, 2 * sizeof(unsigned long long), s));
-    CUDA_TRY(cudaMemsetAsync(d->d_sums_f64.p, 0, 2 * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(d->d_csum_u64.p, 0, 2 * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(d->d_csum_f64.p, 0, 2 * sizeof(double), s));
     if (bytes)
         CUDA_TRY(cudaMemcpyAsync(d->d_frames.p, iq, bytes, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(launch_convert(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, d->d_lut.p, d->d_mag.p, d->d_sums_u64.p,
-                            d->d_sums_f64.p, s));
+    CUDA_TRY(launch_convert(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, d->d_lut.p, d->d_mag.p, d->d_csum_u64.p,
+                            d->d_csum_f64.p, s));
     unsigned long long su[2] = {0, 0};
     double sf[2] = {0, 0};
     if (nsamples)
         CUDA_TRY(cudaMemcpyAsync(mag, d->d_mag.p, (size_t) nsamples * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(su, d->d_sums_u64.p, sizeof(su), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(sf, d->d_sums_f64.p, sizeof(sf), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(su, d->d_csum_u64.p, sizeof(su), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(sf, d->d_csum_f64.p, sizeof(sf), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (d->cfg.input_format == B200_INPUT_UC8) {
         if (mean_level)
@@ -689,35 +813,35 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
         return fail(B200_ERR_CAPACITY, "span exceeds max_span_samples");
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     cudaStream_t s = d->stream;
+    ChunkSet &c = d->sets[0];
     const size_t bytes = (size_t) nsamples * d->bytes_per_sample;
     CUDA_TRY(d->d_iq.ensure(bytes + 256));
     CUDA_TRY(d->d_dbg_masks.ensure((size_t) nsamples + 16));
-    // generous: every position a candidate with five records
     // slabs that can hold every position of a tile as a candidate with five records
     const size_t nt = tiles_for(nsamples);
-    int rc = ensure_span_buffers(d, nsamples, nt * kTile, nt * kTile * 5, std::max<size_t>(d->d_dead.cap, 4096),
-                                 std::max<size_t>(d->d_live.cap, 4096), std::max<size_t>(d->d_liverecs.cap, 4096));
+    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kTile, nt * kTile * 5, std::max<size_t>(c.d_dead.cap, 4096),
+                                  std::max<size_t>(c.d_live.cap, 4096), std::max<size_t>(c.d_liverecs.cap, 4096));
     if (rc != B200_OK)
         return rc;
-    rc = zero_span_outputs(d, nsamples, s);
+    rc = zero_chunk_outputs(d, c, nsamples, s);
     if (rc != B200_OK)
         return rc;
     if (bytes)
         CUDA_TRY(cudaMemcpyAsync(d->d_iq.p, iq, bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(d->d_dbg_masks.p, 0, (size_t) nsamples + 16, s));
-    ScanArgs sa = make_scan_args(d, d->d_iq.p, nsamples, 0, kTile, kTile * 5, nullptr);
+    ScanArgs sa = make_scan_args(d, c, d->d_iq.p, d->d_head.p, nsamples, 0, kTile, kTile * 5, nullptr);
     sa.dbg_masks = d->d_dbg_masks.p;
     CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
-    CUDA_TRY(cudaMemcpyAsync(d->h_counters.p, d->d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (d->h_counters.p->overflow)
+    if (c.h_counters.p->overflow)
         return fail(B200_ERR_CAPACITY, "debug scan overflowed its buffers");
     if (try_masks && nsamples)
         CUDA_TRY(cudaMemcpy(try_masks, d->d_dbg_masks.p, (size_t) nsamples, cudaMemcpyDeviceToHost));
     const uint32_t ntiles = sa.ntiles;
     std::vector<TileDesc> tiles(ntiles);
     if (ntiles)
-        CUDA_TRY(cudaMemcpy(tiles.data(), d->d_tiles.p, ntiles * sizeof(TileDesc), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(tiles.data(), c.d_tiles.p, ntiles * sizeof(TileDesc), cudaMemcpyDeviceToHost));
     uint64_t total = 0;
     std::vector<PhaseRec> tmp;
     for (uint32_t t = 0; t < ntiles; ++t) {
@@ -725,7 +849,7 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
         if (!td.nrec)
             continue;
         tmp.resize(td.nrec);
-        CUDA_TRY(cudaMemcpy(tmp.data(), d->d_recs.p + td.rec_off, td.nrec * sizeof(PhaseRec), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(tmp.data(), c.d_recs.p + td.rec_off, td.nrec * sizeof(PhaseRec), cudaMemcpyDeviceToHost));
         for (uint32_t i = 0; i < td.nrec; ++i) {
             if (records && total < record_cap) {
                 b200_phase_record &o = records[total];

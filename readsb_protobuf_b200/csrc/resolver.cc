@@ -70,7 +70,19 @@ bool IcaoFilter::probe(const uint32_t *t, uint32_t addr) {
 }
 
 bool IcaoFilter::test(uint32_t addr) const {
-    return probe(a_, addr) || probe(b_, addr);
+    // icaoFilterTest probes table a, then table b, from the same hash (icao_filter.c:99-122)
+    const uint32_t h0 = hash(addr);
+    for (const uint32_t *t : {a_, b_}) {
+        uint32_t h = h0;
+        while (t[h] != kEmpty && t[h] != addr) {
+            h = (h + 1) & (kSize - 1);
+            if (h == h0)
+                break;
+        }
+        if (t[h] == addr)
+            return true;
+    }
+    return false;
 }
 
 void IcaoFilter::expire(uint64_t now_ms) {
@@ -221,7 +233,15 @@ void count_dead(const SpanView &v, uint64_t lo, uint64_t hi, DeadCount &dc) {
         const int64_t base = (int64_t) t * kTile - kPosShift;
         const int64_t first = (int64_t) lo + 1 - base; // first tile-local index counted
         const uint32_t rel_lo = first > 0 ? (uint32_t) first : 0;
-        const uint32_t *it = std::lower_bound(d, dend, rel_lo, [](uint32_t e, uint32_t x) { return (e & 0x1fffu) < x; });
+        // the entries are sorted and spread evenly over the tile: guess, then walk (the buffer was just
+        // written by the GPU, so every cache line touched is a miss; a binary search touches several)
+        const uint32_t *it = d + (size_t) ((uint64_t) rel_lo * to.ndead / kTile);
+        if (it > dend)
+            it = dend;
+        while (it != d && (it[-1] & 0x1fffu) >= rel_lo)
+            --it;
+        while (it != dend && (*it & 0x1fffu) < rel_lo)
+            ++it;
         for (; it != dend; ++it) {
             const uint64_t p = (uint64_t) (base + (int64_t) (*it & 0x1fffu));
             if (p > hi)
@@ -247,7 +267,30 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
     const uint64_t nfull = n / B;
     const uint64_t nblocks = nfull + (v.final_span ? 1 : 0);
 
+    msgs.reserve(msgs.size() + 64);
     uint32_t tile = 0, live_i = 0; // cursor over live positions
+    // The lists were just written by DMA, so the first touch of every cache line is a DRAM miss.  A
+    // second cursor runs a few live-holding tiles ahead and prefetches what the walk will read: the
+    // tile's live positions and records, and its dead list (for the skip-ahead correction).
+    uint32_t pf_tile = 0;
+    int pf_ahead = 0;
+    auto prefetch_ahead = [&]() {
+        while (pf_ahead < 12 && pf_tile < v.ntiles) {
+            const TileOut &pt = v.tiles[pf_tile++];
+            if (!pt.nlive)
+                continue;
+            ++pf_ahead;
+            const char *a = reinterpret_cast<const char *>(v.live + pt.live_off);
+            for (size_t o = 0; o < pt.nlive * sizeof(LivePos); o += 64)
+                __builtin_prefetch(a + o);
+            a = reinterpret_cast<const char *>(v.liverecs + pt.liverec_off);
+            for (size_t o = 0; o < pt.nliverec * sizeof(LiveRec); o += 64)
+                __builtin_prefetch(a + o);
+            a = reinterpret_cast<const char *>(v.dead + pt.dead_off);
+            for (size_t o = 0; o < pt.ndead * sizeof(uint32_t); o += 64)
+                __builtin_prefetch(a + o);
+        }
+    };
     auto next_live = [&](const LivePos *&lp, const TileOut *&to) -> bool {
         while (tile < v.ntiles) {
             to = &v.tiles[tile];
@@ -255,11 +298,17 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                 lp = &v.live[to->live_off + live_i];
                 return true;
             }
+            if (to->nlive && pf_ahead > 0)
+                --pf_ahead;
             ++tile;
             live_i = 0;
+            if (pf_tile < tile)
+                pf_tile = tile;
+            prefetch_ahead();
         }
         return false;
     };
+    prefetch_ahead();
 
     for (uint64_t k = 0; k < nblocks; ++k) {
         const uint64_t b0 = k * B, b1 = std::min(n, b0 + B), nk = b1 - b0;
