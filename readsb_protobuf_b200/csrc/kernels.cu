@@ -380,8 +380,10 @@ __device__ __forceinline__ void slice_pass(const ScanArgs &a, WarpCtx &cx, const
 __device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, int &nitems) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
-    // stage 1: one lane per item slices the five DF bits -> frame length (demod_2400.c:188-205)
-    int nvalid = 0;
+    // stage 1: one lane per item slices the five DF bits -> frame length (demod_2400.c:188-205);
+    // long frames are queued from the front of the list, short ones from its back, so that a pass
+    // of four never mixes lengths
+    int nl = 0, ns = 0;
     for (int it = 0; it < nitems; it += 32) {
         const bool active = it + lane < nitems;
         const uint32_t item = cx.items[active ? it + lane : it];
@@ -391,14 +393,20 @@ __device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, in
         for (int b = 0; b < 5; ++b)
             df = (df << 1) | (slice_bit_u32(cx.buf, cx.row0, (int) (item & 511u), ph + 12 * b, cx.coef) ? 1u : 0u);
         const int nb = active ? frame_bytes_for_df(df) : 0;
-        const uint32_t vm = __ballot_sync(0xffffffffu, nb != 0);
-        if (nb)
-            cx.valid[nvalid + __popc(vm & ((1u << lane) - 1u))] = (uint16_t) (item | (nb == 14 ? (1u << 12) : 0u));
-        nvalid += __popc(vm);
+        const uint32_t lm = __ballot_sync(0xffffffffu, nb == 14), sm = __ballot_sync(0xffffffffu, nb == 7);
+        const uint32_t below = (1u << lane) - 1u;
+        if (nb == 14)
+            cx.valid[nl + __popc(lm & below)] = (uint16_t) (item | (1u << 12));
+        else if (nb == 7)
+            cx.valid[kItemCap - 1 - (ns + __popc(sm & below))] = (uint16_t) item;
+        nl += __popc(lm);
+        ns += __popc(sm);
     }
     __syncwarp();
-    for (int it = 0; it < nvalid; it += 4)
-        slice_pass(a, cx, cx.valid, it, nvalid);
+    for (int it = 0; it < nl; it += 4)
+        slice_pass(a, cx, cx.valid, it, nl);
+    for (int it = 0; it < ns; it += 4)
+        slice_pass(a, cx, cx.valid + (kItemCap - ns), it, ns);
     __syncwarp();
     nitems = 0;
 }
@@ -700,30 +708,66 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                 cx.buf = s_buf;
                 cx.row0 = row0;
                 cx.chunk_pos0 = pos0;
-                while (lanes) {
-                    const int L = __ffs(lanes) - 1;
-                    lanes &= lanes - 1;
-                    const uint32_t a45 = __shfl_sync(0xffffffffu, b45, L);
-                    const uint32_t a67 = __shfl_sync(0xffffffffu, b67, L);
-                    const uint32_t a8 = __shfl_sync(0xffffffffu, b8, L);
-                    uint32_t u = a45 | a67 | a8;
-                    while (u) {
-                        const int i = __ffs(u) - 1;
-                        u &= u - 1;
-                        const uint32_t tm = (((a45 >> i) & 1u) * 3u) | (((a67 >> i) & 1u) * 12u) | (((a8 >> i) & 1u) * 16u);
-                        const uint32_t pic = (uint32_t) (L * kLanePos + i);
-                        if (lane == 0) {
-                            if (cx.ncand < cx.cand_cap)
-                                cx.cand_out[cx.ncand] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
+                if (lanes) {
+                    // candidates and (position, phase) items of the step, in position order: every lane
+                    // places its own through a warp prefix sum (candidates low half, items high half)
+                    const uint32_t mine = (uint32_t) __popc(any) | ((uint32_t) (2 * __popc(b45) + 2 * __popc(b67) + __popc(b8)) << 16);
+                    uint32_t inc = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o)
+                            inc += up;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+                    const int tot_c = (int) (total & 0xffffu), tot_i = (int) (total >> 16);
+                    if (tot_i <= kItemCap) {
+                        uint32_t ci = cx.ncand + ((inc - mine) & 0xffffu);
+                        int ii = (int) ((inc - mine) >> 16);
+                        uint32_t u = any;
+                        while (u) {
+                            const int i = __ffs(u) - 1;
+                            u &= u - 1;
+                            const uint32_t tm = (((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u);
+                            const uint32_t pic = (uint32_t) (lane * kLanePos + i);
+                            if (ci < cx.cand_cap)
+                                cx.cand_out[ci] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
+                            ++ci;
 #pragma unroll
                             for (int ph = 0; ph < 5; ++ph)
                                 if ((tm >> ph) & 1u)
-                                    cx.items[nitems + __popc(tm & ((1u << ph) - 1u))] = (uint16_t) (pic | ((uint32_t) ph << 9));
+                                    cx.items[ii++] = (uint16_t) (pic | ((uint32_t) ph << 9));
                         }
-                        ++cx.ncand;
-                        nitems += __popc(tm);
-                        if (nitems > kItemCap - 5)
-                            process_items(a, cx, nitems);
+                        cx.ncand += (uint32_t) tot_c;
+                        nitems = tot_i;
+                    } else {
+                        // a step with more items than the queue holds: lane by lane, flushing as needed
+                        while (lanes) {
+                            const int L = __ffs(lanes) - 1;
+                            lanes &= lanes - 1;
+                            const uint32_t a45 = __shfl_sync(0xffffffffu, b45, L);
+                            const uint32_t a67 = __shfl_sync(0xffffffffu, b67, L);
+                            const uint32_t a8 = __shfl_sync(0xffffffffu, b8, L);
+                            uint32_t u = a45 | a67 | a8;
+                            while (u) {
+                                const int i = __ffs(u) - 1;
+                                u &= u - 1;
+                                const uint32_t tm = (((a45 >> i) & 1u) * 3u) | (((a67 >> i) & 1u) * 12u) | (((a8 >> i) & 1u) * 16u);
+                                const uint32_t pic = (uint32_t) (L * kLanePos + i);
+                                if (lane == 0) {
+                                    if (cx.ncand < cx.cand_cap)
+                                        cx.cand_out[cx.ncand] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
+#pragma unroll
+                                    for (int ph = 0; ph < 5; ++ph)
+                                        if ((tm >> ph) & 1u)
+                                            cx.items[nitems + __popc(tm & ((1u << ph) - 1u))] = (uint16_t) (pic | ((uint32_t) ph << 9));
+                                }
+                                ++cx.ncand;
+                                nitems += __popc(tm);
+                                if (nitems > kItemCap - 5)
+                                    process_items(a, cx, nitems);
+                            }
+                        }
                     }
                 }
                 if (nitems)
@@ -858,7 +902,6 @@ cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stre
 
 constexpr int kClassifyThreads = 256;
 constexpr int kFrameSamples = 296; // samples a frame's slice + power can touch: m[0..290]
-constexpr int kPosPerThread2 = kTile / kClassifyThreads; // 32
 
 __device__ __forceinline__ bool bitmap_test(const uint32_t *__restrict__ bm, uint32_t addr) {
     return (__ldg(&bm[(addr & 0xffffffu) >> 5]) >> (addr & 31u)) & 1u;
@@ -889,11 +932,24 @@ __device__ __forceinline__ uint32_t sample_mag(const ClassifyArgs &a, long long 
     return mag_sc16_word(w, (a.format == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f), magsq, mag);
 }
 
+// index of the candidate entry of tile-local position pl (the entries are in position order)
+__device__ __forceinline__ uint32_t find_cand(const uint32_t *__restrict__ cand, uint32_t ncand, uint32_t pl) {
+    uint32_t lo = 0, hi = ncand;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((__ldg(&cand[mid]) & 0x1fffu) < pl)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const ClassifyArgs a) {
-    // per position of the tile
-    __shared__ __align__(16) uint8_t s_info[kTile]; // trymask[4:0] | live[5] | has a -1 phase[6]
-    __shared__ __align__(16) uint8_t s_nb[kTile];   // which phases own a class record
-    __shared__ uint16_t s_slot[kTile];              // first live-record slot of a live position
+    // per candidate of the tile (K1 emits them in position order)
+    __shared__ __align__(16) uint8_t s_flags[kTile]; // live[0] | has a -1 phase[1]
+    __shared__ __align__(16) uint8_t s_nb[kTile];    // which phases own a class record
+    __shared__ uint16_t s_slot[kTile];               // first live-record slot of a live candidate
     __shared__ int s_warp[40];
     __shared__ uint32_t s_syn[112];
     __shared__ int s_coef[5][4];
@@ -906,6 +962,15 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
         return; // K1 ran out of room: the host places the slabs exactly and runs the span again
     const TileDesc td = a.tiles[tile];
     const long long p0 = (long long) tile * kTile - kPosShift; // position of tile-local index 0
+    const uint32_t *cand = a.cand + td.cand_off;
+    if (td.ncand == 0) {
+        if (tid == 0) {
+            TileOut to;
+            to.dead_off = to.ndead = to.live_off = to.nlive = to.liverec_off = to.nliverec = 0;
+            a.tiles_out[tile] = to;
+        }
+        return;
+    }
 
     if (tid < 112)
         s_syn[tid] = c_bit_syndrome[tid];
@@ -913,56 +978,46 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
         (&s_coef[0][0])[tid] = (&c_slice_coef[0][0])[tid];
     if (tid < 8)
         s_bd[tid] = 0;
-    for (int i = tid; i < kTile / 16; i += kClassifyThreads) {
-        reinterpret_cast<uint4 *>(s_info)[i] = make_uint4(0, 0, 0, 0);
-        reinterpret_cast<uint4 *>(s_nb)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < (td.ncand + 3) / 4; i += kClassifyThreads) {
+        reinterpret_cast<uint32_t *>(s_flags)[i] = 0;
+        reinterpret_cast<uint32_t *>(s_nb)[i] = 0;
     }
     __syncthreads();
 
-    // ---- pass 1: candidates -> try masks by position ----
-    for (uint32_t c = tid; c < td.ncand; c += kClassifyThreads) {
-        const uint32_t e = a.cand[td.cand_off + c];
-        s_info[e & 0x1fffu] = (uint8_t) ((e >> 13) & 31u);
-    }
-    __syncthreads();
-
-    // ---- pass 2: class records -> can the position still be accepted, does it hold a -1 phase ----
+    // ---- pass 1: class records -> can the position still be accepted, does it hold a -1 phase ----
     for (uint32_t r = tid; r < td.nrec; r += kClassifyThreads) {
         const PhaseRec pr = a.recs[td.rec_off + r];
         const uint32_t kind = (pr.w0 >> 24) & 7u;
-        const uint32_t pl = (uint32_t) ((long long) pr.pos - p0);
+        const uint32_t c = find_cand(cand, td.ncand, (uint32_t) ((long long) pr.pos - p0));
         const uint32_t ph = (pr.w1 >> 24) & 15u;
         const bool live = record_is_live(pr.w0, pr.w1, a.addr_bitmap);
-        uint32_t f = live ? 32u : 0u;
+        uint32_t f = live ? 1u : 0u;
         // static score of a phase whose address can never be in the filter:
         // AP -> -1, DF11 with IID != 0 -> -1, Comm-B -> -2 (mode_s.c:343,373,403)
         if (!live && (kind == kKindAP || kind == kKindDF11))
-            f |= 64u;
+            f |= 2u;
         if (f)
-            atomicOr(reinterpret_cast<unsigned int *>(s_info) + (pl >> 2), f << (8 * (pl & 3)));
-        atomicOr(reinterpret_cast<unsigned int *>(s_nb) + (pl >> 2), (1u << (ph - 4)) << (8 * (pl & 3)));
+            atomicOr(reinterpret_cast<unsigned int *>(s_flags) + (c >> 2), f << (8 * (c & 3)));
+        atomicOr(reinterpret_cast<unsigned int *>(s_nb) + (c >> 2), (1u << (ph - 4)) << (8 * (c & 3)));
     }
     __syncthreads();
 
-    // ---- pass 3: ordered dead list / live position list; thread t owns 32 consecutive positions ----
-    const int i0 = tid * kPosPerThread2;
-    int n_dead_mine = 0, n_live_mine = 0, n_liverec_mine = 0;
-#pragma unroll 4
-    for (int i = 0; i < kPosPerThread2; ++i) {
-        const uint32_t inf = s_info[i0 + i];
-        if (inf & 31u) {
-            if (inf & 32u) {
-                ++n_live_mine;
-                n_liverec_mine += __popc((uint32_t) s_nb[i0 + i]);
-            } else {
-                ++n_dead_mine;
-            }
+    // ---- pass 2: count, reserve the tile's output ranges ----
+    int n_dead = 0, n_live = 0, n_liverec = 0;
+    {
+        int mine = 0; // dead[9:0] | live[19:10] | live records[31:20], per batch of kClassifyThreads candidates
+        for (uint32_t c = tid; c < td.ncand; c += kClassifyThreads) {
+            if (s_flags[c] & 1u)
+                mine += (1 << 10) + ((int) __popc((uint32_t) s_nb[c]) << 20);
+            else
+                mine += 1;
         }
+        // counts of one thread stay small (<= 32 candidates per thread), sum them per field
+        int d = mine & 1023, l = (mine >> 10) & 1023, r = (mine >> 20) & 4095;
+        block_exclusive_scan(d, s_warp, n_dead);
+        block_exclusive_scan(l, s_warp, n_live);
+        block_exclusive_scan(r, s_warp, n_liverec);
     }
-    int n_dead, n_live, n_liverec;
-    const int od = block_exclusive_scan(n_dead_mine, s_warp, n_dead);
-    const int ol = block_exclusive_scan(n_live_mine, s_warp, n_live);
-    const int orr = block_exclusive_scan(n_liverec_mine, s_warp, n_liverec);
     if (tid == 0) {
         unsigned long long d_off = atomicAdd(&a.counters->n_dead, (unsigned long long) n_dead);
         unsigned long long l_off = atomicAdd(&a.counters->n_live, (unsigned long long) n_live);
@@ -994,32 +1049,40 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
     if (s_warp[36])
         return; // the host grows the buffers and runs the span again
 
+    // ---- pass 3: ordered dead list / live position list, kClassifyThreads candidates at a time ----
     {
         const long long B = (long long) a.block_samples;
         const long long first_pos = p0 < 0 ? 0 : p0;
         const uint32_t kb0 = (uint32_t) (first_pos / B);
         const bool one_block = ((long long) (kb0 + 1) * B >= p0 + kTile);
         uint32_t bd_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        int d = od, l = ol, r = orr;
-        for (int i = 0; i < kPosPerThread2; ++i) {
-            const uint32_t inf = s_info[i0 + i];
-            const uint32_t tm = inf & 31u;
-            if (!tm)
-                continue;
-            const uint32_t pl = (uint32_t) (i0 + i);
-            if (inf & 32u) {
-                const uint32_t nrec = (uint32_t) __popc((uint32_t) s_nb[pl]);
+        int d_done = 0, l_done = 0, r_done = 0;
+        for (uint32_t cb = 0; cb < td.ncand; cb += kClassifyThreads) { // uniform trip count
+            const uint32_t c = cb + tid;
+            uint32_t e = 0, nrec = 0, fl = 0;
+            bool is_dead = false, is_live = false;
+            if (c < td.ncand) {
+                e = __ldg(&cand[c]);
+                fl = s_flags[c];
+                is_live = (fl & 1u) != 0;
+                is_dead = !is_live;
+                nrec = (uint32_t) __popc((uint32_t) s_nb[c]);
+            }
+            // one scan for the three counts: dead[9:0] | live[19:10] | live records[31:20]
+            int tot;
+            const int packed = (is_dead ? 1 : 0) | (is_live ? (1 << 10) | ((int) nrec << 20) : 0);
+            const int off = block_exclusive_scan(packed, s_warp, tot);
+            const int od = off & 1023, ol = (off >> 10) & 1023, orr = (off >> 20) & 4095;
+            const uint32_t pl = e & 0x1fffu, tm = (e >> 13) & 31u;
+            if (is_live) {
                 LivePos lp;
                 lp.pos = (uint32_t) (p0 + pl);
-                lp.info = tm | (nrec << 8) | ((uint32_t) r << 16);
-                a.live[live_off + l] = lp;
-                s_slot[pl] = (uint16_t) r;
-                ++l;
-                r += (int) nrec;
-            } else {
-                const uint32_t unknown = (inf >> 6) & 1u;
-                a.dead[dead_off + d] = pl | (tm << 13) | (unknown << 18);
-                ++d;
+                lp.info = tm | (nrec << 8) | ((uint32_t) (r_done + orr) << 16);
+                a.live[live_off + l_done + ol] = lp;
+                s_slot[c] = (uint16_t) (r_done + orr);
+            } else if (is_dead) {
+                const uint32_t unknown = (fl >> 1) & 1u;
+                a.dead[dead_off + d_done + od] = pl | (tm << 13) | (unknown << 18);
                 // what demodulate2400 counts for a position whose best score is negative
                 // (demod_2400.c:184,339-347), provided no accepted frame skips over it
                 const uint32_t bd[8] = {1u, unknown ? 0u : 1u, unknown, tm & 1u, (tm >> 1) & 1u, (tm >> 2) & 1u, (tm >> 3) & 1u, (tm >> 4) & 1u};
@@ -1036,6 +1099,9 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
                             atomicAdd(&dst[q], bd[q]);
                 }
             }
+            d_done += tot & 1023;
+            l_done += (tot >> 10) & 1023;
+            r_done += (tot >> 20) & 4095;
         }
         if (one_block) {
 #pragma unroll
@@ -1060,12 +1126,12 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
     // a live position owns consecutive output slots, one per recorded phase in phase order
     for (uint32_t r = warp; r < td.nrec; r += kClassifyThreads / 32) {
         const PhaseRec pr = a.recs[td.rec_off + r];
-        const uint32_t pl = (uint32_t) ((long long) pr.pos - p0);
-        if (!(s_info[pl] & 32u))
+        const uint32_t c = find_cand(cand, td.ncand, (uint32_t) ((long long) pr.pos - p0));
+        if (!(s_flags[c] & 1u))
             continue;
         const int ph = (int) ((pr.w1 >> 24) & 15u);
-        const uint32_t rank = (uint32_t) __popc((uint32_t) s_nb[pl] & ((1u << (ph - 4)) - 1u));
-        const uint32_t slot = liverec_off + s_slot[pl] + rank;
+        const uint32_t rank = (uint32_t) __popc((uint32_t) s_nb[c] & ((1u << (ph - 4)) - 1u));
+        const uint32_t slot = liverec_off + s_slot[c] + rank;
 
         // magnitudes the frame touches: window position pos -> samples pos - kOverlap ...
         uint16_t *fm = s_frame[warp];
