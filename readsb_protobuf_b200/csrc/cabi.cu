@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -563,6 +564,24 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     v.block_dead = c.h_block_dead.p;
     v.block_sums_u64 = c.h_sums_u64.p;
     v.block_sums_f64 = c.h_sums_f64.p;
+    if (const char *dump = getenv("B200_DUMP_SPAN")) {
+        // development aid: write the resolver's inputs of this chunk to a file (tools/resolver_bench.cc)
+        char path[512];
+        snprintf(path, sizeof(path), "%s/span_%llu.bin", dump, (unsigned long long) c.start);
+        if (FILE *f = fopen(path, "wb")) {
+            const uint64_t nblocks = n / v.block_samples + 2;
+            uint64_t hdr[12] = {n, v.first_sample, v.block_samples, v.final_span, v.format, v.ntiles, cnt.n_dead, cnt.n_live, cnt.n_liverec, nblocks, 0, 0};
+            fwrite(hdr, sizeof(hdr), 1, f);
+            fwrite(v.tiles, sizeof(TileOut), v.ntiles, f);
+            fwrite(v.dead, sizeof(uint32_t), cnt.n_dead, f);
+            fwrite(v.live, sizeof(LivePos), cnt.n_live, f);
+            fwrite(v.liverecs, sizeof(LiveRec), cnt.n_liverec, f);
+            fwrite(v.block_dead, sizeof(BlockDead), nblocks, f);
+            fwrite(v.block_sums_u64, sizeof(unsigned long long), 2 * nblocks, f);
+            fwrite(v.block_sums_f64, sizeof(double), 2 * nblocks, f);
+            fclose(f);
+        }
+    }
     d->resolver->resolve(v, d->msgs, d->blocks);
     t.resolve_ms += (float) (now_ms() - t_res0);
     t.n_candidates += cnt.n_cand;

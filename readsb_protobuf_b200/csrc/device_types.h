@@ -69,10 +69,12 @@ struct TileOut {
     uint32_t liverec_off, nliverec;
 };
 
-// K2 -> host: a position the resolver must look at.  8 bytes.
+// K2 -> host: a position the resolver must look at.  16 bytes.
 struct LivePos {
-    uint32_t pos;  // scan position within the span
-    uint32_t info; // trymask[4:0] | nrec[10:8] | first live record (relative to the tile's liverec_off) [31:16]
+    uint32_t pos;       // scan position within the span
+    uint32_t info;      // trymask[4:0] | nrec[10:8] | first live record (relative to the tile's liverec_off) [31:16]
+    uint32_t dead_rank; // dead entries of the tile in front of this position (where a skip-ahead starts counting)
+    uint32_t pad;
 };
 
 // K2 -> host: a sliced frame of a live position.  48 bytes.

@@ -31,6 +31,17 @@ CrcTables::CrcTables(int nfix) {
         msg[i >> 3] = 0;
     }
     memset(&no_errors_, 0, sizeof(no_errors_));
+    pos_ready_ = false;
+    // the CRC is linear: the syndrome of a frame is the XOR of the syndromes of its bytes
+    for (int i = 0; i < 14; ++i)
+        for (uint32_t b = 0; b < 256; ++b) {
+            uint32_t x = 0;
+            for (int k = 0; k < 8; ++k)
+                if (b & (0x80u >> k))
+                    x ^= bit_syndrome_[8 * i + k];
+            pos_table_[i][b] = x;
+        }
+    pos_ready_ = true;
 
     // crc.c:358-383
     if (nfix == 1) {
@@ -44,6 +55,14 @@ CrcTables::CrcTables(int nfix) {
 
 uint32_t CrcTables::checksum(const uint8_t *msg, int bits) const {
     const int n = bits / 8;
+    if (pos_ready_) {
+        // same value as the byte-serial form below, without its dependency chain
+        const int off = 14 - n; // short frames use the tail of the 112-bit positions (crc.c:143)
+        uint32_t x = 0;
+        for (int i = 0; i < n; ++i)
+            x ^= pos_table_[i + off][msg[i]];
+        return x;
+    }
     uint32_t rem = 0;
     for (int i = 0; i < n - 3; ++i)
         rem = ((rem << 8) ^ byte_table_[msg[i] ^ ((rem >> 16) & 0xffu)]) & 0xffffffu;

@@ -28,6 +28,8 @@ class CrcTables {
   private:
     void build(int bits, int max_correct, int max_detect, std::vector<ErrorInfo> &out) const;
     uint32_t byte_table_[256];
+    bool pos_ready_ = false;
+    uint32_t pos_table_[14][256]; // syndrome of byte value b at byte position i of a 112-bit frame
     uint32_t bit_syndrome_[112];
     std::vector<ErrorInfo> short_, long_;
     ErrorInfo no_errors_;

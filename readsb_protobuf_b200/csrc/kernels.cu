@@ -1078,6 +1078,8 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
                 LivePos lp;
                 lp.pos = (uint32_t) (p0 + pl);
                 lp.info = tm | (nrec << 8) | ((uint32_t) (r_done + orr) << 16);
+                lp.dead_rank = (uint32_t) (d_done + od);
+                lp.pad = 0;
                 a.live[live_off + l_done + ol] = lp;
                 s_slot[c] = (uint16_t) (r_done + orr);
             } else if (is_dead) {

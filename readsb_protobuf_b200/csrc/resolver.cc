@@ -30,6 +30,18 @@ void IcaoFilter::reset() {
     memset(b_, 0xff, sizeof(b_));
     active_ = a_;
     next_flip_ = 0;
+    if (bits_a_.empty()) {
+        bits_a_.assign((1u << 24) / 64, 0);
+        bits_b_.assign((1u << 24) / 64, 0);
+    } else {
+        for (uint32_t x : list_a_)
+            bits_a_[x >> 6] = 0;
+        for (uint32_t x : list_b_)
+            bits_b_[x >> 6] = 0;
+    }
+    list_a_.clear();
+    list_b_.clear();
+    dropped_ = false;
 }
 
 void IcaoFilter::add(uint32_t addr) {
@@ -43,10 +55,20 @@ void IcaoFilter::add(uint32_t addr) {
             break;
         }
     }
-    if (full)
+    if (full) {
+        dropped_ = true;
         return; // icao_filter.c:78-81: a full table drops the address (and skips the second insert)
-    if (active_[h] == kEmpty)
+    }
+    if (active_[h] == kEmpty) {
         active_[h] = addr;
+        if (addr < (1u << 24)) {
+            std::vector<uint64_t> &bits = (active_ == a_) ? bits_a_ : bits_b_;
+            bits[addr >> 6] |= 1ull << (addr & 63u);
+            ((active_ == a_) ? list_a_ : list_b_).push_back(addr);
+        } else {
+            dropped_ = true; // not a 24-bit address: let the tables answer
+        }
+    }
     // ... and once more on the chain of its low 16 bits (Data/Parity lookups, icao_filter.c:87-96)
     const uint32_t low = addr & 0x00ffffu;
     h0 = h = hash(low);
@@ -70,6 +92,12 @@ bool IcaoFilter::probe(const uint32_t *t, uint32_t addr) {
 }
 
 bool IcaoFilter::test(uint32_t addr) const {
+    if (!dropped_ && addr < (1u << 24))
+        return ((bits_a_[addr >> 6] | bits_b_[addr >> 6]) >> (addr & 63u)) & 1ull;
+    return test_tables(addr);
+}
+
+bool IcaoFilter::test_tables(uint32_t addr) const {
     // icaoFilterTest probes table a, then table b, from the same hash (icao_filter.c:99-122)
     const uint32_t h0 = hash(addr);
     for (const uint32_t *t : {a_, b_}) {
@@ -90,6 +118,13 @@ void IcaoFilter::expire(uint64_t now_ms) {
         return;
     uint32_t *other = (active_ == a_) ? b_ : a_;
     memset(other, 0xff, sizeof(a_));
+    {
+        std::vector<uint64_t> &bits = (other == a_) ? bits_a_ : bits_b_;
+        std::vector<uint32_t> &list = (other == a_) ? list_a_ : list_b_;
+        for (uint32_t x : list)
+            bits[x >> 6] = 0;
+        list.clear();
+    }
     active_ = other;
     next_flip_ = now_ms + 60000; // MODES_ICAO_FILTER_TTL, icao_filter.c:30
 }
@@ -217,45 +252,58 @@ int Resolver::decode(const LiveRec &r, b200_message &mm) {
 
 namespace {
 
+// what skip-ahead hides, as eight 16-bit counters in two words (a frame body hides at most 268
+// positions): lo = preambles | bad << 16 | unknown << 32 | phase0 << 48, hi = phase1..phase4
 struct DeadCount {
+    uint64_t lo = 0, hi = 0;
+    uint32_t preambles() const { return (uint32_t) (lo & 0xffff); }
+    uint32_t bad() const { return (uint32_t) ((lo >> 16) & 0xffff); }
+    uint32_t unknown() const { return (uint32_t) ((lo >> 32) & 0xffff); }
+    uint32_t phase(int k) const { return (uint32_t) (k == 0 ? (lo >> 48) : (hi >> (16 * (k - 1)))) & 0xffff; }
+};
+
+struct DeadLut {
+    uint64_t lo[64], hi[64]; // indexed by trymask | unknown << 5
+    DeadLut() {
+        for (uint32_t i = 0; i < 64; ++i) {
+            const uint32_t tm = i & 31u, unk = i >> 5;
+            lo[i] = 1ull | ((uint64_t) (unk ? 0 : 1) << 16) | ((uint64_t) unk << 32) | ((uint64_t) (tm & 1u) << 48);
+            hi[i] = (uint64_t) ((tm >> 1) & 1u) | ((uint64_t) ((tm >> 2) & 1u) << 16) | ((uint64_t) ((tm >> 3) & 1u) << 32) |
+                    ((uint64_t) ((tm >> 4) & 1u) << 48);
+        }
+    }
+};
+const DeadLut kDeadLut;
+
+// dead positions in (lo, hi] that a skip-ahead hides (they are in the per-block totals K2 made);
+// `rank` = dead entries of lo's tile in front of lo (LivePos::dead_rank)
+struct HiddenTotals {
     uint32_t preambles = 0, bad = 0, unknown = 0, phase[5] = {0, 0, 0, 0, 0};
 };
 
-// dead positions in (lo, hi] that a skip-ahead hides (they are in the per-block totals K2 made)
-void count_dead(const SpanView &v, uint64_t lo, uint64_t hi, DeadCount &dc) {
+void count_dead(const SpanView &v, uint64_t lo, uint64_t hi, uint32_t rank, HiddenTotals &total) {
     if (hi <= lo)
         return;
     // tile t covers positions [t*kTile - kPosShift, (t+1)*kTile - kPosShift)
-    const uint32_t t0 = (uint32_t) ((lo + 1 + kPosShift) / kTile), t1 = (uint32_t) ((hi + kPosShift) / kTile);
+    const uint32_t t0 = (uint32_t) ((lo + kPosShift) / kTile), t1 = (uint32_t) ((hi + kPosShift) / kTile);
+    DeadCount dc; // one frame body: at most 268 entries, the 16-bit fields cannot overflow
     for (uint32_t t = t0; t <= t1 && t < v.ntiles; ++t) {
         const TileOut &to = v.tiles[t];
         const uint32_t *d = v.dead + to.dead_off, *dend = d + to.ndead;
         const int64_t base = (int64_t) t * kTile - kPosShift;
-        const int64_t first = (int64_t) lo + 1 - base; // first tile-local index counted
-        const uint32_t rel_lo = first > 0 ? (uint32_t) first : 0;
-        // the entries are sorted and spread evenly over the tile: guess, then walk (the buffer was just
-        // written by the GPU, so every cache line touched is a miss; a binary search touches several)
-        const uint32_t *it = d + (size_t) ((uint64_t) rel_lo * to.ndead / kTile);
-        if (it > dend)
-            it = dend;
-        while (it != d && (it[-1] & 0x1fffu) >= rel_lo)
-            --it;
-        while (it != dend && (*it & 0x1fffu) < rel_lo)
-            ++it;
-        for (; it != dend; ++it) {
-            const uint64_t p = (uint64_t) (base + (int64_t) (*it & 0x1fffu));
-            if (p > hi)
-                break;
-            const uint32_t tm = (*it >> 13) & 31u;
-            ++dc.preambles;
-            if ((*it >> 18) & 1u)
-                ++dc.unknown;
-            else
-                ++dc.bad;
-            for (int k = 0; k < 5; ++k)
-                dc.phase[k] += (tm >> k) & 1u;
+        const uint32_t *it = (t == t0) ? d + rank : d;
+        const int64_t last = (int64_t) hi - base; // last tile-local index counted
+        for (; it != dend && (int64_t) (*it & 0x1fffu) <= last; ++it) {
+            const uint32_t key = (*it >> 13) & 63u; // trymask | unknown << 5
+            dc.lo += kDeadLut.lo[key];
+            dc.hi += kDeadLut.hi[key];
         }
     }
+    total.preambles += dc.preambles();
+    total.bad += dc.bad();
+    total.unknown += dc.unknown();
+    for (int k = 0; k < 5; ++k)
+        total.phase[k] += dc.phase(k);
 }
 
 } // namespace
@@ -269,26 +317,33 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
 
     msgs.reserve(msgs.size() + 64);
     uint32_t tile = 0, live_i = 0; // cursor over live positions
-    // The lists were just written by DMA, so the first touch of every cache line is a DRAM miss.  A
-    // second cursor runs a few live-holding tiles ahead and prefetches what the walk will read: the
-    // tile's live positions and records, and its dead list (for the skip-ahead correction).
-    uint32_t pf_tile = 0;
-    int pf_ahead = 0;
+    // The lists were just written by DMA, so the first touch of a cache line misses the core's caches.
+    // Two cursors run ahead of the walk over the tiles that hold live positions: the far one
+    // prefetches the tile's live-position entries, the near one reads them (by then cached) and
+    // prefetches what the walk will touch: the records and the dead-list line where a skip starts.
+    uint32_t pf_far = 0, pf_near = 0;
+    int far_ahead = 0, near_ahead = 0;
     auto prefetch_ahead = [&]() {
-        while (pf_ahead < 12 && pf_tile < v.ntiles) {
-            const TileOut &pt = v.tiles[pf_tile++];
+        while (far_ahead < 24 && pf_far < v.ntiles) {
+            const TileOut &pt = v.tiles[pf_far++];
             if (!pt.nlive)
                 continue;
-            ++pf_ahead;
+            ++far_ahead;
             const char *a = reinterpret_cast<const char *>(v.live + pt.live_off);
             for (size_t o = 0; o < pt.nlive * sizeof(LivePos); o += 64)
                 __builtin_prefetch(a + o);
-            a = reinterpret_cast<const char *>(v.liverecs + pt.liverec_off);
+        }
+        while (near_ahead < 8 && pf_near < pf_far) {
+            const TileOut &pt = v.tiles[pf_near++];
+            if (!pt.nlive)
+                continue;
+            ++near_ahead;
+            const char *a = reinterpret_cast<const char *>(v.liverecs + pt.liverec_off);
             for (size_t o = 0; o < pt.nliverec * sizeof(LiveRec); o += 64)
                 __builtin_prefetch(a + o);
-            a = reinterpret_cast<const char *>(v.dead + pt.dead_off);
-            for (size_t o = 0; o < pt.ndead * sizeof(uint32_t); o += 64)
-                __builtin_prefetch(a + o);
+            const LivePos *lv = v.live + pt.live_off;
+            for (uint32_t i = 0; i < pt.nlive; i += 2)
+                __builtin_prefetch(v.dead + pt.dead_off + lv[i].dead_rank);
         }
     };
     auto next_live = [&](const LivePos *&lp, const TileOut *&to) -> bool {
@@ -298,12 +353,18 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                 lp = &v.live[to->live_off + live_i];
                 return true;
             }
-            if (to->nlive && pf_ahead > 0)
-                --pf_ahead;
+            if (to->nlive) {
+                if (far_ahead > 0)
+                    --far_ahead;
+                if (near_ahead > 0)
+                    --near_ahead;
+            }
             ++tile;
             live_i = 0;
-            if (pf_tile < tile)
-                pf_tile = tile;
+            if (pf_near < tile)
+                pf_near = tile;
+            if (pf_far < pf_near)
+                pf_far = pf_near;
             prefetch_ahead();
         }
         return false;
@@ -331,7 +392,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
 
         ifile_now_ = sysTimestamp; // demod_2400.c:253-255
         uint64_t sum_scaled_signal_power = 0;
-        DeadCount hidden;
+        HiddenTotals hidden;
         bool skipping = false;
         uint64_t skip_until = 0; // positions <= skip_until are skipped while `skipping`
 
@@ -411,7 +472,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             // demod_2400.c:416: skip the frame body; the for loop ends at the block boundary
             skipping = true;
             skip_until = std::min<uint64_t>(p + (uint64_t) signal_len, b1 - 1);
-            count_dead(v, p, skip_until, hidden);
+            count_dead(v, p, skip_until, lp->dead_rank, hidden);
 
             stats_.messages_total++; // useModesMessage, mode_s.c:2149
             memset(mm.msg + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);

@@ -32,9 +32,16 @@ class IcaoFilter {
     static constexpr uint32_t kSize = 8192, kEmpty = 0xffffffffu;
     static uint32_t hash(uint32_t a);
     static bool probe(const uint32_t *t, uint32_t addr);
+    bool test_tables(uint32_t addr) const;
     uint32_t a_[kSize], b_[kSize];
     uint32_t *active_;
     uint64_t next_flip_;
+    // Shadow of the two tables for O(1) membership: one bit per 24-bit address and table, plus the
+    // list of addresses each table holds (to clear its bits at a flip).  Exact as long as no insert
+    // was ever dropped by a full table; after that the tables themselves answer.
+    std::vector<uint64_t> bits_a_, bits_b_;
+    std::vector<uint32_t> list_a_, list_b_;
+    bool dropped_;
 };
 
 struct SpanView {
