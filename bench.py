@@ -272,14 +272,16 @@ def run_ours(args):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k1, k2, nmsg, d2h = [], [], 0, 0
+        k1, k2, nmsg, d2h, launches, chunks = [], [], 0, 0, 0, 1
         e0.record(stream)
         for _ in range(steps):
             r = fn()
             k1.append(r.timing["scan_ms"])
             k2.append(r.timing["classify_ms"])
             nmsg = len(r.msgs)
-            d2h = r.msgs.nbytes
+            d2h = r.timing["d2h_bytes"]
+            launches += r.timing["scan_launches"]
+            chunks = r.timing["chunks"]
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -287,13 +289,13 @@ def run_ours(args):
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, k1, k2, nmsg, d2h
+        return ms, k1, k2, nmsg, d2h, launches, chunks
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, k1_ms, k2_ms, nmsg, _ = timed(step_device, args.steps, args.warmup)
+    ms_dev, k1_ms, k2_ms, nmsg, _, n_launches, n_chunks = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop()
-    ms_host, _, _, _, d2h_bytes = timed(step_host, args.steps, max(1, args.warmup // 2))
+    ms_host, _, _, _, d2h_bytes, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
 
     # scan kernel alone, both modes (device-resident, same stream)
     scan_only, scan_full = [], []
@@ -327,11 +329,12 @@ def run_ours(args):
                        "decoded_msgs_per_stream": nmsg, "msgs_per_s": nmsg * world * args.steps / (ms_dev * 1e-3)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": ms_host / args.steps},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": int(n_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "scan_kernel<uc8, slice+crc> (K1)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": nbytes, "kernel_ms": k1_mean,
+                         "launches_per_step": int(n_chunks), "algorithmic_bytes_per_launch": nbytes // max(int(n_chunks), 1),
+                         "kernel_ms_per_launch": k1_mean / max(int(n_chunks), 1), "kernel_ms_per_step": k1_mean,
                          "scan_only": {"kernel": "scan_kernel<uc8, scan only> (magnitude + preamble scan)",
                                        "kernel_ms": so_mean, "achieved": nbytes / (so_mean * 1e-3) / 1e9,
                                        "frac": nbytes / (so_mean * 1e-3) / 1e9 / peak},

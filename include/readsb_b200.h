@@ -114,7 +114,8 @@ typedef struct b200_timing {
     uint64_t n_phase_records;/* (position, phase) pairs that survived the CRC class test */
     uint64_t n_live;         /* positions handed to the host resolver */
     uint32_t scan_launches;  /* kernels launched by the call */
-    uint32_t reserved;
+    uint32_t chunks;         /* pipeline chunks the span was cut into */
+    uint64_t d2h_bytes;      /* bytes copied device -> host by the call (counters, lists, survivors) */
 } b200_timing;
 
 /* ---- lifetime ---- */

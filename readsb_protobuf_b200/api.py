@@ -60,7 +60,7 @@ class Timing(ctypes.Structure):
         ("h2d_ms", ctypes.c_float), ("scan_ms", ctypes.c_float), ("classify_ms", ctypes.c_float),
         ("d2h_ms", ctypes.c_float), ("resolve_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
         ("n_candidates", ctypes.c_uint64), ("n_phase_records", ctypes.c_uint64), ("n_live", ctypes.c_uint64),
-        ("scan_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+        ("scan_launches", ctypes.c_uint32), ("chunks", ctypes.c_uint32), ("d2h_bytes", ctypes.c_uint64),
     ]
 
     def as_dict(self):

@@ -105,3 +105,15 @@ def ensure_ref() -> Path | None:
         if not _newer(binary, [ORACLE / "ref_harness.c", ORACLE / "ref_shim" / "stubs.c", ORACLE / "Makefile"]):
             _run(["make", "-C", ORACLE, "ref", "CC=gcc", f"REF={REFERENCE}"])
     return binary if binary.exists() else None
+
+
+def ensure_dropin() -> Path | None:
+    """TEST INFRASTRUCTURE: the reference's own program linked with the shim + libreadsb_b200.so
+    in place of convert.o / demod_2400.o / sdr_ifile.o (oracle/_ref/readsb_b200)."""
+    binary = ORACLE / "_ref" / "readsb_b200"
+    if have_reference_sources():
+        lib = ensure_cuda()
+        shim = PKG / "shim" / "readsb_b200_shim.c"
+        if not _newer(binary, [shim, lib, ORACLE / "Makefile", ROOT / "include" / "readsb_b200.h"]):
+            _run(["make", "-C", ORACLE, "ref", "dropin", "CC=gcc", f"REF={REFERENCE}"])
+    return binary if binary.exists() else None

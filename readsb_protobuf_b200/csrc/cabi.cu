@@ -137,6 +137,7 @@ struct ChunkSet {
     bool final_chunk = false;
     uint32_t head_valid = 0;
     const uint8_t *iq = nullptr, *head = nullptr;
+    size_t small_d2h_bytes = 0;
 
     void release() {
         d_cand.release(); d_dead.release(); d_tile_off.release(); d_recs.release(); d_tiles.release();
@@ -465,6 +466,8 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
         CUDA_TRY(cudaMemcpyAsync(c.h_block_dead.p, c.d_block_dead.p, nblocks * sizeof(BlockDead), cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaEventRecord(c.ev_small, s));
+    c.small_d2h_bytes = sizeof(ScanCounters) + ntiles * sizeof(TileOut) +
+                        nblocks * (2 * sizeof(unsigned long long) + 2 * sizeof(double) + sizeof(BlockDead));
     return B200_OK;
 }
 
@@ -584,6 +587,8 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     }
     d->resolver->resolve(v, d->msgs, d->blocks);
     t.resolve_ms += (float) (now_ms() - t_res0);
+    t.d2h_bytes += c.small_d2h_bytes + (size_t) cnt.n_dead * sizeof(uint32_t) + (size_t) cnt.n_live * sizeof(LivePos) +
+                   (size_t) cnt.n_liverec * sizeof(LiveRec);
     t.n_candidates += cnt.n_cand;
     t.n_phase_records += cnt.n_rec;
     t.n_live += cnt.n_live;
@@ -672,6 +677,7 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
     }
     t.total_ms = (float) (now_ms() - t_start);
     t.scan_launches = launches;
+    t.chunks = (uint32_t) nchunks;
     d->timing = t;
     return B200_OK;
 }

@@ -268,3 +268,52 @@ def test_crc_batch_and_tables(nfix):
             if e is not None:
                 assert list(bits2[i]) == list(e["bit"])
     assert (err[:3000:3] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------
+# drop-in: the reference's own program on top of the shim
+# ------------------------------------------------------------------------------------------
+
+def test_reference_program_with_the_shim_prints_the_same_messages():
+    """oracle/_ref/readsb_b200 = readsb's main(), FIFO, CRC, field decoder and tracker objects linked
+    with readsb_protobuf_b200/shim/readsb_b200_shim.c + libreadsb_b200.so instead of convert.o,
+    demod_2400.o and sdr_ifile.o.  Its --raw --mlat output must equal the reference path's."""
+    import os
+    import subprocess
+    import tempfile
+    from readsb_protobuf_b200 import build
+
+    exe = build.ORACLE / "_ref" / "readsb_b200"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/readsb_b200 not built (needs /root/reference at build time)")
+    cfg = synth.SynthConfig(seed=91, nsamples=3_000_000, frames_per_s=3000, frac_biterror=0.2)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "uc8")
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "in.bin")
+        iq.tofile(path)
+        out = subprocess.run([str(exe), "--device-type", "ifile", "--ifile", path, "--preamble-threshold", "58",
+                              "--raw", "--mlat"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        stats = subprocess.run([str(exe), "--device-type", "ifile", "--ifile", path, "--preamble-threshold", "58",
+                                "--quiet", "--stats"], capture_output=True, text=True, timeout=300)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("@")]
+    expect = ["@%012X%s;" % (int(m["timestampMsg"]), bytes(m["msg"][: m["msgbits"] // 8]).hex()) for m in want.msgs]
+    assert len(expect) > 1000
+    assert lines == expect
+    assert "disagrees" not in out.stderr
+    # the --stats block readsb prints at exit (stats.c:80-125) carries the same demodulator counters
+    text = stats.stdout
+    st = want.stats
+    for line in (f"{int(st['samples_processed'])} samples processed",
+                 f"{int(st['demod_preambles'])} Mode-S message preambles received",
+                 f"{int(st['demod_rejected_bad'])} with bad message format or invalid CRC",
+                 f"{int(st['demod_rejected_unknown_icao'])} with unrecognized ICAO address",
+                 f"{int(st['demod_accepted'][0])} accepted with correct CRC",
+                 f"{int(st['demod_accepted'][1])} accepted with 1-bit error repaired",
+                 f"{int(st['messages_total'])} total usable messages"):
+        assert line in text, (line, text[:1500])
+    phase_rows = [" ".join(str(int(x)) for x in st["demod_preamblePhase"]), " ".join(str(int(x)) for x in st["demod_bestPhase"])]
+    squashed = " ".join(text.split())
+    for row in phase_rows:
+        assert row in squashed, (row, text[:1500])
