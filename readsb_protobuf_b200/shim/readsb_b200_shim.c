@@ -17,7 +17,8 @@
  *       raw magnitudes (other SDR front-ends, Mode A/C); forwards to b200_convert()
  *
  * The reference's fifo_enqueue() loses buffers when more than one is queued (it never advances
- * fifo_tail, fifo.c:192-197), so the reader hands blocks over one at a time (fifo_drain()).
+ * fifo_tail, fifo.c:192-197), so the reader hands blocks over one at a time and waits until
+ * demodulate2400() has consumed the block before queueing the next.
  */
 #include "readsb.h"
 
@@ -46,6 +47,9 @@ struct block_result {
     bool has_delta;
 };
 static struct block_result pending;
+static pthread_mutex_t pending_mutex = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t pending_cond = PTHREAD_COND_INITIALIZER;
+static bool pending_ready; /* set by the reader, cleared by demodulate2400 */
 
 void ifileInitConfig(void) {
     memset(&ifile, 0, sizeof (ifile));
@@ -186,8 +190,23 @@ void ifileRun(void) {
                 pending.delta.signal_power_sum -= before.signal_power_sum;
                 pending.delta.signal_power_count -= before.signal_power_count;
             }
+            pthread_mutex_lock(&pending_mutex);
+            pending_ready = true;
+            pthread_mutex_unlock(&pending_mutex);
             fifo_enqueue(outbuf);
-            fifo_drain(); /* one block in flight: see the header comment */
+            /* one block in flight: wait until demodulate2400() is done with it */
+            pthread_mutex_lock(&pending_mutex);
+            while (pending_ready && !Modes.exit) {
+                struct timespec deadline;
+                clock_gettime(CLOCK_REALTIME, &deadline);
+                deadline.tv_nsec += 100 * 1000 * 1000;
+                if (deadline.tv_nsec >= 1000000000) {
+                    deadline.tv_sec += 1;
+                    deadline.tv_nsec -= 1000000000;
+                }
+                pthread_cond_timedwait(&pending_cond, &pending_mutex, &deadline);
+            }
+            pthread_mutex_unlock(&pending_mutex);
             sampleCounter += n_k;
         }
         before = after;
@@ -257,6 +276,10 @@ void demodulate2400(struct mag_buf *mag) {
     }
     pending.nmsgs = 0;
     pending.has_delta = false;
+    pthread_mutex_lock(&pending_mutex);
+    pending_ready = false;
+    pthread_cond_signal(&pending_cond);
+    pthread_mutex_unlock(&pending_mutex);
 }
 
 void demodulate2400AC(struct mag_buf *mag) {
