@@ -28,7 +28,7 @@ constexpr int kScanThreads = kScanWarps * 32;
 constexpr int kRowWords = kLanePos + 4;     // 20
 constexpr int kRows = 64;                   // 2 chunks x 32 lanes
 constexpr int kWarpBuf = kRows * kRowWords; // u32 words per warp (5120 bytes)
-constexpr int kItemCap = 64;               // (position, phase) items a warp queues before slicing them
+constexpr int kItemCap = 96;               // (position, phase) items a warp queues before slicing them (>= 80: one lane's worst case)
 
 inline uint32_t tiles_for(uint64_t nsamples) {
     // every position < nsamples and every sample < nsamples must fall into a tile

@@ -403,12 +403,21 @@ __device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, in
         ns += __popc(sm);
     }
     __syncwarp();
-    for (int it = 0; it < nl; it += 4)
-        slice_pass(a, cx, cx.valid, it, nl);
-    for (int it = 0; it < ns; it += 4)
-        slice_pass(a, cx, cx.valid + (kItemCap - ns), it, ns);
+    // one call site (one copy of the unrolled slicer in the instruction cache): long passes, then short
+    const int npl = (nl + 3) >> 2, nps = (ns + 3) >> 2;
+    for (int pass = 0; pass < npl + nps; ++pass) {
+        const bool lp = pass < npl;
+        slice_pass(a, cx, lp ? cx.valid : cx.valid + (kItemCap - ns), lp ? 4 * pass : 4 * (pass - npl), lp ? nl : ns);
+    }
     __syncwarp();
     nitems = 0;
+}
+
+// debug tap (b200_debug_scan): the 5-bit try mask of every position of a lane's step
+__device__ __noinline__ void store_dbg_masks(uint8_t *dst, uint32_t b45, uint32_t b67, uint32_t b8, uint32_t vmask) {
+    for (int i = 0; i < kLanePos; ++i)
+        if ((vmask >> i) & 1u)
+            dst[i] = (uint8_t) ((((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u));
 }
 
 // uc8 table index with the shared-memory bank swizzle applied to both samples of a word:
@@ -694,11 +703,8 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                 }
             }
 
-            if (a.dbg_masks) {
-                for (int i = 0; i < kLanePos; ++i)
-                    if ((vmask >> i) & 1u)
-                        a.dbg_masks[lp0 + i] = (uint8_t) ((((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u));
-            }
+            if (a.dbg_masks)
+                store_dbg_masks(a.dbg_masks + lp0, b45, b67, b8, vmask);
 
             const uint32_t any = b45 | b67 | b8;
             if (!SLICE) {
@@ -710,7 +716,9 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                 cx.chunk_pos0 = pos0;
                 if (lanes) {
                     // candidates and (position, phase) items of the step, in position order: every lane
-                    // places its own through a warp prefix sum (candidates low half, items high half)
+                    // places its own through a warp prefix sum (candidates low half, items high half).
+                    // A lane's items (<= 80) always fit the queue; a step with more items than the queue
+                    // holds is taken in rounds of as many whole lanes as fit.
                     const uint32_t mine = (uint32_t) __popc(any) | ((uint32_t) (2 * __popc(b45) + 2 * __popc(b67) + __popc(b8)) << 16);
                     uint32_t inc = mine;
 #pragma unroll
@@ -719,59 +727,42 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                         if (lane >= o)
                             inc += up;
                     }
-                    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-                    const int tot_c = (int) (total & 0xffffu), tot_i = (int) (total >> 16);
-                    if (tot_i <= kItemCap) {
-                        uint32_t ci = cx.ncand + ((inc - mine) & 0xffffu);
-                        int ii = (int) ((inc - mine) >> 16);
-                        uint32_t u = any;
-                        while (u) {
-                            const int i = __ffs(u) - 1;
-                            u &= u - 1;
-                            const uint32_t tm = (((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u);
-                            const uint32_t pic = (uint32_t) (lane * kLanePos + i);
-                            if (ci < cx.cand_cap)
-                                cx.cand_out[ci] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
-                            ++ci;
-#pragma unroll
-                            for (int ph = 0; ph < 5; ++ph)
-                                if ((tm >> ph) & 1u)
-                                    cx.items[ii++] = (uint16_t) (pic | ((uint32_t) ph << 9));
-                        }
-                        cx.ncand += (uint32_t) tot_c;
-                        nitems = tot_i;
-                    } else {
-                        // a step with more items than the queue holds: lane by lane, flushing as needed
-                        while (lanes) {
-                            const int L = __ffs(lanes) - 1;
-                            lanes &= lanes - 1;
-                            const uint32_t a45 = __shfl_sync(0xffffffffu, b45, L);
-                            const uint32_t a67 = __shfl_sync(0xffffffffu, b67, L);
-                            const uint32_t a8 = __shfl_sync(0xffffffffu, b8, L);
-                            uint32_t u = a45 | a67 | a8;
+                    const uint32_t exc = inc - mine;
+                    const uint32_t cand_base = cx.ncand;
+                    cx.ncand += __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
+                    int first_lane = 0;      // lanes below were queued in earlier rounds
+                    uint32_t base_items = 0; // their items
+                    while (first_lane < 32) { // uniform
+                        const bool fits = lane >= first_lane && (inc >> 16) - base_items <= (uint32_t) kItemCap;
+                        const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> first_lane;
+                        const int nl_round = __ffs(~fm) - 1; // consecutive lanes from first_lane that fit (>= 1)
+                        const int end_lane = first_lane + (nl_round < 0 ? 32 - first_lane : nl_round);
+                        if (lane >= first_lane && lane < end_lane) {
+                            uint32_t ci = cand_base + (exc & 0xffffu);
+                            int ii = (int) ((exc >> 16) - base_items);
+                            uint32_t u = any;
                             while (u) {
                                 const int i = __ffs(u) - 1;
                                 u &= u - 1;
-                                const uint32_t tm = (((a45 >> i) & 1u) * 3u) | (((a67 >> i) & 1u) * 12u) | (((a8 >> i) & 1u) * 16u);
-                                const uint32_t pic = (uint32_t) (L * kLanePos + i);
-                                if (lane == 0) {
-                                    if (cx.ncand < cx.cand_cap)
-                                        cx.cand_out[cx.ncand] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
+                                const uint32_t tm = (((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u);
+                                const uint32_t pic = (uint32_t) (lane * kLanePos + i);
+                                if (ci < cx.cand_cap)
+                                    cx.cand_out[ci] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
+                                ++ci;
 #pragma unroll
-                                    for (int ph = 0; ph < 5; ++ph)
-                                        if ((tm >> ph) & 1u)
-                                            cx.items[nitems + __popc(tm & ((1u << ph) - 1u))] = (uint16_t) (pic | ((uint32_t) ph << 9));
-                                }
-                                ++cx.ncand;
-                                nitems += __popc(tm);
-                                if (nitems > kItemCap - 5)
-                                    process_items(a, cx, nitems);
+                                for (int ph = 0; ph < 5; ++ph)
+                                    if ((tm >> ph) & 1u)
+                                        cx.items[ii++] = (uint16_t) (pic | ((uint32_t) ph << 9));
                             }
                         }
+                        const uint32_t upto = __shfl_sync(0xffffffffu, inc, end_lane - 1) >> 16;
+                        nitems = (int) (upto - base_items);
+                        base_items = upto;
+                        first_lane = end_lane;
+                        if (nitems)
+                            process_items(a, cx, nitems);
                     }
                 }
-                if (nitems)
-                    process_items(a, cx, nitems);
             }
             __syncwarp();
         }
