@@ -413,6 +413,44 @@ __device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, in
     nitems = 0;
 }
 
+__device__ __noinline__ void flush_sums_u64(unsigned long long *dst, unsigned long long level, unsigned long long power) {
+    const unsigned long long l = warp_sum_u64(level), p = warp_sum_u64(power);
+    if ((threadIdx.x & 31) == 0 && (l | p)) {
+        atomicAdd(&dst[0], l);
+        atomicAdd(&dst[1], p);
+    }
+}
+
+__device__ __noinline__ void flush_sums_f64(double *dst, double level, double power) {
+    const double l = warp_sum_f64(level), p = warp_sum_f64(power);
+    if ((threadIdx.x & 31) == 0 && (l != 0 || p != 0)) {
+        atomicAdd(&dst[0], l);
+        atomicAdd(&dst[1], p);
+    }
+}
+
+// a mag_buf boundary inside a chunk: every 16-byte unit lies on one side of it and adds its sums itself
+__device__ __noinline__ void unit_sums_u64(unsigned long long *block_sums, long long kb, uint4 lo, uint4 hi) {
+    const uint32_t m[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    unsigned long long cl = 0, cp = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        cl += m[j];
+        cp += (unsigned long long) m[j] * m[j];
+    }
+    if (cl | cp) {
+        atomicAdd(&block_sums[2 * kb], cl);
+        atomicAdd(&block_sums[2 * kb + 1], cp);
+    }
+}
+
+__device__ __noinline__ void unit_sums_f64(double *block_sums, long long kb, float4 mag, float4 magsq) {
+    const double fl = (double) mag.x + (double) mag.y + (double) mag.z + (double) mag.w;
+    const double fp = (double) magsq.x + (double) magsq.y + (double) magsq.z + (double) magsq.w;
+    atomicAdd(&block_sums[2 * kb], fl);
+    atomicAdd(&block_sums[2 * kb + 1], fp);
+}
+
 // debug tap (b200_debug_scan): the 5-bit try mask of every position of a lane's step
 __device__ __noinline__ void store_dbg_masks(uint8_t *dst, uint32_t b45, uint32_t b67, uint32_t b8, uint32_t vmask) {
     for (int i = 0; i < kLanePos; ++i)
@@ -460,20 +498,11 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
     unsigned long long sum_level = 0, sum_power = 0;
     double fsum_level = 0, fsum_power = 0;
     long long blk = (c0 > 0 ? c0 : 0) / B, next_bound = (blk + 1) * B;
-    auto flush_sums = [&]() {
-        if (FORMAT == 0) {
-            const unsigned long long l = warp_sum_u64(sum_level), p = warp_sum_u64(sum_power);
-            if (lane == 0 && (l | p)) {
-                atomicAdd(&a.block_sums_u64[2 * blk], l);
-                atomicAdd(&a.block_sums_u64[2 * blk + 1], p);
-            }
-        } else {
-            const double l = warp_sum_f64(fsum_level), p = warp_sum_f64(fsum_power);
-            if (lane == 0 && (l != 0 || p != 0)) {
-                atomicAdd(&a.block_sums_f64[2 * blk], l);
-                atomicAdd(&a.block_sums_f64[2 * blk + 1], p);
-            }
-        }
+    auto flush_sums = [&]() { // rare (once per tile and per mag_buf boundary): kept out of the hot code
+        if (FORMAT == 0)
+            flush_sums_u64(a.block_sums_u64 + 2 * blk, sum_level, sum_power);
+        else
+            flush_sums_f64(a.block_sums_f64 + 2 * blk, fsum_level, fsum_power);
         sum_level = sum_power = 0;
         fsum_level = fsum_power = 0;
     };
@@ -606,27 +635,12 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                         const long long us = ls + u * US;
                         if (us >= 0 && us < n) {
                             const long long kb = us / B;
-                            if (FORMAT == 0) {
-                                unsigned long long cl = 0, cp = 0;
-#pragma unroll
-                                for (int j = 0; j < US; ++j) {
-                                    cl += m[u * US + j];
-                                    cp += (unsigned long long) m[u * US + j] * m[u * US + j];
-                                }
-                                if (cl | cp) {
-                                    atomicAdd(&a.block_sums_u64[2 * kb], cl);
-                                    atomicAdd(&a.block_sums_u64[2 * kb + 1], cp);
-                                }
-                            } else {
-                                double fl = 0, fp = 0;
-#pragma unroll
-                                for (int j = 0; j < US; ++j) {
-                                    fl += (double) fmag[u * US + j];
-                                    fp += (double) fmagsq[u * US + j];
-                                }
-                                atomicAdd(&a.block_sums_f64[2 * kb], fl);
-                                atomicAdd(&a.block_sums_f64[2 * kb + 1], fp);
-                            }
+                            if (FORMAT == 0)
+                                unit_sums_u64(a.block_sums_u64, kb, make_uint4(m[u * US], m[u * US + 1], m[u * US + 2], m[u * US + 3]),
+                                              make_uint4(m[u * US + 4 % US], m[u * US + 5 % US], m[u * US + 6 % US], m[u * US + 7 % US]));
+                            else
+                                unit_sums_f64(a.block_sums_f64, kb, make_float4(fmag[u * US], fmag[u * US + 1], fmag[u * US + 2], fmag[u * US + 3]),
+                                              make_float4(fmagsq[u * US], fmagsq[u * US + 1], fmagsq[u * US + 2], fmagsq[u * US + 3]));
                         }
                     }
                     blk = own_hi / B;
