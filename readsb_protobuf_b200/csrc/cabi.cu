@@ -304,8 +304,18 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
 
     d->h_lut.resize(65536);
     build_uc8_table(d->h_lut.data());
-    CUDA_TRY(d->d_lut.ensure(65536));
-    CUDA_TRY(cudaMemcpy(d->d_lut.p, d->h_lut.data(), 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    // second copy in the bank-swizzled shared-memory layout of K1 (32-bit word j of row Q at j ^ (Q & 31)),
+    // so that every CTA stages the table with straight 16-byte copies
+    {
+        std::vector<uint32_t> both(65536);
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(d->h_lut.data());
+        for (uint32_t i = 0; i < 32768; ++i) {
+            both[i] = words[i];
+            both[32768 + (i ^ ((i >> 7) & 31u))] = words[i];
+        }
+        CUDA_TRY(d->d_lut.ensure(2 * 65536));
+        CUDA_TRY(cudaMemcpy(d->d_lut.p, both.data(), 2 * 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
 
     const auto &ts = d->crc->short_table();
     const auto &tl = d->crc->long_table();
@@ -363,6 +373,7 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     a.block_samples = d->cfg.block_samples;
     a.ntiles = tiles_for(nsamples);
     a.lut = d->d_lut.p;
+    a.lut_swz = d->d_lut.p + 65536;
     a.tab_short = d->d_tab_short.p;
     a.tab_long = d->d_tab_long.p;
     a.n_short = (int32_t) d->crc->short_table().size();

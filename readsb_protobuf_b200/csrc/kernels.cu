@@ -270,8 +270,12 @@ struct Fmt<2> { // sc16q11
 };
 
 constexpr size_t kSmemLut = 65536 * sizeof(uint16_t);
-constexpr size_t kSmemWarp = kWarpBuf * sizeof(uint32_t) + 3 * kItemCap * sizeof(uint16_t);
-constexpr size_t kSmemTail = 112 * sizeof(uint32_t) + 5 * sizeof(int4);
+constexpr int kBatch = 16;     // frames sliced per batch (their message words live in shared memory)
+constexpr int kMsgWords = 5;   // 4 message words + the CRC syndrome
+constexpr int kGroupsLong = 23, kGroupsShort = 12; // 5-bit groups of a 112 / 56 bit frame
+constexpr size_t kSmemWarp = kWarpBuf * sizeof(uint32_t) + 2 * kItemCap * sizeof(uint16_t) + kBatch * kMsgWords * sizeof(uint32_t);
+// CTA-wide tables: group syndromes [23 + 12][32], slicer taps [5 phases][5 bits] (int4 taps + sample offset)
+constexpr size_t kSmemTail = (kGroupsLong + kGroupsShort) * 32 * sizeof(uint32_t) + 25 * sizeof(int4) + 25 * sizeof(int);
 
 size_t scan_smem_bytes(uint32_t format) {
     return (format == 0 ? kSmemLut : 0) + kScanWarps * kSmemWarp + kSmemTail;
@@ -300,24 +304,14 @@ __device__ __forceinline__ uint4 load_unit(const ScanArgs &a, long long s, int &
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// One PPM bit decision on the warp buffer (u32 magnitudes, padded rows); see slice_bit() for the
-// closed form.  x = window start of the frame as a sample offset from the chunk's first row.
-__device__ __forceinline__ bool slice_bit_u32(const uint32_t *buf, int row0, int x, int t, const int4 *coef) {
-    const int s = (t * 52429) >> 18; // t / 5 for 0 <= t < 43690
-    const int r = t - 5 * s;
-    const int4 c = coef[r];
-    const int x0 = x + 19 + s;
-    const uint32_t *p = buf + ((row0 + (x0 >> 4)) & (kRows - 1)) * kRowWords + (x0 & 15);
-    const int v = c.x * (int) p[0] + c.y * (int) p[1] + c.z * (int) p[2] + c.w * (int) p[3];
-    return v > 0;
-}
-
 struct WarpCtx {
     const uint32_t *buf;   // the warp's magnitude rows
     int row0;              // first row of the chunk being scanned
-    const uint32_t *syn;   // 112 single-bit syndromes (shared)
-    const int4 *coef;      // 5 correlators (shared)
+    const uint32_t *gsyn;  // group syndromes (shared): [23 long groups + 12 short groups][32]
+    const int4 *taps;      // [phase - 4][bit of the group]: correlator taps (shared)
+    const int *soff;       // [phase - 4][bit of the group]: first sample of the bit, relative to the group
     uint16_t *items, *valid;
+    uint32_t *msg;         // [kBatch][kMsgWords]
     long long chunk_pos0;  // scan position of window start 0 of the chunk
     // tile output cursors
     uint32_t *cand_out;
@@ -325,76 +319,51 @@ struct WarpCtx {
     uint32_t cand_cap, rec_cap, ncand, nrec;
 };
 
-// stage 2: up to 4 frames per pass, 8 lanes per frame, lane l decides bit l of every byte.
-// list entries: position in chunk [8:0] | phase - 4 [11:9] | long frame [12]
-__device__ __forceinline__ void slice_pass(const ScanArgs &a, WarpCtx &cx, const uint16_t *list, int first, int count) {
-    const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
-    const bool active = first + g < count;
-    const uint32_t item = list[active ? first + g : first];
-    const uint32_t pic = item & 511u; // position in chunk
-    const int ph = (int) ((item >> 9) & 7u) + 4;
-    const bool is_long = (item >> 12) & 1u;
-    const int off = is_long ? 0 : 56; // crc.c:143: short frames use the tail of the syndrome list
-    const bool any_long = __any_sync(0xffffffffu, active && is_long);
-    uint32_t w[4] = {0, 0, 0, 0};
-    uint32_t x = 0;
-    int t = ph + 12 * l;
+// Five consecutive PPM bit decisions (demod_2400.c:73-177 in closed form).  Frame bit b of a
+// candidate tried at phase p sits t = p + 12 b fifths of a sample after m[19]; five bits later the
+// pattern repeats 12 samples on, so group k of a frame (bits 5k .. 5k+4) reads the 15 samples from
+// m[19 + 12k] with offsets and correlators that depend on the phase only.  x = window start of the
+// frame in the chunk, phi = phase - 4.  Returns the five decisions, bit c = frame bit 5k + c.
+// A row of the warp buffer holds 16 magnitudes and a copy of the next row's first 4, so the four
+// samples of one bit never straddle a row: they start in the group's first row or in the next one.
+__device__ __forceinline__ uint32_t slice_group(const WarpCtx &cx, int x, int phi, int k) {
+    const int y = x + 19 + 12 * k;
+    const int row = (cx.row0 + (y >> 4)) & (kRows - 1);
+    const int col0 = y & 15;
+    const uint32_t *r0 = cx.buf + row * kRowWords;
+    const uint32_t *r1 = cx.buf + ((row + 1) & (kRows - 1)) * kRowWords - 16;
+    const int4 *tp = cx.taps + phi * 5;
+    const int *so = cx.soff + phi * 5;
+    uint32_t v5 = 0;
 #pragma unroll
-    for (int k = 0; k < 14; ++k, t += 96) {
-        if (k == 7 && !any_long)
-            break;
-        const bool bit = slice_bit_u32(cx.buf, cx.row0, (int) pic, t, cx.coef) && (is_long || k < 7);
-        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-        w[k >> 2] |= ((bal >> (8 * g)) & 0xffu) << (8 * (k & 3)); // frame bit b -> bit b%32 of w[b/32]
-        if (bit)
-            x ^= cx.syn[8 * k + l + off];
+    for (int c = 0; c < 5; ++c) {
+        const int4 t = tp[c];
+        const int col = col0 + so[c];
+        const uint32_t *p = (col <= 16 ? r0 : r1) + col;
+        const int v = t.x * (int) p[0] + t.y * (int) p[1] + t.z * (int) p[2] + t.w * (int) p[3];
+        v5 |= (v > 0) ? (1u << c) : 0u;
     }
-    x ^= __shfl_xor_sync(0xffffffffu, x, 1);
-    x ^= __shfl_xor_sync(0xffffffffu, x, 2);
-    x ^= __shfl_xor_sync(0xffffffffu, x, 4);
-    const uint32_t syn = x;
-    const uint32_t head32 = __brev(w[0]); // frame bits 0..31, MSB first
-    const uint32_t df = head32 >> 27, aa = head32 & 0xffffffu;
-    const FrameClass fc = classify_frame(df, aa, syn, (w[0] | w[1] | w[2] | w[3]) == 0, a.tab_short, a.n_short, a.tab_long, a.n_long);
-    const bool has = active && l == 0 && fc.kind != kKindBad;
-    const uint32_t mask = __ballot_sync(0xffffffffu, has);
-    if (has) {
-        const uint32_t slot = cx.nrec + __popc(mask & ((1u << lane) - 1u));
-        if (slot < cx.rec_cap) {
-            PhaseRec pr;
-            pr.pos = (uint32_t) (cx.chunk_pos0 + pic);
-            pr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
-            pr.w1 = fc.key | ((uint32_t) ph << 24);
-            pr.pad = 0;
-            *reinterpret_cast<uint4 *>(&cx.rec_out[slot]) = *reinterpret_cast<const uint4 *>(&pr);
-        }
-        // mode_s.c:717-726: only a clean DF17, or a clean DF11 with IID 0, can ever be added to the
-        // ICAO filter; remember every such address of the stream
-        if (syn == 0 && (df == 17 || df == 11))
-            atomicOr(&a.addr_bitmap[aa >> 5], 1u << (aa & 31u));
-    }
-    cx.nrec += __popc(mask);
+    return v5;
 }
 
-// stage 1 + 2 for the queued items of the chunk
+// Slice the queued (position, phase) items of the chunk.
+//   1. one lane per item slices group 0 = the DF field -> frame length (demod_2400.c:188-205);
+//      long frames are listed from the front of `valid`, short ones from its back
+//   2. in batches of kBatch frames: one lane per (frame, group) slices five bits, ORs them into the
+//      frame's message words and XORs the group's CRC contribution (crc.c:59-64: the syndrome is
+//      linear in the bits) into its syndrome, both in shared memory
+//   3. one lane per frame classifies it and appends the class record
 __device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, int &nitems) {
     const int lane = threadIdx.x & 31;
+    const uint32_t below = (1u << lane) - 1u;
     __syncwarp();
-    // stage 1: one lane per item slices the five DF bits -> frame length (demod_2400.c:188-205);
-    // long frames are queued from the front of the list, short ones from its back, so that a pass
-    // of four never mixes lengths
     int nl = 0, ns = 0;
     for (int it = 0; it < nitems; it += 32) {
         const bool active = it + lane < nitems;
         const uint32_t item = cx.items[active ? it + lane : it];
-        const int ph = (int) ((item >> 9) & 7u) + 4;
-        uint32_t df = 0;
-#pragma unroll
-        for (int b = 0; b < 5; ++b)
-            df = (df << 1) | (slice_bit_u32(cx.buf, cx.row0, (int) (item & 511u), ph + 12 * b, cx.coef) ? 1u : 0u);
-        const int nb = active ? frame_bytes_for_df(df) : 0;
+        const uint32_t v5 = slice_group(cx, (int) (item & 511u), (int) ((item >> 9) & 7u), 0);
+        const int nb = active ? frame_bytes_for_df(__brev(v5) >> 27) : 0;
         const uint32_t lm = __ballot_sync(0xffffffffu, nb == 14), sm = __ballot_sync(0xffffffffu, nb == 7);
-        const uint32_t below = (1u << lane) - 1u;
         if (nb == 14)
             cx.valid[nl + __popc(lm & below)] = (uint16_t) (item | (1u << 12));
         else if (nb == 7)
@@ -403,13 +372,81 @@ __device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, in
         ns += __popc(sm);
     }
     __syncwarp();
-    // one call site (one copy of the unrolled slicer in the instruction cache): long passes, then short
-    const int npl = (nl + 3) >> 2, nps = (ns + 3) >> 2;
-    for (int pass = 0; pass < npl + nps; ++pass) {
-        const bool lp = pass < npl;
-        slice_pass(a, cx, lp ? cx.valid : cx.valid + (kItemCap - ns), lp ? 4 * pass : 4 * (pass - npl), lp ? nl : ns);
+    const int nframes = nl + ns;
+    for (int q0 = 0; q0 < nframes; q0 += kBatch) { // uniform
+        const int nb = min(kBatch, nframes - q0);
+        const int nlb = max(0, min(nb, nl - q0)); // long frames of the batch come first
+        const int ntasks = kGroupsLong * nlb + kGroupsShort * (nb - nlb);
+        for (int i = lane; i < nb * kMsgWords; i += 32)
+            cx.msg[i] = 0;
+        __syncwarp();
+        for (int t0 = 0; t0 < ntasks; t0 += 32) {
+            const int t = t0 + lane;
+            if (t < ntasks) {
+                int bi, k;
+                const int ts = t - kGroupsLong * nlb;
+                if (ts < 0) {
+                    bi = (t * 2850) >> 16; // t / 23 for t < 23 * 16
+                    k = t - kGroupsLong * bi;
+                } else {
+                    const int sb = (ts * 5462) >> 16; // ts / 12
+                    bi = nlb + sb;
+                    k = ts - kGroupsShort * sb;
+                }
+                const int q = q0 + bi;
+                const uint32_t item = (q < nl) ? cx.valid[q] : cx.valid[kItemCap - 1 - (q - nl)];
+                const bool is_long = ts < 0;
+                uint32_t v5 = slice_group(cx, (int) (item & 511u), (int) ((item >> 9) & 7u), k);
+                const int left = (is_long ? 112 : 56) - 5 * k; // the last group of a frame is partial
+                if (left < 5)
+                    v5 &= (1u << left) - 1u;
+                uint32_t *mw = cx.msg + bi * kMsgWords;
+                const int b0 = 5 * k, wi = b0 >> 5, sh = b0 & 31;
+                if (v5) {
+                    atomicOr(&mw[wi], v5 << sh); // frame bit b -> bit b % 32 of word b / 32
+                    if (sh > 27 && (v5 >> (32 - sh)))
+                        atomicOr(&mw[wi + 1], v5 >> (32 - sh));
+                    atomicXor(&mw[4], cx.gsyn[((is_long ? 0 : kGroupsLong) + k) * 32 + v5]);
+                }
+            }
+        }
+        __syncwarp();
+        // one lane per frame: class record
+        const bool active = lane < nb;
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, syn = 0, item = 0;
+        if (active) {
+            const uint32_t *mw = cx.msg + lane * kMsgWords;
+            w0 = mw[0], w1 = mw[1], w2 = mw[2], w3 = mw[3], syn = mw[4];
+            const int q = q0 + lane;
+            item = (q < nl) ? cx.valid[q] : cx.valid[kItemCap - 1 - (q - nl)];
+        }
+        const uint32_t head32 = __brev(w0); // frame bits 0..31, MSB first
+        const uint32_t df = head32 >> 27, aa = head32 & 0xffffffu;
+        FrameClass fc;
+        fc.kind = kKindBad;
+        if (active)
+            fc = classify_frame(df, aa, syn, (w0 | w1 | w2 | w3) == 0, a.tab_short, a.n_short, a.tab_long, a.n_long);
+        const bool has = active && fc.kind != kKindBad;
+        const uint32_t mask = __ballot_sync(0xffffffffu, has);
+        if (has) {
+            const uint32_t slot = cx.nrec + __popc(mask & below);
+            const uint32_t ph = ((item >> 9) & 7u) + 4u;
+            if (slot < cx.rec_cap) {
+                PhaseRec pr;
+                pr.pos = (uint32_t) (cx.chunk_pos0 + (item & 511u));
+                pr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
+                pr.w1 = fc.key | (ph << 24);
+                pr.pad = 0;
+                *reinterpret_cast<uint4 *>(&cx.rec_out[slot]) = *reinterpret_cast<const uint4 *>(&pr);
+            }
+            // mode_s.c:717-726: only a clean DF17, or a clean DF11 with IID 0, can ever be added to the
+            // ICAO filter; remember every such address of the stream
+            if (syn == 0 && (df == 17 || df == 11))
+                atomicOr(&a.addr_bitmap[aa >> 5], 1u << (aa & 31u));
+        }
+        cx.nrec += __popc(mask);
+        __syncwarp();
     }
-    __syncwarp();
     nitems = 0;
 }
 
@@ -682,34 +719,42 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                         w[4 * q + 3] = v.w;
                     }
                 }
-                // shared partial sums of the three correlators (demod_2400.c:298-330):
-                //   Q[x] = m[x] + m[x+3], D[x] = m[x] - m[x+1], T[x] = m[x] + m[x+1] + m[x+2]
-                int Q[kLanePos + 9], D[kLanePos + 11], T[kLanePos];
+                // The three correlators (demod_2400.c:298-330) as sign tests.  With
+                //   Q[x] = m[x] + m[x+3], D[x] = m[x] - m[x+1], T = m[16] + m[17] + m[18]
+                // base_noise = Q[5] + T and common3456 = Q[1] + Q[9] - D[2]; since
+                // X >= (N >> 5)  <=>  32 X + 31 - N >= 0 for integers (N >= 0), every test is the sign of
+                //   E0  = 32 (Q[1] + Q[9] - D[2]) + 31 - thr * base_noise
+                //   E45 = E0 - 32 D[10]      E67 = E0 + 32 D[10]      E8 = E67 + 96 D[2] - 32 m[9]
+                // (|32 X| < 2^24 and N < 2^28: no overflow).  The pre-check of demod_2400.c:276 is the sign
+                // of (m[7]-m[1]) & (m[14]-m[12]) & (m[15]-m[12]).  Signs are shifted into per-lane masks
+                // with one funnel shift each; positions run downwards so that bit i is position i.
+                int Q[kLanePos + 9], D[kLanePos + 11];
 #pragma unroll
                 for (int x2 = 1; x2 < kLanePos + 9; ++x2)
                     Q[x2] = (int) (w[x2] + w[x2 + 3]);
 #pragma unroll
                 for (int x2 = 2; x2 < kLanePos + 11; ++x2)
                     D[x2] = (int) w[x2] - (int) w[x2 + 1];
+                uint32_t s45 = 0, s67 = 0, s8 = 0, pm = 0;
+                const int nthr = -thr;
 #pragma unroll
-                for (int i = 0; i < kLanePos; ++i)
-                    T[i] = (int) (w[i + 16] + w[i + 17] + w[i + 18]);
-#pragma unroll
-                for (int i = 0; i < kLanePos; ++i) {
-                    // demod_2400.c:276
-                    const bool pre_ok = w[i + 1] > w[i + 7] && w[i + 12] > w[i + 14] && w[i + 12] > w[i + 15];
-                    // demod_2400.c:281-292: base_noise = pa[5] + pa[8] + pa[16] + pa[17] + pa[18]
-                    const int ref_level = ((Q[i + 5] + T[i]) * thr) >> 5;
-                    // common3456 = pa[1] + pa[4] - (pa[2] - pa[3]) + pa[9] + pa[12]
-                    const int v = Q[i + 1] - D[i + 2] + Q[i + 9] - ref_level;
-                    const int d10 = D[i + 10];
-                    const bool t45 = v >= d10;                                  // :306 common3456 - diff_10_11 >= ref
-                    const bool t67 = v + d10 >= 0;                              // :316 common3456 + diff_10_11 >= ref
-                    const bool t8 = v + d10 + 3 * D[i + 2] - (int) w[i + 9] >= 0; // :327 sum_1_4 + 2 diff_2_3 + diff_10_11 + pa[12] >= ref
-                    b45 |= (pre_ok && t45) ? (1u << i) : 0u;
-                    b67 |= (pre_ok && t67) ? (1u << i) : 0u;
-                    b8 |= (pre_ok && t8) ? (1u << i) : 0u;
+                for (int i = kLanePos - 1; i >= 0; --i) {
+                    const int T = (int) (w[i + 16] + w[i + 17] + w[i + 18]);
+                    const int c = Q[i + 1] + Q[i + 9] - D[i + 2];
+                    const int bn = Q[i + 5] + T;
+                    const int E0 = nthr * bn + (c * 32 + 31);
+                    const int E45 = D[i + 10] * -32 + E0;
+                    const int E67 = D[i + 10] * 32 + E0;
+                    const int E8 = (int) w[i + 9] * -32 + (D[i + 2] * 96 + E67);
+                    const int g = ((int) w[i + 7] - (int) w[i + 1]) & ((int) w[i + 14] - (int) w[i + 12]) & ((int) w[i + 15] - (int) w[i + 12]);
+                    s45 = __funnelshift_l((uint32_t) E45, s45, 1);
+                    s67 = __funnelshift_l((uint32_t) E67, s67, 1);
+                    s8 = __funnelshift_l((uint32_t) E8, s8, 1);
+                    pm = __funnelshift_l((uint32_t) g, pm, 1);
                 }
+                b45 = pm & ~s45;
+                b67 = pm & ~s67;
+                b8 = pm & ~s8;
                 if (EDGE) {
                     b45 &= vmask;
                     b67 &= vmask;
@@ -821,33 +866,58 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         sp += kSmemLut;
     uint32_t *s_buf = reinterpret_cast<uint32_t *>(sp + (size_t) warp * kWarpBuf * sizeof(uint32_t));
     sp += (size_t) kScanWarps * kWarpBuf * sizeof(uint32_t);
-    uint16_t *s_lists = reinterpret_cast<uint16_t *>(sp) + (size_t) warp * 3 * kItemCap;
-    sp += (size_t) kScanWarps * 3 * kItemCap * sizeof(uint16_t);
-    uint32_t *s_syn = reinterpret_cast<uint32_t *>(sp);
-    sp += 112 * sizeof(uint32_t);
-    int4 *s_coef = reinterpret_cast<int4 *>(sp);
+    uint16_t *s_lists = reinterpret_cast<uint16_t *>(sp) + (size_t) warp * 2 * kItemCap;
+    sp += (size_t) kScanWarps * 2 * kItemCap * sizeof(uint16_t);
+    uint32_t *s_msg = reinterpret_cast<uint32_t *>(sp) + (size_t) warp * kBatch * kMsgWords;
+    sp += (size_t) kScanWarps * kBatch * kMsgWords * sizeof(uint32_t);
+    uint32_t *s_gsyn = reinterpret_cast<uint32_t *>(sp);
+    sp += (kGroupsLong + kGroupsShort) * 32 * sizeof(uint32_t);
+    int4 *s_taps = reinterpret_cast<int4 *>(sp);
+    sp += 25 * sizeof(int4);
+    int *s_soff = reinterpret_cast<int *>(sp);
 
-    // one-time staging of the tables (the only block-wide barrier of the kernel); the magnitude
-    // table is stored bank-swizzled: 32-bit word j of row Q goes to word j ^ (Q & 31)
+    // one-time staging of the tables (the only block-wide barrier of the kernel).  The magnitude
+    // table arrives pre-swizzled (32-bit word j of row Q at word j ^ (Q & 31)): all of a thread's
+    // 16-byte loads are in flight at once, one round trip to L2 per CTA.
     if (FORMAT == 0) {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.lut);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(smem_raw);
-        for (int i = tid; i < 65536 / 2; i += kScanThreads) {
-            const int row = i >> 7;
-            dst[i ^ (row & 31)] = __ldg(src + i);
-        }
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.lut_swz);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+        constexpr int kPer = (int) (kSmemLut / 16) / kScanThreads; // 16
+        uint4 v[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q)
+            v[q] = __ldg(src + q * kScanThreads + tid);
+#pragma unroll
+        for (int q = 0; q < kPer; ++q)
+            dst[q * kScanThreads + tid] = v[q];
     }
-    if (tid < 112)
-        s_syn[tid] = c_bit_syndrome[tid];
-    if (tid < 5)
-        s_coef[tid] = make_int4(c_slice_coef[tid][0], c_slice_coef[tid][1], c_slice_coef[tid][2], c_slice_coef[tid][3]);
+    // group syndromes: row g < 23 = bits 5g .. 5g+4 of a long frame, row 23 + g = of a short frame
+    // (crc.c:143: a short frame uses the tail of the 112-entry single-bit syndrome list)
+    for (int i = tid; i < (kGroupsLong + kGroupsShort) * 32; i += kScanThreads) {
+        const int g = i >> 5, v = i & 31;
+        const bool is_long = g < kGroupsLong;
+        const int b0 = 5 * (is_long ? g : g - kGroupsLong), nbits = is_long ? 112 : 56;
+        uint32_t x = 0;
+        for (int c = 0; c < 5; ++c)
+            if (((v >> c) & 1) && b0 + c < nbits)
+                x ^= c_bit_syndrome[b0 + c + (112 - nbits)];
+        s_gsyn[i] = x;
+    }
+    if (tid < 25) { // bit c of a group at phase p: t = p + 12 c fifths, sample t / 5, correlator t % 5
+        const int t = (tid / 5 + 4) + 12 * (tid % 5);
+        const int r = t % 5;
+        s_taps[tid] = make_int4(c_slice_coef[r][0], c_slice_coef[r][1], c_slice_coef[r][2], c_slice_coef[r][3]);
+        s_soff[tid] = t / 5;
+    }
     __syncthreads();
 
     WarpCtx cx;
-    cx.syn = s_syn;
-    cx.coef = s_coef;
+    cx.gsyn = s_gsyn;
+    cx.taps = s_taps;
+    cx.soff = s_soff;
     cx.items = s_lists;
     cx.valid = s_lists + kItemCap;
+    cx.msg = s_msg;
 
     const long long n = (long long) a.nsamples;
     for (;;) {

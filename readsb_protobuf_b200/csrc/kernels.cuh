@@ -20,6 +20,7 @@ struct ScanArgs {
     uint32_t ntiles;
     // tables
     const uint16_t *lut;  // uc8 magnitude table (65536 entries)
+    const uint16_t *lut_swz; // the same table in K1's bank-swizzled shared-memory layout
     const ErrorInfo *tab_short;
     const ErrorInfo *tab_long;
     int32_t n_short, n_long;
