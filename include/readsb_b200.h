@@ -105,7 +105,7 @@ typedef struct b200_block_info {
 /* Device-side timing of the last process call, CUDA events on the library's stream (ms). */
 typedef struct b200_timing {
     float h2d_ms;      /* host -> device copy of the span (0 for device-resident input) */
-    float scan_ms;     /* K1: magnitude + preamble scan + slice + CRC */
+    float scan_ms;     /* K1a: magnitude + preamble scan (+ candidate list, magnitudes for K1b) */
     float classify_ms; /* K2: address-set test, re-slice and signal power of survivors */
     float d2h_ms;      /* survivors and counters back to the host */
     float resolve_ms;  /* host: order-dependent resolve (wall clock) */
@@ -116,6 +116,8 @@ typedef struct b200_timing {
     uint32_t scan_launches;  /* kernels launched by the call */
     uint32_t chunks;         /* pipeline chunks the span was cut into */
     uint64_t d2h_bytes;      /* bytes copied device -> host by the call (counters, lists, survivors) */
+    float slice_ms;          /* K1b: PPM slice + CRC class of every (candidate, phase) */
+    uint32_t reserved;
 } b200_timing;
 
 /* ---- lifetime ---- */
@@ -153,8 +155,10 @@ int b200_demod_get_timing(const b200_demod *d, b200_timing *out);
 
 /* ---- kernel-level entry points (measurement and unit parity; device pointers) ---- */
 
-/* Only K1 over a device-resident span, no host work and no result download: the kernel the
- * roofline is quoted on.  mode 0 = magnitude + preamble scan only, 1 = + slice + CRC.
+/* Only K1 over a device-resident span, no host work and no result download: the kernels the
+ * roofline is quoted on.  mode 0 = magnitude + preamble scan only (candidates counted), 1 = K1a as
+ * the pipeline runs it (+ candidate list + u16 magnitudes for K1b), 2 = K1a followed by K1b
+ * (slice + CRC class of every candidate phase).
  * Returns the kernel's duration in *ms_out (CUDA events on `cuda_stream`). */
 int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsamples, int mode,
                      void *cuda_stream, float *ms_out, uint64_t *n_candidates_out);

@@ -61,6 +61,7 @@ class Timing(ctypes.Structure):
         ("d2h_ms", ctypes.c_float), ("resolve_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
         ("n_candidates", ctypes.c_uint64), ("n_phase_records", ctypes.c_uint64), ("n_live", ctypes.c_uint64),
         ("scan_launches", ctypes.c_uint32), ("chunks", ctypes.c_uint32), ("d2h_bytes", ctypes.c_uint64),
+        ("slice_ms", ctypes.c_float), ("reserved", ctypes.c_uint32),
     ]
 
     def as_dict(self):

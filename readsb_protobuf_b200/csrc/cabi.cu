@@ -113,6 +113,8 @@ const uint64_t kChunkTarget = 32ull << 20;
 // everything one in-flight chunk owns
 struct ChunkSet {
     DevBuf<uint32_t> d_cand, d_dead, d_tile_off;
+    DevBuf<uint16_t> d_magbuf; // K1a's magnitudes of the chunk
+    DevBuf<uint16_t> d_step_off;
     DevBuf<PhaseRec> d_recs;
     DevBuf<TileDesc> d_tiles;
     DevBuf<TileOut> d_tiles_out;
@@ -130,7 +132,7 @@ struct ChunkSet {
     PinnedBuf<unsigned long long> h_sums_u64;
     PinnedBuf<double> h_sums_f64;
     PinnedBuf<BlockDead> h_block_dead;
-    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr;
 
     // what is in flight
     uint64_t start = 0, nsamples = 0;
@@ -140,12 +142,12 @@ struct ChunkSet {
     size_t small_d2h_bytes = 0;
 
     void release() {
-        d_cand.release(); d_dead.release(); d_tile_off.release(); d_recs.release(); d_tiles.release();
+        d_cand.release(); d_dead.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
         d_tiles_out.release(); d_live.release(); d_liverecs.release(); d_counters.release();
         d_sums_u64.release(); d_sums_f64.release(); d_block_dead.release();
         h_counters.release(); h_tiles_out.release(); h_dead.release(); h_live.release(); h_liverecs.release();
         h_sums_u64.release(); h_sums_f64.release(); h_block_dead.release();
-        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k2, &ev_small, &ev_lists})
+        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists})
             if (*e) {
                 cudaEventDestroy(*e);
                 *e = nullptr;
@@ -159,7 +161,7 @@ struct b200_demod {
     b200_demod_config cfg;
     int bytes_per_sample = 2;
     int sm_count = 0;
-    int scan_grid = 0;
+    int scan_grid = 0, slice_grid = 0;
     std::unique_ptr<CrcTables> crc;
     std::unique_ptr<Resolver> resolver;
 
@@ -230,6 +232,8 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
     CUDA_TRY(c.d_live.ensure(live_cap));
     CUDA_TRY(c.d_liverecs.ensure(liverec_cap));
     CUDA_TRY(c.d_tiles.ensure(ntiles + 1));
+    CUDA_TRY(c.d_magbuf.ensure(ntiles * (size_t) kTile + kMagSlack));
+    CUDA_TRY(c.d_step_off.ensure((ntiles + 1) * (size_t) kScanSteps));
     CUDA_TRY(c.d_tiles_out.ensure(ntiles + 1));
     CUDA_TRY(c.d_counters.ensure(1));
     CUDA_TRY(c.d_sums_u64.ensure(2 * nblocks));
@@ -243,6 +247,7 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
     if (!c.ev_begin) {
         CUDA_TRY(cudaEventCreate(&c.ev_begin));
         CUDA_TRY(cudaEventCreate(&c.ev_k1));
+        CUDA_TRY(cudaEventCreate(&c.ev_k1b));
         CUDA_TRY(cudaEventCreate(&c.ev_k2));
         CUDA_TRY(cudaEventCreate(&c.ev_small));
         CUDA_TRY(cudaEventCreate(&c.ev_lists));
@@ -300,6 +305,7 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_begin));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_end));
     CUDA_TRY(scan_configure());
+    CUDA_TRY(slice_configure());
     CUDA_TRY(upload_constants(d->crc->bit_syndromes()));
 
     d->h_lut.resize(65536);
@@ -335,6 +341,7 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
 
     // one persistent CTA per SM (the uc8 table takes most of an SM's shared memory)
     d->scan_grid = d->sm_count;
+    d->slice_grid = d->sm_count;
     *out = d.release();
     return B200_OK;
 }
@@ -382,6 +389,8 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     a.cand = c.d_cand.p;
     a.recs = c.d_recs.p;
     a.tiles = c.d_tiles.p;
+    a.mag = c.d_magbuf.p;
+    a.step_off = c.d_step_off.p;
     a.cand_slab = cand_slab;
     a.rec_slab = rec_slab;
     a.tile_off = tile_off;
@@ -390,6 +399,27 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     a.block_sums_f64 = c.d_sums_f64.p;
     a.dbg_masks = nullptr;
     return a;
+}
+
+static SliceArgs make_slice_args(const ScanArgs &sa) {
+    SliceArgs b;
+    memset(&b, 0, sizeof(b));
+    b.mag = sa.mag;
+    b.cand = sa.cand;
+    b.step_off = sa.step_off;
+    b.recs = sa.recs;
+    b.tiles = sa.tiles;
+    b.ntiles = sa.ntiles;
+    b.cand_slab = sa.cand_slab;
+    b.rec_slab = sa.rec_slab;
+    b.tile_off = sa.tile_off;
+    b.tab_short = sa.tab_short;
+    b.tab_long = sa.tab_long;
+    b.n_short = sa.n_short;
+    b.n_long = sa.n_long;
+    b.addr_bitmap = sa.addr_bitmap;
+    b.counters = sa.counters;
+    return b;
 }
 
 static int zero_chunk_outputs(b200_demod *d, ChunkSet &c, uint64_t nsamples, cudaStream_t s) {
@@ -435,6 +465,8 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     CUDA_TRY(cudaEventRecord(c.ev_begin, s));
     CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
     CUDA_TRY(cudaEventRecord(c.ev_k1, s));
+    CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
+    CUDA_TRY(cudaEventRecord(c.ev_k1b, s));
 
     ClassifyArgs ca;
     memset(&ca, 0, sizeof(ca));
@@ -467,7 +499,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     CUDA_TRY(launch_classify(ca, s));
     CUDA_TRY(cudaEventRecord(c.ev_k2, s));
     if (launches)
-        *launches += ntiles ? 2 : 0;
+        *launches += ntiles ? 3 : 0;
     CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
     if (ntiles)
         CUDA_TRY(cudaMemcpyAsync(c.h_tiles_out.p, c.d_tiles_out.p, ntiles * sizeof(TileOut), cudaMemcpyDeviceToHost, s));
@@ -494,9 +526,12 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
         float ms = 0;
         cudaEventElapsedTime(&ms, c.ev_begin, c.ev_k1);
         t.scan_ms += ms;
-        cudaEventElapsedTime(&ms, c.ev_k1, c.ev_k2);
+        cudaEventElapsedTime(&ms, c.ev_k1, c.ev_k1b);
+        t.slice_ms += ms;
+        cudaEventElapsedTime(&ms, c.ev_k1b, c.ev_k2);
         t.classify_ms += ms;
     }
+    bool prev_exact = false; // did the run that overflowed already use exact slabs?
     for (int attempt = 0; cnt.overflow; ++attempt) {
         if (attempt >= 3)
             return fail(B200_ERR_CAPACITY, "candidate buffers overflowed after %d attempts (flags 0x%x)", attempt + 1, cnt.overflow);
@@ -512,7 +547,8 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
                 off[2 * i] = (uint32_t) co;
                 off[2 * i + 1] = (uint32_t) ro;
                 co += tiles[i].ncand;
-                ro += tiles[i].nrec;
+                // K1b saw only the candidates that fit: a truncated tile gets the upper bound (5 phases each)
+                ro += (tiles[i].ncand > kCandSlab && !prev_exact) ? (uint64_t) 5 * tiles[i].ncand : tiles[i].nrec;
             }
             off[2 * (size_t) ntiles] = (uint32_t) co;
             off[2 * (size_t) ntiles + 1] = (uint32_t) ro;
@@ -537,12 +573,15 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
         int rc = issue_chunk(d, c, exec, exact, cand_total, rec_total, dead_cap, live_cap, liverec_cap, launches);
         if (rc != B200_OK)
             return rc;
+        prev_exact = exact;
         CUDA_TRY(cudaEventSynchronize(c.ev_small));
         cnt = *c.h_counters.p;
         float ms = 0;
         cudaEventElapsedTime(&ms, c.ev_begin, c.ev_k1);
         t.scan_ms += ms;
-        cudaEventElapsedTime(&ms, c.ev_k1, c.ev_k2);
+        cudaEventElapsedTime(&ms, c.ev_k1, c.ev_k1b);
+        t.slice_ms += ms;
+        cudaEventElapsedTime(&ms, c.ev_k1b, c.ev_k2);
         t.classify_ms += ms;
     }
 
@@ -783,6 +822,8 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
     ScanArgs sa = make_scan_args(d, c, (const uint8_t *) d_iq, d->d_head.p, nsamples, 0, kCandSlab, kRecSlab, nullptr);
     CUDA_TRY(cudaEventRecord(c.ev_begin, s));
     CUDA_TRY(launch_scan(sa, mode ? 1 : 0, d->scan_grid, s));
+    if (mode >= 2)
+        CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
     CUDA_TRY(cudaEventRecord(c.ev_k1, s));
     CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -868,6 +909,7 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
     ScanArgs sa = make_scan_args(d, c, d->d_iq.p, d->d_head.p, nsamples, 0, kTile, kTile * 5, nullptr);
     sa.dbg_masks = d->d_dbg_masks.p;
     CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
+    CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
     CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (c.h_counters.p->overflow)

@@ -22,13 +22,12 @@ constexpr int kLookahead = 296;            // samples past the last window start
 constexpr int kScanWarps = 16;             // warps per CTA (shared memory: 128 KiB table + 5.4 KiB per warp)
 constexpr int kScanThreads = kScanWarps * 32;
 // Warp buffer: a ring of two chunks of u32 magnitudes, one row per lane.  A row is the lane's 16
-// magnitudes followed by a copy of the next row's first 4: the 80-byte row stride makes every
-// 128-bit access of a quarter warp hit 8 distinct 16-byte bank groups, and the copy lets the slicer
-// read 4 consecutive magnitudes from any start without crossing a row.
+// magnitudes plus 16 bytes of padding: the 80-byte row stride makes every 128-bit access of a
+// quarter warp hit 8 distinct 16-byte bank groups.
 constexpr int kRowWords = kLanePos + 4;     // 20
 constexpr int kRows = 64;                   // 2 chunks x 32 lanes
 constexpr int kWarpBuf = kRows * kRowWords; // u32 words per warp (5120 bytes)
-constexpr int kItemCap = 96;               // (position, phase) items a warp queues before slicing them (>= 80: one lane's worst case)
+constexpr int kMagSlack = 1024;            // magnitudes K1b may stage past the last tile (never used by a frame)
 
 inline uint32_t tiles_for(uint64_t nsamples) {
     // every position < nsamples and every sample < nsamples must fall into a tile
@@ -103,7 +102,9 @@ struct ScanCounters {
     unsigned long long n_live;
     unsigned long long n_liverec;
     unsigned int overflow; // bit0 cand, bit1 rec, bit2 dead, bit3 live, bit4 liverec
-    unsigned int next_tile; // K1 work queue
+    unsigned int next_tile; // K1a work queue
+    unsigned int next_tile_slice; // K1b work queue
+    unsigned int pad;
 };
 
 struct ErrorInfo { // struct errorinfo, crc.h:32-37

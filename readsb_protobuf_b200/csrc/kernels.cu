@@ -141,9 +141,21 @@ struct FrameClass {
     int bit0, bit1;
 };
 
+// bloom: optional 2^14-bit filter over the syndromes of both tables (bit hash(s) set for every
+// entry): a miss proves the syndrome is in neither table without walking it.
+constexpr int kBloomBits = 1 << 14;
+__device__ __forceinline__ uint32_t bloom_hash(uint32_t syn) {
+    return (syn ^ (syn >> 10)) & (kBloomBits - 1);
+}
+__device__ __forceinline__ bool bloom_miss(const uint32_t *bloom, uint32_t syn) {
+    const uint32_t h = bloom_hash(syn);
+    return bloom && !((bloom[h >> 5] >> (h & 31u)) & 1u);
+}
+
 __device__ __forceinline__ FrameClass classify_frame(uint32_t df, uint32_t aa, uint32_t syn, bool all_zero,
                                                      const ErrorInfo *__restrict__ tab_short, int n_short,
-                                                     const ErrorInfo *__restrict__ tab_long, int n_long) {
+                                                     const ErrorInfo *__restrict__ tab_long, int n_long,
+                                                     const uint32_t *bloom = nullptr) {
     FrameClass fc;
     fc.kind = kKindBad;
     fc.errors = 0;
@@ -161,6 +173,8 @@ __device__ __forceinline__ FrameClass classify_frame(uint32_t df, uint32_t aa, u
         case 11: { // mode_s.c:345-374
             uint32_t c2 = syn & 0xffff80u;
             if (c2 != 0) {
+                if (bloom_miss(bloom, c2))
+                    return fc;
                 int idx = find_syndrome(tab_short, n_short, c2);
                 if (idx < 0)
                     return fc;
@@ -177,6 +191,8 @@ __device__ __forceinline__ FrameClass classify_frame(uint32_t df, uint32_t aa, u
         }
         case 17: case 18: { // mode_s.c:376-389
             if (syn != 0) {
+                if (bloom_miss(bloom, syn))
+                    return fc;
                 int idx = find_syndrome(tab_long, n_long, syn);
                 if (idx < 0)
                     return fc;
@@ -270,12 +286,8 @@ struct Fmt<2> { // sc16q11
 };
 
 constexpr size_t kSmemLut = 65536 * sizeof(uint16_t);
-constexpr int kBatch = 16;     // frames sliced per batch (their message words live in shared memory)
-constexpr int kMsgWords = 5;   // 4 message words + the CRC syndrome
-constexpr int kGroupsLong = 23, kGroupsShort = 12; // 5-bit groups of a 112 / 56 bit frame
-constexpr size_t kSmemWarp = kWarpBuf * sizeof(uint32_t) + 2 * kItemCap * sizeof(uint16_t) + kBatch * kMsgWords * sizeof(uint32_t);
-// CTA-wide tables: group syndromes [23 + 12][32], slicer taps [5 phases][5 bits] (int4 taps + sample offset)
-constexpr size_t kSmemTail = (kGroupsLong + kGroupsShort) * 32 * sizeof(uint32_t) + 25 * sizeof(int4) + 25 * sizeof(int);
+constexpr size_t kSmemWarp = kWarpBuf * sizeof(uint32_t);
+constexpr size_t kSmemTail = 0;
 
 size_t scan_smem_bytes(uint32_t format) {
     return (format == 0 ? kSmemLut : 0) + kScanWarps * kSmemWarp + kSmemTail;
@@ -304,151 +316,11 @@ __device__ __forceinline__ uint4 load_unit(const ScanArgs &a, long long s, int &
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-struct WarpCtx {
-    const uint32_t *buf;   // the warp's magnitude rows
-    int row0;              // first row of the chunk being scanned
-    const uint32_t *gsyn;  // group syndromes (shared): [23 long groups + 12 short groups][32]
-    const int4 *taps;      // [phase - 4][bit of the group]: correlator taps (shared)
-    const int *soff;       // [phase - 4][bit of the group]: first sample of the bit, relative to the group
-    uint16_t *items, *valid;
-    uint32_t *msg;         // [kBatch][kMsgWords]
-    long long chunk_pos0;  // scan position of window start 0 of the chunk
-    // tile output cursors
+struct WarpCtx { // a tile's candidate output cursor
     uint32_t *cand_out;
-    PhaseRec *rec_out;
-    uint32_t cand_cap, rec_cap, ncand, nrec;
+    uint32_t cand_cap, ncand;
+    unsigned long long ncand_total; // over the warp's tiles
 };
-
-// Five consecutive PPM bit decisions (demod_2400.c:73-177 in closed form).  Frame bit b of a
-// candidate tried at phase p sits t = p + 12 b fifths of a sample after m[19]; five bits later the
-// pattern repeats 12 samples on, so group k of a frame (bits 5k .. 5k+4) reads the 15 samples from
-// m[19 + 12k] with offsets and correlators that depend on the phase only.  x = window start of the
-// frame in the chunk, phi = phase - 4.  Returns the five decisions, bit c = frame bit 5k + c.
-// A row of the warp buffer holds 16 magnitudes and a copy of the next row's first 4, so the four
-// samples of one bit never straddle a row: they start in the group's first row or in the next one.
-__device__ __forceinline__ uint32_t slice_group(const WarpCtx &cx, int x, int phi, int k) {
-    const int y = x + 19 + 12 * k;
-    const int row = (cx.row0 + (y >> 4)) & (kRows - 1);
-    const int col0 = y & 15;
-    const uint32_t *r0 = cx.buf + row * kRowWords;
-    const uint32_t *r1 = cx.buf + ((row + 1) & (kRows - 1)) * kRowWords - 16;
-    const int4 *tp = cx.taps + phi * 5;
-    const int *so = cx.soff + phi * 5;
-    uint32_t v5 = 0;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const int4 t = tp[c];
-        const int col = col0 + so[c];
-        const uint32_t *p = (col <= 16 ? r0 : r1) + col;
-        const int v = t.x * (int) p[0] + t.y * (int) p[1] + t.z * (int) p[2] + t.w * (int) p[3];
-        v5 |= (v > 0) ? (1u << c) : 0u;
-    }
-    return v5;
-}
-
-// Slice the queued (position, phase) items of the chunk.
-//   1. one lane per item slices group 0 = the DF field -> frame length (demod_2400.c:188-205);
-//      long frames are listed from the front of `valid`, short ones from its back
-//   2. in batches of kBatch frames: one lane per (frame, group) slices five bits, ORs them into the
-//      frame's message words and XORs the group's CRC contribution (crc.c:59-64: the syndrome is
-//      linear in the bits) into its syndrome, both in shared memory
-//   3. one lane per frame classifies it and appends the class record
-__device__ __forceinline__ void process_items(const ScanArgs &a, WarpCtx &cx, int &nitems) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t below = (1u << lane) - 1u;
-    __syncwarp();
-    int nl = 0, ns = 0;
-    for (int it = 0; it < nitems; it += 32) {
-        const bool active = it + lane < nitems;
-        const uint32_t item = cx.items[active ? it + lane : it];
-        const uint32_t v5 = slice_group(cx, (int) (item & 511u), (int) ((item >> 9) & 7u), 0);
-        const int nb = active ? frame_bytes_for_df(__brev(v5) >> 27) : 0;
-        const uint32_t lm = __ballot_sync(0xffffffffu, nb == 14), sm = __ballot_sync(0xffffffffu, nb == 7);
-        if (nb == 14)
-            cx.valid[nl + __popc(lm & below)] = (uint16_t) (item | (1u << 12));
-        else if (nb == 7)
-            cx.valid[kItemCap - 1 - (ns + __popc(sm & below))] = (uint16_t) item;
-        nl += __popc(lm);
-        ns += __popc(sm);
-    }
-    __syncwarp();
-    const int nframes = nl + ns;
-    for (int q0 = 0; q0 < nframes; q0 += kBatch) { // uniform
-        const int nb = min(kBatch, nframes - q0);
-        const int nlb = max(0, min(nb, nl - q0)); // long frames of the batch come first
-        const int ntasks = kGroupsLong * nlb + kGroupsShort * (nb - nlb);
-        for (int i = lane; i < nb * kMsgWords; i += 32)
-            cx.msg[i] = 0;
-        __syncwarp();
-        for (int t0 = 0; t0 < ntasks; t0 += 32) {
-            const int t = t0 + lane;
-            if (t < ntasks) {
-                int bi, k;
-                const int ts = t - kGroupsLong * nlb;
-                if (ts < 0) {
-                    bi = (t * 2850) >> 16; // t / 23 for t < 23 * 16
-                    k = t - kGroupsLong * bi;
-                } else {
-                    const int sb = (ts * 5462) >> 16; // ts / 12
-                    bi = nlb + sb;
-                    k = ts - kGroupsShort * sb;
-                }
-                const int q = q0 + bi;
-                const uint32_t item = (q < nl) ? cx.valid[q] : cx.valid[kItemCap - 1 - (q - nl)];
-                const bool is_long = ts < 0;
-                uint32_t v5 = slice_group(cx, (int) (item & 511u), (int) ((item >> 9) & 7u), k);
-                const int left = (is_long ? 112 : 56) - 5 * k; // the last group of a frame is partial
-                if (left < 5)
-                    v5 &= (1u << left) - 1u;
-                uint32_t *mw = cx.msg + bi * kMsgWords;
-                const int b0 = 5 * k, wi = b0 >> 5, sh = b0 & 31;
-                if (v5) {
-                    atomicOr(&mw[wi], v5 << sh); // frame bit b -> bit b % 32 of word b / 32
-                    if (sh > 27 && (v5 >> (32 - sh)))
-                        atomicOr(&mw[wi + 1], v5 >> (32 - sh));
-                    atomicXor(&mw[4], cx.gsyn[((is_long ? 0 : kGroupsLong) + k) * 32 + v5]);
-                }
-            }
-        }
-        __syncwarp();
-        // one lane per frame: class record
-        const bool active = lane < nb;
-        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, syn = 0, item = 0;
-        if (active) {
-            const uint32_t *mw = cx.msg + lane * kMsgWords;
-            w0 = mw[0], w1 = mw[1], w2 = mw[2], w3 = mw[3], syn = mw[4];
-            const int q = q0 + lane;
-            item = (q < nl) ? cx.valid[q] : cx.valid[kItemCap - 1 - (q - nl)];
-        }
-        const uint32_t head32 = __brev(w0); // frame bits 0..31, MSB first
-        const uint32_t df = head32 >> 27, aa = head32 & 0xffffffu;
-        FrameClass fc;
-        fc.kind = kKindBad;
-        if (active)
-            fc = classify_frame(df, aa, syn, (w0 | w1 | w2 | w3) == 0, a.tab_short, a.n_short, a.tab_long, a.n_long);
-        const bool has = active && fc.kind != kKindBad;
-        const uint32_t mask = __ballot_sync(0xffffffffu, has);
-        if (has) {
-            const uint32_t slot = cx.nrec + __popc(mask & below);
-            const uint32_t ph = ((item >> 9) & 7u) + 4u;
-            if (slot < cx.rec_cap) {
-                PhaseRec pr;
-                pr.pos = (uint32_t) (cx.chunk_pos0 + (item & 511u));
-                pr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
-                pr.w1 = fc.key | (ph << 24);
-                pr.pad = 0;
-                *reinterpret_cast<uint4 *>(&cx.rec_out[slot]) = *reinterpret_cast<const uint4 *>(&pr);
-            }
-            // mode_s.c:717-726: only a clean DF17, or a clean DF11 with IID 0, can ever be added to the
-            // ICAO filter; remember every such address of the stream
-            if (syn == 0 && (df == 17 || df == 11))
-                atomicOr(&a.addr_bitmap[aa >> 5], 1u << (aa & 31u));
-        }
-        cx.nrec += __popc(mask);
-        __syncwarp();
-    }
-    nitems = 0;
-}
 
 __device__ __noinline__ void flush_sums_u64(unsigned long long *dst, unsigned long long level, unsigned long long power) {
     const unsigned long long l = warp_sum_u64(level), p = warp_sum_u64(power);
@@ -513,22 +385,19 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
     const int thr = a.threshold;
 
     const long long c0 = (long long) tile * kTile - kHead; // first window-start sample of the tile
+    // the tile's slab of the candidate array (and, for K1b, of the record array)
     uint32_t cand_off, rec_off;
     if (a.tile_off) {
         cand_off = a.tile_off[2 * tile];
         rec_off = a.tile_off[2 * tile + 1];
         cx.cand_cap = a.tile_off[2 * tile + 2] - cand_off;
-        cx.rec_cap = a.tile_off[2 * tile + 3] - rec_off;
     } else {
         cand_off = tile * a.cand_slab;
         rec_off = tile * a.rec_slab;
         cx.cand_cap = a.cand_slab;
-        cx.rec_cap = a.rec_slab;
     }
     cx.cand_out = a.cand + cand_off;
-    cx.rec_out = a.recs + rec_off;
-    cx.ncand = cx.nrec = 0;
-    int nitems = 0;
+    cx.ncand = 0;
     uint32_t ncand_lane = 0; // scan-only mode: candidates seen by this lane
 
     // block sums of the samples this tile owns: [c0, c0 + kTile) within [0, n)
@@ -606,16 +475,20 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
         if (k < kScanSteps)
             prefetch(k + 1);
 
-        // store: chunk k occupies rows (k&1)*32 + lane; the first four magnitudes are also copied into
-        // the pad of the previous row
+        // store: chunk k occupies rows (k&1)*32 + lane of the warp's ring
         {
             const int row = (k & 1) * 32 + lane;
             uint4 *dst = reinterpret_cast<uint4 *>(s_buf + row * kRowWords);
 #pragma unroll
             for (int q = 0; q < kLanePos / 4; ++q)
                 dst[q] = make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-            uint4 *pad = reinterpret_cast<uint4 *>(s_buf + ((row - 1) & (kRows - 1)) * kRowWords + kLanePos);
-            *pad = make_uint4(m[0], m[1], m[2], m[3]);
+        }
+        // the tile's own 16 chunks also go to the u16 magnitude array K1b and K2 slice from
+        // (index = sample + kHead; samples outside the stream are 0)
+        if (SLICE && k < kScanSteps) {
+            uint4 *g = reinterpret_cast<uint4 *>(a.mag + (size_t) tile * kTile + (size_t) k * kStep + lane * kLanePos);
+            g[0] = make_uint4(m[0] | (m[1] << 16), m[2] | (m[3] << 16), m[4] | (m[5] << 16), m[6] | (m[7] << 16));
+            g[1] = make_uint4(m[8] | (m[9] << 16), m[10] | (m[11] << 16), m[12] | (m[13] << 16), m[14] | (m[15] << 16));
         }
 
         // block sums: chunks 0..kScanSteps-1 are owned by this tile
@@ -766,19 +639,16 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                 store_dbg_masks(a.dbg_masks + lp0, b45, b67, b8, vmask);
 
             const uint32_t any = b45 | b67 | b8;
+            if (SLICE && lane == 0) // where step j's candidates start in the tile's list (K1b cuts the list into units)
+                a.step_off[tile * kScanSteps + j] = (uint16_t) cx.ncand;
             if (!SLICE) {
                 ncand_lane += __popc(any);
             } else {
-                uint32_t lanes = __ballot_sync(0xffffffffu, any != 0);
-                cx.buf = s_buf;
-                cx.row0 = row0;
-                cx.chunk_pos0 = pos0;
+                const uint32_t lanes = __ballot_sync(0xffffffffu, any != 0);
                 if (lanes) {
-                    // candidates and (position, phase) items of the step, in position order: every lane
-                    // places its own through a warp prefix sum (candidates low half, items high half).
-                    // A lane's items (<= 80) always fit the queue; a step with more items than the queue
-                    // holds is taken in rounds of as many whole lanes as fit.
-                    const uint32_t mine = (uint32_t) __popc(any) | ((uint32_t) (2 * __popc(b45) + 2 * __popc(b67) + __popc(b8)) << 16);
+                    // candidate entries of the step in position order: every lane places its own through
+                    // a warp prefix sum
+                    const uint32_t mine = (uint32_t) __popc(any);
                     uint32_t inc = mine;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -786,40 +656,16 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                         if (lane >= o)
                             inc += up;
                     }
-                    const uint32_t exc = inc - mine;
-                    const uint32_t cand_base = cx.ncand;
-                    cx.ncand += __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
-                    int first_lane = 0;      // lanes below were queued in earlier rounds
-                    uint32_t base_items = 0; // their items
-                    while (first_lane < 32) { // uniform
-                        const bool fits = lane >= first_lane && (inc >> 16) - base_items <= (uint32_t) kItemCap;
-                        const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> first_lane;
-                        const int nl_round = __ffs(~fm) - 1; // consecutive lanes from first_lane that fit (>= 1)
-                        const int end_lane = first_lane + (nl_round < 0 ? 32 - first_lane : nl_round);
-                        if (lane >= first_lane && lane < end_lane) {
-                            uint32_t ci = cand_base + (exc & 0xffffu);
-                            int ii = (int) ((exc >> 16) - base_items);
-                            uint32_t u = any;
-                            while (u) {
-                                const int i = __ffs(u) - 1;
-                                u &= u - 1;
-                                const uint32_t tm = (((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u);
-                                const uint32_t pic = (uint32_t) (lane * kLanePos + i);
-                                if (ci < cx.cand_cap)
-                                    cx.cand_out[ci] = (uint32_t) (j * kStep + (int) pic) | (tm << 13);
-                                ++ci;
-#pragma unroll
-                                for (int ph = 0; ph < 5; ++ph)
-                                    if ((tm >> ph) & 1u)
-                                        cx.items[ii++] = (uint16_t) (pic | ((uint32_t) ph << 9));
-                            }
-                        }
-                        const uint32_t upto = __shfl_sync(0xffffffffu, inc, end_lane - 1) >> 16;
-                        nitems = (int) (upto - base_items);
-                        base_items = upto;
-                        first_lane = end_lane;
-                        if (nitems)
-                            process_items(a, cx, nitems);
+                    uint32_t ci = cx.ncand + inc - mine;
+                    cx.ncand += __shfl_sync(0xffffffffu, inc, 31);
+                    uint32_t u = any;
+                    while (u) {
+                        const int i = __ffs(u) - 1;
+                        u &= u - 1;
+                        const uint32_t tm = (((b45 >> i) & 1u) * 3u) | (((b67 >> i) & 1u) * 12u) | (((b8 >> i) & 1u) * 16u);
+                        if (ci < cx.cand_cap)
+                            cx.cand_out[ci] = (uint32_t) (j * kStep + lane * kLanePos + i) | (tm << 13);
+                        ++ci;
                     }
                 }
             }
@@ -841,17 +687,13 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
             td.cand_off = cand_off;
             td.ncand = cx.ncand;
             td.rec_off = rec_off;
-            td.nrec = cx.nrec;
+            td.nrec = 0; // K1b
             a.tiles[tile] = td;
-            unsigned int ovf = (cx.ncand > cx.cand_cap ? 1u : 0u) | (cx.nrec > cx.rec_cap ? 2u : 0u);
-            if (ovf)
-                atomicOr(&a.counters->overflow, ovf);
-            if (cx.nrec)
-                atomicAdd(&a.counters->n_rec, (unsigned long long) cx.nrec);
+            if (cx.ncand > cx.cand_cap)
+                atomicOr(&a.counters->overflow, 1u);
         }
-        if (cx.ncand)
-            atomicAdd(&a.counters->n_cand, (unsigned long long) cx.ncand);
     }
+    cx.ncand_total += cx.ncand;
 }
 
 template <int FORMAT, bool SLICE>
@@ -866,15 +708,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         sp += kSmemLut;
     uint32_t *s_buf = reinterpret_cast<uint32_t *>(sp + (size_t) warp * kWarpBuf * sizeof(uint32_t));
     sp += (size_t) kScanWarps * kWarpBuf * sizeof(uint32_t);
-    uint16_t *s_lists = reinterpret_cast<uint16_t *>(sp) + (size_t) warp * 2 * kItemCap;
-    sp += (size_t) kScanWarps * 2 * kItemCap * sizeof(uint16_t);
-    uint32_t *s_msg = reinterpret_cast<uint32_t *>(sp) + (size_t) warp * kBatch * kMsgWords;
-    sp += (size_t) kScanWarps * kBatch * kMsgWords * sizeof(uint32_t);
-    uint32_t *s_gsyn = reinterpret_cast<uint32_t *>(sp);
-    sp += (kGroupsLong + kGroupsShort) * 32 * sizeof(uint32_t);
-    int4 *s_taps = reinterpret_cast<int4 *>(sp);
-    sp += 25 * sizeof(int4);
-    int *s_soff = reinterpret_cast<int *>(sp);
 
     // one-time staging of the tables (the only block-wide barrier of the kernel).  The magnitude
     // table arrives pre-swizzled (32-bit word j of row Q at word j ^ (Q & 31)): all of a thread's
@@ -891,33 +724,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         for (int q = 0; q < kPer; ++q)
             dst[q * kScanThreads + tid] = v[q];
     }
-    // group syndromes: row g < 23 = bits 5g .. 5g+4 of a long frame, row 23 + g = of a short frame
-    // (crc.c:143: a short frame uses the tail of the 112-entry single-bit syndrome list)
-    for (int i = tid; i < (kGroupsLong + kGroupsShort) * 32; i += kScanThreads) {
-        const int g = i >> 5, v = i & 31;
-        const bool is_long = g < kGroupsLong;
-        const int b0 = 5 * (is_long ? g : g - kGroupsLong), nbits = is_long ? 112 : 56;
-        uint32_t x = 0;
-        for (int c = 0; c < 5; ++c)
-            if (((v >> c) & 1) && b0 + c < nbits)
-                x ^= c_bit_syndrome[b0 + c + (112 - nbits)];
-        s_gsyn[i] = x;
-    }
-    if (tid < 25) { // bit c of a group at phase p: t = p + 12 c fifths, sample t / 5, correlator t % 5
-        const int t = (tid / 5 + 4) + 12 * (tid % 5);
-        const int r = t % 5;
-        s_taps[tid] = make_int4(c_slice_coef[r][0], c_slice_coef[r][1], c_slice_coef[r][2], c_slice_coef[r][3]);
-        s_soff[tid] = t / 5;
-    }
     __syncthreads();
 
     WarpCtx cx;
-    cx.gsyn = s_gsyn;
-    cx.taps = s_taps;
-    cx.soff = s_soff;
-    cx.items = s_lists;
-    cx.valid = s_lists + kItemCap;
-    cx.msg = s_msg;
+    cx.ncand_total = 0;
 
     const long long n = (long long) a.nsamples;
     for (;;) {
@@ -936,6 +746,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         else
             process_tile<FORMAT, SLICE, true>(a, cx, tile, s_lut, s_buf);
     }
+    if (lane == 0 && cx.ncand_total) // one same-address atomic per warp, not per tile
+        atomicAdd(&a.counters->n_cand, cx.ncand_total);
 }
 
 cudaError_t scan_configure() {
@@ -968,6 +780,354 @@ cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stre
         default: return cudaErrorInvalidValue;
     }
 #undef LAUNCH
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b: slice kernel -- PPM slice + CRC class of every (candidate position, phase)
+//
+// Warp-autonomous like K1a: a warp takes a unit (1024 scan positions = two K1a steps of a tile) from
+// a queue, stages the unit's magnitudes (+ the 297 a frame can reach past the last window) into its
+// own shared-memory pair array, expands the unit's candidates into (position, phase) items, and then
+//   1. one lane per item slices group 0 = the DF field -> frame length (demod_2400.c:188-205)
+//   2. one lane per (frame, 5-bit group) slices five bits, ORs them into the frame's message words
+//      and XORs the group's CRC contribution (crc.c:59-64: the syndrome is linear in the bits) into
+//      its syndrome, both in shared memory
+//   3. one lane per frame classifies it and appends the class record to the tile's slab
+// Work is pooled over the unit, so the rounds of step 2 run with nearly all lanes busy, and there is
+// no block-wide barrier after the table set-up: 32 independent warps per SM hide each other's latency.
+// ------------------------------------------------------------------------------------------
+
+constexpr int kSliceWarps = 32;
+constexpr int kSliceThreads = kSliceWarps * 32;
+constexpr int kUnit = 2 * kStep;              // scan positions per unit
+constexpr int kUnitsPerTile = kTile / kUnit;  // 8
+constexpr int kUnitMag = kUnit + 304;         // staged magnitudes (a frame reaches 297 past its window start)
+constexpr int kItemMax = 5 * 32;              // (position, phase) items of a batch of 32 candidates
+constexpr int kFrameBytes = 24;               // one byte per 5-bit group of a frame (23 used)
+constexpr int kGroupsLong = 23, kGroupsShort = 12; // 5-bit groups of a 112 / 56 bit frame
+
+// dynamic shared memory: per warp the pair array, item list, frame list and 32 frames' group bytes
+constexpr size_t kSliceWarpSmem = kUnitMag * sizeof(uint32_t) + 2 * kItemMax * sizeof(uint16_t) + 32 * kFrameBytes;
+constexpr size_t kSliceSmem = kSliceWarps * kSliceWarpSmem + (kGroupsLong + kGroupsShort) * 32 * sizeof(uint32_t) + 32 * sizeof(int2) + kBloomBits / 8;
+static_assert(kSliceWarpSmem % 16 == 0, "per-warp slice buffers must stay 16-byte aligned");
+
+__device__ __forceinline__ int dp2a_lo(uint32_t pair, int taps, int acc) {
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair), "r"(taps), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t pair, int taps, int acc) {
+    int d;
+    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair), "r"(taps), "r"(acc));
+    return d;
+}
+
+// Five consecutive PPM bit decisions (demod_2400.c:73-177 in closed form).  Frame bit b of a
+// candidate tried at phase p sits t = p + 12 b fifths of a sample after m[19]; five bits later the
+// pattern repeats 12 samples on, so group k of a frame (bits 5k .. 5k+4) reads the 15 samples from
+// m[19 + 12k] with offsets and correlators that depend on the phase only.
+// P = the pair array at the frame's window start: P[x] = m[x] | m[x+1] << 16, so the four samples
+// of a bit are two aligned 32-bit loads whatever x is, and the correlator is two 16x8-bit dot
+// products (taps.x = the four taps as signed bytes, taps.y = first sample of the bit).
+// phi = phase - 4.  Returns the five decisions, bit c = frame bit 5k + c.
+// The pair array is stored swizzled: pair x lives at word x ^ ((x >> 5) & 3).  The groups of one
+// frame are 12 samples apart, which without the swizzle puts lanes k, k + 8 and k + 16 of a round on
+// the same bank (a 3-way conflict on every load); the swizzle moves them to different banks.
+__device__ __forceinline__ int pair_slot(int x) {
+    return x ^ ((x >> 5) & 3);
+}
+
+// x0 = the frame's window start in the unit
+__device__ __forceinline__ uint32_t slice_group(const uint32_t *P, int x0, int phi, int k, const int2 *taps) {
+    const int g = x0 + 19 + 12 * k;
+    const int2 *tp = taps + phi * 5;
+    uint32_t v5 = 0;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const int2 t = tp[c];
+        const int x = g + t.y;
+        const int v = dp2a_hi(P[pair_slot(x + 2)], t.x, dp2a_lo(P[pair_slot(x)], t.x, 0));
+        v5 |= (v > 0) ? (1u << c) : 0u;
+    }
+    return v5;
+}
+
+__global__ void __launch_bounds__(kSliceThreads, 1) slice_kernel(const SliceArgs a) {
+    extern __shared__ __align__(16) unsigned char slice_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *wp = slice_smem + (size_t) warp * kSliceWarpSmem;
+    uint32_t *s_pair = reinterpret_cast<uint32_t *>(wp);
+    uint8_t *s_bits = reinterpret_cast<uint8_t *>(s_pair + kUnitMag); // [32 frames][kFrameBytes]: five sliced bits per group
+    uint16_t *s_items = reinterpret_cast<uint16_t *>(s_bits + 32 * kFrameBytes); // pos_in_unit[9:0] | (phase - 4)[12:10]
+    uint16_t *s_frames = s_items + kItemMax;                                  // long frames from the front, short from the back
+    uint32_t *s_gsyn = reinterpret_cast<uint32_t *>(slice_smem + (size_t) kSliceWarps * kSliceWarpSmem);
+    int2 *s_taps = reinterpret_cast<int2 *>(s_gsyn + (kGroupsLong + kGroupsShort) * 32);
+    uint32_t *s_bloom = reinterpret_cast<uint32_t *>(s_taps + 32);
+
+    for (int i = tid; i < kBloomBits / 32; i += kSliceThreads)
+        s_bloom[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < a.n_short + a.n_long; i += kSliceThreads) {
+        const uint32_t h = bloom_hash(i < a.n_short ? a.tab_short[i].syndrome : a.tab_long[i - a.n_short].syndrome);
+        atomicOr(&s_bloom[h >> 5], 1u << (h & 31u));
+    }
+    // group syndromes: row g < 23 = bits 5g .. 5g+4 of a long frame, row 23 + g = of a short frame
+    // (crc.c:143: a short frame uses the tail of the 112-entry single-bit syndrome list)
+    for (int i = tid; i < (kGroupsLong + kGroupsShort) * 32; i += kSliceThreads) {
+        const int g = i >> 5, v = i & 31;
+        const bool is_long = g < kGroupsLong;
+        const int b0 = 5 * (is_long ? g : g - kGroupsLong), nbits = is_long ? 112 : 56;
+        uint32_t x = 0;
+        for (int c = 0; c < 5; ++c)
+            if (((v >> c) & 1) && b0 + c < nbits)
+                x ^= c_bit_syndrome[b0 + c + (112 - nbits)];
+        s_gsyn[i] = x;
+    }
+    if (tid < 25) { // bit c of a group at phase p: t = p + 12 c fifths, sample t / 5, correlator t % 5
+        const int t = (tid / 5 + 4) + 12 * (tid % 5);
+        const int r = t % 5;
+        const uint32_t packed = (uint32_t) (uint8_t) c_slice_coef[r][0] | ((uint32_t) (uint8_t) c_slice_coef[r][1] << 8) |
+                                ((uint32_t) (uint8_t) c_slice_coef[r][2] << 16) | ((uint32_t) (uint8_t) c_slice_coef[r][3] << 24);
+        s_taps[tid] = make_int2((int) packed, t / 5);
+    }
+    __syncthreads(); // the only block-wide barrier
+
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t nunits = a.ntiles * kUnitsPerTile;
+    // Units are dealt round-robin to the warps of the grid (a shared atomic queue would serialise
+    // 140 K same-address atomics per 144 M samples); the next unit's descriptors are requested one
+    // iteration before they are needed, so nothing here waits on L2.
+    auto load_desc = [&](uint32_t u, uint4 &td, uint32_t &so) {
+        if (u < nunits) {
+            const uint32_t t = u / kUnitsPerTile, sb = u % kUnitsPerTile;
+            td = *reinterpret_cast<const uint4 *>(&a.tiles[t]); // cand_off, ncand, rec_off, (nrec: being updated, unused)
+            // candidates in front of the unit's two steps [15:0] and in front of the next unit [31:16]
+            so = (uint32_t) a.step_off[t * kScanSteps + 2 * sb] |
+                 ((sb + 1 < kUnitsPerTile ? (uint32_t) a.step_off[t * kScanSteps + 2 * sb + 2] : 0xffffu) << 16);
+        }
+    };
+    unsigned long long nrec_warp = 0;
+    const uint32_t unit_stride = gridDim.x * kSliceWarps;
+    uint32_t unit = blockIdx.x * kSliceWarps + warp;
+    uint4 desc = make_uint4(0, 0, 0, 0);
+    uint32_t desc_so = 0;
+    load_desc(unit, desc, desc_so);
+    for (; unit < nunits;) {
+        const uint32_t tile = unit / kUnitsPerTile, sub = unit % kUnitsPerTile;
+        const uint4 td = desc;
+        const uint32_t so = desc_so;
+        unit += unit_stride;
+        load_desc(unit, desc, desc_so);
+
+        const uint32_t t_ncand = td.y, t_cand_off = td.x, t_rec_off = td.z;
+        uint32_t cand_cap, rec_cap;
+        if (a.tile_off) {
+            cand_cap = a.tile_off[2 * tile + 2] - a.tile_off[2 * tile];
+            rec_cap = a.tile_off[2 * tile + 3] - a.tile_off[2 * tile + 1];
+        } else {
+            cand_cap = a.cand_slab;
+            rec_cap = a.rec_slab;
+        }
+        const uint32_t ncand = t_ncand < cand_cap ? t_ncand : cand_cap; // a truncated tile is run again by the host
+        // the unit's slice of the tile's (position-ordered) candidate list: K1a noted the count at every step
+        uint32_t c_lo = so & 0xffffu;
+        uint32_t c_hi = (sub + 1 < kUnitsPerTile) ? (so >> 16) : t_ncand;
+        c_lo = c_lo < ncand ? c_lo : ncand;
+        c_hi = c_hi < ncand ? c_hi : ncand;
+        if (c_hi <= c_lo)
+            continue;
+        const uint32_t *cand = a.cand + t_cand_off;
+        // first batch of candidates: requested now, used after the staging
+        uint32_t e_first = 0;
+        if (c_lo + lane < c_hi)
+            e_first = __ldg(&cand[c_lo + lane]);
+
+        // ---- stage the unit's magnitudes as the pair array (loads in two waves of three) ----
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.mag + (size_t) tile * kTile + (size_t) sub * kUnit);
+            constexpr int kUnits16 = kUnitMag / 8; // 166 sixteen-byte units
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint4 w[3];
+                uint32_t nx[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int i = (half * 3 + q) * 32 + lane;
+                    if (i < kUnits16) {
+                        w[q] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+                        nx[q] = __ldg(src + 4 * i + 4); // first pair of the next unit (kMagSlack keeps it addressable)
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int i = (half * 3 + q) * 32 + lane;
+                    if (i < kUnits16) {
+                        // pairs 8i .. 8i+7 lie in one block of 32, whose swizzle (i >> 2) & 3 = (lane >> 2) & 3 permutes
+                        // each aligned group of four: word j of the group goes to j ^ f
+                        uint4 lo = make_uint4(w[q].x, __funnelshift_r(w[q].x, w[q].y, 16), w[q].y, __funnelshift_r(w[q].y, w[q].z, 16));
+                        uint4 hi = make_uint4(w[q].z, __funnelshift_r(w[q].z, w[q].w, 16), w[q].w, __funnelshift_r(w[q].w, nx[q], 16));
+                        if (lane & 4) {
+                            lo = make_uint4(lo.y, lo.x, lo.w, lo.z);
+                            hi = make_uint4(hi.y, hi.x, hi.w, hi.z);
+                        }
+                        if (lane & 8) {
+                            lo = make_uint4(lo.z, lo.w, lo.x, lo.y);
+                            hi = make_uint4(hi.z, hi.w, hi.x, hi.y);
+                        }
+                        uint4 *dst = reinterpret_cast<uint4 *>(s_pair + 8 * i);
+                        dst[0] = lo;
+                        dst[1] = hi;
+                    }
+                }
+            }
+        }
+        PhaseRec *recs = a.recs + t_rec_off;
+        const long long p0 = (long long) tile * kTile + (long long) sub * kUnit - kPosShift; // scan position of unit-local index 0
+
+        for (uint32_t cb = c_lo; cb < c_hi; cb += 32) { // uniform
+            // ---- candidates -> (position, phase) items ----
+            uint32_t e = e_first;
+            if (cb != c_lo)
+                e = (cb + lane < c_hi) ? __ldg(&cand[cb + lane]) : 0u;
+            const uint32_t tm = (e >> 13) & 31u;
+            const uint32_t ul = (e & 0x1fffu) - sub * kUnit;
+            int inc = __popc(tm);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += up;
+            }
+            const int nitems = __shfl_sync(0xffffffffu, inc, 31);
+            int off = inc - __popc(tm);
+#pragma unroll
+            for (int ph = 0; ph < 5; ++ph)
+                if ((tm >> ph) & 1u)
+                    s_items[off++] = (uint16_t) (ul | ((uint32_t) ph << 10));
+            __syncwarp(); // items and magnitudes are in place
+
+            // ---- 1. DF field -> frame length ----
+            int nl = 0, ns = 0;
+            for (int it0 = 0; it0 < nitems; it0 += 32) { // uniform
+                const bool active = it0 + lane < nitems;
+                const uint32_t item = s_items[active ? it0 + lane : 0];
+                const uint32_t v5 = slice_group(s_pair, (int) (item & 1023u), (int) (item >> 10), 0, s_taps);
+                const int nb = active ? frame_bytes_for_df(__brev(v5) >> 27) : 0;
+                const uint32_t lm = __ballot_sync(0xffffffffu, nb == 14), sm = __ballot_sync(0xffffffffu, nb == 7);
+                if (nb == 14)
+                    s_frames[nl + __popc(lm & below)] = (uint16_t) item;
+                else if (nb == 7)
+                    s_frames[kItemMax - 1 - (ns + __popc(sm & below))] = (uint16_t) item;
+                nl += __popc(lm);
+                ns += __popc(sm);
+            }
+            const int nframes = nl + ns;
+            for (int q0 = 0; q0 < nframes; q0 += 32) { // uniform
+                const int nb = min(32, nframes - q0);
+                const int nlb = max(0, min(nb, nl - q0)); // long frames come first
+                const int ntasks = kGroupsLong * nlb + kGroupsShort * (nb - nlb);
+                __syncwarp(); // s_frames complete, the previous batch is done with s_bits
+                // ---- 2. one lane per (frame, group): five bits into the frame's group byte ----
+                for (int t = lane; t < ntasks; t += 32) {
+                    int bi, k;
+                    const int ts = t - kGroupsLong * nlb;
+                    if (ts < 0) {
+                        bi = (t * 2850) >> 16; // t / 23 for t < 23 * 32
+                        k = t - kGroupsLong * bi;
+                    } else {
+                        const int sb = (ts * 5462) >> 16; // ts / 12 for ts < 12 * 32
+                        bi = nlb + sb;
+                        k = ts - kGroupsShort * sb;
+                    }
+                    const int q = q0 + bi;
+                    const uint32_t item = (q < nl) ? s_frames[q] : s_frames[kItemMax - 1 - (q - nl)];
+                    uint32_t v5 = slice_group(s_pair, (int) (item & 1023u), (int) (item >> 10), k, s_taps);
+                    const int left = (ts < 0 ? 112 : 56) - 5 * k; // the last group of a frame is partial
+                    if (left < 5)
+                        v5 &= (1u << left) - 1u;
+                    s_bits[bi * kFrameBytes + k] = (uint8_t) v5;
+                }
+                __syncwarp();
+                // ---- 3. one lane per frame: message words (frame bit b -> bit b % 32 of word b / 32), CRC
+                // syndrome (crc.c:59-64: linear in the bits, so the XOR of the groups' syndromes), class record
+                FrameClass fc;
+                fc.kind = kKindBad;
+                uint32_t syn = 0, item = 0, df = 0, aa = 0;
+                if (lane < nb) {
+                    const bool is_long = lane < nlb;
+                    const int ng = is_long ? kGroupsLong : kGroupsShort;
+                    const uint32_t *gs = s_gsyn + (is_long ? 0 : kGroupsLong * 32);
+                    const uint32_t *bw = reinterpret_cast<const uint32_t *>(s_bits + lane * kFrameBytes);
+                    uint32_t w[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+                    for (int kw = 0; kw < 6; ++kw) {
+                        const uint32_t four = bw[kw];
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int k = 4 * kw + kk;
+                            if (k < kGroupsLong && k < ng) {
+                                const uint32_t v5 = (four >> (8 * kk)) & 31u;
+                                syn ^= gs[k * 32 + v5];
+                                w[(5 * k) >> 5] |= v5 << ((5 * k) & 31);
+                                if (((5 * k) & 31) > 27)
+                                    w[((5 * k) >> 5) + 1] |= v5 >> (32 - ((5 * k) & 31));
+                            }
+                        }
+                    }
+                    const int q = q0 + lane;
+                    item = (q < nl) ? s_frames[q] : s_frames[kItemMax - 1 - (q - nl)];
+                    const uint32_t head32 = __brev(w[0]); // frame bits 0..31, MSB first
+                    df = head32 >> 27;
+                    aa = head32 & 0xffffffu;
+                    fc = classify_frame(df, aa, syn, (w[0] | w[1] | w[2] | w[3]) == 0, a.tab_short, a.n_short, a.tab_long, a.n_long, s_bloom);
+                }
+                const bool has = fc.kind != kKindBad;
+                const uint32_t mask = __ballot_sync(0xffffffffu, has);
+                if (mask) {
+                    const uint32_t cnt = (uint32_t) __popc(mask);
+                    uint32_t base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd(&a.tiles[tile].nrec, cnt); // the tile's units share its slab
+                        if (base + cnt > rec_cap)
+                            atomicOr(&a.counters->overflow, 2u);
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    nrec_warp += cnt;
+                    if (has) {
+                        const uint32_t slot = base + __popc(mask & below);
+                        if (slot < rec_cap) {
+                            PhaseRec pr;
+                            pr.pos = (uint32_t) (p0 + (item & 1023u));
+                            pr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
+                            pr.w1 = fc.key | (((item >> 10) + 4u) << 24);
+                            pr.pad = 0;
+                            *reinterpret_cast<uint4 *>(&recs[slot]) = *reinterpret_cast<const uint4 *>(&pr);
+                        }
+                        // mode_s.c:717-726: only a clean DF17, or a clean DF11 with IID 0, can ever be added to
+                        // the ICAO filter; remember every such address of the stream
+                        if (syn == 0 && (df == 17 || df == 11))
+                            atomicOr(&a.addr_bitmap[aa >> 5], 1u << (aa & 31u));
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0 && nrec_warp) // one same-address atomic per warp, not per unit
+        atomicAdd(&a.counters->n_rec, (unsigned long long) nrec_warp);
+}
+
+cudaError_t slice_configure() {
+    return cudaFuncSetAttribute(slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSliceSmem);
+}
+
+cudaError_t launch_slice(const SliceArgs &a, int grid, cudaStream_t stream) {
+    if (a.ntiles == 0)
+        return cudaSuccess;
+    const uint32_t useful = (a.ntiles * kUnitsPerTile + kSliceWarps - 1) / kSliceWarps;
+    if ((uint32_t) grid > useful)
+        grid = (int) useful;
+    slice_kernel<<<grid, kSliceThreads, kSliceSmem, stream>>>(a);
     return cudaGetLastError();
 }
 

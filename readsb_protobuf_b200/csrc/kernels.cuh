@@ -29,6 +29,8 @@ struct ScanArgs {
     uint32_t *cand;
     PhaseRec *recs;
     TileDesc *tiles;
+    uint16_t *step_off;   // [ntiles][kScanSteps]: candidates of the tile in front of each scan step
+    uint16_t *mag;        // [ntiles * kTile + kMagSlack] magnitudes, index = sample + kHead (K1a writes, K1b/K2 read)
     // slab placement: tile t owns cand[t*cand_slab ...) / recs[t*rec_slab ...), or, when tile_off is
     // given (the exact-fit retry), cand[tile_off[2t] .. ) and recs[tile_off[2t+1] ..) with the caps
     // taken from the next tile's offsets
@@ -38,6 +40,22 @@ struct ScanArgs {
     unsigned long long *block_sums_u64; // [nblocks][2]: sum mag, sum mag^2 (table formats)
     double *block_sums_f64;             // [nblocks][2]: sum mag, sum magsq (float formats)
     uint8_t *dbg_masks;                 // optional: try mask per scan position
+};
+
+struct SliceArgs {
+    const uint16_t *mag;  // K1a's magnitudes
+    const uint32_t *cand; // K1a's candidate entries
+    const uint16_t *step_off;
+    PhaseRec *recs;
+    TileDesc *tiles;      // cand_off / ncand / rec_off from K1a; K1b fills nrec
+    uint32_t ntiles;
+    uint32_t cand_slab, rec_slab;
+    const uint32_t *tile_off; // as ScanArgs
+    const ErrorInfo *tab_short;
+    const ErrorInfo *tab_long;
+    int32_t n_short, n_long;
+    uint32_t *addr_bitmap;
+    ScanCounters *counters;
 };
 
 struct ClassifyArgs {
@@ -69,8 +87,10 @@ struct ClassifyArgs {
 // dynamic shared memory the scan kernel needs for a format
 size_t scan_smem_bytes(uint32_t format);
 cudaError_t scan_configure();
+cudaError_t slice_configure();
 // mode 0: magnitude + preamble scan only (candidates counted); 1: + slice + CRC + records
 cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
+cudaError_t launch_slice(const SliceArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream);
 
 // IQ -> u16 magnitudes materialised in global memory (+ sums into sums_u64[2] / sums_f64[2])

@@ -18,7 +18,7 @@ for i in range(reps):
     d.reset()
     r = d.process_device(dev.data_ptr(), cfg.nsamples, final=True, stream=torch.cuda.current_stream().cuda_stream)
     print(i, len(r.msgs), r.timing)
-for mode in (0, 1):
+for mode in (0, 1, 2):
     for i in range(reps):
         ms, nc = d.scan_device(dev.data_ptr(), cfg.nsamples, mode=mode, stream=torch.cuda.current_stream().cuda_stream)
         print("scan mode", mode, "ms", ms, "cands", nc, "Gsamples/s", cfg.nsamples / ms / 1e6, "GB/s", cfg.nsamples * synth.BYTES_PER_SAMPLE[fmt] / ms / 1e6)

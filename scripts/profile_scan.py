@@ -12,6 +12,6 @@ if fmt != "uc8":
 iq, _ = synth.generate(cfg)
 dev = torch.from_numpy(iq).cuda()
 d = api.Demodulator(fmt=fmt, max_span_samples=cfg.nsamples + (1 << 20))
-for mode in (0, 1, 0, 1):
+for mode in (0, 1, 2, 0, 1, 2):
     ms, nc = d.scan_device(dev.data_ptr(), cfg.nsamples, mode=mode, stream=torch.cuda.current_stream().cuda_stream)
     print("scan mode", mode, "ms", ms, "cands", nc)
