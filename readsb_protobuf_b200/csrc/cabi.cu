@@ -486,6 +486,8 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     ca.cand = c.d_cand.p;
     ca.recs = c.d_recs.p;
     ca.tiles = c.d_tiles.p;
+    ca.mag = c.d_magbuf.p;
+    ca.max_cand_per_tile = exact ? 0xffffffffu : kCandSlab;
     ca.dead = c.d_dead.p;
     ca.live = c.d_live.p;
     ca.liverecs = c.d_liverecs.p;
@@ -652,7 +654,11 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
     const size_t bps = (size_t) d->bytes_per_sample;
     const double t_start = now_ms();
 
-    const uint64_t chunk = std::max<uint64_t>(1, kChunkTarget / B) * B;
+    // whole mag_bufs, and close to two tiles per resident K1a warp: a chunk is then two full waves
+    // of the scan kernel instead of one full wave and a ragged one
+    const uint64_t two_waves = (uint64_t) 2 * d->scan_grid * kScanWarps * kTile - kTile; // tiles_for() adds one tile for the tail
+    const uint64_t chunk_target = (d->sm_count > 0 && two_waves >= (16ull << 20) && two_waves <= (64ull << 20)) ? two_waves : kChunkTarget;
+    const uint64_t chunk = std::max<uint64_t>(1, chunk_target / B) * B;
     const uint64_t nchunks = nsamples ? (nsamples + chunk - 1) / chunk : 1;
     b200_timing t;
     memset(&t, 0, sizeof(t));

@@ -1413,10 +1413,278 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K2, warp-per-tile variant: the same passes as classify_kernel with no block-wide barrier, for the
+// normal case of fixed per-tile slabs (at most kCwCap candidates per tile).  A warp keeps the tile's
+// candidate entries and per-candidate flags in its own shared memory; survivors are re-sliced
+// straight from K1a's magnitude array.
+// ------------------------------------------------------------------------------------------
+
+constexpr int kCwWarps = 8;
+constexpr int kCwCap = 640; // candidates per tile this kernel can hold (== the default candidate slab)
+
+__device__ __forceinline__ uint32_t find_cand_smem(const uint32_t *cand, uint32_t ncand, uint32_t pl) {
+    uint32_t lo = 0, hi = ncand;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((cand[mid] & 0x1fffu) < pl)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kCwWarps * 32) classify_warp_kernel(const ClassifyArgs a) {
+    __shared__ uint32_t s_cand[kCwWarps][kCwCap];
+    __shared__ uint32_t s_flagw[kCwWarps][kCwCap / 4]; // per candidate byte: live[0] | has a -1 phase[1]
+    __shared__ uint32_t s_nbw[kCwWarps][kCwCap / 4];   // per candidate byte: which phases own a class record
+    __shared__ uint16_t s_slot[kCwWarps][kCwCap];      // first live-record slot of a live candidate
+    __shared__ uint32_t s_syn[112];
+    __shared__ int s_coef[5][4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 112)
+        s_syn[tid] = c_bit_syndrome[tid];
+    if (tid < 20)
+        (&s_coef[0][0])[tid] = (&c_slice_coef[0][0])[tid];
+    __syncthreads(); // the only block-wide barrier
+    if (a.counters->overflow & 3u)
+        return; // K1 ran out of room: the host places the slabs exactly and runs the span again
+
+    uint32_t *cand = s_cand[warp];
+    uint32_t *flagw = s_flagw[warp], *nbw = s_nbw[warp];
+    const uint8_t *flags = reinterpret_cast<const uint8_t *>(flagw), *nbs = reinterpret_cast<const uint8_t *>(nbw);
+    uint16_t *slot = s_slot[warp];
+    const uint32_t below = (1u << lane) - 1u;
+    const long long B = (long long) a.block_samples;
+
+    for (uint32_t tile = blockIdx.x * kCwWarps + warp; tile < a.ntiles; tile += gridDim.x * kCwWarps) {
+        const TileDesc td = a.tiles[tile];
+        const long long p0 = (long long) tile * kTile - kPosShift; // position of tile-local index 0
+        __syncwarp();
+        if (td.ncand == 0) {
+            if (lane == 0) {
+                TileOut to;
+                to.dead_off = to.ndead = to.live_off = to.nlive = to.liverec_off = to.nliverec = 0;
+                a.tiles_out[tile] = to;
+            }
+            continue;
+        }
+        const uint32_t ncand = td.ncand; // <= kCwCap: K1a's slab
+        for (uint32_t i = lane; i < ncand; i += 32)
+            cand[i] = __ldg(&a.cand[td.cand_off + i]);
+        for (uint32_t i = lane; i < (ncand + 3) / 4; i += 32) {
+            flagw[i] = 0;
+            nbw[i] = 0;
+        }
+        __syncwarp();
+
+        // ---- pass 1: class records -> can the position still be accepted, does it hold a -1 phase ----
+        for (uint32_t r = lane; r < td.nrec; r += 32) {
+            const PhaseRec pr = a.recs[td.rec_off + r];
+            const uint32_t kind = (pr.w0 >> 24) & 7u;
+            const uint32_t c = find_cand_smem(cand, ncand, (uint32_t) ((long long) pr.pos - p0));
+            const uint32_t ph = (pr.w1 >> 24) & 15u;
+            const bool live = record_is_live(pr.w0, pr.w1, a.addr_bitmap);
+            uint32_t f = live ? 1u : 0u;
+            // static score of a phase whose address can never be in the filter:
+            // AP -> -1, DF11 with IID != 0 -> -1, Comm-B -> -2 (mode_s.c:343,373,403)
+            if (!live && (kind == kKindAP || kind == kKindDF11))
+                f |= 2u;
+            if (f)
+                atomicOr(&flagw[c >> 2], f << (8 * (c & 3)));
+            atomicOr(&nbw[c >> 2], (1u << (ph - 4)) << (8 * (c & 3)));
+        }
+        __syncwarp();
+
+        // ---- pass 2: count, reserve the tile's output ranges ----
+        uint32_t n_dead = 0, n_live = 0, n_liverec = 0;
+        for (uint32_t cb = 0; cb < ncand; cb += 32) {
+            const uint32_t c = cb + lane;
+            const bool valid = c < ncand;
+            const bool is_live = valid && (flags[valid ? c : 0] & 1u);
+            const uint32_t lm = __ballot_sync(0xffffffffu, is_live);
+            n_live += __popc(lm);
+            n_dead += __popc(__ballot_sync(0xffffffffu, valid)) - __popc(lm);
+            n_liverec += __reduce_add_sync(0xffffffffu, is_live ? (uint32_t) __popc((uint32_t) nbs[c]) : 0u);
+        }
+        uint32_t dead_off = 0, live_off = 0, liverec_off = 0, ovf = 0;
+        if (lane == 0) {
+            const unsigned long long d_off = atomicAdd(&a.counters->n_dead, (unsigned long long) n_dead);
+            const unsigned long long l_off = atomicAdd(&a.counters->n_live, (unsigned long long) n_live);
+            const unsigned long long r_off = atomicAdd(&a.counters->n_liverec, (unsigned long long) n_liverec);
+            if (d_off + n_dead > a.dead_cap)
+                ovf |= 4u;
+            if (l_off + n_live > a.live_cap)
+                ovf |= 8u;
+            if (r_off + n_liverec > a.liverec_cap)
+                ovf |= 16u;
+            if (ovf)
+                atomicOr(&a.counters->overflow, ovf);
+            TileOut to;
+            to.dead_off = (uint32_t) d_off;
+            to.ndead = n_dead;
+            to.live_off = (uint32_t) l_off;
+            to.nlive = n_live;
+            to.liverec_off = (uint32_t) r_off;
+            to.nliverec = n_liverec;
+            a.tiles_out[tile] = to;
+            dead_off = to.dead_off;
+            live_off = to.live_off;
+            liverec_off = to.liverec_off;
+        }
+        ovf = __shfl_sync(0xffffffffu, ovf, 0);
+        if (ovf)
+            continue; // the host grows the buffers and runs the span again
+        dead_off = __shfl_sync(0xffffffffu, dead_off, 0);
+        live_off = __shfl_sync(0xffffffffu, live_off, 0);
+        liverec_off = __shfl_sync(0xffffffffu, liverec_off, 0);
+
+        // ---- pass 3: ordered dead list / live position list ----
+        {
+            const long long first_pos = p0 < 0 ? 0 : p0;
+            const uint32_t kb0 = (uint32_t) (first_pos / B);
+            const bool one_block = ((long long) (kb0 + 1) * B >= p0 + kTile);
+            uint32_t bd_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t d_done = 0, l_done = 0, r_done = 0;
+            for (uint32_t cb = 0; cb < ncand; cb += 32) {
+                const uint32_t c = cb + lane;
+                const bool valid = c < ncand;
+                const uint32_t e = valid ? cand[c] : 0u, fl = valid ? flags[c] : 0u;
+                const bool is_live = valid && (fl & 1u), is_dead = valid && !is_live;
+                const uint32_t nrec = is_live ? (uint32_t) __popc((uint32_t) nbs[c]) : 0u;
+                const uint32_t dm = __ballot_sync(0xffffffffu, is_dead), lm = __ballot_sync(0xffffffffu, is_live);
+                const uint32_t pl = e & 0x1fffu, tm = (e >> 13) & 31u;
+                if (lm) {
+                    uint32_t inc = nrec; // live records in front of this candidate (rare path)
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o)
+                            inc += up;
+                    }
+                    if (is_live) {
+                        const uint32_t rs = r_done + inc - nrec;
+                        LivePos lp;
+                        lp.pos = (uint32_t) (p0 + pl);
+                        lp.info = tm | (nrec << 8) | (rs << 16);
+                        lp.dead_rank = d_done + __popc(dm & below);
+                        lp.pad = 0;
+                        a.live[live_off + l_done + __popc(lm & below)] = lp;
+                        slot[c] = (uint16_t) rs;
+                    }
+                    r_done += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (is_dead) {
+                    const uint32_t unknown = (fl >> 1) & 1u;
+                    a.dead[dead_off + d_done + __popc(dm & below)] = pl | (tm << 13) | (unknown << 18);
+                    // what demodulate2400 counts for a position whose best score is negative
+                    // (demod_2400.c:184,339-347), provided no accepted frame skips over it
+                    const uint32_t bd[8] = {1u, unknown ? 0u : 1u, unknown, tm & 1u, (tm >> 1) & 1u, (tm >> 2) & 1u, (tm >> 3) & 1u, (tm >> 4) & 1u};
+                    if (one_block) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            bd_local[q] += bd[q];
+                    } else {
+                        const uint32_t kb = (uint32_t) ((p0 + pl) / B);
+                        uint32_t *dst = reinterpret_cast<uint32_t *>(&a.block_dead[kb]);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (bd[q])
+                                atomicAdd(&dst[q], bd[q]);
+                    }
+                }
+                d_done += __popc(dm);
+                l_done += __popc(lm);
+            }
+            if (one_block) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t v = __reduce_add_sync(0xffffffffu, bd_local[q]);
+                    if (lane == q && v)
+                        atomicAdd(reinterpret_cast<uint32_t *>(&a.block_dead[kb0]) + q, v);
+                }
+            }
+        }
+        if (n_liverec == 0)
+            continue;
+        __syncwarp();
+
+        // ---- pass 4: class records of live positions: re-slice the frame, signal power ----
+        // a live position owns consecutive output slots, one per recorded phase in phase order
+        for (uint32_t rb = 0; rb < td.nrec; rb += 32) {
+            const uint32_t r = rb + lane;
+            PhaseRec pr;
+            pr.pos = pr.w0 = pr.w1 = pr.pad = 0;
+            uint32_t c = 0;
+            bool mine = false;
+            if (r < td.nrec) {
+                pr = a.recs[td.rec_off + r];
+                c = find_cand_smem(cand, ncand, (uint32_t) ((long long) pr.pos - p0));
+                mine = flags[c] & 1u;
+            }
+            uint32_t todo = __ballot_sync(0xffffffffu, mine);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t pos = __shfl_sync(0xffffffffu, pr.pos, src);
+                const uint32_t w1 = __shfl_sync(0xffffffffu, pr.w1, src);
+                const uint32_t cc = __shfl_sync(0xffffffffu, c, src);
+                const int ph = (int) ((w1 >> 24) & 15u);
+                const uint32_t rank = (uint32_t) __popc((uint32_t) nbs[cc] & ((1u << (ph - 4)) - 1u));
+                const uint32_t out = liverec_off + slot[cc] + rank;
+                // K1a's magnitudes: window position pos starts at magnitude index pos + kPosShift
+                const uint16_t *fm = a.mag + (size_t) pos + kPosShift;
+
+                uint32_t w[4], syn;
+                // DF from the first five bits decides the length (demod_2400.c:193-205)
+                uint32_t df = 0;
+                for (int b = 0; b < 5; ++b)
+                    df = (df << 1) | (slice_bit(fm, ph, b, s_coef) ? 1u : 0u);
+                const int nbits = (df & 0x10u) ? 112 : 56;
+                warp_slice_frame(fm, ph, nbits, s_coef, s_syn, w, syn);
+
+                // demod_2400.c:387-396: sum of m^2 over msglen*12/5 samples from m[19]
+                const int signal_len = nbits * 12 / 5;
+                unsigned long long power = 0;
+                for (int k = lane; k < signal_len; k += 32) {
+                    const unsigned long long v = fm[19 + k];
+                    power += v * v;
+                }
+                power = warp_sum_u64(power);
+
+                const FrameClass fc = classify_frame(df, __brev(w[0]) & 0xffffffu, syn, (w[0] | w[1] | w[2] | w[3]) == 0,
+                                                     a.tab_short, a.n_short, a.tab_long, a.n_long);
+                if (lane == 0) {
+                    LiveRec lr;
+                    lr.pos = pos;
+                    lr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
+                    lr.w1 = fc.key | ((uint32_t) ph << 24);
+                    lr.errbits = (uint32_t) (uint8_t) fc.bit0 | ((uint32_t) (uint8_t) fc.bit1 << 8);
+                    lr.power = power;
+#pragma unroll
+                    for (int k = 0; k < 14; ++k)
+                        lr.msg[k] = (uint8_t) ((__brev(w[k >> 2]) >> (24 - 8 * (k & 3))) & 0xffu);
+                    lr.pad[0] = lr.pad[1] = 0;
+                    a.liverecs[out] = lr;
+                }
+            }
+        }
+    }
+}
+
 cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream) {
     if (a.ntiles == 0)
         return cudaSuccess;
-    classify_kernel<<<a.ntiles, kClassifyThreads, 0, stream>>>(a);
+    if (a.mag && a.max_cand_per_tile <= (uint32_t) kCwCap) {
+        int grid = (int) ((a.ntiles + kCwWarps - 1) / kCwWarps);
+        if (grid > 148 * 5)
+            grid = 148 * 5;
+        classify_warp_kernel<<<grid, kCwWarps * 32, 0, stream>>>(a);
+    } else {
+        classify_kernel<<<a.ntiles, kClassifyThreads, 0, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -74,6 +74,8 @@ struct ClassifyArgs {
     const uint32_t *cand;
     const PhaseRec *recs;
     const TileDesc *tiles;
+    const uint16_t *mag;         // K1a's magnitudes (index = sample + kHead), or nullptr
+    uint32_t max_cand_per_tile;  // the candidate slab K1a ran with (bounds a tile's list)
     // output
     uint32_t *dead;
     LivePos *live;
