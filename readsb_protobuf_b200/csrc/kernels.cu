@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         const uint4 *src = reinterpret_cast<const uint4 *>(a.lut_swz);
         uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
         constexpr int kPer = (int) (kSmemLut / 16) / kScanThreads; // 16
+        static_assert(kPer * kScanThreads * 16 == (int) kSmemLut, "the table staging assumes the CTA size divides the table");
         uint4 v[kPer];
 #pragma unroll
         for (int q = 0; q < kPer; ++q)
