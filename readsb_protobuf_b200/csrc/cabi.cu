@@ -104,6 +104,12 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// a typed window into a larger allocation (not owning)
+template <typename T>
+struct View {
+    T *p = nullptr;
+};
+
 // per-tile slabs K1 writes into on the first attempt: ~6x the candidate / record density of noise at
 // the default threshold; a chunk that needs more is run again with slabs placed exactly
 const uint32_t kCandSlab = 640, kRecSlab = 448;
@@ -112,26 +118,26 @@ const uint64_t kChunkTarget = 32ull << 20;
 
 // everything one in-flight chunk owns
 struct ChunkSet {
-    DevBuf<uint32_t> d_cand, d_dead, d_tile_off;
+    DevBuf<uint32_t> d_cand, d_tile_off, d_dead;
     DevBuf<uint16_t> d_magbuf; // K1a's magnitudes of the chunk
     DevBuf<uint16_t> d_step_off;
     DevBuf<PhaseRec> d_recs;
     DevBuf<TileDesc> d_tiles;
-    DevBuf<TileOut> d_tiles_out;
-    DevBuf<LivePos> d_live;
-    DevBuf<LiveRec> d_liverecs;
-    DevBuf<ScanCounters> d_counters;
-    DevBuf<unsigned long long> d_sums_u64;
-    DevBuf<double> d_sums_f64;
-    DevBuf<BlockDead> d_block_dead;
-    PinnedBuf<ScanCounters> h_counters;
-    PinnedBuf<TileOut> h_tiles_out;
+    // the small per-chunk outputs share one device allocation and one pinned mirror, so that a chunk
+    // costs one memset and one download: [counters | block sums | block dead counters || tile outputs]
+    DevBuf<uint8_t> d_small;
+    PinnedBuf<uint8_t> h_small;
+    size_t small_zero_bytes = 0, small_bytes = 0;
+    View<ScanCounters> d_counters, h_counters;
+    View<unsigned long long> d_sums_u64, h_sums_u64;
+    View<double> d_sums_f64, h_sums_f64;
+    View<BlockDead> d_block_dead, h_block_dead;
+    View<TileOut> d_tiles_out, h_tiles_out;
+    // K2 writes the live positions and records straight into pinned (device-mapped) host memory; the
+    // (much longer) dead list stays in device memory and is downloaded behind the resolver's back
     PinnedBuf<uint32_t> h_dead;
     PinnedBuf<LivePos> h_live;
     PinnedBuf<LiveRec> h_liverecs;
-    PinnedBuf<unsigned long long> h_sums_u64;
-    PinnedBuf<double> h_sums_f64;
-    PinnedBuf<BlockDead> h_block_dead;
     cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr;
 
     // what is in flight
@@ -142,11 +148,9 @@ struct ChunkSet {
     size_t small_d2h_bytes = 0;
 
     void release() {
-        d_cand.release(); d_dead.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
-        d_tiles_out.release(); d_live.release(); d_liverecs.release(); d_counters.release();
-        d_sums_u64.release(); d_sums_f64.release(); d_block_dead.release();
-        h_counters.release(); h_tiles_out.release(); h_dead.release(); h_live.release(); h_liverecs.release();
-        h_sums_u64.release(); h_sums_f64.release(); h_block_dead.release();
+        d_cand.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
+        d_small.release(); h_small.release(); d_dead.release();
+        h_dead.release(); h_live.release(); h_liverecs.release();
         for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists})
             if (*e) {
                 cudaEventDestroy(*e);
@@ -229,21 +233,32 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
     CUDA_TRY(c.d_cand.ensure(cand_total + 1));
     CUDA_TRY(c.d_recs.ensure(rec_total + 1));
     CUDA_TRY(c.d_dead.ensure(dead_cap));
-    CUDA_TRY(c.d_live.ensure(live_cap));
-    CUDA_TRY(c.d_liverecs.ensure(liverec_cap));
+    CUDA_TRY(c.h_dead.ensure(dead_cap));
+    CUDA_TRY(c.h_live.ensure(live_cap));
+    CUDA_TRY(c.h_liverecs.ensure(liverec_cap));
     CUDA_TRY(c.d_tiles.ensure(ntiles + 1));
     CUDA_TRY(c.d_magbuf.ensure(ntiles * (size_t) kTile + kMagSlack));
     CUDA_TRY(c.d_step_off.ensure((ntiles + 1) * (size_t) kScanSteps));
-    CUDA_TRY(c.d_tiles_out.ensure(ntiles + 1));
-    CUDA_TRY(c.d_counters.ensure(1));
-    CUDA_TRY(c.d_sums_u64.ensure(2 * nblocks));
-    CUDA_TRY(c.d_sums_f64.ensure(2 * nblocks));
-    CUDA_TRY(c.d_block_dead.ensure(nblocks));
-    CUDA_TRY(c.h_counters.ensure(1));
-    CUDA_TRY(c.h_tiles_out.ensure(ntiles + 1));
-    CUDA_TRY(c.h_sums_u64.ensure(2 * nblocks));
-    CUDA_TRY(c.h_sums_f64.ensure(2 * nblocks));
-    CUDA_TRY(c.h_block_dead.ensure(nblocks));
+    {
+        auto up = [](size_t x) { return (x + 63) & ~(size_t) 63; };
+        const size_t o_cnt = 0, o_su = up(sizeof(ScanCounters)), o_sf = o_su + up(2 * nblocks * sizeof(unsigned long long)),
+                     o_bd = o_sf + up(2 * nblocks * sizeof(double)), o_to = o_bd + up(nblocks * sizeof(BlockDead)),
+                     total = o_to + up((ntiles + 1) * sizeof(TileOut));
+        CUDA_TRY(c.d_small.ensure(total));
+        CUDA_TRY(c.h_small.ensure(total));
+        c.small_zero_bytes = o_to;
+        c.small_bytes = total;
+        auto bind = [&](uint8_t *base, View<ScanCounters> &cnt, View<unsigned long long> &su, View<double> &sf, View<BlockDead> &bd,
+                        View<TileOut> &to) {
+            cnt.p = reinterpret_cast<ScanCounters *>(base + o_cnt);
+            su.p = reinterpret_cast<unsigned long long *>(base + o_su);
+            sf.p = reinterpret_cast<double *>(base + o_sf);
+            bd.p = reinterpret_cast<BlockDead *>(base + o_bd);
+            to.p = reinterpret_cast<TileOut *>(base + o_to);
+        };
+        bind(c.d_small.p, c.d_counters, c.d_sums_u64, c.d_sums_f64, c.d_block_dead, c.d_tiles_out);
+        bind(c.h_small.p, c.h_counters, c.h_sums_u64, c.h_sums_f64, c.h_block_dead, c.h_tiles_out);
+    }
     if (!c.ev_begin) {
         CUDA_TRY(cudaEventCreate(&c.ev_begin));
         CUDA_TRY(cudaEventCreate(&c.ev_k1));
@@ -422,12 +437,8 @@ static SliceArgs make_slice_args(const ScanArgs &sa) {
     return b;
 }
 
-static int zero_chunk_outputs(b200_demod *d, ChunkSet &c, uint64_t nsamples, cudaStream_t s) {
-    const size_t nblocks = (size_t) (nsamples / d->cfg.block_samples + 2);
-    CUDA_TRY(cudaMemsetAsync(c.d_counters.p, 0, sizeof(ScanCounters), s));
-    CUDA_TRY(cudaMemsetAsync(c.d_sums_u64.p, 0, 2 * nblocks * sizeof(unsigned long long), s));
-    CUDA_TRY(cudaMemsetAsync(c.d_sums_f64.p, 0, 2 * nblocks * sizeof(double), s));
-    CUDA_TRY(cudaMemsetAsync(c.d_block_dead.p, 0, nblocks * sizeof(BlockDead), s));
+static int zero_chunk_outputs(b200_demod *, ChunkSet &c, uint64_t, cudaStream_t s) {
+    CUDA_TRY(cudaMemsetAsync(c.d_small.p, 0, c.small_zero_bytes, s));
     return B200_OK;
 }
 
@@ -489,12 +500,12 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     ca.mag = c.d_magbuf.p;
     ca.max_cand_per_tile = exact ? 0xffffffffu : kCandSlab;
     ca.dead = c.d_dead.p;
-    ca.live = c.d_live.p;
-    ca.liverecs = c.d_liverecs.p;
+    ca.live = c.h_live.p;
+    ca.liverecs = c.h_liverecs.p;
     ca.tiles_out = c.d_tiles_out.p;
     ca.dead_cap = (uint32_t) std::min<size_t>(c.d_dead.cap, 0xffffffffu);
-    ca.live_cap = (uint32_t) std::min<size_t>(c.d_live.cap, 0xffffffffu);
-    ca.liverec_cap = (uint32_t) std::min<size_t>(c.d_liverecs.cap, 0xffffffffu);
+    ca.live_cap = (uint32_t) std::min<size_t>(c.h_live.cap, 0xffffffffu);
+    ca.liverec_cap = (uint32_t) std::min<size_t>(c.h_liverecs.cap, 0xffffffffu);
     ca.counters = c.d_counters.p;
     ca.block_dead = c.d_block_dead.p;
     // K2 looks at K1's overflow flag itself and does nothing when K1 did not fit
@@ -502,14 +513,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     CUDA_TRY(cudaEventRecord(c.ev_k2, s));
     if (launches)
         *launches += ntiles ? 3 : 0;
-    CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
-    if (ntiles)
-        CUDA_TRY(cudaMemcpyAsync(c.h_tiles_out.p, c.d_tiles_out.p, ntiles * sizeof(TileOut), cudaMemcpyDeviceToHost, s));
-    if (nblocks) {
-        CUDA_TRY(cudaMemcpyAsync(c.h_sums_u64.p, c.d_sums_u64.p, 2 * nblocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(c.h_sums_f64.p, c.d_sums_f64.p, 2 * nblocks * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(c.h_block_dead.p, c.d_block_dead.p, nblocks * sizeof(BlockDead), cudaMemcpyDeviceToHost, s));
-    }
+    CUDA_TRY(cudaMemcpyAsync(c.h_small.p, c.d_small.p, c.small_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(c.ev_small, s));
     c.small_d2h_bytes = sizeof(ScanCounters) + ntiles * sizeof(TileOut) +
                         nblocks * (2 * sizeof(unsigned long long) + 2 * sizeof(double) + sizeof(BlockDead));
@@ -520,7 +524,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
 static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t *launches, b200_timing &t) {
     const uint64_t n = c.nsamples;
     const uint32_t ntiles = tiles_for(n);
-    size_t dead_cap = c.d_dead.cap, live_cap = c.d_live.cap, liverec_cap = c.d_liverecs.cap;
+    size_t dead_cap = c.h_dead.cap, live_cap = c.h_live.cap, liverec_cap = c.h_liverecs.cap;
 
     CUDA_TRY(cudaEventSynchronize(c.ev_small));
     ScanCounters cnt = *c.h_counters.p;
@@ -587,22 +591,13 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
         t.classify_ms += ms;
     }
 
-    // survivors back to the host, on their own stream so that the next chunk's kernels are not in the way
-    const double t_d2h = now_ms();
-    CUDA_TRY(c.h_dead.ensure(std::max<size_t>((size_t) cnt.n_dead, 1)));
-    CUDA_TRY(c.h_live.ensure(std::max<size_t>((size_t) cnt.n_live, 1)));
-    CUDA_TRY(c.h_liverecs.ensure(std::max<size_t>((size_t) cnt.n_liverec, 1)));
-    cudaStream_t ls = d->list_stream;
+    // K2 wrote the live positions and records straight into pinned host memory (posted writes over
+    // PCIe, done when the kernel is).  The dead list (4 B per noise candidate, only consulted where an
+    // accepted frame skips ahead) is downloaded now, on its own stream, and waited for by the resolver
+    // the first time it needs it.
     if (cnt.n_dead)
-        CUDA_TRY(cudaMemcpyAsync(c.h_dead.p, c.d_dead.p, (size_t) cnt.n_dead * sizeof(uint32_t), cudaMemcpyDeviceToHost, ls));
-    if (cnt.n_live)
-        CUDA_TRY(cudaMemcpyAsync(c.h_live.p, c.d_live.p, (size_t) cnt.n_live * sizeof(LivePos), cudaMemcpyDeviceToHost, ls));
-    if (cnt.n_liverec)
-        CUDA_TRY(cudaMemcpyAsync(c.h_liverecs.p, c.d_liverecs.p, (size_t) cnt.n_liverec * sizeof(LiveRec), cudaMemcpyDeviceToHost, ls));
-    CUDA_TRY(cudaEventRecord(c.ev_lists, ls));
-    CUDA_TRY(cudaEventSynchronize(c.ev_lists));
-    t.d2h_ms += (float) (now_ms() - t_d2h);
-
+        CUDA_TRY(cudaMemcpyAsync(c.h_dead.p, c.d_dead.p, (size_t) cnt.n_dead * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->list_stream));
+    CUDA_TRY(cudaEventRecord(c.ev_lists, d->list_stream));
     // host: the order-dependent tail
     const double t_res0 = now_ms();
     SpanView v;
@@ -619,10 +614,13 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     v.block_dead = c.h_block_dead.p;
     v.block_sums_u64 = c.h_sums_u64.p;
     v.block_sums_f64 = c.h_sums_f64.p;
+    v.dead_ready = [](void *ev) { cudaEventSynchronize((cudaEvent_t) ev); };
+    v.dead_ctx = c.ev_lists;
     if (const char *dump = getenv("B200_DUMP_SPAN")) {
         // development aid: write the resolver's inputs of this chunk to a file (tools/resolver_bench.cc)
         char path[512];
         snprintf(path, sizeof(path), "%s/span_%llu.bin", dump, (unsigned long long) c.start);
+        cudaEventSynchronize(c.ev_lists);
         if (FILE *f = fopen(path, "wb")) {
             const uint64_t nblocks = n / v.block_samples + 2;
             uint64_t hdr[12] = {n, v.first_sample, v.block_samples, v.final_span, v.format, v.ntiles, cnt.n_dead, cnt.n_live, cnt.n_liverec, nblocks, 0, 0};
@@ -701,9 +699,9 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
             CUDA_TRY(cudaStreamWaitEvent(exec, d->ev_chunk_h2d[i], 0));
         const uint32_t ntiles = tiles_for(c.nsamples);
         return issue_chunk(d, c, exec, false, (size_t) ntiles * kCandSlab, (size_t) ntiles * kRecSlab,
-                           std::max<size_t>(c.d_dead.cap, (size_t) (c.nsamples / 24 + 4096)),
-                           std::max<size_t>(c.d_live.cap, (size_t) (c.nsamples / 128 + 4096)),
-                           std::max<size_t>(c.d_liverecs.cap, (size_t) (c.nsamples / 64 + 4096)), &launches);
+                           std::max<size_t>(c.h_dead.cap, (size_t) (c.nsamples / 24 + 4096)),
+                           std::max<size_t>(c.h_live.cap, (size_t) (c.nsamples / 128 + 4096)),
+                           std::max<size_t>(c.h_liverecs.cap, (size_t) (c.nsamples / 64 + 4096)), &launches);
     };
 
     int rc = setup(0);
@@ -818,8 +816,8 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
     cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
     ChunkSet &c = d->sets[0];
     const size_t nt = tiles_for(nsamples);
-    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kCandSlab, nt * kRecSlab, std::max<size_t>(c.d_dead.cap, 4096),
-                                  std::max<size_t>(c.d_live.cap, 4096), std::max<size_t>(c.d_liverecs.cap, 4096));
+    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kCandSlab, nt * kRecSlab, std::max<size_t>(c.h_dead.cap, 4096),
+                                  std::max<size_t>(c.h_live.cap, 4096), std::max<size_t>(c.h_liverecs.cap, 4096));
     if (rc != B200_OK)
         return rc;
     rc = zero_chunk_outputs(d, c, nsamples, s);
@@ -902,8 +900,8 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
     CUDA_TRY(d->d_dbg_masks.ensure((size_t) nsamples + 16));
     // slabs that can hold every position of a tile as a candidate with five records
     const size_t nt = tiles_for(nsamples);
-    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kTile, nt * kTile * 5, std::max<size_t>(c.d_dead.cap, 4096),
-                                  std::max<size_t>(c.d_live.cap, 4096), std::max<size_t>(c.d_liverecs.cap, 4096));
+    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kTile, nt * kTile * 5, std::max<size_t>(c.h_dead.cap, 4096),
+                                  std::max<size_t>(c.h_live.cap, 4096), std::max<size_t>(c.h_liverecs.cap, 4096));
     if (rc != B200_OK)
         return rc;
     rc = zero_chunk_outputs(d, c, nsamples, s);

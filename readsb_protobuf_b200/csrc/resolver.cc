@@ -316,6 +316,12 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
     const uint64_t nblocks = nfull + (v.final_span ? 1 : 0);
 
     msgs.reserve(msgs.size() + 64);
+    // what skip-ahead hides is un-counted after the walk: the dead list it needs may still be arriving
+    struct Skip {
+        uint64_t lo, hi;
+        uint32_t rank;
+    };
+    std::vector<Skip> skips;
     uint32_t tile = 0, live_i = 0; // cursor over live positions
     // The lists were just written by DMA, so the first touch of a cache line misses the core's caches.
     // Two cursors run ahead of the walk over the tiles that hold live positions: the far one
@@ -392,7 +398,6 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
 
         ifile_now_ = sysTimestamp; // demod_2400.c:253-255
         uint64_t sum_scaled_signal_power = 0;
-        HiddenTotals hidden;
         bool skipping = false;
         uint64_t skip_until = 0; // positions <= skip_until are skipped while `skipping`
 
@@ -472,7 +477,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             // demod_2400.c:416: skip the frame body; the for loop ends at the block boundary
             skipping = true;
             skip_until = std::min<uint64_t>(p + (uint64_t) signal_len, b1 - 1);
-            count_dead(v, p, skip_until, lp->dead_rank, hidden);
+            skips.push_back({p, skip_until, lp->dead_rank});
 
             stats_.messages_total++; // useModesMessage, mode_s.c:2149
             memset(mm.msg + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
@@ -483,11 +488,11 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
         // positions no message can come from: K2's per-block totals minus what skip-ahead hid
         if (nk) {
             const BlockDead &bd = v.block_dead[k];
-            stats_.demod_preambles += bd.preambles - hidden.preambles;
-            stats_.demod_rejected_bad += bd.rejected_bad - hidden.bad;
-            stats_.demod_rejected_unknown_icao += bd.rejected_unknown - hidden.unknown;
+            stats_.demod_preambles += bd.preambles;
+            stats_.demod_rejected_bad += bd.rejected_bad;
+            stats_.demod_rejected_unknown_icao += bd.rejected_unknown;
             for (int q = 0; q < 5; ++q)
-                stats_.demod_preamblePhase[q] += bd.phase[q] - hidden.phase[q];
+                stats_.demod_preamblePhase[q] += bd.phase[q];
         }
 
         // demod_2400.c:423-427
@@ -498,6 +503,19 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
 
         filter_.expire(ifile_now_); // readsb.c:331
     }
+
+    // dead positions hidden by skip-ahead were counted in K2's per-block totals: take them out again
+    // (the counters are sums, so the order does not matter)
+    if (v.dead_ready)
+        v.dead_ready(v.dead_ctx); // also: the caller reuses the buffers once we return
+    HiddenTotals hidden;
+    for (const Skip &sk : skips)
+        count_dead(v, sk.lo, sk.hi, sk.rank, hidden);
+    stats_.demod_preambles -= hidden.preambles;
+    stats_.demod_rejected_bad -= hidden.bad;
+    stats_.demod_rejected_unknown_icao -= hidden.unknown;
+    for (int q = 0; q < 5; ++q)
+        stats_.demod_preamblePhase[q] -= hidden.phase[q];
 }
 
 } // namespace b200

@@ -58,6 +58,9 @@ struct SpanView {
     const BlockDead *block_dead;               // [nblocks]
     const unsigned long long *block_sums_u64;  // [nblocks][2]
     const double *block_sums_f64;              // [nblocks][2]
+    // the dead list may still be arriving: called once, before its first use (nullptr = it is there)
+    void (*dead_ready)(void *ctx) = nullptr;
+    void *dead_ctx = nullptr;
 };
 
 class Resolver {
