@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 /* input_format_t of the reference (convert.h:25-31), same numeric values */
 enum { B200_INPUT_UC8 = 0, B200_INPUT_SC16 = 1, B200_INPUT_SC16Q11 = 2 };
@@ -56,6 +56,8 @@ typedef struct b200_demod_config {
     uint32_t block_samples;      /* samples per mag_buf     (readsb.h:98-99); 0 = default */
     uint64_t startup_time_ms;    /* Modes.startup_time      (readsb.c:739) */
     uint64_t max_span_samples;   /* largest span one process call may carry; 0 = 64 Mi samples */
+    int32_t mode_ac;             /* Modes.mode_ac (--modeac, readsb.c:831-833): also demodulate Mode A/C replies */
+    int32_t reserved;
 } b200_demod_config;
 
 /* One accepted message: the fields of struct modesMessage (readsb.h:340-547) that the path
@@ -152,6 +154,11 @@ const b200_block_info *b200_demod_blocks(const b200_demod *d);
 /* running totals since create/reset (Modes.stats_current of the reference) */
 int b200_demod_get_stats(const b200_demod *d, b200_demod_stats *out);
 int b200_demod_get_timing(const b200_demod *d, b200_timing *out);
+/* Modes.stats_current.demod_modeac (demod_2400.c:708): Mode A/C replies since create/reset.  With
+ * mode_ac set, a block's replies follow its Mode S messages in the message list as entries with
+ * msgtype 32, msgbits 16, msg[0..1] = the Mode A code, addr = (code & 0xFF7F) | 1 << 24
+ * (decodeModeAMessage, mode_ac.c:168-181), timestamped at the second framing pulse. */
+uint64_t b200_demod_modeac_count(const b200_demod *d);
 
 /* ---- kernel-level entry points (measurement and unit parity; device pointers) ---- */
 

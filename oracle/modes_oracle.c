@@ -723,6 +723,104 @@ static double thread_cpu_s(void) {
     return ts.tv_sec + ts.tv_nsec * 1e-9;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Mode A/C (demod_2400.c:522-708, mode_ac.c:168-203), only with mo_config.modeac
+ *
+ * A reply is 20 bit periods of 1.45 us (87 ticks of a 60 MHz clock; a sample is 25 ticks): framing
+ * pulses F1 (bit 0) and F2 (bit 14), data pulses between and after, quiet zones at bits 7, 15, 16,
+ * 18, 19.  Whether a reply with F1 at data index f1 decodes is a pure function of the magnitudes
+ * and of the block's noise level; the only sequential part is the skip over an accepted reply.
+ * ------------------------------------------------------------------------------------------ */
+
+/* demod_2400.c:529-530 */
+unsigned mo_modeac_noise_level(double mean_level, double mean_power) {
+    double noise_stddev = sqrt(mean_power - mean_level * mean_level);
+    return (unsigned) ((mean_power + noise_stddev) * 65535 + 0.5);
+}
+
+/* a framing pulse at sample s: rising edge, quiet third sample, 6 dB above noise (:577-588, :604-614) */
+static int ac_framing_pulse(const uint16_t *m, uint32_t s, unsigned noise_level, unsigned *level) {
+    if (!(m[s - 1] < m[s]))
+        return 0;
+    if (m[s + 2] > m[s] || m[s + 2] > m[s + 1])
+        return 0;
+    *level = (unsigned) ((m[s] + m[s + 1]) / 2);
+    return !(noise_level * 2 > *level);
+}
+
+/* Returns 1 and the F1 clock (60 MHz ticks from data[0]) and the Mode A code if a reply with F1 at
+ * data index f1 >= 1 decodes (demod_2400.c:577-683). */
+int mo_modeac_at(const uint16_t *m, uint32_t f1, unsigned noise_level, uint32_t *f1_clock_out, uint32_t *modeac_out) {
+    unsigned f1_level, f2_level;
+    if (!ac_framing_pulse(m, f1, noise_level, &f1_level))
+        return 0;
+
+    /* clock phase from the share of power in the second sample (:593-596) */
+    float pa = (float) m[f1] * m[f1];
+    float pb = (float) m[f1 + 1] * m[f1 + 1];
+    float fraction = pb / (pa + pb);
+    unsigned f1_clock = (unsigned) (25 * (f1 + fraction * fraction) + 0.5);
+
+    unsigned f2_clock = f1_clock + 87 * 14; /* :600 */
+    if (!ac_framing_pulse(m, f2_clock / 25, noise_level, &f2_level))
+        return 0;
+
+    unsigned top = f1_level > f2_level ? f1_level : f2_level;
+    float midpoint = sqrtf(noise_level * top);                          /* :618 */
+    unsigned signal_threshold = (unsigned) (midpoint * M_SQRT2 + 0.5);  /* +3 dB */
+    unsigned noise_threshold = (unsigned) (midpoint / M_SQRT2 + 0.5);   /* -3 dB */
+
+    unsigned bits = 0, bad = 0; /* bad = noisy or uncertain (:629-651, :664) */
+    for (unsigned bit = 0, clock = f1_clock; bit < 20; ++bit, clock += 87) {
+        const uint16_t *p = m + clock / 25;
+        bits <<= 1;
+        if (p[2] >= signal_threshold)
+            bad = 1;
+        if (p[0] >= signal_threshold || p[1] >= signal_threshold)
+            bits |= 1;
+        else if (p[0] > noise_threshold && p[1] > noise_threshold)
+            bad = 1;
+    }
+    if ((bits & 0x80020) != 0x80020 || (bits & 0x0101B) != 0 || bad)
+        return 0;
+
+    /* 00 A4 A2 A1  00 B4 B2 B1  SPI C4 C2 C1  00 D4 D2 D1 (:670-683) */
+    static const struct { unsigned from, to; } map[13] = {
+        {0x40000, 0x0010}, {0x20000, 0x1000}, {0x10000, 0x0020}, {0x08000, 0x2000}, {0x04000, 0x0040},
+        {0x02000, 0x4000}, {0x00800, 0x0100}, {0x00400, 0x0001}, {0x00200, 0x0200}, {0x00100, 0x0002},
+        {0x00080, 0x0400}, {0x00040, 0x0004}, {0x00004, 0x0080},
+    };
+    unsigned modeac = 0;
+    for (int i = 0; i < 13; ++i)
+        if (bits & map[i].from)
+            modeac |= map[i].to;
+    *f1_clock_out = f1_clock;
+    *modeac_out = modeac;
+    return 1;
+}
+
+static void demod_block_ac(demod_state *s, const uint16_t *m, uint32_t mlen, uint64_t sampleTimestamp, uint64_t sysTimestamp,
+                           double mean_level, double mean_power, msg_list *out) {
+    unsigned noise_level = mo_modeac_noise_level(mean_level, mean_power);
+    for (uint32_t f1 = 1; f1 < mlen; ++f1) {
+        uint32_t f1_clock, modeac;
+        if (!mo_modeac_at(m, f1, noise_level, &f1_clock, &modeac))
+            continue;
+        mo_msg mm;
+        memset(&mm, 0, sizeof (mm));
+        mm.timestampMsg = sampleTimestamp + (f1_clock + 87 * 14) / 5;                   /* :697, at F2 */
+        mm.sysTimestampMsg = sysTimestamp + (mm.timestampMsg - sampleTimestamp) / 12000U; /* :700 */
+        mm.msgtype = 32;                                                                 /* mode_ac.c:171 */
+        mm.msgbits = 16;
+        mm.msg[0] = mm.verbatim[0] = (uint8_t) (modeac >> 8);
+        mm.msg[1] = mm.verbatim[1] = (uint8_t) modeac;
+        mm.addr = (modeac & 0x0000FF7F) | (1u << 24);                                    /* mode_ac.c:180 */
+        push_msg(out, &mm);
+        s->stats.messages_total++; /* useModesMessage, mode_s.c:2149 */
+        f1 += (20 * 87 / 25);      /* :707 */
+    }
+}
+
 int mo_run(const mo_config *cfg, const void *iq, uint64_t nsamples, mo_result *res) {
     memset(res, 0, sizeof (*res));
     if (cfg->format < MO_UC8 || cfg->format > MO_SC16Q11 || cfg->block_samples == 0)
@@ -766,6 +864,8 @@ int mo_run(const mo_config *cfg, const void *iq, uint64_t nsamples, mo_result *r
 
         t0 = thread_cpu_s();
         demod_block(s, data, n, sampleTimestamp, sysTimestamp, mean_power, &list);
+        if (cfg->modeac) /* readsb.c:831-833 */
+            demod_block_ac(s, data, n, sampleTimestamp, sysTimestamp, mean_level, mean_power, &list);
         s->stats.demod_cpu_s += thread_cpu_s() - t0;
         s->stats.samples_processed += MO_OVERLAP + n; /* readsb.c:835 */
 

@@ -96,6 +96,11 @@ int mo_try_mask(const uint16_t *m, uint32_t j, int threshold);
 /* demod_2400.c:98-209: slice nbytes message bytes for (j, try_phase) */
 void mo_slice(const uint16_t *m, uint32_t j, int try_phase, int nbytes, uint8_t *msg);
 
+/* demod_2400.c:529-530: noise level of a block from the converter's means */
+unsigned mo_modeac_noise_level(double mean_level, double mean_power);
+/* demod_2400.c:577-683: does a Mode A/C reply with F1 at data index f1 (>= 1) decode? */
+int mo_modeac_at(const uint16_t *m, uint32_t f1, unsigned noise_level, uint32_t *f1_clock_out, uint32_t *modeac_out);
+
 /* ---- whole-stream run: ifileRun + fifo overlap + demodulate2400 + backgroundTasks ---- */
 
 typedef struct {
@@ -103,6 +108,7 @@ typedef struct {
     int32_t nfix;          /* Modes.nfix_crc: 0, 1 or 2 */
     int32_t threshold;     /* Modes.preambleThreshold */
     uint32_t block_samples; /* samples per mag_buf (MO_BLOCK_SAMPLES) */
+    int32_t modeac;        /* Modes.mode_ac: also run the Mode A/C demodulator on every block */
 } mo_config;
 
 typedef struct {

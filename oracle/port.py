@@ -19,7 +19,7 @@ ERRORINFO_DTYPE = np.dtype([("syndrome", "<u4"), ("errors", "<i4"), ("bit", "i1"
 
 class _Config(ctypes.Structure):
     _fields_ = [("format", ctypes.c_int32), ("nfix", ctypes.c_int32), ("threshold", ctypes.c_int32),
-                ("block_samples", ctypes.c_uint32)]
+                ("block_samples", ctypes.c_uint32), ("modeac", ctypes.c_int32)]
 
 
 class _Result(ctypes.Structure):
@@ -65,12 +65,12 @@ def lib():
 
 
 def run(iq: np.ndarray, fmt: str = "uc8", nfix: int = 1, threshold: int = 58,
-        block_samples: int = BLOCK_SAMPLES) -> DemodResult:
+        block_samples: int = BLOCK_SAMPLES, modeac: bool = False) -> DemodResult:
     """Demodulate a whole stream of raw IQ bytes with the CPU restatement."""
     iq = np.ascontiguousarray(iq).view(np.uint8).reshape(-1)
     bps = 2 if fmt == "uc8" else 4
     nsamples = iq.size // bps
-    cfg = _Config(FORMATS[fmt], nfix, threshold, block_samples)
+    cfg = _Config(FORMATS[fmt], nfix, threshold, block_samples, 1 if modeac else 0)
     res = _Result()
     rc = lib().mo_run(ctypes.byref(cfg), iq.ctypes.data, nsamples, ctypes.byref(res))
     if rc != 0:

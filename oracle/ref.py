@@ -28,7 +28,7 @@ def available() -> bool:
 
 
 def run_file(path, fmt: str = "uc8", nfix: int = 1, threshold: int = 58, block_samples: int | None = None,
-             max_samples: int | None = None, repeat: int = 1, mag_out=None) -> DemodResult:
+             max_samples: int | None = None, repeat: int = 1, mag_out=None, modeac: bool = False) -> DemodResult:
     exe = binary()
     if exe is None:
         raise RuntimeError("oracle/_ref/ref_demod is not built and /root/reference is absent")
@@ -42,6 +42,8 @@ def run_file(path, fmt: str = "uc8", nfix: int = 1, threshold: int = 58, block_s
             cmd += ["--max-samples", str(max_samples)]
         if mag_out:
             cmd += ["--mag-out", str(mag_out)]
+        if modeac:
+            cmd += ["--modeac"]
         subprocess.run(cmd, check=True, capture_output=True)
         return read_result_file(out)
 

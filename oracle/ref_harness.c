@@ -21,7 +21,7 @@
  *
  * usage: ref_demod --in FILE --out FILE [--format uc8|sc16|sc16q11] [--nfix 0|1|2]
  *                  [--threshold N] [--block N] [--dcfilter] [--mag-out FILE]
- *                  [--max-samples N] [--repeat R]
+ *                  [--max-samples N] [--repeat R] [--modeac]
  */
 #include "readsb.h"
 
@@ -120,7 +120,7 @@ static double thread_cpu_s(void) {
 int main(int argc, char **argv) {
     const char *in_path = NULL, *out_path = NULL, *mag_path = NULL;
     input_format_t format = INPUT_UC8;
-    int nfix = 1, threshold = 58, dcfilter = 0, repeat = 1;
+    int nfix = 1, threshold = 58, dcfilter = 0, repeat = 1, modeac = 0;
     unsigned block = MODES_MAG_BUF_SAMPLES;
     uint64_t max_samples = UINT64_MAX;
 
@@ -136,6 +136,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(a, "--max-samples") && v) { max_samples = strtoull(v, NULL, 10); ++i; }
         else if (!strcmp(a, "--repeat") && v) { repeat = atoi(v); ++i; }
         else if (!strcmp(a, "--dcfilter")) { dcfilter = 1; }
+        else if (!strcmp(a, "--modeac")) { modeac = 1; }
         else if (!strcmp(a, "--format") && v) {
             if (!strcasecmp(v, "uc8")) format = INPUT_UC8;
             else if (!strcasecmp(v, "sc16")) format = INPUT_SC16;
@@ -161,6 +162,7 @@ int main(int argc, char **argv) {
     Modes.nfix_crc = (int8_t) nfix;
     Modes.sdr_type = SDR_IFILE;
     Modes.dc_filter = (int8_t) dcfilter;
+    Modes.mode_ac = (int8_t) modeac;
     Modes.quiet = 1;
     Modes.net = 1;
     Modes.net_verbatim = 1;
@@ -262,6 +264,8 @@ int main(int argc, char **argv) {
             /* readsb.c:828-837 */
             t0 = thread_cpu_s();
             demodulate2400(&buf);
+            if (Modes.mode_ac) /* readsb.c:831-833 */
+                demodulate2400AC(&buf);
             demod_cpu += thread_cpu_s() - t0;
             Modes.stats_current.samples_processed += buf.validLength;
 

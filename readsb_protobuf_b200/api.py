@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "b200_demod_block_count", "b200_demod_blocks", "b200_demod_get_stats", "b200_demod_get_timing",
     "b200_scan_device", "b200_convert", "b200_uc8_table", "b200_debug_scan", "b200_crc_batch",
     "b200_error_table", "b200_abi_sizeof", "b200_host_checksum", "b200_host_error_table", "b200_host_uc8_table",
-    "b200_host_filter_script",
+    "b200_host_filter_script", "b200_demod_modeac_count",
 )
 
 
@@ -47,11 +47,15 @@ class B200Error(RuntimeError):
         self.code = code
 
 
+ABI_VERSION = 2  # B200_ABI_VERSION
+
+
 class _Config(ctypes.Structure):
     _fields_ = [
         ("abi_version", ctypes.c_int32), ("device", ctypes.c_int32), ("input_format", ctypes.c_int32),
         ("nfix_crc", ctypes.c_int32), ("preamble_threshold", ctypes.c_int32), ("block_samples", ctypes.c_uint32),
         ("startup_time_ms", ctypes.c_uint64), ("max_span_samples", ctypes.c_uint64),
+        ("mode_ac", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -87,6 +91,8 @@ def load():
     L.b200_demod_create.argtypes = [ctypes.POINTER(_Config), ctypes.POINTER(vp)]
     L.b200_demod_destroy.restype = None
     L.b200_demod_destroy.argtypes = [vp]
+    L.b200_demod_modeac_count.restype = u64
+    L.b200_demod_modeac_count.argtypes = [vp]
     L.b200_demod_reset.restype = i32
     L.b200_demod_reset.argtypes = [vp]
     L.b200_demod_process.restype = i32
@@ -184,12 +190,13 @@ class Demodulator:
 
     def __init__(self, fmt: str = "uc8", nfix: int = 1, threshold: int = 58,
                  block_samples: int = DEFAULT_BLOCK_SAMPLES, device: int = 0,
-                 max_span_samples: int = 0, startup_time_ms: int = 0):
+                 max_span_samples: int = 0, startup_time_ms: int = 0, modeac: bool = False):
         self._L = load()
         self.fmt = fmt
         self.bytes_per_sample = BYTES_PER_SAMPLE[fmt]
         self.block_samples = block_samples
-        cfg = _Config(1, device, FORMATS[fmt], nfix, threshold, block_samples, startup_time_ms, max_span_samples)
+        cfg = _Config(ABI_VERSION, device, FORMATS[fmt], nfix, threshold, block_samples, startup_time_ms, max_span_samples,
+                      1 if modeac else 0, 0)
         h = ctypes.c_void_p()
         _check(self._L.b200_demod_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
@@ -246,6 +253,10 @@ class Demodulator:
         s = np.zeros(1, dtype=STATS_DTYPE)
         _check(self._L.b200_demod_get_stats(self._h, s.ctypes.data))
         return s[0]
+
+    def modeac_count(self) -> int:
+        """Modes.stats_current.demod_modeac: Mode A/C replies decoded since create/reset."""
+        return int(self._L.b200_demod_modeac_count(self._h))
 
     def crc_mismatches(self) -> int:
         """Kernel-vs-host CRC disagreements seen by the resolver (must be 0)."""

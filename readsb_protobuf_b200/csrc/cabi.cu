@@ -138,6 +138,9 @@ struct ChunkSet {
     PinnedBuf<uint32_t> h_dead;
     PinnedBuf<LivePos> h_live;
     PinnedBuf<LiveRec> h_liverecs;
+    // Mode A/C (only with cfg.mode_ac): per-block noise levels, unordered hit list in pinned host memory
+    DevBuf<uint32_t> d_ac_noise;
+    PinnedBuf<AcHit> h_ac_hits;
     cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr;
 
     // what is in flight
@@ -150,7 +153,7 @@ struct ChunkSet {
     void release() {
         d_cand.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
         d_small.release(); h_small.release(); d_dead.release();
-        h_dead.release(); h_live.release(); h_liverecs.release();
+        h_dead.release(); h_live.release(); h_liverecs.release(); d_ac_noise.release(); h_ac_hits.release();
         for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists})
             if (*e) {
                 cudaEventDestroy(*e);
@@ -166,6 +169,7 @@ struct b200_demod {
     int bytes_per_sample = 2;
     int sm_count = 0;
     int scan_grid = 0, slice_grid = 0;
+    size_t ac_hit_cap = 0; // grown when a chunk's Mode A/C hits did not fit
     std::unique_ptr<CrcTables> crc;
     std::unique_ptr<Resolver> resolver;
 
@@ -239,6 +243,10 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
     CUDA_TRY(c.d_tiles.ensure(ntiles + 1));
     CUDA_TRY(c.d_magbuf.ensure(ntiles * (size_t) kTile + kMagSlack));
     CUDA_TRY(c.d_step_off.ensure((ntiles + 1) * (size_t) kScanSteps));
+    if (d->cfg.mode_ac) {
+        CUDA_TRY(c.d_ac_noise.ensure(nblocks));
+        CUDA_TRY(c.h_ac_hits.ensure(std::max<size_t>(c.h_ac_hits.cap, std::max<size_t>(d->ac_hit_cap, (size_t) (nsamples / 256 + 4096)))));
+    }
     {
         auto up = [](size_t x) { return (x + 63) & ~(size_t) 63; };
         const size_t o_cnt = 0, o_su = up(sizeof(ScanCounters)), o_sf = o_su + up(2 * nblocks * sizeof(unsigned long long)),
@@ -511,6 +519,25 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     // K2 looks at K1's overflow flag itself and does nothing when K1 did not fit
     CUDA_TRY(launch_classify(ca, s));
     CUDA_TRY(cudaEventRecord(c.ev_k2, s));
+    if (d->cfg.mode_ac && n) {
+        // demodulate2400AC (readsb.c:831-833) over the same magnitudes
+        ModeacArgs ma;
+        memset(&ma, 0, sizeof(ma));
+        ma.mag = c.d_magbuf.p;
+        ma.nsamples = n;
+        ma.block_samples = B;
+        ma.format = sa.format;
+        ma.nblocks = (uint32_t) ((n + B - 1) / B);
+        ma.sums_u64 = c.d_sums_u64.p;
+        ma.sums_f64 = c.d_sums_f64.p;
+        ma.noise_level = c.d_ac_noise.p;
+        ma.hits = c.h_ac_hits.p;
+        ma.hit_cap = (uint32_t) std::min<size_t>(c.h_ac_hits.cap, 0xffffffffu);
+        ma.counters = c.d_counters.p;
+        CUDA_TRY(launch_modeac(ma, s));
+        if (launches)
+            *launches += 2;
+    }
     if (launches)
         *launches += ntiles ? 3 : 0;
     CUDA_TRY(cudaMemcpyAsync(c.h_small.p, c.d_small.p, c.small_bytes, cudaMemcpyDeviceToHost, s));
@@ -569,6 +596,9 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
             dead_cap = std::max<size_t>(dead_cap, cand_total);
             live_cap = std::max<size_t>(live_cap, cand_total);
             liverec_cap = std::max<size_t>(liverec_cap, rec_total);
+        } else if (cnt.overflow & 32u) {
+            // the Mode A/C hit list was too small; its counter kept counting
+            d->ac_hit_cap = (size_t) cnt.n_modeac_hits + 4096;
         } else {
             // K2's lists were too small; its counters kept counting past the capacity
             dead_cap = std::max<size_t>(dead_cap, (size_t) cnt.n_dead + 4096);
@@ -614,6 +644,8 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     v.block_dead = c.h_block_dead.p;
     v.block_sums_u64 = c.h_sums_u64.p;
     v.block_sums_f64 = c.h_sums_f64.p;
+    v.ac_hits = d->cfg.mode_ac ? c.h_ac_hits.p : nullptr;
+    v.n_ac_hits = d->cfg.mode_ac ? cnt.n_modeac_hits : 0;
     v.dead_ready = [](void *ev) { cudaEventSynchronize((cudaEvent_t) ev); };
     v.dead_ctx = c.ev_lists;
     if (const char *dump = getenv("B200_DUMP_SPAN")) {
@@ -795,6 +827,10 @@ extern "C" int b200_demod_get_stats(const b200_demod *d, b200_demod_stats *out) 
     // reserved[0]: kernel/host CRC disagreements (must stay 0)
     out->reserved[0] = (double) d->resolver->gpu_host_mismatches();
     return B200_OK;
+}
+
+extern "C" uint64_t b200_demod_modeac_count(const b200_demod *d) {
+    return d ? d->resolver->modeac_count() : 0;
 }
 
 extern "C" int b200_demod_get_timing(const b200_demod *d, b200_timing *out) {

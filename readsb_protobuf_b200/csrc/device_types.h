@@ -87,6 +87,14 @@ struct LiveRec {
     uint8_t pad[2];
 };
 
+// Mode A/C kernel -> host: a position where a reply decodes (demod_2400.c:577-683).  16 bytes.
+struct AcHit {
+    uint32_t q;        // block * block_samples + data index of F1 (data[0] = 326 samples before the block's first new one)
+    uint32_t f1_clock; // 60 MHz ticks from data[0] (demod_2400.c:596)
+    uint32_t modeac;   // 00 A4 A2 A1  00 B4 B2 B1  SPI C4 C2 C1  00 D4 D2 D1
+    uint32_t pad;
+};
+
 // per mag_buf counters of positions that can never be accepted (K2)
 struct BlockDead {
     uint32_t preambles;
@@ -101,10 +109,10 @@ struct ScanCounters {
     unsigned long long n_dead;
     unsigned long long n_live;
     unsigned long long n_liverec;
-    unsigned int overflow; // bit0 cand, bit1 rec, bit2 dead, bit3 live, bit4 liverec
+    unsigned int overflow; // bit0 cand, bit1 rec, bit2 dead, bit3 live, bit4 liverec, bit5 Mode A/C hits
     unsigned int next_tile; // K1a work queue
-    unsigned int next_tile_slice; // K1b work queue
-    unsigned int pad;
+    unsigned int next_tile_slice; // (unused since K1b deals its units round-robin)
+    unsigned int n_modeac_hits;   // Mode A/C kernel
 };
 
 struct ErrorInfo { // struct errorinfo, crc.h:32-37

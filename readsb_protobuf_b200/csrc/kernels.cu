@@ -1690,6 +1690,125 @@ cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Mode A/C (demodulate2400AC, demod_2400.c:522-708): F1/F2 framing-pulse search over K1a's magnitudes
+//
+// Whether a reply with its first framing pulse at data index f1 of a mag_buf decodes is a pure
+// function of the magnitudes and of the block's noise level, so every position is tested
+// independently (one thread each; the first two comparisons reject almost all of them) and the hits
+// go to an unordered list.  The only sequential part -- skipping 69 samples past an accepted reply
+// (demod_2400.c:707) -- is left to the host, over the sorted hits.
+// Float steps are spelled out (no FMA, round-to-nearest) exactly as the scalar C code takes them.
+// ------------------------------------------------------------------------------------------
+
+// demod_2400.c:529-530 from the block's converter sums (convert.c:104-110 / 246-252)
+__global__ void modeac_noise_kernel(const ModeacArgs a) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.nblocks)
+        return;
+    const unsigned long long B = a.block_samples, b0 = (unsigned long long) k * B;
+    const unsigned nk = (unsigned) (a.nsamples > b0 ? (a.nsamples - b0 < B ? a.nsamples - b0 : B) : 0);
+    double mean_level, mean_power;
+    if (a.format == 0) {
+        mean_level = __ddiv_rn(__ddiv_rn((double) a.sums_u64[2 * k], 65536.0), (double) nk); // sic: 65536
+        mean_power = __ddiv_rn(__ddiv_rn(__ddiv_rn((double) a.sums_u64[2 * k + 1], 65535.0), 65535.0), (double) nk);
+    } else {
+        mean_level = (double) __fdiv_rn((float) a.sums_f64[2 * k], (float) nk);
+        mean_power = (double) __fdiv_rn((float) a.sums_f64[2 * k + 1], (float) nk);
+    }
+    const double noise_stddev = __dsqrt_rn(__dsub_rn(mean_power, __dmul_rn(mean_level, mean_level)));
+    a.noise_level[k] = nk ? __double2uint_rz(__dadd_rn(__dmul_rn(__dadd_rn(mean_power, noise_stddev), 65535.0), 0.5)) : 0u;
+}
+
+// a framing pulse at m[0]: rising edge, quiet third sample, 6 dB above noise (demod_2400.c:577-588, 604-614)
+__device__ __forceinline__ bool ac_framing_pulse(const uint16_t *m, uint32_t noise_level, uint32_t &level) {
+    const uint32_t m0 = m[0], m1 = m[1], m2 = m[2];
+    if (!(m[-1] < m0) || m2 > m0 || m2 > m1)
+        return false;
+    level = (m0 + m1) >> 1;
+    return !(noise_level * 2u > level);
+}
+
+__global__ void __launch_bounds__(256) modeac_kernel(const ModeacArgs a) {
+    const uint32_t B = a.block_samples;
+    const uint32_t lane = threadIdx.x & 31;
+    // q = block * B + data index of F1 (data[0] of a block is 326 samples before its first new sample);
+    // the loop is warp-uniform so that the hit list can be appended to with one atomic per warp
+    const unsigned long long total = a.nsamples, stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
+        const unsigned long long q = base + lane;
+        bool hit = false;
+        uint32_t f1_clock = 0, modeac = 0;
+        const uint32_t k = (uint32_t) (q / B), f1 = (uint32_t) (q - (unsigned long long) k * B);
+        if (q < total && f1 >= 1) { // demod_2400.c:532: f1_sample runs from 1 to mlen - 1
+            const uint16_t *d = a.mag + (size_t) k * B + kPosShift; // data[] of the block
+            const uint32_t noise_level = a.noise_level[k];
+            uint32_t f1_level, f2_level;
+            if (ac_framing_pulse(d + f1, noise_level, f1_level)) {
+                // clock phase from the share of power in the second sample (:593-596)
+                const float fa = __uint2float_rn(d[f1]), fb = __uint2float_rn(d[f1 + 1]);
+                const float pa = __fmul_rn(fa, fa), pb = __fmul_rn(fb, fb);
+                const float fraction = __fdiv_rn(pb, __fadd_rn(pa, pb));
+                const float pos = __fmul_rn(25.0f, __fadd_rn(__uint2float_rn(f1), __fmul_rn(fraction, fraction)));
+                f1_clock = __double2uint_rz(__dadd_rn((double) pos, 0.5));
+                const uint32_t f2_clock = f1_clock + 87 * 14; // :600
+                if (ac_framing_pulse(d + f2_clock / 25, noise_level, f2_level)) {
+                    const uint32_t top = f1_level > f2_level ? f1_level : f2_level;
+                    const float midpoint = __fsqrt_rn(__uint2float_rn(noise_level * top)); // :618
+                    const uint32_t signal_threshold = __double2uint_rz(__dadd_rn(__dmul_rn((double) midpoint, 1.41421356237309504880), 0.5));
+                    const uint32_t noise_threshold = __double2uint_rz(__dadd_rn(__ddiv_rn((double) midpoint, 1.41421356237309504880), 0.5));
+                    uint32_t bits = 0;
+                    bool bad = false; // noisy or uncertain (:629-651, :664)
+                    uint32_t clock = f1_clock;
+                    for (int bit = 0; bit < 20; ++bit, clock += 87) {
+                        const uint16_t *p = d + clock / 25;
+                        const uint32_t p0 = p[0], p1 = p[1], p2 = p[2];
+                        bits <<= 1;
+                        if (p2 >= signal_threshold)
+                            bad = true;
+                        if (p0 >= signal_threshold || p1 >= signal_threshold)
+                            bits |= 1u;
+                        else if (p0 > noise_threshold && p1 > noise_threshold)
+                            bad = true;
+                    }
+                    if ((bits & 0x80020u) == 0x80020u && (bits & 0x0101Bu) == 0 && !bad) {
+                        // 00 A4 A2 A1  00 B4 B2 B1  SPI C4 C2 C1  00 D4 D2 D1 (:670-683)
+                        modeac = ((bits & 0x40000u) ? 0x0010u : 0) | ((bits & 0x20000u) ? 0x1000u : 0) | ((bits & 0x10000u) ? 0x0020u : 0) |
+                                 ((bits & 0x08000u) ? 0x2000u : 0) | ((bits & 0x04000u) ? 0x0040u : 0) | ((bits & 0x02000u) ? 0x4000u : 0) |
+                                 ((bits & 0x00800u) ? 0x0100u : 0) | ((bits & 0x00400u) ? 0x0001u : 0) | ((bits & 0x00200u) ? 0x0200u : 0) |
+                                 ((bits & 0x00100u) ? 0x0002u : 0) | ((bits & 0x00080u) ? 0x0400u : 0) | ((bits & 0x00040u) ? 0x0004u : 0) |
+                                 ((bits & 0x00004u) ? 0x0080u : 0);
+                        hit = true;
+                    }
+                }
+            }
+        }
+        const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+        if (hm) {
+            uint32_t slot = 0;
+            if (lane == 0)
+                slot = atomicAdd(&a.counters->n_modeac_hits, (unsigned int) __popc(hm));
+            slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(hm & ((1u << lane) - 1u));
+            if (hit) {
+                if (slot < a.hit_cap)
+                    a.hits[slot] = AcHit{(uint32_t) q, f1_clock, modeac, 0u};
+                else
+                    atomicOr(&a.counters->overflow, 32u);
+            }
+        }
+    }
+}
+
+cudaError_t launch_modeac(const ModeacArgs &a, cudaStream_t stream) {
+    if (a.nsamples == 0 || a.nblocks == 0)
+        return cudaSuccess;
+    modeac_noise_kernel<<<(a.nblocks + 127) / 128, 128, 0, stream>>>(a);
+    unsigned long long want = (a.nsamples + 255) / 256;
+    const int grid = (int) (want < 148ull * 8 ? want : 148ull * 8);
+    modeac_kernel<<<grid, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // convert_kernel: the iq_convert_fn boundary (convert.h:33-38), magnitudes materialised
 // ------------------------------------------------------------------------------------------
 

@@ -86,6 +86,20 @@ struct ClassifyArgs {
     BlockDead *block_dead; // [nblocks]
 };
 
+struct ModeacArgs {
+    const uint16_t *mag;  // K1a's magnitudes (index = chunk sample + kHead)
+    uint64_t nsamples;    // new samples of the chunk
+    uint32_t block_samples;
+    uint32_t format;
+    uint32_t nblocks;     // mag_bufs of the chunk, the short final one included
+    const unsigned long long *sums_u64; // K1a's block sums
+    const double *sums_f64;
+    uint32_t *noise_level; // [nblocks] scratch
+    AcHit *hits;
+    uint32_t hit_cap;
+    ScanCounters *counters;
+};
+
 // dynamic shared memory the scan kernel needs for a format
 size_t scan_smem_bytes(uint32_t format);
 cudaError_t scan_configure();
@@ -94,6 +108,8 @@ cudaError_t slice_configure();
 cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
 cudaError_t launch_slice(const SliceArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream);
+// Mode A/C framing-pulse search over K1a's magnitudes (after K1a of the same chunk)
+cudaError_t launch_modeac(const ModeacArgs &a, cudaStream_t stream);
 
 // IQ -> u16 magnitudes materialised in global memory (+ sums into sums_u64[2] / sums_f64[2])
 cudaError_t launch_convert(const uint8_t *iq, uint32_t format, uint32_t nsamples, const uint16_t *lut,

@@ -1,9 +1,9 @@
 // resolver.cc -- see resolver.h.
 #include "resolver.h"
 
-#include <string.h>
-
 #include <algorithm>
+
+#include <string.h>
 
 namespace b200 {
 
@@ -147,6 +147,7 @@ void Resolver::reset() {
     memset(&stats_, 0, sizeof(stats_));
     ifile_now_ = 0;
     mismatches_ = 0;
+    modeac_ = 0;
 }
 
 // scoreModesMessage (mode_s.c:311-409) for a frame K1 already classified
@@ -322,6 +323,10 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
         uint32_t rank;
     };
     std::vector<Skip> skips;
+    // Mode A/C hits in stream order (the kernel appends them as it finds them)
+    if (v.n_ac_hits > 1)
+        std::sort(v.ac_hits, v.ac_hits + v.n_ac_hits, [](const AcHit &a, const AcHit &b) { return a.q < b.q; });
+    uint32_t ac_i = 0;
     uint32_t tile = 0, live_i = 0; // cursor over live positions
     // The lists were just written by DMA, so the first touch of a cache line misses the core's caches.
     // Two cursors run ahead of the walk over the tiles that hold live positions: the far one
@@ -483,6 +488,31 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             memset(mm.msg + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
             memset(mm.verbatim + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
             msgs.push_back(mm);
+        }
+
+        // demodulate2400AC (readsb.c:831-833, demod_2400.c:522-708) runs after demodulate2400 on the same
+        // mag_buf: the block's hits in order, skipping 69 samples past every reply that is taken (:707)
+        {
+            uint64_t next_ok = 0; // first data index that may be examined again
+            for (; ac_i < v.n_ac_hits && (uint64_t) v.ac_hits[ac_i].q < (k + 1) * B; ++ac_i) {
+                const AcHit h = v.ac_hits[ac_i];
+                const uint64_t f1 = (uint64_t) h.q - k * B;
+                if (f1 < next_ok)
+                    continue;
+                b200_message mm;
+                memset(&mm, 0, sizeof(mm));
+                mm.timestampMsg = sampleTimestamp + (h.f1_clock + 87 * 14) / 5;                           // :697, at F2
+                mm.sysTimestampMsg = sysTimestamp + (mm.timestampMsg - sampleTimestamp) / 12000U; // :700
+                mm.msgtype = 32;                                                                   // mode_ac.c:171
+                mm.msgbits = 16;
+                mm.msg[0] = mm.verbatim[0] = (uint8_t) (h.modeac >> 8);
+                mm.msg[1] = mm.verbatim[1] = (uint8_t) h.modeac;
+                mm.addr = (h.modeac & 0x0000FF7Fu) | (1u << 24);                                        // mode_ac.c:180
+                msgs.push_back(mm);
+                stats_.messages_total++; // useModesMessage, mode_s.c:2149
+                ++modeac_;
+                next_ok = f1 + 70; // f1_sample += 69, then the loop's ++
+            }
         }
 
         // positions no message can come from: K2's per-block totals minus what skip-ahead hid

@@ -58,6 +58,9 @@ struct SpanView {
     const BlockDead *block_dead;               // [nblocks]
     const unsigned long long *block_sums_u64;  // [nblocks][2]
     const double *block_sums_f64;              // [nblocks][2]
+    // Mode A/C hits of the span, unordered; the resolver sorts them in place
+    AcHit *ac_hits = nullptr;
+    uint32_t n_ac_hits = 0;
     // the dead list may still be arriving: called once, before its first use (nullptr = it is there)
     void (*dead_ready)(void *ctx) = nullptr;
     void *dead_ctx = nullptr;
@@ -72,6 +75,7 @@ class Resolver {
     const b200_demod_stats &stats() const { return stats_; }
     const IcaoFilter &filter() const { return filter_; }
     uint64_t gpu_host_mismatches() const { return mismatches_; }
+    uint64_t modeac_count() const { return modeac_; } // Modes.stats_current.demod_modeac
 
   private:
     int score(const LiveRec &r) const;
@@ -82,6 +86,7 @@ class Resolver {
     b200_demod_stats stats_;
     uint64_t ifile_now_;
     uint64_t mismatches_;
+    uint64_t modeac_;
 };
 
 } // namespace b200

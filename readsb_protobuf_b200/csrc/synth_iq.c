@@ -6,7 +6,9 @@
  * in (readsb's own description of the waveform: demod_2400.c:31-37, 264-273): preamble
  * pulses at 0, 1.0, 3.5 and 4.5 us, each 0.5 us wide; data bit i occupies 8+i us with the
  * high half first for a 1.  One 2.4 MHz sample integrates 5 ticks, so the frame's start tick
- * modulo 5 exercises all five demodulator phases.
+ * modulo 5 exercises all five demodulator phases.  Mode A/C replies (df = 32 in the plan) follow
+ * readsb's description at demod_2400.c:513-520, 532-557: 20 bit periods of 1.45 us (87 cycles of a
+ * 60 MHz clock) with a 0.45 us (27 cycle) pulse where the bit is set, F1 at bit 0, F2 at bit 14.
  *
  * Determinism: the frame plan comes from one sequential PRNG; noise is seeded per 65536
  * sample chunk from (seed, chunk index), so any span renders identically whatever the
@@ -30,6 +32,7 @@ typedef struct {
     double amp_min, amp_max; /* frame amplitude, uniform, fraction of full scale */
     double frac_biterror; /* fraction of frames with one flipped bit in bits 5..n-1 */
     double frac_df17, frac_df11; /* the rest is split between DF4, DF5, DF20, DF21 */
+    double modeac_per_s; /* Mode A/C replies (a second, independent Poisson process; 0 = none) */
 } synth_cfg;
 
 typedef struct {
@@ -227,6 +230,60 @@ int64_t synth_plan(const synth_cfg *cfg, synth_frame *frames, int64_t cap) {
     }
 
     free(pool);
+
+    /* Mode A/C replies: their own PRNG stream, so that a plan without them is unchanged */
+    if (cfg->modeac_per_s > 0) {
+        rng_t ra;
+        rng_seed(&ra, cfg->seed, 0x6d6f6461);
+        const double gap_ac = 12e6 / cfg->modeac_per_s;
+        const int64_t n_s = n < cap ? n : cap; /* Mode S frames actually stored */
+        int64_t n_ac = 0, stored = n_s;
+        double ta = 0;
+        for (;;) {
+            ta += -log(1.0 - rng_uniform(&ra)) * gap_ac;
+            if (!(ta < total_ticks))
+                break;
+            synth_frame f;
+            memset(&f, 0, sizeof (f));
+            f.start_tick = (uint64_t) ta;
+            f.amp = (float) (cfg->amp_min + (cfg->amp_max - cfg->amp_min) * rng_uniform(&ra));
+            f.phase0 = (float) (rng_uniform(&ra) * 6.283185307179586);
+            f.dphase = (float) ((rng_uniform(&ra) - 0.5) * 2.0 * 6.283185307179586 * 100e3 / 2.4e6);
+            f.errbit = -1;
+            f.df = 32;
+            f.nbytes = 3;
+            /* pulse pattern, bit 19 = F1 ... bit 0 = X5 (the order demod_2400.c:629-651 shifts them in):
+             * framing pulses, twelve random data pulses, SPI in one reply of sixteen */
+            uint64_t x = rng_next(&ra);
+            uint32_t pat = 0x80020u;
+            static const int data_bits[12] = {18, 17, 16, 15, 14, 13, 11, 10, 9, 8, 7, 6};
+            for (int i = 0; i < 12; ++i)
+                if ((x >> i) & 1)
+                    pat |= 1u << data_bits[i];
+            if (((x >> 12) & 15) == 0)
+                pat |= 1u << 2;
+            f.msg[0] = (uint8_t) (pat >> 16);
+            f.msg[1] = (uint8_t) (pat >> 8);
+            f.msg[2] = (uint8_t) pat;
+            if (stored < cap)
+                frames[stored++] = f;
+            ++n_ac;
+        }
+        /* merge by start tick (insertion from the back: both runs are sorted) */
+        if (stored == n_s + n_ac && n == n_s) {
+            synth_frame *tmp = malloc(sizeof (synth_frame) * (size_t) (stored > 0 ? stored : 1));
+            int64_t i = 0, j = n_s, k = 0;
+            while (i < n_s || j < stored) {
+                if (j >= stored || (i < n_s && frames[i].start_tick <= frames[j].start_tick))
+                    tmp[k++] = frames[i++];
+                else
+                    tmp[k++] = frames[j++];
+            }
+            memcpy(frames, tmp, sizeof (synth_frame) * (size_t) stored);
+            free(tmp);
+        }
+        n += n_ac;
+    }
     return n;
 }
 
@@ -277,6 +334,28 @@ static void render_chunk(const synth_cfg *cfg, const synth_frame *frames, int64_
     uint8_t ticks[FRAME_TICKS_MAX + 16];
     for (int64_t i = a; i < nframes && frames[i].start_tick < chunk_tick1; ++i) {
         const synth_frame *f = &frames[i];
+        if (f->df == 32) { /* Mode A/C reply on the 60 MHz grid: a sample is 25 cycles */
+            const uint32_t pat = ((uint32_t) f->msg[0] << 16) | ((uint32_t) f->msg[1] << 8) | f->msg[2];
+            const int64_t cyc0 = (int64_t) f->start_tick * 5;
+            const uint64_t s_first_ac = f->start_tick / 5;
+            for (int bit = 0; bit < 20; ++bit) {
+                if (!((pat >> (19 - bit)) & 1))
+                    continue;
+                const int64_t on0 = cyc0 + 87 * bit, on1 = on0 + 27;
+                for (int64_t s = on0 / 25; s * 25 < on1; ++s) {
+                    if (s < (int64_t) c0 || s >= (int64_t) (c0 + SYNTH_CHUNK))
+                        continue;
+                    const int64_t lo25 = s * 25 > on0 ? s * 25 : on0, hi25 = (s + 1) * 25 < on1 ? (s + 1) * 25 : on1;
+                    if (hi25 <= lo25)
+                        continue;
+                    float env = f->amp * (float) (hi25 - lo25) * 0.04f;
+                    float ph = f->phase0 + f->dphase * (float) (s - (int64_t) s_first_ac);
+                    bi[s - c0] += env * cosf(ph);
+                    bq[s - c0] += env * sinf(ph);
+                }
+            }
+            continue;
+        }
         int nticks;
         frame_ticks(f, ticks, &nticks);
         uint64_t s_first = f->start_tick / 5;

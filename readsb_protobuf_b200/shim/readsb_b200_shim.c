@@ -102,6 +102,7 @@ bool ifileOpen(void) {
     cfg.block_samples = MODES_MAG_BUF_SAMPLES;
     cfg.startup_time_ms = Modes.startup_time;
     cfg.max_span_samples = (uint64_t) SPAN_BLOCKS * MODES_MAG_BUF_SAMPLES;
+    cfg.mode_ac = Modes.mode_ac ? 1 : 0; /* --modeac: the library also runs demodulate2400AC's search */
     if (Modes.dc_filter) {
         fprintf(stderr, "ifile: --dcfilter is not available on the GPU path\n");
         return false;
@@ -228,6 +229,14 @@ void ifileClose(void) {
     }
 }
 
+static void release_pending(void) {
+    pending.nmsgs = 0;
+    pthread_mutex_lock(&pending_mutex);
+    pending_ready = false;
+    pthread_cond_signal(&pending_cond);
+    pthread_mutex_unlock(&pending_mutex);
+}
+
 /* demod_2400.h:37 -- the block's frames were resolved on the GPU path; this is the hand-over to
  * readsb's own field decoder, tracker and outputs */
 void demodulate2400(struct mag_buf *mag) {
@@ -237,6 +246,8 @@ void demodulate2400(struct mag_buf *mag) {
 
     for (uint64_t i = 0; i < pending.nmsgs; ++i) {
         const b200_message *m = &pending.msgs[i];
+        if (m->msgtype == 32)
+            continue; /* a Mode A/C reply: demodulate2400AC hands it over */
         struct modesMessage mm = zeroMessage;
         mm.timestampMsg = m->timestampMsg;
         mm.sysTimestampMsg = m->sysTimestampMsg;
@@ -274,16 +285,28 @@ void demodulate2400(struct mag_buf *mag) {
         if (d->peak_signal_power > st->peak_signal_power)
             st->peak_signal_power = d->peak_signal_power;
     }
-    pending.nmsgs = 0;
     pending.has_delta = false;
-    pthread_mutex_lock(&pending_mutex);
-    pending_ready = false;
-    pthread_cond_signal(&pending_cond);
-    pthread_mutex_unlock(&pending_mutex);
+    if (!Modes.mode_ac)
+        release_pending(); /* otherwise demodulate2400AC follows on the same mag_buf (readsb.c:831-833) */
 }
 
+/* demod_2400.h:38 -- the block's Mode A/C replies (library message entries with msgtype 32), handed to
+ * readsb's own decodeModeAMessage / useModesMessage exactly as demod_2400.c:686-708 does */
 void demodulate2400AC(struct mag_buf *mag) {
-    MODES_NOTUSED(mag); /* Mode A/C is a "next" row; off unless --modeac */
+    MODES_NOTUSED(mag);
+    struct modesMessage mm;
+    memset(&mm, 0, sizeof (mm)); /* once per block, like the reference (demod_2400.c:527) */
+    for (uint64_t i = 0; i < pending.nmsgs; ++i) {
+        const b200_message *m = &pending.msgs[i];
+        if (m->msgtype != 32)
+            continue;
+        mm.timestampMsg = m->timestampMsg;
+        mm.sysTimestampMsg = m->sysTimestampMsg;
+        decodeModeAMessage(&mm, (m->msg[0] << 8) | m->msg[1]);
+        useModesMessage(&mm);
+        Modes.stats_current.demod_modeac++;
+    }
+    release_pending();
 }
 
 /* ---- convert.h: a converter for callers that want the magnitudes themselves ---- */

@@ -31,6 +31,7 @@ class _Cfg(ctypes.Structure):
         ("frac_biterror", ctypes.c_double),
         ("frac_df17", ctypes.c_double),
         ("frac_df11", ctypes.c_double),
+        ("modeac_per_s", ctypes.c_double),
     ]
 
 
@@ -63,12 +64,13 @@ class SynthConfig:
     n_icao: int = 200
     frac_df17: float = 0.6
     frac_df11: float = 0.2
+    modeac_per_s: float = 0.0  # Mode A/C replies per second (frames with df == 32 in the plan)
 
     def _c(self) -> _Cfg:
         return _Cfg(
             self.seed, self.nsamples, FORMATS[self.fmt], self.n_icao, self.frames_per_s,
             self.noise_sigma, self.amp_min, self.amp_max, self.frac_biterror,
-            self.frac_df17, self.frac_df11,
+            self.frac_df17, self.frac_df11, self.modeac_per_s,
         )
 
 

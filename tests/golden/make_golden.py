@@ -38,6 +38,10 @@ FIXTURES = {
                          dict(nfix=1, threshold=58, block_samples=32768)),
     "sc16": (synth.SynthConfig(seed=105, nsamples=120_000, fmt="sc16", frames_per_s=3000, frac_biterror=0.2),
              dict(nfix=1, threshold=58, block_samples=131072)),
+    # Mode A/C replies next to Mode S traffic, --modeac: a block's replies follow its Mode S messages
+    "uc8_modeac": (synth.SynthConfig(seed=107, nsamples=300_000, fmt="uc8", frames_per_s=1500, frac_biterror=0.2,
+                                     modeac_per_s=4000),
+                   dict(nfix=1, threshold=58, block_samples=131072, modeac=True)),
     "sc16q11": (synth.SynthConfig(seed=106, nsamples=120_000, fmt="sc16q11", frames_per_s=3000, frac_biterror=0.2),
                 dict(nfix=1, threshold=58, block_samples=131072)),
 }
@@ -63,9 +67,11 @@ def render_single_frame(frame: bytes, start_tick: int, nsamples: int, amp: float
     return np.stack([i, q], axis=1).reshape(-1)
 
 
-def main():
+def main(only=None):
     assert ref.available(), "needs /root/reference (or a prebuilt oracle/_ref)"
     for name, (cfg, flags) in FIXTURES.items():
+        if only and name not in only:
+            continue
         iq, frames = synth.generate(cfg)
         res = ref.run(iq, cfg.fmt, **flags)
         meta = dict(fmt=cfg.fmt, flags=flags, generator=cfg.__dict__, sha256=synth.sha256(iq), n_frames=len(frames),
@@ -74,6 +80,8 @@ def main():
                             meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
         print(f"{name}: {len(frames)} frames, {len(res.msgs)} reference messages, {iq.nbytes} IQ bytes")
 
+    if only and "kat_frame" not in only:
+        return
     frame = bytes.fromhex(KAT_FRAME_HEX)
     iq = np.concatenate([render_single_frame(frame, 100003, 24000), render_single_frame(frame, 20001, 8000)])
     res = ref.run(iq, "uc8")
@@ -85,4 +93,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(set(sys.argv[1:]) or None)

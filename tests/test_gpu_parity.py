@@ -95,6 +95,41 @@ def test_span_split_is_invisible():
     assert_parity(run_gpu(iq[:200_000], "uc8", span_samples=256, block_samples=256), want, "uc8")
 
 
+@pytest.mark.parametrize("seed,nsamples,block", [(311, 1_000_000, 131072), (312, 600_001, 50000), (313, 4 * 131072, 131072)])
+def test_modeac_matches_oracle(seed, nsamples, block):
+    """--modeac (demodulate2400AC, demod_2400.c:522-708): a block's Mode A/C replies follow its Mode S
+    messages; bit-exact for uc8 (the noise level comes from the exact integer block sums)."""
+    cfg = synth.SynthConfig(seed=seed, nsamples=nsamples, frames_per_s=2000, frac_biterror=0.2, modeac_per_s=4000)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "uc8", block_samples=block, modeac=True)
+    assert int(np.sum(want.msgs["msgtype"] == 32)) > 100
+    with api.Demodulator(block_samples=block, modeac=True) as d:
+        got = d.run(iq)
+        assert d.modeac_count() == int(np.sum(want.msgs["msgtype"] == 32))
+    assert_parity(got, want, "uc8")
+    # span by span (one mag_buf per call, like a live SDR) gives the same list
+    with api.Demodulator(block_samples=block, modeac=True) as d:
+        assert_parity(d.run(iq, span_samples=block), want, "uc8")
+
+
+def test_modeac_off_by_default_and_dense_hits():
+    """Without the flag no Mode A/C kernel runs; with it, a pulse train that decodes almost everywhere
+    exercises the grow-and-retry of the hit list and the 69-sample skip."""
+    n = 400_000
+    i = np.full(n, 128, dtype=np.uint8)
+    # F1 and F2 pulses every 87 * 14 / 25 = 48.72 samples: period 1218 ticks of 60 MHz
+    t = (np.arange(0, n * 25 - 2000, 1218) // 25).astype(np.int64)
+    i[t] = 250
+    i[t + 1] = 200
+    iq = np.stack([i, np.full(n, 128, dtype=np.uint8)], axis=1).reshape(-1)
+    want = port.run(iq, "uc8", modeac=True)
+    assert int(np.sum(want.msgs["msgtype"] == 32)) > 1000
+    assert_parity(run_gpu(iq, "uc8", modeac=True), want, "uc8")
+    plain = run_gpu(iq, "uc8")
+    assert int(np.sum(plain.msgs["msgtype"] == 32)) == 0
+    assert_parity(plain, port.run(iq, "uc8"), "uc8")
+
+
 def test_icao_filter_flips_across_minutes():
     """> 120 s of stream so that addresses age out (icao_filter.c:150-164) -- sparse, to stay fast."""
     cfg = synth.SynthConfig(seed=82, nsamples=int(130 * 2.4e6), frames_per_s=20, n_icao=5, noise_sigma=0.004)
@@ -274,7 +309,8 @@ def test_crc_batch_and_tables(nfix):
 # drop-in: the reference's own program on top of the shim
 # ------------------------------------------------------------------------------------------
 
-def test_reference_program_with_the_shim_prints_the_same_messages():
+@pytest.mark.parametrize("modeac", [False, True], ids=["modes", "modeac"])
+def test_reference_program_with_the_shim_prints_the_same_messages(modeac):
     """oracle/_ref/readsb_b200 = readsb's main(), FIFO, CRC, field decoder and tracker objects linked
     with readsb_protobuf_b200/shim/readsb_b200_shim.c + libreadsb_b200.so instead of convert.o,
     demod_2400.o and sdr_ifile.o.  Its --raw --mlat output must equal the reference path's."""
@@ -286,17 +322,19 @@ def test_reference_program_with_the_shim_prints_the_same_messages():
     exe = build.ORACLE / "_ref" / "readsb_b200"
     if not exe.exists():
         pytest.skip("oracle/_ref/readsb_b200 not built (needs /root/reference at build time)")
-    cfg = synth.SynthConfig(seed=91, nsamples=3_000_000, frames_per_s=3000, frac_biterror=0.2)
+    cfg = synth.SynthConfig(seed=91, nsamples=3_000_000, frames_per_s=3000, frac_biterror=0.2,
+                            modeac_per_s=3000 if modeac else 0)
     iq, _ = synth.generate(cfg)
-    want = port.run(iq, "uc8")
+    want = port.run(iq, "uc8", modeac=modeac)
+    extra = ["--modeac"] if modeac else []
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "in.bin")
         iq.tofile(path)
         out = subprocess.run([str(exe), "--device-type", "ifile", "--ifile", path, "--preamble-threshold", "58",
-                              "--raw", "--mlat"], capture_output=True, text=True, timeout=300)
+                              "--raw", "--mlat", *extra], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         stats = subprocess.run([str(exe), "--device-type", "ifile", "--ifile", path, "--preamble-threshold", "58",
-                                "--quiet", "--stats"], capture_output=True, text=True, timeout=300)
+                                "--quiet", "--stats", *extra], capture_output=True, text=True, timeout=300)
     lines = [l for l in out.stdout.splitlines() if l.startswith("@")]
     expect = ["@%012X%s;" % (int(m["timestampMsg"]), bytes(m["msg"][: m["msgbits"] // 8]).hex()) for m in want.msgs]
     assert len(expect) > 1000
@@ -311,8 +349,11 @@ def test_reference_program_with_the_shim_prints_the_same_messages():
                  f"{int(st['demod_rejected_unknown_icao'])} with unrecognized ICAO address",
                  f"{int(st['demod_accepted'][0])} accepted with correct CRC",
                  f"{int(st['demod_accepted'][1])} accepted with 1-bit error repaired",
-                 f"{int(st['messages_total'])} total usable messages"):
+                 f"{int(st['messages_total'])} total usable messages",
+                 f"{int(np.sum(want.msgs['msgtype'] == 32))} Mode A/C messages received"):
         assert line in text, (line, text[:1500])
+    if modeac:
+        assert int(np.sum(want.msgs["msgtype"] == 32)) > 100
     phase_rows = [" ".join(str(int(x)) for x in st["demod_preamblePhase"]), " ".join(str(int(x)) for x in st["demod_bestPhase"])]
     squashed = " ".join(text.split())
     for row in phase_rows:

@@ -121,3 +121,31 @@ def test_generator_is_deterministic_and_chunk_invariant():
         msg = bytes(f["msg"][: f["nbytes"]])
         if f["errbit"] < 0 and f["df"] in (11, 17):
             assert port.checksum(msg) == 0
+
+
+# ------------------------------------------------------------------------------------------
+# Mode A/C (demodulate2400AC), SURVEY.md 8f row 2
+# ------------------------------------------------------------------------------------------
+
+def test_modeac_golden_holds_replies():
+    iq, want, meta = load_golden("uc8_modeac")
+    ac = want.msgs[want.msgs["msgtype"] == 32]
+    assert len(ac) > 50 and np.all(ac["msgbits"] == 16) and np.all(ac["addr"] >> 24 == 1)
+    # decodeModeAMessage (mode_ac.c:168-181): msg[0..1] is the code, the address drops the SPI bit
+    code = (ac["msg"][:, 0].astype(np.uint32) << 8) | ac["msg"][:, 1]
+    assert np.array_equal(ac["addr"] & 0xffff, code & 0xff7f)
+
+
+@pytest.mark.skipif(not ref.available(), reason="needs /root/reference or a prebuilt oracle/_ref")
+@pytest.mark.parametrize("fmt,seed", [("uc8", 301), ("uc8", 302), ("sc16", 303)])
+def test_port_modeac_matches_live_reference(fmt, seed):
+    cfg = synth.SynthConfig(seed=seed, nsamples=700_000, fmt=fmt, frames_per_s=1500, frac_biterror=0.1,
+                            modeac_per_s=3000, noise_sigma=0.01 if seed == 302 else 0.02)
+    iq, frames = synth.generate(cfg)
+    want = ref.run(iq, fmt, modeac=True)
+    got = port.run(iq, fmt, modeac=True)
+    assert int(np.sum(want.msgs["msgtype"] == 32)) > 100 and int(np.sum(want.msgs["msgtype"] != 32)) > 100
+    assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
+    # without the flag nothing changes for Mode S
+    plain = port.run(iq, fmt)
+    assert np.array_equal(plain.msgs, got.msgs[got.msgs["msgtype"] != 32])
