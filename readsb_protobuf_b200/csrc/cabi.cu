@@ -141,20 +141,22 @@ struct ChunkSet {
     // Mode A/C (only with cfg.mode_ac): per-block noise levels, unordered hit list in pinned host memory
     DevBuf<uint32_t> d_ac_noise;
     PinnedBuf<AcHit> h_ac_hits;
-    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr,
+                ev_zeroed = nullptr, ev_fsums = nullptr;
 
     // what is in flight
     uint64_t start = 0, nsamples = 0;
     bool final_chunk = false;
     uint32_t head_valid = 0;
     const uint8_t *iq = nullptr, *head = nullptr;
+    const double *span_fsums = nullptr; // float formats, device-resident span: this chunk's slice of the span's block sums
     size_t small_d2h_bytes = 0;
 
     void release() {
         d_cand.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
         d_small.release(); h_small.release(); d_dead.release();
         h_dead.release(); h_live.release(); h_liverecs.release(); d_ac_noise.release(); h_ac_hits.release();
-        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists})
+        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists, &ev_zeroed, &ev_fsums})
             if (*e) {
                 cudaEventDestroy(*e);
                 *e = nullptr;
@@ -176,6 +178,7 @@ struct b200_demod {
     cudaStream_t stream = nullptr;      // exec stream of the host-buffer entry
     cudaStream_t copy_stream = nullptr; // H2D
     cudaStream_t list_stream = nullptr; // survivor lists D2H
+    cudaStream_t aux_stream = nullptr;  // sc16 / sc16q11: the sequential float block sums, next to K1a
     cudaEvent_t ev_h2d_begin = nullptr, ev_h2d_end = nullptr;
     std::vector<cudaEvent_t> ev_chunk_h2d;
 
@@ -195,6 +198,7 @@ struct b200_demod {
     DevBuf<uint8_t> d_iq;
     ChunkSet sets[2];
     DevBuf<uint8_t> d_dbg_masks;
+    DevBuf<double> d_span_fsums; // float formats: [mag_bufs of the span][2]
     DevBuf<uint16_t> d_mag;
     DevBuf<uint8_t> d_frames;
     DevBuf<uint32_t> d_syn;
@@ -212,7 +216,7 @@ struct b200_demod {
         d_lut.release(); d_tab_short.release(); d_tab_long.release(); d_bitmap.release();
         d_head.release(); d_head_tmp.release(); d_iq.release();
         sets[0].release(); sets[1].release();
-        d_dbg_masks.release(); d_mag.release(); d_frames.release(); d_syn.release(); d_err.release(); d_bits.release();
+        d_span_fsums.release(); d_dbg_masks.release(); d_mag.release(); d_frames.release(); d_syn.release(); d_err.release(); d_bits.release();
         d_csum_u64.release(); d_csum_f64.release();
         for (cudaEvent_t e : ev_chunk_h2d)
             cudaEventDestroy(e);
@@ -220,7 +224,7 @@ struct b200_demod {
             cudaEventDestroy(ev_h2d_begin);
         if (ev_h2d_end)
             cudaEventDestroy(ev_h2d_end);
-        for (cudaStream_t s : {stream, copy_stream, list_stream})
+        for (cudaStream_t s : {stream, copy_stream, list_stream, aux_stream})
             if (s)
                 cudaStreamDestroy(s);
     }
@@ -274,6 +278,8 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
         CUDA_TRY(cudaEventCreate(&c.ev_k2));
         CUDA_TRY(cudaEventCreate(&c.ev_small));
         CUDA_TRY(cudaEventCreate(&c.ev_lists));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_zeroed, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_fsums, cudaEventDisableTiming));
     }
     return B200_OK;
 }
@@ -325,6 +331,7 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->list_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->aux_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_begin));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_end));
     CUDA_TRY(scan_configure());
@@ -481,6 +488,22 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     const size_t nblocks = (size_t) (n / B + (c.final_chunk ? 1 : 0));
 
     ScanArgs sa = make_scan_args(d, c, c.iq, c.head, n, c.head_valid, kCandSlab, kRecSlab, exact ? c.d_tile_off.p : nullptr);
+    const bool float_format = d->cfg.input_format != B200_INPUT_UC8;
+    if (float_format && n) {
+        // mean_level / mean_power of the float converters are sequential float sums (convert.c:228,241-242):
+        // K1a leaves them alone, float_block_sums_kernel walks every mag_buf's chain in order.  That kernel
+        // is latency-bound (a dependent add per sample) and runs best alone: for a device-resident span it
+        // ran once over all mag_bufs before the first chunk (c.span_fsums), for host buffers it runs here,
+        // behind the chunk's H2D, where the GPU would otherwise wait for the next copy.
+        sa.block_sums_f64 = nullptr;
+        const uint32_t nb = (uint32_t) ((n + B - 1) / B);
+        if (c.span_fsums)
+            CUDA_TRY(cudaMemcpyAsync(c.d_sums_f64.p, c.span_fsums, 2 * (size_t) nb * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        else
+            CUDA_TRY(launch_float_block_sums(c.iq, sa.format, n, B, nb, c.d_sums_f64.p, s));
+        if (launches)
+            *launches += c.span_fsums ? 0 : 1;
+    }
     CUDA_TRY(cudaEventRecord(c.ev_begin, s));
     CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
     CUDA_TRY(cudaEventRecord(c.ev_k1, s));
@@ -714,12 +737,22 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
         CUDA_TRY(cudaEventRecord(d->ev_h2d_end, d->copy_stream));
     }
 
+    // float formats, device-resident span: every mag_buf's sequential float sums in one launch up front
+    const bool span_sums = !host_src && d->cfg.input_format != B200_INPUT_UC8 && nsamples > 0;
+    if (span_sums) {
+        const uint32_t nb = (uint32_t) ((nsamples + B - 1) / B);
+        CUDA_TRY(d->d_span_fsums.ensure(2 * (size_t) nb + 2));
+        CUDA_TRY(launch_float_block_sums(d_iq, (uint32_t) d->cfg.input_format, nsamples, B, nb, d->d_span_fsums.p, exec));
+        launches += 1;
+    }
+
     auto setup = [&](uint64_t i) -> int {
         ChunkSet &c = d->sets[i & 1];
         c.start = std::min(nsamples, i * chunk);
         c.nsamples = std::min(nsamples, c.start + chunk) - c.start;
         c.final_chunk = final_span && (i + 1 == nchunks);
         c.iq = d_iq + c.start * bps;
+        c.span_fsums = span_sums ? d->d_span_fsums.p + 2 * (c.start / B) : nullptr;
         if (i == 0) {
             c.head = d->d_head.p;
             c.head_valid = d->head_valid;
@@ -892,6 +925,8 @@ extern "C" int b200_convert(b200_demod *d, const void *iq, uint32_t nsamples, ui
         CUDA_TRY(cudaMemcpyAsync(d->d_frames.p, iq, bytes, cudaMemcpyHostToDevice, s));
     CUDA_TRY(launch_convert(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, d->d_lut.p, d->d_mag.p, d->d_csum_u64.p,
                             d->d_csum_f64.p, s));
+    if (d->cfg.input_format != B200_INPUT_UC8 && nsamples) // the float converters' sums in the reference's order
+        CUDA_TRY(launch_float_block_sums(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, (nsamples + 7u) & ~7u, 1, d->d_csum_f64.p, s));
     unsigned long long su[2] = {0, 0};
     double sf[2] = {0, 0};
     if (nsamples)

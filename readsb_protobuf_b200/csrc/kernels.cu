@@ -331,6 +331,8 @@ __device__ __noinline__ void flush_sums_u64(unsigned long long *dst, unsigned lo
 }
 
 __device__ __noinline__ void flush_sums_f64(double *dst, double level, double power) {
+    if (!dst)
+        return; // the float formats' block sums come from float_block_sums_kernel
     const double l = warp_sum_f64(level), p = warp_sum_f64(power);
     if ((threadIdx.x & 31) == 0 && (l != 0 || p != 0)) {
         atomicAdd(&dst[0], l);
@@ -354,6 +356,8 @@ __device__ __noinline__ void unit_sums_u64(unsigned long long *block_sums, long 
 }
 
 __device__ __noinline__ void unit_sums_f64(double *block_sums, long long kb, float4 mag, float4 magsq) {
+    if (!block_sums)
+        return;
     const double fl = (double) mag.x + (double) mag.y + (double) mag.z + (double) mag.w;
     const double fp = (double) magsq.x + (double) magsq.y + (double) magsq.z + (double) magsq.w;
     atomicAdd(&block_sums[2 * kb], fl);
@@ -408,7 +412,7 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
         if (FORMAT == 0)
             flush_sums_u64(a.block_sums_u64 + 2 * blk, sum_level, sum_power);
         else
-            flush_sums_f64(a.block_sums_f64 + 2 * blk, fsum_level, fsum_power);
+            flush_sums_f64(a.block_sums_f64 ? a.block_sums_f64 + 2 * blk : nullptr, fsum_level, fsum_power);
         sum_level = sum_power = 0;
         fsum_level = fsum_power = 0;
     };
@@ -1686,6 +1690,107 @@ cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream) {
     } else {
         classify_kernel<<<a.ntiles, kClassifyThreads, 0, stream>>>(a);
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// float_block_sums_kernel: mean_level / mean_power of the float converters, bit-exactly
+//
+// convert_sc16_nodc / convert_sc16q11_nodc add mag and magsq of every sample to two float
+// accumulators in stream order (convert.c:228,241-242 / 345,358-359).  Float addition is not
+// associative, so the only way to the same bits is the same order: per mag_buf one warp converts 128
+// samples at a time in parallel (4 per lane) and two lanes of a second warp walk the chains in order.
+// 131072 dependent adds at 4 cycles each = 0.27 ms per mag_buf at best, all mag_bufs in parallel,
+// on a side stream next to K1a.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(64) float_block_sums_kernel(const uint8_t *__restrict__ iq, uint32_t format, uint64_t nsamples,
+                                                               uint32_t block_samples, uint32_t nblocks, double *__restrict__ sums) {
+    // one CTA of two warps per mag_buf: warp 0 converts the next batch of 128 samples into the other half
+    // of a double buffer while lanes 0 and 1 of warp 1 walk the two chains over the current one
+    __shared__ __align__(16) float s_val[2][2][128]; // [buffer][0 = mag, 1 = magsq][sample]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t k = blockIdx.x;
+    const uint64_t b0 = (uint64_t) k * block_samples;
+    const uint64_t nk = nsamples > b0 ? (nsamples - b0 < block_samples ? nsamples - b0 : block_samples) : 0;
+    const float inv_scale = (format == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(iq) + b0; // one 32-bit word per sample
+
+    // 4 samples per lane (block_samples % 8 == 0 and 16-byte aligned spans: whole uint4s except in the
+    // stream's ragged last batch)
+    auto load = [&](uint64_t base) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        const uint64_t s0 = base + 4 * (uint64_t) lane;
+        if (s0 + 4 <= nk) {
+            v = ldg_stream(reinterpret_cast<const uint4 *>(src + s0));
+        } else if (s0 < nk) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int j = 0; j < 4; ++j)
+                if (s0 + j < nk)
+                    w[j] = __ldg(src + s0 + j);
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return v;
+    };
+    auto put = [&](int buf, uint4 v) {
+        float mg[4], sq[4];
+        mag_sc16_word(v.x, inv_scale, sq[0], mg[0]);
+        mag_sc16_word(v.y, inv_scale, sq[1], mg[1]);
+        mag_sc16_word(v.z, inv_scale, sq[2], mg[2]);
+        mag_sc16_word(v.w, inv_scale, sq[3], mg[3]);
+        *reinterpret_cast<float4 *>(&s_val[buf][0][4 * lane]) = make_float4(mg[0], mg[1], mg[2], mg[3]);
+        *reinterpret_cast<float4 *>(&s_val[buf][1][4 * lane]) = make_float4(sq[0], sq[1], sq[2], sq[3]);
+    };
+
+    const uint64_t nbatches = (nk + 127) / 128;
+    uint4 ahead[3] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}; // batches b+1 .. b+3 in flight
+    if (warp == 0 && nbatches) {
+        put(0, load(0));
+        ahead[0] = load(128);
+        ahead[1] = load(256);
+        ahead[2] = load(384);
+    }
+    float acc = 0.0f; // warp 1, lane 0: sum_level, lane 1: sum_power
+    __syncthreads();
+    for (uint64_t b = 0; b < nbatches; ++b) {
+        if (warp == 0) {
+            if (b + 1 < nbatches) {
+                put((int) ((b + 1) & 1), ahead[0]);
+                ahead[0] = ahead[1];
+                ahead[1] = ahead[2];
+                ahead[2] = load((b + 4) * 128);
+            }
+        } else if (lane < 2) {
+            const float *mine = s_val[b & 1][lane];
+            const uint64_t left = nk - b * 128;
+            if (left >= 128) {
+                float4 r[32]; // all loads first: they do not depend on the chain
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    r[i] = reinterpret_cast<const float4 *>(mine)[i];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    acc = __fadd_rn(acc, r[i].x);
+                    acc = __fadd_rn(acc, r[i].y);
+                    acc = __fadd_rn(acc, r[i].z);
+                    acc = __fadd_rn(acc, r[i].w);
+                }
+            } else {
+                for (int i = 0; i < (int) left; ++i)
+                    acc = __fadd_rn(acc, mine[i]);
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 1 && lane < 2)
+        sums[2 * k + lane] = (double) acc; // exactly the float the reference divides by nsamples
+}
+
+cudaError_t launch_float_block_sums(const uint8_t *iq, uint32_t format, uint64_t nsamples, uint32_t block_samples, uint32_t nblocks,
+                                    double *sums, cudaStream_t stream) {
+    if (nblocks == 0 || format == 0)
+        return cudaSuccess;
+    float_block_sums_kernel<<<nblocks, 64, 0, stream>>>(iq, format, nsamples, block_samples, nblocks, sums);
     return cudaGetLastError();
 }
 

@@ -1,11 +1,11 @@
 """GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle and the goldens.
 
-Bar: bit-exact for everything integer (message bytes, CRC, corrected bits, score, 12 MHz and ms
-timestamps, every demod counter, the uc8 block sums) and for signalLevel (an integer sum divided
-twice; north_star allows 1e-5).  The float-path converters (sc16 / sc16q11) produce bit-exact
-magnitudes; their per-block mean_level / mean_power are sequential float32 sums in the reference
-(convert.c:228,241-242) and are compared to 2e-4 relative (the reference's own accumulation
-error), as is the noise_power_sum derived from them.
+Bar: bit-exact for everything -- message bytes, CRC, corrected bits, score, 12 MHz and ms
+timestamps, every demod counter, the block means and signalLevel (an integer sum divided twice;
+north_star allows 1e-5).  The float-path converters' (sc16 / sc16q11) per-block mean_level /
+mean_power are sequential float32 sums in the reference (convert.c:228,241-242); the library walks
+them in the same order (float_block_sums_kernel), so they and the noise_power_sum derived from them
+are bit-exact too.
 """
 import numpy as np
 import pytest
@@ -16,7 +16,7 @@ from readsb_protobuf_b200 import api, results, synth
 
 pytestmark = pytest.mark.gpu
 
-FLOAT_SUM_RTOL = 2e-4  # only for sc16 / sc16q11 block means and noise_power_sum
+FLOAT_SUM_RTOL = 0.0  # sc16 / sc16q11 block means and noise_power_sum: exact as well
 
 
 def rtol_for(fmt):
@@ -110,6 +110,17 @@ def test_modeac_matches_oracle(seed, nsamples, block):
     # span by span (one mag_buf per call, like a live SDR) gives the same list
     with api.Demodulator(block_samples=block, modeac=True) as d:
         assert_parity(d.run(iq, span_samples=block), want, "uc8")
+
+
+@pytest.mark.parametrize("fmt", ["sc16", "sc16q11"])
+def test_modeac_float_formats(fmt):
+    """Mode A/C thresholds derive from the block's mean level / power, which for the float converters
+    are order-dependent float sums: exact only because the library sums in the reference's order."""
+    cfg = synth.SynthConfig(seed=314, nsamples=800_000, fmt=fmt, frames_per_s=1500, modeac_per_s=4000, frac_biterror=0.1)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, fmt, modeac=True)
+    assert int(np.sum(want.msgs["msgtype"] == 32)) > 100
+    assert_parity(run_gpu(iq, fmt, modeac=True), want, fmt)
 
 
 def test_modeac_off_by_default_and_dense_hits():
@@ -211,10 +222,7 @@ def test_converter_bit_exact(fmt):
         mag, ml, mp = d.convert(iq)
     want, wl, wp = port.convert(iq, fmt)
     assert np.array_equal(mag, want)
-    if fmt == "uc8":
-        assert ml == wl and mp == wp
-    else:
-        assert ml == pytest.approx(wl, rel=FLOAT_SUM_RTOL) and mp == pytest.approx(wp, rel=FLOAT_SUM_RTOL)
+    assert ml == wl and mp == wp  # the float formats too: sums taken in the reference's order
 
 
 def test_try_masks_and_phase_records():
