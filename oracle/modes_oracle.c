@@ -524,6 +524,39 @@ static int score_message(demod_state *s, const uint8_t *msg, int validbits) {
 
 /* The part of decodeModesMessage() that can reject a message or touch the filter
  * (mode_s.c:424-555 and 717-726).  msg is corrected in place. */
+/* DF18: is the AA field something other than an ICAO address?  The extended-squitter decoder then
+ * flags mm->addr with MODES_NON_ICAO_ADDRESS (1 << 24): by CF alone (mode_s.c:1379-1428), or for CF 2 / 3 /
+ * 6 by the IMF bit of the ME field, whose position depends on the ME type (mode_s.c:806, 927, 966-968,
+ * 1054, 1064, 1259, 1404-1406).  msg = the frame after CRC repair. */
+static int me_bit(const uint8_t *me, int n) { /* 1-based, MSB first (getbit, mode_s.c) */
+    return (me[(n - 1) >> 3] >> (7 - ((n - 1) & 7))) & 1;
+}
+
+static int df18_non_icao(const uint8_t *msg) {
+    const uint8_t *me = msg + 4;
+    const unsigned cf = msg[0] & 7, metype = me[0] >> 3, mesub3 = me[0] & 7;
+    switch (cf) {
+        case 0: return 0;
+        case 1: case 5: return 1;
+        case 3: return me_bit(me, 1);
+        case 2: case 6: break; /* look for the IMF bit */
+        default: return 1;     /* unknown format: assumed non-ICAO */
+    }
+    if (metype == 19)
+        return mesub3 >= 1 && mesub3 <= 4 && me_bit(me, 9);
+    if (metype >= 5 && metype <= 8)
+        return me_bit(me, 21);
+    if (metype == 0 || (metype >= 9 && metype <= 18) || (metype >= 20 && metype <= 22))
+        return me_bit(me, 8);
+    if (metype == 28)
+        return mesub3 == 1 && me_bit(me, 56);
+    if (metype == 29)
+        return me_bit(me, 51);
+    if (metype == 31)
+        return me_bit(me, 56);
+    return 0;
+}
+
 static int decode_crc_part(demod_state *s, mo_msg *mm, const uint8_t *raw) {
     static const uint8_t zeros[7] = {0};
     uint8_t *msg = mm->msg;
@@ -587,6 +620,9 @@ static int decode_crc_part(demod_state *s, mo_msg *mm, const uint8_t *raw) {
     /* mode_s.c:717-726: the only place addresses enter the filter */
     if (!mm->correctedbits && (mm->msgtype == 17 || (mm->msgtype == 11 && iid == 0)))
         filter_add(&s->filter, mm->addr);
+    /* decodeExtendedSquitter (mode_s.c:1373-1428) runs later in decodeModesMessage and may flag the address */
+    if (mm->msgtype == 18 && df18_non_icao(mm->msg))
+        mm->addr |= 1u << 24;
     return 0;
 }
 

@@ -141,8 +141,7 @@ struct ChunkSet {
     // Mode A/C (only with cfg.mode_ac): per-block noise levels, unordered hit list in pinned host memory
     DevBuf<uint32_t> d_ac_noise;
     PinnedBuf<AcHit> h_ac_hits;
-    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr,
-                ev_zeroed = nullptr, ev_fsums = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr;
 
     // what is in flight
     uint64_t start = 0, nsamples = 0;
@@ -156,7 +155,7 @@ struct ChunkSet {
         d_cand.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
         d_small.release(); h_small.release(); d_dead.release();
         h_dead.release(); h_live.release(); h_liverecs.release(); d_ac_noise.release(); h_ac_hits.release();
-        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists, &ev_zeroed, &ev_fsums})
+        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists})
             if (*e) {
                 cudaEventDestroy(*e);
                 *e = nullptr;
@@ -178,7 +177,6 @@ struct b200_demod {
     cudaStream_t stream = nullptr;      // exec stream of the host-buffer entry
     cudaStream_t copy_stream = nullptr; // H2D
     cudaStream_t list_stream = nullptr; // survivor lists D2H
-    cudaStream_t aux_stream = nullptr;  // sc16 / sc16q11: the sequential float block sums, next to K1a
     cudaEvent_t ev_h2d_begin = nullptr, ev_h2d_end = nullptr;
     std::vector<cudaEvent_t> ev_chunk_h2d;
 
@@ -224,7 +222,7 @@ struct b200_demod {
             cudaEventDestroy(ev_h2d_begin);
         if (ev_h2d_end)
             cudaEventDestroy(ev_h2d_end);
-        for (cudaStream_t s : {stream, copy_stream, list_stream, aux_stream})
+        for (cudaStream_t s : {stream, copy_stream, list_stream})
             if (s)
                 cudaStreamDestroy(s);
     }
@@ -278,8 +276,6 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
         CUDA_TRY(cudaEventCreate(&c.ev_k2));
         CUDA_TRY(cudaEventCreate(&c.ev_small));
         CUDA_TRY(cudaEventCreate(&c.ev_lists));
-        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_zeroed, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_fsums, cudaEventDisableTiming));
     }
     return B200_OK;
 }
@@ -331,7 +327,6 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->list_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&d->aux_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_begin));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_end));
     CUDA_TRY(scan_configure());

@@ -179,6 +179,39 @@ static inline uint32_t aa_field(const uint8_t *msg) { // getbits(msg, 9, 32)
 // The part of decodeModesMessage that can reject the frame or touches the filter
 // (mode_s.c:424-555, 560-562, 717-726).  CRC and repair are recomputed on the host from the
 // sliced bytes; a disagreement with the kernel's values is counted, never hidden.
+/* DF18: is the AA field something other than an ICAO address?  The extended-squitter decoder then
+ * flags mm->addr with MODES_NON_ICAO_ADDRESS (1 << 24): by CF alone (mode_s.c:1379-1428), or for CF 2 / 3 /
+ * 6 by the IMF bit of the ME field, whose position depends on the ME type (mode_s.c:806, 927, 966-968,
+ * 1054, 1064, 1259, 1404-1406).  msg = the frame after CRC repair. */
+static inline int me_bit(const uint8_t *me, int n) { /* 1-based, MSB first (getbit, mode_s.c) */
+    return (me[(n - 1) >> 3] >> (7 - ((n - 1) & 7))) & 1;
+}
+
+static int df18_non_icao(const uint8_t *msg) {
+    const uint8_t *me = msg + 4;
+    const unsigned cf = msg[0] & 7, metype = me[0] >> 3, mesub3 = me[0] & 7;
+    switch (cf) {
+        case 0: return 0;
+        case 1: case 5: return 1;
+        case 3: return me_bit(me, 1);
+        case 2: case 6: break; /* look for the IMF bit */
+        default: return 1;     /* unknown format: assumed non-ICAO */
+    }
+    if (metype == 19)
+        return mesub3 >= 1 && mesub3 <= 4 && me_bit(me, 9);
+    if (metype >= 5 && metype <= 8)
+        return me_bit(me, 21);
+    if (metype == 0 || (metype >= 9 && metype <= 18) || (metype >= 20 && metype <= 22))
+        return me_bit(me, 8);
+    if (metype == 28)
+        return mesub3 == 1 && me_bit(me, 56);
+    if (metype == 29)
+        return me_bit(me, 51);
+    if (metype == 31)
+        return me_bit(me, 56);
+    return 0;
+}
+
 int Resolver::decode(const LiveRec &r, b200_message &mm) {
     memcpy(mm.msg, r.msg, 14);
     memcpy(mm.verbatim, r.msg, 14);
@@ -244,6 +277,9 @@ int Resolver::decode(const LiveRec &r, b200_message &mm) {
     // the only place addresses enter the filter
     if (!mm.correctedbits && (mm.msgtype == 17 || (mm.msgtype == 11 && iid == 0)))
         filter_.add(mm.addr);
+    // decodeExtendedSquitter (mode_s.c:1373-1428) runs later in decodeModesMessage and may flag the address
+    if (mm.msgtype == 18 && df18_non_icao(mm.msg))
+        mm.addr |= 1u << 24;
     return 0;
 }
 

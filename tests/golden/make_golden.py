@@ -67,6 +67,36 @@ def render_single_frame(frame: bytes, start_tick: int, nsamples: int, amp: float
     return np.stack([i, q], axis=1).reshape(-1)
 
 
+def df18_frames():
+    """DF18 frames for every CF value and the ME types whose IMF bit decodeExtendedSquitter looks at
+    (mode_s.c:1373-1470): the reference flags mm->addr with MODES_NON_ICAO_ADDRESS for some of them."""
+    rng = np.random.default_rng(18)
+    frames = []
+    metypes = [0, 4, 5, 8, 9, 18, 19, 20, 22, 23, 28, 29, 31]
+    for cf in range(8):
+        for metype in metypes:
+            for variant in range(3):
+                msg = bytearray(14)
+                msg[0] = (18 << 3) | cf
+                msg[1:4] = bytes(rng.integers(1, 255, 3, dtype=np.uint8))
+                me = bytearray(rng.integers(0, 256, 7, dtype=np.uint8))
+                sub = [1, 0, 5][variant] if metype in (19, 28) else int(rng.integers(0, 8))
+                me[0] = (metype << 3) | sub
+                msg[4:11] = me
+                pi = synth._load().synth_crc24(bytes(msg), 14)
+                msg[11:14] = bytes([(pi >> 16) & 0xff, (pi >> 8) & 0xff, pi & 0xff])
+                frames.append(bytes(msg))
+    return frames
+
+
+def render_frames(frames, gap=600, amp=0.5):
+    """Noise-free uc8 rendering of frames one after another, start ticks cycling through the five phases."""
+    parts = []
+    for i, f in enumerate(frames):
+        parts.append(render_single_frame(f, 100 * 5 + (i % 5), gap, amp))
+    return np.concatenate(parts)
+
+
 def main(only=None):
     assert ref.available(), "needs /root/reference (or a prebuilt oracle/_ref)"
     for name, (cfg, flags) in FIXTURES.items():
@@ -80,6 +110,16 @@ def main(only=None):
                             meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
         print(f"{name}: {len(frames)} frames, {len(res.msgs)} reference messages, {iq.nbytes} IQ bytes")
 
+    if not only or "uc8_df18" in only:
+        frames = df18_frames()
+        iq = render_frames(frames)
+        res = ref.run(iq, "uc8")
+        meta = dict(fmt="uc8", flags=dict(nfix=1, threshold=58, block_samples=131072), sha256=synth.sha256(iq), n_frames=len(frames),
+                    source="oracle/_ref/ref_demod (unmodified reference objects)")
+        np.savez_compressed(HERE / "uc8_df18.npz", iq=iq, msgs=res.msgs, stats=np.array([res.stats]), blocks=res.blocks,
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        flagged = int(np.sum((res.msgs["addr"] >> 24) & 1))
+        print(f"uc8_df18: {len(frames)} frames, {len(res.msgs)} reference messages, {flagged} with a non-ICAO address")
     if only and "kat_frame" not in only:
         return
     frame = bytes.fromhex(KAT_FRAME_HEX)

@@ -197,6 +197,29 @@ def test_full_size_stream_matches_the_reference_itself():
     assert_parity(again, want, "uc8")
 
 
+@pytest.mark.skipif(not ref.available(), reason="prebuilt oracle/_ref not present")
+def test_full_size_sc16_stream_matches_the_reference_itself():
+    """BASELINE configs[2] at full size (60 s of sc16, 576 MB) against the unmodified reference, block
+    means included (the float sums are order-dependent)."""
+    cfg = synth.baseline_config(2)
+    iq, frames = synth.generate(cfg)
+    want = ref.run(iq, cfg.fmt)
+    got = run_gpu(iq, cfg.fmt, max_span_samples=cfg.nsamples + 1024)
+    assert len(want.msgs) > 0.7 * len(frames)
+    assert_parity(got, want, cfg.fmt)
+
+
+def test_dense_traffic_two_minutes():
+    """BASELINE configs[3] shape (5000 frames/s with overlaps, 20 % with a flipped bit) over 120 s of
+    stream: several pipeline chunks, two ICAO-filter flips, the 1-bit repair path on thousands of frames."""
+    cfg = synth.SynthConfig(seed=4, nsamples=int(120 * 2.4e6), frames_per_s=5000, frac_biterror=0.2)
+    iq, frames = synth.generate(cfg)
+    want = port.run(iq, "uc8")
+    got = run_gpu(iq, "uc8", max_span_samples=cfg.nsamples + 1024)
+    assert len(want.msgs) > 0.4 * len(frames) and int(want.stats["demod_accepted"][1]) > 20_000
+    assert_parity(got, want, "uc8")
+
+
 # ------------------------------------------------------------------------------------------
 # kernel-level parity
 # ------------------------------------------------------------------------------------------

@@ -149,3 +149,17 @@ def test_port_modeac_matches_live_reference(fmt, seed):
     # without the flag nothing changes for Mode S
     plain = port.run(iq, fmt)
     assert np.array_equal(plain.msgs, got.msgs[got.msgs["msgtype"] != 32])
+
+
+def test_df18_non_icao_address_flag():
+    """decodeExtendedSquitter flags mm->addr with MODES_NON_ICAO_ADDRESS for DF18 depending on CF and the
+    ME field's IMF bit (mode_s.c:1373-1470); golden uc8_df18 holds every CF x ME-type combination."""
+    iq, want, meta = load_golden("uc8_df18")
+    assert len(want.msgs) == meta["n_frames"] and np.all(want.msgs["msgtype"] == 18)
+    flagged = (want.msgs["addr"] >> 24) & 1
+    assert 0 < int(flagged.sum()) < len(flagged)
+    cf = want.msgs["msg"][:, 0] & 7
+    assert np.all(flagged[cf == 0] == 0) and np.all(flagged[np.isin(cf, (1, 4, 5, 7))] == 1)
+    assert 0 < int(flagged[np.isin(cf, (2, 3, 6))].sum()) < int(np.isin(cf, (2, 3, 6)).sum())
+    got = port.run(iq, "uc8")
+    assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
