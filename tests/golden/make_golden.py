@@ -89,6 +89,54 @@ def df18_frames():
     return frames
 
 
+def all_df_frames():
+    """Every downlink format demodulate2400 accepts (DF 0, 4, 5, 11, 16, 17, 18, 20, 21, 24-31) from a pool
+    of six aircraft: squitters first so that Address/Parity replies find their address in the ICAO
+    filter, all-call replies with IID != 0, and one-bit errors in each family."""
+    crc24 = synth._load().synth_crc24
+    rng = np.random.default_rng(77)
+    icaos = [int(x) for x in rng.integers(1, 0xffffff, 6)]
+
+    def es(df, icao):
+        m = bytearray(14)
+        m[0] = (df << 3) | int(rng.integers(0, 8))
+        m[1:4] = icao.to_bytes(3, "big")
+        m[4:11] = bytes(rng.integers(0, 256, 7, dtype=np.uint8))
+        m[11:14] = crc24(bytes(m), 14).to_bytes(3, "big")
+        return bytes(m)
+
+    def ap(df, icao, nbytes):
+        m = bytearray(nbytes)
+        m[0] = (df << 3) | int(rng.integers(0, 8))
+        m[1:nbytes - 3] = bytes(rng.integers(0, 256, nbytes - 4, dtype=np.uint8))
+        m[nbytes - 3:] = (crc24(bytes(m), nbytes) ^ icao).to_bytes(3, "big")
+        return bytes(m)
+
+    def df11(icao, iid=0):
+        m = bytearray(7)
+        m[0] = (11 << 3) | 5
+        m[1:4] = icao.to_bytes(3, "big")
+        m[4:7] = (crc24(bytes(m), 7) ^ iid).to_bytes(3, "big")
+        return bytes(m)
+
+    def flip(frame, lo, hi):
+        f = bytearray(frame)
+        b = int(rng.integers(lo, hi))
+        f[b >> 3] ^= 0x80 >> (b & 7)
+        return bytes(f)
+
+    frames = []
+    for ic in icaos:
+        frames += [es(17, ic), df11(ic)]
+    for _ in range(12):
+        for ic in icaos:
+            for df, nb in ((0, 7), (4, 7), (5, 7), (16, 14), (20, 14), (21, 14), (24, 14), (25, 14), (27, 14), (31, 14)):
+                frames.append(ap(df, ic, nb))
+            frames += [es(17, ic), es(18, ic), df11(ic, int(rng.integers(0, 64))),
+                       flip(es(17, ic), 5, 112), flip(df11(ic), 5, 56), flip(ap(20, ic, 14), 5, 112)]
+    return frames
+
+
 def render_frames(frames, gap=600, amp=0.5):
     """Noise-free uc8 rendering of frames one after another, start ticks cycling through the five phases."""
     parts = []
@@ -120,6 +168,19 @@ def main(only=None):
                             meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
         flagged = int(np.sum((res.msgs["addr"] >> 24) & 1))
         print(f"uc8_df18: {len(frames)} frames, {len(res.msgs)} reference messages, {flagged} with a non-ICAO address")
+    for name, nfix in (("uc8_all_df", 1), ("uc8_all_df_nofix", 0)):
+        if only and name not in only:
+            continue
+        frames = all_df_frames()
+        iq = render_frames(frames)
+        flags = dict(nfix=nfix, threshold=58, block_samples=131072)
+        res = ref.run(iq, "uc8", **flags)
+        meta = dict(fmt="uc8", flags=flags, sha256=synth.sha256(iq), n_frames=len(frames),
+                    source="oracle/_ref/ref_demod (unmodified reference objects)")
+        np.savez_compressed(HERE / f"{name}.npz", iq=iq, msgs=res.msgs, stats=np.array([res.stats]), blocks=res.blocks,
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        print(f"{name}: {len(frames)} frames, {len(res.msgs)} reference messages, DFs",
+              sorted(set(int(x) for x in res.msgs["msgtype"])))
     if only and "kat_frame" not in only:
         return
     frame = bytes.fromhex(KAT_FRAME_HEX)
