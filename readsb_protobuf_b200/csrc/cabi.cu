@@ -707,7 +707,26 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
     const uint64_t two_waves = (uint64_t) 2 * d->scan_grid * kScanWarps * kTile - kTile; // tiles_for() adds one tile for the tail
     const uint64_t chunk_target = (d->sm_count > 0 && two_waves >= (16ull << 20) && two_waves <= (64ull << 20)) ? two_waves : kChunkTarget;
     const uint64_t chunk = std::max<uint64_t>(1, chunk_target / B) * B;
-    const uint64_t nchunks = nsamples ? (nsamples + chunk - 1) / chunk : 1;
+    // chunk i = [starts[i], starts[i + 1]), whole mag_bufs.  For host buffers the pipeline is bound by the
+    // H2D copies, so what counts is the work left when the last byte has landed: the last chunk is split so
+    // that its tail is small (kernels + resolve of 4 M samples instead of up to 38 M).
+    std::vector<uint64_t> starts;
+    for (uint64_t at = 0; at < nsamples; at += chunk)
+        starts.push_back(at);
+    if (starts.empty())
+        starts.push_back(0);
+    if (host_src) {
+        for (uint64_t back : {16ull << 20, 4ull << 20}) { // cuts about 16 M and 4 M samples before the end
+            const uint64_t tail = std::max<uint64_t>(1, back / B) * B;
+            if (nsamples <= tail)
+                continue;
+            const uint64_t cut = (nsamples - tail) / B * B;
+            if (cut > starts.back() + (2ull << 20) && cut < nsamples)
+                starts.push_back(cut);
+        }
+    }
+    starts.push_back(nsamples);
+    const uint64_t nchunks = starts.size() - 1;
     b200_timing t;
     memset(&t, 0, sizeof(t));
     uint32_t launches = 0;
@@ -723,7 +742,7 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
         }
         CUDA_TRY(cudaEventRecord(d->ev_h2d_begin, d->copy_stream));
         for (uint64_t i = 0; i < nchunks; ++i) {
-            const uint64_t s0 = i * chunk, s1 = std::min(nsamples, s0 + chunk);
+            const uint64_t s0 = starts[i], s1 = starts[i + 1];
             if (s1 > s0)
                 CUDA_TRY(cudaMemcpyAsync(const_cast<uint8_t *>(d_iq) + s0 * bps, (const uint8_t *) host_src + s0 * bps, (s1 - s0) * bps,
                                          cudaMemcpyHostToDevice, d->copy_stream));
@@ -743,8 +762,8 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
 
     auto setup = [&](uint64_t i) -> int {
         ChunkSet &c = d->sets[i & 1];
-        c.start = std::min(nsamples, i * chunk);
-        c.nsamples = std::min(nsamples, c.start + chunk) - c.start;
+        c.start = starts[i];
+        c.nsamples = starts[i + 1] - starts[i];
         c.final_chunk = final_span && (i + 1 == nchunks);
         c.iq = d_iq + c.start * bps;
         c.span_fsums = span_sums ? d->d_span_fsums.p + 2 * (c.start / B) : nullptr;
