@@ -721,7 +721,7 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
             if (nsamples <= tail)
                 continue;
             const uint64_t cut = (nsamples - tail) / B * B;
-            if (cut > starts.back() + (2ull << 20) && cut < nsamples)
+            if (cut > starts.back() + back / 2 && cut < nsamples)
                 starts.push_back(cut);
         }
     }

@@ -352,13 +352,18 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
     const uint64_t nfull = n / B;
     const uint64_t nblocks = nfull + (v.final_span ? 1 : 0);
 
-    msgs.reserve(msgs.size() + 64);
+    {
+        // room for every live position of the span: no reallocation (and no first-touch page faults after the
+        // first span of this size) inside the walk
+        size_t nlive = v.n_ac_hits;
+        for (uint32_t t = 0; t < v.ntiles; ++t)
+            nlive += v.tiles[t].nlive;
+        msgs.reserve(msgs.size() + nlive + 64);
+        skips_.clear();
+        skips_.reserve(nlive + 64);
+    }
     // what skip-ahead hides is un-counted after the walk: the dead list it needs may still be arriving
-    struct Skip {
-        uint64_t lo, hi;
-        uint32_t rank;
-    };
-    std::vector<Skip> skips;
+    std::vector<Skip> &skips = skips_;
     // Mode A/C hits in stream order (the kernel appends them as it finds them)
     if (v.n_ac_hits > 1)
         std::sort(v.ac_hits, v.ac_hits + v.n_ac_hits, [](const AcHit &a, const AcHit &b) { return a.q < b.q; });

@@ -87,6 +87,11 @@ class Resolver {
     uint64_t ifile_now_;
     uint64_t mismatches_;
     uint64_t modeac_;
+    struct Skip { // an accepted frame's skip-ahead: dead positions in (lo, hi] are un-counted afterwards
+        uint64_t lo, hi;
+        uint32_t rank;
+    };
+    std::vector<Skip> skips_;
 };
 
 } // namespace b200

@@ -74,5 +74,19 @@ int main(int argc, char **argv) {
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         printf("rep %d: %.3f ms, %zu msgs\n", rep, ms, msgs.size());
     }
+    // digest of everything the resolver produced (to compare two builds)
+    auto fnv = [](const void *p, size_t n, uint64_t h) {
+        const unsigned char *b = (const unsigned char *) p;
+        for (size_t i = 0; i < n; ++i)
+            h = (h ^ b[i]) * 1099511628211ull;
+        return h;
+    };
+    uint64_t h = 1469598103934665603ull;
+    h = fnv(msgs.data(), msgs.size() * sizeof(b200_message), h);
+    h = fnv(blocks.data(), blocks.size() * sizeof(b200_block_info), h);
+    const b200_demod_stats st = res.stats();
+    h = fnv(&st, sizeof(st), h);
+    printf("digest %016llx  (%zu msgs, %zu blocks, mismatches %llu)\n", (unsigned long long) h, msgs.size(), blocks.size(),
+           (unsigned long long) res.gpu_host_mismatches());
     return 0;
 }
