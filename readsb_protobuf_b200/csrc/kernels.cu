@@ -1,16 +1,22 @@
 // kernels.cu -- sm_100a kernels of the Mode S demodulator.
 //
-//   K1  scan_kernel      IQ -> magnitude (never leaves the SM) -> preamble scan -> PPM slice ->
-//                        CRC-24 syndrome + error-table lookup -> class records
-//                        replaces convert.c:63-111/215-253/332-370, demod_2400.c:98-229,257-335,
-//                        crc.c:67-82,389-412 and the filter-independent half of mode_s.c:311-409
-//   K2  classify_kernel  address-set test, ordered dead/live lists, re-slice + signal power of the
-//                        survivors (demod_2400.c:387-399)
-//   convert_kernel       IQ -> u16 magnitudes in global memory (the iq_convert_fn boundary)
-//   crc_batch_kernel     CRC + diagnose for a batch of frames (the crc.h boundary)
+//   K1a scan_kernel            IQ -> magnitude -> per-block sums, preamble pre-check + three correlators for
+//                              every scan position -> position-ordered candidate list per tile; the u16
+//                              magnitudes go to HBM for K1b / K2 / Mode A/C
+//                              replaces convert.c:63-111/215-253/332-370 and demod_2400.c:257-335
+//   K1b slice_kernel           PPM slice of every (candidate, phase), CRC-24 syndrome, error-table lookup ->
+//                              class records; replaces demod_2400.c:98-229, crc.c:67-82,389-412 and the
+//                              filter-independent half of mode_s.c:311-409
+//   K2  classify_warp_kernel   address-set test, ordered dead / live lists, re-slice + signal power of the
+//       (classify_kernel)      survivors (demod_2400.c:387-399); the CTA-per-tile variant serves the
+//                              exact-slab retry of very dense chunks
+//   modeac_kernel              demodulate2400AC's framing-pulse search (demod_2400.c:522-683), --modeac only
+//   float_block_sums_kernel    sc16 / sc16q11 mean_level / mean_power in the reference's summation order
+//   convert_kernel             IQ -> u16 magnitudes in global memory (the iq_convert_fn boundary)
+//   crc_batch_kernel           CRC + diagnose for a batch of frames (the crc.h boundary)
 //
-// Everything here is integer/byte work bounded by HBM bandwidth or instruction issue; there is
-// no dense contraction, so no tensor-core path.
+// Everything here is integer/byte work bounded by instruction issue (and, behind that, HBM bandwidth);
+// there is no dense contraction, so no tensor-core path.
 
 #include "kernels.cuh"
 
