@@ -93,6 +93,13 @@ def test_span_split_is_invisible():
     # small blocks, spans shorter than the 326-sample overlap history
     want = port.run(iq[:200_000], "uc8", block_samples=256)
     assert_parity(run_gpu(iq[:200_000], "uc8", span_samples=256, block_samples=256), want, "uc8")
+    # a float format, one mag_buf per call like a live SDR, with Mode A/C on: the per-block float sums and
+    # the thresholds derived from them must not depend on how the stream is cut
+    cfg = synth.SynthConfig(seed=85, nsamples=1_500_000, fmt="sc16q11", frames_per_s=3000, frac_biterror=0.2, modeac_per_s=2000)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "sc16q11", modeac=True)
+    for span in (131072, 131072 * 3):
+        assert_parity(run_gpu(iq, "sc16q11", span_samples=span, modeac=True), want, "sc16q11")
 
 
 @pytest.mark.parametrize("seed,nsamples,block", [(311, 1_000_000, 131072), (312, 600_001, 50000), (313, 4 * 131072, 131072)])
