@@ -88,7 +88,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in line.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.5)  # nvidia-smi takes driver locks: sample sparsely
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -256,21 +256,21 @@ def run_ours(args):
         stats_vec[: len(vals)] = torch.tensor(vals, dtype=torch.int64)
         dist.all_reduce(stats_vec)
 
+    # A step is one pass of the path over one stream per GPU; the ranks' streams are independent, so the
+    # steps run unsynchronised and the merged-statistics all-reduce (the path's only collective, "final
+    # message-count/stats reduction") happens once, after the last step, inside the timed region.
     def step_device():
         demod.reset()
-        r = demod.process_device(dev.data_ptr(), nsamples, final=True, stream=sptr)
-        reduce_stats()
-        return r
+        return demod.process_device(dev.data_ptr(), nsamples, final=True, stream=sptr)
 
     def step_host():
         demod.reset()
-        r = demod.process_ptr(host.data_ptr(), nsamples, final=True)
-        reduce_stats()
-        return r
+        return demod.process_ptr(host.data_ptr(), nsamples, final=True)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
+        reduce_stats()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k1, k1b, k2, nmsg, d2h, launches, chunks = [], [], [], 0, 0, 0, 1
@@ -284,6 +284,7 @@ def run_ours(args):
             d2h = r.timing["d2h_bytes"]
             launches += r.timing["scan_launches"]
             chunks = r.timing["chunks"]
+        reduce_stats()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -293,10 +294,11 @@ def run_ours(args):
             ms = float(t.item())
         return ms, k1, k1b, k2, nmsg, d2h, launches, chunks
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # one sampler per job: nvidia-smi is not free
+    if sampler:
+        sampler.start()
     ms_dev, k1_ms, k1b_ms, k2_ms, nmsg, _, n_launches, n_chunks = timed(step_device, args.steps, args.warmup)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     ms_host, _, _, _, _, d2h_bytes, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
 
     # scan kernel alone, both modes (device-resident, same stream)
