@@ -160,6 +160,17 @@ int b200_demod_get_timing(const b200_demod *d, b200_timing *out);
  * (decodeModeAMessage, mode_ac.c:168-181), timestamped at the second framing pulse. */
 uint64_t b200_demod_modeac_count(const b200_demod *d);
 
+/* ---- output formats (host; no device needed) ---- */
+
+/* replaces: modesSendBeastOutput (net_io.c:769-835): Beast binary frames (0x1a, type '1' | '2' | '3', 48-bit
+ * big-endian 12 MHz timestamp, signal byte round(sqrt(signalLevel) * 255), payload; every 0x1a doubled)
+ * of n messages, in order.  net_verbatim = Modes.net_verbatim (send the frame as sliced, not as
+ * repaired).  Returns the byte count needed; only the first `cap` bytes are stored (out may be NULL). */
+uint64_t b200_format_beast(const b200_message *msgs, uint64_t n, int net_verbatim, uint8_t *out, uint64_t cap);
+/* replaces: modesSendRawOutput (net_io.c:870-896): "*<hex>;\n", or "@<12 hex digits of the timestamp><hex>;\n"
+ * with mlat (Modes.mlat) and a non-zero timestamp.  Same return convention. */
+uint64_t b200_format_raw(const b200_message *msgs, uint64_t n, int net_verbatim, int mlat, char *out, uint64_t cap);
+
 /* ---- kernel-level entry points (measurement and unit parity; device pointers) ---- */
 
 /* Only K1 over a device-resident span, no host work and no result download: the kernels the

@@ -7,6 +7,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <time.h>
 
@@ -928,6 +929,82 @@ int mo_run(const mo_config *cfg, const void *iq, uint64_t nsamples, mo_result *r
     free(s);
     free(data);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Output writers: what the Beast and raw TCP services put on the wire for a
+ * message.  Restated from modesSendBeastOutput (net_io.c:769-835) and modesSendRawOutput
+ * (net_io.c:870-896); pinned against those functions themselves through oracle/ref_netfmt.c.
+ * Both return the number of bytes the messages need; bytes past `cap` are not written.
+ * ------------------------------------------------------------------------------------------ */
+
+static size_t put_escaped(uint8_t *out, size_t cap, size_t at, uint8_t ch) { /* 0x1a is doubled */
+    if (at < cap)
+        out[at] = ch;
+    ++at;
+    if (ch == 0x1a) {
+        if (at < cap)
+            out[at] = ch;
+        ++at;
+    }
+    return at;
+}
+
+size_t mo_format_beast(const mo_msg *msgs, uint64_t n, int net_verbatim, uint8_t *out, size_t cap) {
+    size_t at = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const mo_msg *mm = &msgs[i];
+        const int len = mm->msgbits / 8;
+        const uint8_t *msg = net_verbatim ? mm->verbatim : mm->msg;
+        char type;
+        if (len == 7) type = '2';
+        else if (len == 14) type = '3';
+        else if (len == 2) type = '1';
+        else continue; /* net_io.c:781-789 */
+        if (at < cap) out[at] = 0x1a;
+        ++at;
+        if (at < cap) out[at] = (uint8_t) type;
+        ++at;
+        for (int shift = 40; shift >= 0; shift -= 8) /* 12 MHz timestamp, big-endian */
+            at = put_escaped(out, cap, at, (uint8_t) (mm->timestampMsg >> shift));
+        int sig = (int) round(sqrt(mm->signalLevel) * 255); /* net_io.c:817-821 */
+        if (mm->signalLevel > 0 && sig < 1)
+            sig = 1;
+        if (sig > 255)
+            sig = 255;
+        at = put_escaped(out, cap, at, (uint8_t) sig);
+        for (int j = 0; j < len; ++j)
+            at = put_escaped(out, cap, at, msg[j]);
+    }
+    return at;
+}
+
+size_t mo_format_raw(const mo_msg *msgs, uint64_t n, int net_verbatim, int mlat, char *out, size_t cap) {
+    static const char hex[] = "0123456789ABCDEF";
+    size_t at = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const mo_msg *mm = &msgs[i];
+        const int len = mm->msgbits / 8;
+        const uint8_t *msg = net_verbatim ? mm->verbatim : mm->msg;
+        char head[16];
+        int nh = 1;
+        head[0] = '*';
+        if (mlat && mm->timestampMsg) /* net_io.c:879-884 */
+            nh = snprintf(head, sizeof (head), "@%012llX", (unsigned long long) mm->timestampMsg);
+        for (int j = 0; j < nh; ++j, ++at)
+            if (at < cap) out[at] = head[j];
+        for (int j = 0; j < len; ++j) {
+            if (at < cap) out[at] = hex[msg[j] >> 4];
+            ++at;
+            if (at < cap) out[at] = hex[msg[j] & 15];
+            ++at;
+        }
+        if (at < cap) out[at] = ';';
+        ++at;
+        if (at < cap) out[at] = '\n';
+        ++at;
+    }
+    return at;
 }
 
 void mo_result_free(mo_result *res) {

@@ -16,6 +16,7 @@
 #ifndef MODES_ORACLE_H
 #define MODES_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -119,6 +120,10 @@ typedef struct {
     mo_stats stats;
     uint64_t n_samples;
 } mo_result;
+
+/* net_io.c:769-835 / 870-896: the bytes the Beast and raw output services write for these messages */
+size_t mo_format_beast(const mo_msg *msgs, uint64_t n, int net_verbatim, uint8_t *out, size_t cap);
+size_t mo_format_raw(const mo_msg *msgs, uint64_t n, int net_verbatim, int mlat, char *out, size_t cap);
 
 /* Runs the whole stream; result arrays are malloc'd, release with mo_result_free. */
 int mo_run(const mo_config *cfg, const void *iq, uint64_t nsamples, mo_result *res);

@@ -50,6 +50,10 @@ def lib():
         L.mo_convert.restype = ctypes.c_int
         L.mo_convert.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
                                  ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.mo_format_beast.restype = ctypes.c_size_t
+        L.mo_format_beast.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+        L.mo_format_raw.restype = ctypes.c_size_t
+        L.mo_format_raw.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
         L.mo_checksum.restype = ctypes.c_uint32
         L.mo_checksum.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.mo_single_bit_syndrome.restype = ctypes.c_uint32
@@ -137,3 +141,21 @@ def slice_bytes(mag: np.ndarray, j: int, try_phase: int, nbytes: int) -> bytes:
     out = (ctypes.c_uint8 * nbytes)()
     lib().mo_slice(mag.ctypes.data, j, try_phase, nbytes, out)
     return bytes(out)
+
+
+def format_beast(msgs: np.ndarray, net_verbatim: bool = True) -> bytes:
+    """net_io.c:769-835 restated: Beast binary frames of a message array (MSG_DTYPE)."""
+    msgs = np.ascontiguousarray(msgs, dtype=MSG_DTYPE)
+    need = lib().mo_format_beast(msgs.ctypes.data, len(msgs), int(net_verbatim), None, 0)
+    buf = np.empty(max(need, 1), dtype=np.uint8)
+    lib().mo_format_beast(msgs.ctypes.data, len(msgs), int(net_verbatim), buf.ctypes.data, need)
+    return buf[:need].tobytes()
+
+
+def format_raw(msgs: np.ndarray, net_verbatim: bool = True, mlat: bool = False) -> bytes:
+    """net_io.c:870-896 restated: raw-service lines of a message array."""
+    msgs = np.ascontiguousarray(msgs, dtype=MSG_DTYPE)
+    need = lib().mo_format_raw(msgs.ctypes.data, len(msgs), int(net_verbatim), int(mlat), None, 0)
+    buf = np.empty(max(need, 1), dtype=np.uint8)
+    lib().mo_format_raw(msgs.ctypes.data, len(msgs), int(net_verbatim), int(mlat), buf.ctypes.data, need)
+    return buf[:need].tobytes()

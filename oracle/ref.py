@@ -63,3 +63,27 @@ def magnitudes(iq: np.ndarray, fmt: str = "uc8") -> np.ndarray:
         np.ascontiguousarray(iq).view(np.uint8).tofile(path)
         run_file(path, fmt, mag_out=mag)
         return np.fromfile(mag, dtype=np.uint16)
+
+
+def netfmt_binary() -> Path | None:
+    p = HERE / "_ref" / "ref_netfmt"
+    return p if p.exists() else None
+
+
+def format_outputs(res: DemodResult, net_verbatim: bool = True, mlat: bool = False):
+    """(beast bytes, raw bytes): the reference's own modesSendBeastOutput / modesSendRawOutput
+    (net_io.c:769-896) over the messages of a result (oracle/ref_netfmt.c)."""
+    from readsb_protobuf_b200.results import write_result_file
+    exe = netfmt_binary()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/ref_netfmt is not built and /root/reference is absent")
+    with tempfile.TemporaryDirectory() as td:
+        rp, bp, tp = os.path.join(td, "r.res"), os.path.join(td, "beast.bin"), os.path.join(td, "raw.txt")
+        write_result_file(rp, res)
+        cmd = [str(exe), "--in", rp, "--beast-out", bp, "--raw-out", tp]
+        if mlat:
+            cmd.append("--mlat")
+        if not net_verbatim:
+            cmd.append("--no-verbatim")
+        subprocess.run(cmd, check=True, capture_output=True)
+        return open(bp, "rb").read(), open(tp, "rb").read()

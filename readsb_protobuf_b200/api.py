@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "b200_demod_block_count", "b200_demod_blocks", "b200_demod_get_stats", "b200_demod_get_timing",
     "b200_scan_device", "b200_convert", "b200_uc8_table", "b200_debug_scan", "b200_crc_batch",
     "b200_error_table", "b200_abi_sizeof", "b200_host_checksum", "b200_host_error_table", "b200_host_uc8_table",
-    "b200_host_filter_script", "b200_demod_modeac_count",
+    "b200_host_filter_script", "b200_demod_modeac_count", "b200_format_beast", "b200_format_raw",
 )
 
 
@@ -91,6 +91,10 @@ def load():
     L.b200_demod_create.argtypes = [ctypes.POINTER(_Config), ctypes.POINTER(vp)]
     L.b200_demod_destroy.restype = None
     L.b200_demod_destroy.argtypes = [vp]
+    L.b200_format_beast.restype = u64
+    L.b200_format_beast.argtypes = [vp, u64, i32, vp, u64]
+    L.b200_format_raw.restype = u64
+    L.b200_format_raw.argtypes = [vp, u64, i32, i32, vp, u64]
     L.b200_demod_modeac_count.restype = u64
     L.b200_demod_modeac_count.argtypes = [vp]
     L.b200_demod_reset.restype = i32
@@ -179,6 +183,28 @@ class SpanResult:
     msgs: np.ndarray
     blocks: np.ndarray
     timing: dict
+
+
+def format_beast(msgs: np.ndarray, net_verbatim: bool = True) -> bytes:
+    """Beast binary frames of a message array (MSG_DTYPE), as modesSendBeastOutput writes them."""
+    L = load()
+    msgs = np.ascontiguousarray(msgs, dtype=MSG_DTYPE)
+    need = int(L.b200_format_beast(msgs.ctypes.data, len(msgs), 1 if net_verbatim else 0, None, 0))
+    buf = np.empty(max(need, 1), dtype=np.uint8)
+    got = int(L.b200_format_beast(msgs.ctypes.data, len(msgs), 1 if net_verbatim else 0, buf.ctypes.data, need))
+    assert got == need
+    return buf[:need].tobytes()
+
+
+def format_raw(msgs: np.ndarray, net_verbatim: bool = True, mlat: bool = False) -> bytes:
+    """Raw-service lines of a message array, as modesSendRawOutput writes them."""
+    L = load()
+    msgs = np.ascontiguousarray(msgs, dtype=MSG_DTYPE)
+    need = int(L.b200_format_raw(msgs.ctypes.data, len(msgs), 1 if net_verbatim else 0, 1 if mlat else 0, None, 0))
+    buf = np.empty(max(need, 1), dtype=np.uint8)
+    got = int(L.b200_format_raw(msgs.ctypes.data, len(msgs), 1 if net_verbatim else 0, 1 if mlat else 0, buf.ctypes.data, need))
+    assert got == need
+    return buf[:need].tobytes()
 
 
 class Demodulator:

@@ -102,7 +102,9 @@ def ensure_ref() -> Path | None:
     """
     binary = ORACLE / "_ref" / "ref_demod"
     if have_reference_sources():
-        if not _newer(binary, [ORACLE / "ref_harness.c", ORACLE / "ref_shim" / "stubs.c", ORACLE / "Makefile"]):
+        netfmt = ORACLE / "_ref" / "ref_netfmt"
+        deps = [ORACLE / "ref_harness.c", ORACLE / "ref_netfmt.c", ORACLE / "ref_shim" / "stubs.c", ORACLE / "Makefile"]
+        if not _newer(binary, deps) or not _newer(netfmt, deps):
             _run(["make", "-C", ORACLE, "ref", "CC=gcc", f"REF={REFERENCE}"])
     return binary if binary.exists() else None
 

@@ -656,18 +656,27 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
             } else {
                 const uint32_t lanes = __ballot_sync(0xffffffffu, any != 0);
                 if (lanes) {
-                    // candidate entries of the step in position order: every lane places its own through
-                    // a warp prefix sum
+                    // candidate entries of the step in position order.  Almost always a lane holds at most one
+                    // (6 candidates per 512 positions on noise): its slot then follows from the ballot alone;
+                    // only a lane with several sends the warp through a prefix sum.
                     const uint32_t mine = (uint32_t) __popc(any);
-                    uint32_t inc = mine;
+                    const uint32_t multi = __ballot_sync(0xffffffffu, mine > 1);
+                    uint32_t ci, total;
+                    if (!multi) {
+                        ci = cx.ncand + __popc(lanes & ((1u << lane) - 1u));
+                        total = (uint32_t) __popc(lanes);
+                    } else {
+                        uint32_t inc = mine;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o)
-                            inc += up;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o)
+                                inc += up;
+                        }
+                        ci = cx.ncand + inc - mine;
+                        total = __shfl_sync(0xffffffffu, inc, 31);
                     }
-                    uint32_t ci = cx.ncand + inc - mine;
-                    cx.ncand += __shfl_sync(0xffffffffu, inc, 31);
+                    cx.ncand += total;
                     uint32_t u = any;
                     while (u) {
                         const int i = __ffs(u) - 1;

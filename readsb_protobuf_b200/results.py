@@ -92,6 +92,21 @@ def read_result_file(path) -> DemodResult:
     return DemodResult(msgs, stats, blocks, int(hdr["n_samples"]))
 
 
+def write_result_file(path, res: DemodResult) -> None:
+    """The inverse of read_result_file (same layout as oracle/ref_harness.c writes)."""
+    hdr = np.zeros(1, dtype=HEADER_DTYPE)
+    hdr["magic"] = b"MDSR"
+    hdr["version"] = 1
+    hdr["n_msgs"] = len(res.msgs)
+    hdr["n_blocks"] = len(res.blocks)
+    hdr["n_samples"] = res.n_samples
+    with open(path, "wb") as f:
+        f.write(hdr.tobytes())
+        f.write(np.asarray(res.stats, dtype=STATS_DTYPE).reshape(1).tobytes())
+        f.write(np.ascontiguousarray(res.msgs, dtype=MSG_DTYPE).tobytes())
+        f.write(np.ascontiguousarray(res.blocks, dtype=BLOCK_DTYPE).tobytes())
+
+
 def compare_results(got: DemodResult, want: DemodResult, float_rtol: float = 0.0,
                     signal_atol: float = 1e-5, check_blocks: bool = True) -> list[str]:
     """Differences between two results as human-readable strings (empty list = parity)."""

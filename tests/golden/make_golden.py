@@ -145,6 +145,35 @@ def render_frames(frames, gap=600, amp=0.5):
     return np.concatenate(parts)
 
 
+def netfmt_messages():
+    """Messages for the output writers (net_io.c:769-896): the uc8_modeac reference messages plus crafted
+    ones that hit every escape and clamp: 0x1a in the timestamp, the signal byte and the payload, signal
+    levels 0 / tiny / 1.0 / above full scale, a zero timestamp (raw falls back to '*'), a length that is
+    not sent at all."""
+    from readsb_protobuf_b200.results import MSG_DTYPE
+    z = np.load(HERE / "uc8_modeac.npz")
+    base = z["msgs"]
+    rng = np.random.default_rng(26)
+    n = 400
+    m = np.zeros(n, dtype=MSG_DTYPE)
+    m["msgbits"] = rng.choice([16, 56, 112, 112, 56, 40], n)
+    m["timestampMsg"] = rng.integers(0, 1 << 48, n, dtype=np.uint64)
+    m["msg"] = rng.integers(0, 256, (n, 14), dtype=np.uint8)
+    m["verbatim"] = rng.integers(0, 256, (n, 14), dtype=np.uint8)
+    m["signalLevel"] = rng.random(n) ** 4
+    for i in range(0, n, 7):      # 0x1a everywhere an escape can be needed
+        m["timestampMsg"][i] = (int(m["timestampMsg"][i]) & ~(0xff << (8 * (i % 6)))) | (0x1a << (8 * (i % 6)))
+        m["msg"][i, i % 14] = 0x1a
+        m["verbatim"][i, (i + 3) % 14] = 0x1a
+    m["signalLevel"][::11] = (26.0 / 255.0) ** 2   # signal byte 0x1a
+    m["signalLevel"][1::13] = 0.0
+    m["signalLevel"][2::17] = 1e-12                # rounds to 0 -> forced to 1
+    m["signalLevel"][3::19] = 1.0
+    m["signalLevel"][4::23] = 1.7                  # above full scale -> 255
+    m["timestampMsg"][5::29] = 0                   # raw: '*' even with mlat
+    return np.concatenate([base, m])
+
+
 def main(only=None):
     assert ref.available(), "needs /root/reference (or a prebuilt oracle/_ref)"
     for name, (cfg, flags) in FIXTURES.items():
@@ -181,6 +210,19 @@ def main(only=None):
                             meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
         print(f"{name}: {len(frames)} frames, {len(res.msgs)} reference messages, DFs",
               sorted(set(int(x) for x in res.msgs["msgtype"])))
+    if not only or "netfmt" in only:
+        from readsb_protobuf_b200.results import DemodResult
+        msgs = netfmt_messages()
+        res = DemodResult(msgs, np.zeros((), dtype=np.load(HERE / "uc8_modeac.npz")["stats"].dtype), np.zeros(0, dtype=np.load(HERE / "uc8_modeac.npz")["blocks"].dtype), 0)
+        out = {"msgs": msgs}
+        for verb in (0, 1):
+            for mlat in (0, 1):
+                beast, raw = ref.format_outputs(res, net_verbatim=bool(verb), mlat=bool(mlat))
+                out[f"beast_v{verb}"] = np.frombuffer(beast, dtype=np.uint8)
+                out[f"raw_v{verb}_m{mlat}"] = np.frombuffer(raw, dtype=np.uint8)
+        np.savez_compressed(HERE / "netfmt.npz", **out)
+        print(f"netfmt: {len(msgs)} messages, beast {len(out['beast_v1'])} bytes, raw {len(out['raw_v1_m1'])} bytes "
+              "(oracle/_ref/ref_netfmt: the reference's own writers)")
     if only and "kat_frame" not in only:
         return
     frame = bytes.fromhex(KAT_FRAME_HEX)

@@ -90,3 +90,22 @@ def test_host_icao_filter_semantics():
     addrs = [0x100000 + 7 * i for i in range(n)]
     res = api.host_filter_script(ops, addrs + addrs)
     assert 4000 <= int(res[n:].sum()) < n
+
+
+@pytest.mark.parametrize("verbatim", [False, True])
+def test_output_writers_match_the_reference(verbatim):
+    """b200_format_beast / b200_format_raw (host functions of the library, no device needed) against bytes
+    the reference's own modesSendBeastOutput / modesSendRawOutput produced (tests/golden/netfmt.npz)."""
+    from conftest import GOLDEN
+    z = np.load(GOLDEN / "netfmt.npz")
+    msgs, v = z["msgs"], int(verbatim)
+    assert api.format_beast(msgs, verbatim) == z[f"beast_v{v}"].tobytes()
+    for mlat in (False, True):
+        assert api.format_raw(msgs, verbatim, mlat) == z[f"raw_v{v}_m{int(mlat)}"].tobytes()
+    # capacity handling: the byte count is returned whatever fits, nothing is written past cap
+    L = api.load()
+    m = np.ascontiguousarray(msgs)
+    need = L.b200_format_beast(m.ctypes.data, len(m), v, None, 0)
+    buf = np.full(101, 0xEE, dtype=np.uint8)
+    assert L.b200_format_beast(m.ctypes.data, len(m), v, buf.ctypes.data, 100) == need
+    assert buf[100] == 0xEE and bytes(buf[:100]) == z[f"beast_v{v}"].tobytes()[:100]

@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_NAMES, load_golden
+from conftest import GOLDEN as GOLDEN_DIR, GOLDEN_NAMES, load_golden
 from oracle import port, ref
 from readsb_protobuf_b200 import results, synth
 
@@ -163,3 +163,37 @@ def test_df18_non_icao_address_flag():
     assert 0 < int(flagged[np.isin(cf, (2, 3, 6))].sum()) < int(np.isin(cf, (2, 3, 6)).sum())
     got = port.run(iq, "uc8")
     assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
+
+
+# ------------------------------------------------------------------------------------------
+# Beast / raw output writers (net_io.c:769-896), SURVEY.md 8f row 1
+# ------------------------------------------------------------------------------------------
+
+def _netfmt_golden():
+    z = np.load(GOLDEN_DIR / "netfmt.npz")
+    return z["msgs"], {k: z[k].tobytes() for k in z.files if k != "msgs"}
+
+
+@pytest.mark.parametrize("verbatim", [False, True])
+def test_port_writers_match_reference_golden(verbatim):
+    msgs, want = _netfmt_golden()
+    assert len(msgs) > 500 and int(np.sum(msgs["msgbits"] == 40)) > 0  # a length that is not sent
+    v = int(verbatim)
+    beast = port.format_beast(msgs, verbatim)
+    assert beast == want[f"beast_v{v}"] and beast.count(b"\x1a\x1a") > 20
+    for mlat in (False, True):
+        assert port.format_raw(msgs, verbatim, mlat) == want[f"raw_v{v}_m{int(mlat)}"]
+    assert b"\n*" in want[f"raw_v{v}_m1"]  # zero timestamps print '*' even with --mlat
+
+
+@pytest.mark.skipif(ref.netfmt_binary() is None, reason="needs /root/reference or a prebuilt oracle/_ref")
+def test_port_writers_match_live_reference():
+    cfg = synth.SynthConfig(seed=401, nsamples=600_000, frames_per_s=3000, frac_biterror=0.2, modeac_per_s=2000)
+    iq, _ = synth.generate(cfg)
+    res = ref.run(iq, "uc8", modeac=True)
+    assert len(res.msgs) > 300
+    for verbatim in (False, True):
+        for mlat in (False, True):
+            wb, wr = ref.format_outputs(res, net_verbatim=verbatim, mlat=mlat)
+            assert port.format_beast(res.msgs, verbatim) == wb
+            assert port.format_raw(res.msgs, verbatim, mlat) == wr
