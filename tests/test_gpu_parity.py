@@ -45,6 +45,9 @@ def test_matches_reference_golden(name):
     got = run_gpu(iq, meta["fmt"], **meta["flags"])
     assert len(got.msgs) == len(want.msgs) > 0
     assert_parity(got, want, meta["fmt"])
+    # ... and so are the bytes the Beast / raw services would send for them (net_io.c:769-896)
+    assert api.format_beast(got.msgs) == port.format_beast(want.msgs)
+    assert api.format_raw(got.msgs, mlat=True) == port.format_raw(want.msgs, mlat=True)
 
 
 CASES = [
