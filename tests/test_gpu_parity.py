@@ -151,6 +151,27 @@ def test_modeac_off_by_default_and_dense_hits():
     assert_parity(plain, port.run(iq, "uc8"), "uc8")
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_randomized_configurations(seed):
+    """Random corners of the parameter space: format, repair depth, threshold, mag_buf size, stream
+    length (ragged), traffic density, noise level, Mode A/C, span size -- all against the oracle, bit-exact."""
+    rng = np.random.default_rng(1000 + seed)
+    fmt = ["uc8", "uc8", "sc16", "sc16q11"][int(rng.integers(0, 4))]
+    block = int(rng.integers(125, 25000)) * 8
+    nsamples = int(rng.integers(1, 1_200_000))
+    modeac = bool(rng.integers(0, 2))
+    cfg = synth.SynthConfig(seed=2000 + seed, nsamples=nsamples, fmt=fmt, frames_per_s=float(rng.choice([50, 500, 3000, 9000])),
+                            frac_biterror=float(rng.choice([0.0, 0.2, 0.6])), noise_sigma=float(rng.choice([0.002, 0.02, 0.08])),
+                            amp_max=float(rng.choice([0.3, 0.9, 1.3])), n_icao=int(rng.choice([3, 200])),
+                            modeac_per_s=float(rng.choice([0, 2000])) if modeac else 0.0)
+    flags = dict(nfix=int(rng.integers(0, 3)), threshold=int(rng.choice([40, 58, 75, 130, 400])), block_samples=block)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, fmt, modeac=modeac, **flags)
+    span = None if rng.integers(0, 2) else block * int(rng.integers(1, 6))
+    got = run_gpu(iq, fmt, span_samples=span, modeac=modeac, **flags)
+    assert_parity(got, want, fmt)
+
+
 def test_icao_filter_flips_across_minutes():
     """> 120 s of stream so that addresses age out (icao_filter.c:150-164) -- sparse, to stay fast."""
     cfg = synth.SynthConfig(seed=82, nsamples=int(130 * 2.4e6), frames_per_s=20, n_icao=5, noise_sigma=0.004)
