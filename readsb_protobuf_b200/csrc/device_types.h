@@ -19,7 +19,7 @@ constexpr int kStep = 512;                 // samples one warp converts per step
 constexpr int kLanePos = kStep / 32;       // 16 scan positions per lane per step
 constexpr int kScanSteps = kTile / kStep;  // 16 steps of window starts
 constexpr int kLookahead = 296;            // samples past the last window start a slice can touch (290) rounded to 8
-constexpr int kScanWarps = 16;             // warps per K1a CTA (shared memory: 128 KiB table + 5 KiB ring per warp)
+constexpr int kScanWarps = 19;             // warps per K1a CTA (shared memory: 128 KiB table + 5 KiB ring per warp)
 constexpr int kScanThreads = kScanWarps * 32;
 // Warp buffer: a ring of two chunks of u32 magnitudes, one row per lane.  A row is the lane's 16
 // magnitudes plus 16 bytes of padding: the 80-byte row stride makes every 128-bit access of a

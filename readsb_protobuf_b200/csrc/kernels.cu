@@ -734,15 +734,17 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     if (FORMAT == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.lut_swz);
         uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
-        constexpr int kPer = (int) (kSmemLut / 16) / kScanThreads; // 16
-        static_assert(kPer * kScanThreads * 16 == (int) kSmemLut, "the table staging assumes the CTA size divides the table");
+        constexpr int kUnits = (int) (kSmemLut / 16);                      // 8192 sixteen-byte units
+        constexpr int kPer = (kUnits + kScanThreads - 1) / kScanThreads;  // per thread, all in flight at once
         uint4 v[kPer];
 #pragma unroll
         for (int q = 0; q < kPer; ++q)
-            v[q] = __ldg(src + q * kScanThreads + tid);
+            if (q * kScanThreads + tid < kUnits)
+                v[q] = __ldg(src + q * kScanThreads + tid);
 #pragma unroll
         for (int q = 0; q < kPer; ++q)
-            dst[q * kScanThreads + tid] = v[q];
+            if (q * kScanThreads + tid < kUnits)
+                dst[q * kScanThreads + tid] = v[q];
     }
     __syncthreads();
 
