@@ -707,25 +707,33 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
     const uint64_t two_waves = (uint64_t) 2 * d->scan_grid * kScanWarps * kTile - kTile; // tiles_for() adds one tile for the tail
     const uint64_t chunk_target = (d->sm_count > 0 && two_waves >= (16ull << 20) && two_waves <= (64ull << 20)) ? two_waves : kChunkTarget;
     const uint64_t chunk = std::max<uint64_t>(1, chunk_target / B) * B;
-    // chunk i = [starts[i], starts[i + 1]), whole mag_bufs.  For host buffers the pipeline is bound by the
-    // H2D copies, so what counts is the work left when the last byte has landed: the last chunk is split so
-    // that its tail is small (kernels + resolve of 4 M samples instead of up to 38 M).
+    // chunk i = [starts[i], starts[i + 1]), whole mag_bufs, as equal as possible (a short last chunk would run
+    // the kernels nearly empty).  For host buffers the pipeline is bound by the H2D copies, so what counts
+    // is the work left when the last byte has landed: the end of the span is cut into chunks that shrink
+    // (main chunks of at most 32 M samples, then 12 M and 4 M), each small enough to be through the kernels
+    // and the resolver while the rest is still being copied (processing a chunk takes about half as long
+    // as copying it).
     std::vector<uint64_t> starts;
-    for (uint64_t at = 0; at < nsamples; at += chunk)
-        starts.push_back(at);
-    if (starts.empty())
-        starts.push_back(0);
-    if (host_src) {
-        for (uint64_t back : {16ull << 20, 4ull << 20}) { // cuts about 16 M and 4 M samples before the end
-            const uint64_t tail = std::max<uint64_t>(1, back / B) * B;
-            if (nsamples <= tail)
-                continue;
-            const uint64_t cut = (nsamples - tail) / B * B;
-            if (cut > starts.back() + back / 2 && cut < nsamples)
-                starts.push_back(cut);
+    {
+        const uint64_t nb = (nsamples + B - 1) / B, big = std::max<uint64_t>(1, chunk / B);
+        uint64_t tails[2] = {std::max<uint64_t>(1, (12ull << 20) / B), std::max<uint64_t>(1, (4ull << 20) / B)};
+        const uint64_t tail_total = tails[0] + tails[1];
+        const bool ramp = host_src && nb > tail_total + big / 2;
+        const uint64_t main_blocks = ramp ? nb - tail_total : nb;
+        const uint64_t main_big = ramp ? std::min<uint64_t>(big, std::max<uint64_t>(1, (32ull << 20) / B)) : big;
+        const uint64_t nmain = std::max<uint64_t>(1, (main_blocks + main_big - 1) / main_big);
+        uint64_t at = 0; // in mag_bufs
+        for (uint64_t i = 0; i < nmain; ++i) {
+            starts.push_back(std::min(nsamples, at * B));
+            at += main_blocks / nmain + (i < main_blocks % nmain ? 1 : 0);
         }
+        if (ramp)
+            for (uint64_t tsz : tails) {
+                starts.push_back(std::min(nsamples, at * B));
+                at += tsz;
+            }
+        starts.push_back(nsamples);
     }
-    starts.push_back(nsamples);
     const uint64_t nchunks = starts.size() - 1;
     b200_timing t;
     memset(&t, 0, sizeof(t));
