@@ -723,9 +723,23 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
         const uint64_t main_big = ramp ? std::min<uint64_t>(big, std::max<uint64_t>(1, (32ull << 20) / B)) : big;
         const uint64_t nmain = std::max<uint64_t>(1, (main_blocks + main_big - 1) / main_big);
         uint64_t at = 0; // in mag_bufs
-        for (uint64_t i = 0; i < nmain; ++i) {
-            starts.push_back(std::min(nsamples, at * B));
-            at += main_blocks / nmain + (i < main_blocks % nmain ? 1 : 0);
+        // one wave of K1a = one tile per resident warp (tiles_for() adds a tile for the tail of a chunk)
+        const uint64_t wave = ((uint64_t) d->scan_grid * kScanWarps - 1) * kTile / B;
+        if (!ramp && wave > 0 && nb > 3 * wave) {
+            // device-resident span: whole waves per chunk, so that only the last launch ends on a partial
+            // wave -- one wave first (the host resolver starts early), then two at a time
+            starts.push_back(0);
+            at = wave;
+            while (nb - at > 3 * wave) {
+                starts.push_back(at * B);
+                at += 2 * wave;
+            }
+            starts.push_back(at * B);
+        } else {
+            for (uint64_t i = 0; i < nmain; ++i) {
+                starts.push_back(std::min(nsamples, at * B));
+                at += main_blocks / nmain + (i < main_blocks % nmain ? 1 : 0);
+            }
         }
         if (ramp)
             for (uint64_t tsz : tails) {
