@@ -55,12 +55,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_bytes():
-    """dram read+write bytes of one K1 launch from the committed ncu summary, if any."""
+def ncu_traffic_ratio():
+    """DRAM bytes (read + write) per algorithmic byte of a K1a launch, from the committed ncu capture."""
     p = ROOT / "profiles" / "k1_traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+            j = json.loads(p.read_text())
+            return float(j["dram_bytes_per_launch"]) / float(j["algorithmic_bytes_per_launch"])
         except Exception:
             return None
     return None
@@ -319,6 +320,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         k1_mean = float(np.mean(k1_ms))
+        ratio = ncu_traffic_ratio()
+        traffic = None if ratio is None else ratio * nbytes / max(int(n_chunks), 1)
         achieved = nsamples * 2 / (k1_mean * 1e-3) / 1e9
         so_mean = float(np.mean(scan_only))
         sf_mean = float(np.mean(scan_full))
@@ -342,7 +345,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "scan_kernel<uc8> (K1a: IQ -> magnitude + preamble scan + candidates)",
                          "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/k1_traffic.json: DRAM bytes per algorithmic byte of the ncu-captured launch x this run's bytes per launch", "peak_source": peak_src,
                          "launches_per_step": int(n_chunks), "algorithmic_bytes_per_launch": nbytes // max(int(n_chunks), 1),
                          "kernel_ms_per_launch": k1_mean / max(int(n_chunks), 1), "kernel_ms_per_step": k1_mean,
                          "scan_only": {"kernel": "scan_kernel<uc8, scan only> (magnitude + preamble scan)",
