@@ -18,7 +18,6 @@ constexpr int kTile = 8192;
 constexpr int kStep = 512;                 // samples one warp converts per step (16 per lane)
 constexpr int kLanePos = kStep / 32;       // 16 scan positions per lane per step
 constexpr int kScanSteps = kTile / kStep;  // 16 steps of window starts
-constexpr int kLookahead = 296;            // samples past the last window start a slice can touch (290) rounded to 8
 constexpr int kScanWarps = 19;             // warps per K1a CTA (shared memory: 128 KiB table + 5 KiB ring per warp)
 constexpr int kScanThreads = kScanWarps * 32;
 // Warp buffer: a ring of two chunks of u32 magnitudes, one row per lane.  A row is the lane's 16
@@ -111,7 +110,7 @@ struct ScanCounters {
     unsigned long long n_liverec;
     unsigned int overflow; // bit0 cand, bit1 rec, bit2 dead, bit3 live, bit4 liverec, bit5 Mode A/C hits
     unsigned int next_tile; // K1a work queue
-    unsigned int next_tile_slice; // (unused since K1b deals its units round-robin)
+    unsigned int reserved;
     unsigned int n_modeac_hits;   // Mode A/C kernel
 };
 
