@@ -210,6 +210,32 @@ def run_reference_arm(args):
 # our arm
 # ------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Keep this rank's threads (host resolver, CUDA workers) and its first-touch allocations on the NUMA
+    node its GPU hangs off: the resolver reads memory the GPU has just written over PCIe.  Returns a
+    short description, or None when the topology is not visible (single node, container without sysfs)."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={gpu_index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     from readsb_protobuf_b200 import api, synth
@@ -219,6 +245,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the demodulator has no CPU fallback")
+    binding = bind_to_gpu_numa_node(local_rank)
+    print(f"rank {rank}: gpu {local_rank}, cpu binding: {binding}", file=sys.stderr)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -337,7 +365,7 @@ def run_ours(args):
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "samples_per_gpu": nsamples, "bytes_per_gpu": nbytes,
-                       "l2": "input 288 MB per GPU > 126 MB L2, no flush needed", "streams": world,
+                       "l2": "input 288 MB per GPU > 126 MB L2, no flush needed", "streams": world, "cpu_binding": binding,
                        "decoded_msgs_per_stream": nmsg, "msgs_per_s": nmsg * world * args.steps / (ms_dev * 1e-3)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": ms_host / args.steps},
