@@ -386,6 +386,61 @@ static void convert_sc16_scaled(const uint8_t *in, uint32_t n, float scale, uint
         *mean_power = sum_power / n;
 }
 
+/* convert.c:113-162 (uc8), 164-213 (sc16), 374-423 (sc16q11): the "generic" float converters that
+ * --dcfilter selects.  A one-pole DC block z = f*a + z*b runs per rail over the whole stream (its state
+ * is carried from call to call in struct converter_state), the magnitude is taken of f - z.  Every step
+ * is a separate float operation in the order the C code spells (no contraction: -ffp-contract=off,
+ * like the reference's x86-64 -O2 build). */
+void mo_dc_init(mo_dc_state *st, double sample_rate) {
+    /* init_converter, convert.c:476-488 with filter_dc != 0: float fields assigned from double expressions */
+    st->z1_I = 0;
+    st->z1_Q = 0;
+    st->dc_b = (float) exp(-2.0 * M_PI * 1.0 / sample_rate);
+    st->dc_a = (float) (1.0 - st->dc_b);
+}
+
+int mo_convert_dc(int format, const void *iq, uint32_t n, mo_dc_state *st, uint16_t *mag, double *mean_level,
+                  double *mean_power) {
+    if (format < MO_UC8 || format > MO_SC16Q11)
+        return -1;
+    const uint8_t *in = iq;
+    float z1_I = st->z1_I, z1_Q = st->z1_Q;
+    const float dc_a = st->dc_a, dc_b = st->dc_b;
+    float sum_level = 0, sum_power = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        float fI, fQ;
+        if (format == MO_UC8) { /* convert.c:131-134 */
+            fI = (in[2 * i] - 127.5f) / 127.5f;
+            fQ = (in[2 * i + 1] - 127.5f) / 127.5f;
+        } else { /* convert.c:182-185 / 392-395 */
+            const float scale = (format == MO_SC16) ? 32768.0f : 2048.0f;
+            int16_t I = (int16_t) ((uint16_t) in[4 * i] | ((uint16_t) in[4 * i + 1] << 8));
+            int16_t Q = (int16_t) ((uint16_t) in[4 * i + 2] | ((uint16_t) in[4 * i + 3] << 8));
+            fI = I / scale;
+            fQ = Q / scale;
+        }
+        /* DC block, convert.c:136-140 */
+        z1_I = fI * dc_a + z1_I * dc_b;
+        z1_Q = fQ * dc_a + z1_Q * dc_b;
+        fI -= z1_I;
+        fQ -= z1_Q;
+        float magsq = fI * fI + fQ * fQ;
+        if (magsq > 1)
+            magsq = 1;
+        float m = sqrtf(magsq);
+        sum_power += magsq;
+        sum_level += m;
+        mag[i] = (uint16_t) (m * 65535.0f + 0.5f);
+    }
+    st->z1_I = z1_I;
+    st->z1_Q = z1_Q;
+    if (mean_level)
+        *mean_level = sum_level / n;
+    if (mean_power)
+        *mean_power = sum_power / n;
+    return 0;
+}
+
 int mo_convert(int format, const void *iq, uint32_t n, uint16_t *mag, double *mean_level, double *mean_power) {
     /* converter choice: convert.c:425-444 with filter_dc == 0 */
     switch (format) {
@@ -875,6 +930,9 @@ int mo_run(const mo_config *cfg, const void *iq, uint64_t nsamples, mo_result *r
     uint16_t carry[MO_OVERLAP];
     memset(carry, 0, sizeof (carry)); /* fifo.c:47 */
 
+    mo_dc_state dc;
+    mo_dc_init(&dc, 2400000.0); /* Modes.sample_rate, readsb.c:141 */
+
     msg_list list = {0};
     mo_block *blocks = NULL;
     uint64_t n_blocks = 0, cap_blocks = 0;
@@ -892,8 +950,12 @@ int mo_run(const mo_config *cfg, const void *iq, uint64_t nsamples, mo_result *r
 
         double mean_level, mean_power;
         double t0 = thread_cpu_s();
-        mo_convert(cfg->format, (const uint8_t *) iq + sampleCounter * bps, n, data + MO_OVERLAP,
-                   &mean_level, &mean_power);
+        if (cfg->dcfilter) /* init_converter(..., Modes.dc_filter, ...), sdr_ifile.c:151 */
+            mo_convert_dc(cfg->format, (const uint8_t *) iq + sampleCounter * bps, n, &dc, data + MO_OVERLAP,
+                          &mean_level, &mean_power);
+        else
+            mo_convert(cfg->format, (const uint8_t *) iq + sampleCounter * bps, n, data + MO_OVERLAP,
+                       &mean_level, &mean_power);
         s->stats.convert_cpu_s += thread_cpu_s() - t0;
 
         memcpy(data, carry, sizeof (carry)); /* fifo.c:184 */

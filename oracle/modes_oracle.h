@@ -85,6 +85,15 @@ void mo_uc8_table(uint16_t *table65536);
 int mo_convert(int format, const void *iq, uint32_t nsamples, uint16_t *mag,
                double *mean_level, double *mean_power);
 
+/* struct converter_state (convert.c:25-30) and the --dcfilter converters convert_*_generic
+ * (convert.c:113-213, 374-423): one call = one mag_buf, the filter state runs on across calls */
+typedef struct {
+    float dc_a, dc_b, z1_I, z1_Q;
+} mo_dc_state;
+void mo_dc_init(mo_dc_state *st, double sample_rate); /* init_converter, convert.c:476-488 */
+int mo_convert_dc(int format, const void *iq, uint32_t nsamples, mo_dc_state *st, uint16_t *mag,
+                  double *mean_level, double *mean_power);
+
 /* crc.c:67-82 */
 uint32_t mo_checksum(const uint8_t *msg, int bits);
 /* crc.c:42-65: syndrome of a single flipped bit, indexed from the start of a 112-bit frame */
@@ -110,6 +119,7 @@ typedef struct {
     int32_t threshold;     /* Modes.preambleThreshold */
     uint32_t block_samples; /* samples per mag_buf (MO_BLOCK_SAMPLES) */
     int32_t modeac;        /* Modes.mode_ac: also run the Mode A/C demodulator on every block */
+    int32_t dcfilter;      /* Modes.dc_filter (--dcfilter): the convert_*_generic converters */
 } mo_config;
 
 typedef struct {

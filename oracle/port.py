@@ -19,7 +19,7 @@ ERRORINFO_DTYPE = np.dtype([("syndrome", "<u4"), ("errors", "<i4"), ("bit", "i1"
 
 class _Config(ctypes.Structure):
     _fields_ = [("format", ctypes.c_int32), ("nfix", ctypes.c_int32), ("threshold", ctypes.c_int32),
-                ("block_samples", ctypes.c_uint32), ("modeac", ctypes.c_int32)]
+                ("block_samples", ctypes.c_uint32), ("modeac", ctypes.c_int32), ("dcfilter", ctypes.c_int32)]
 
 
 class _Result(ctypes.Structure):
@@ -69,12 +69,12 @@ def lib():
 
 
 def run(iq: np.ndarray, fmt: str = "uc8", nfix: int = 1, threshold: int = 58,
-        block_samples: int = BLOCK_SAMPLES, modeac: bool = False) -> DemodResult:
+        block_samples: int = BLOCK_SAMPLES, modeac: bool = False, dcfilter: bool = False) -> DemodResult:
     """Demodulate a whole stream of raw IQ bytes with the CPU restatement."""
     iq = np.ascontiguousarray(iq).view(np.uint8).reshape(-1)
     bps = 2 if fmt == "uc8" else 4
     nsamples = iq.size // bps
-    cfg = _Config(FORMATS[fmt], nfix, threshold, block_samples, 1 if modeac else 0)
+    cfg = _Config(FORMATS[fmt], nfix, threshold, block_samples, 1 if modeac else 0, 1 if dcfilter else 0)
     res = _Result()
     rc = lib().mo_run(ctypes.byref(cfg), iq.ctypes.data, nsamples, ctypes.byref(res))
     if rc != 0:
@@ -110,6 +110,38 @@ def convert(iq: np.ndarray, fmt: str):
     rc = lib().mo_convert(FORMATS[fmt], iq.ctypes.data, n, mag.ctypes.data, ctypes.byref(ml), ctypes.byref(mp))
     assert rc == 0
     return mag, ml.value, mp.value
+
+
+class _DcState(ctypes.Structure):
+    _fields_ = [("dc_a", ctypes.c_float), ("dc_b", ctypes.c_float), ("z1_I", ctypes.c_float), ("z1_Q", ctypes.c_float)]
+
+
+def convert_dc(iq: np.ndarray, fmt: str, calls=None):
+    """--dcfilter converters (convert.c:113-213, 374-423): magnitudes of the whole input, converted in
+    consecutive calls of the given sample counts (the filter state runs on across calls), and the
+    (mean_level, mean_power) of every call."""
+    iq = np.ascontiguousarray(iq).view(np.uint8).reshape(-1)
+    bps = 2 if fmt == "uc8" else 4
+    n = iq.size // bps
+    calls = [n] if calls is None else list(calls)
+    assert sum(calls) == n
+    L = lib()
+    L.mo_dc_init.argtypes = [ctypes.POINTER(_DcState), ctypes.c_double]
+    L.mo_convert_dc.restype = ctypes.c_int
+    L.mo_convert_dc.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(_DcState), ctypes.c_void_p,
+                                ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    st = _DcState()
+    L.mo_dc_init(ctypes.byref(st), 2400000.0)
+    mag = np.empty(n, dtype=np.uint16)
+    means, at = [], 0
+    for c in calls:
+        ml, mp = ctypes.c_double(), ctypes.c_double()
+        rc = L.mo_convert_dc(FORMATS[fmt], iq.ctypes.data + at * bps, c, ctypes.byref(st), mag.ctypes.data + 2 * at,
+                             ctypes.byref(ml), ctypes.byref(mp))
+        assert rc == 0
+        means.append((ml.value, mp.value))
+        at += c
+    return mag, means
 
 
 def checksum(msg: bytes) -> int:

@@ -28,7 +28,8 @@ def available() -> bool:
 
 
 def run_file(path, fmt: str = "uc8", nfix: int = 1, threshold: int = 58, block_samples: int | None = None,
-             max_samples: int | None = None, repeat: int = 1, mag_out=None, modeac: bool = False) -> DemodResult:
+             max_samples: int | None = None, repeat: int = 1, mag_out=None, modeac: bool = False,
+             dcfilter: bool = False) -> DemodResult:
     exe = binary()
     if exe is None:
         raise RuntimeError("oracle/_ref/ref_demod is not built and /root/reference is absent")
@@ -44,6 +45,8 @@ def run_file(path, fmt: str = "uc8", nfix: int = 1, threshold: int = 58, block_s
             cmd += ["--mag-out", str(mag_out)]
         if modeac:
             cmd += ["--modeac"]
+        if dcfilter:
+            cmd += ["--dcfilter"]
         subprocess.run(cmd, check=True, capture_output=True)
         return read_result_file(out)
 
@@ -55,13 +58,13 @@ def run(iq: np.ndarray, fmt: str = "uc8", **kw) -> DemodResult:
         return run_file(path, fmt, **kw)
 
 
-def magnitudes(iq: np.ndarray, fmt: str = "uc8") -> np.ndarray:
+def magnitudes(iq: np.ndarray, fmt: str = "uc8", dcfilter: bool = False) -> np.ndarray:
     """The reference converter's u16 magnitudes for the whole stream."""
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "in.bin")
         mag = os.path.join(td, "mag.bin")
         np.ascontiguousarray(iq).view(np.uint8).tofile(path)
-        run_file(path, fmt, mag_out=mag)
+        run_file(path, fmt, mag_out=mag, dcfilter=dcfilter)
         return np.fromfile(mag, dtype=np.uint16)
 
 

@@ -55,7 +55,7 @@ class _Config(ctypes.Structure):
         ("abi_version", ctypes.c_int32), ("device", ctypes.c_int32), ("input_format", ctypes.c_int32),
         ("nfix_crc", ctypes.c_int32), ("preamble_threshold", ctypes.c_int32), ("block_samples", ctypes.c_uint32),
         ("startup_time_ms", ctypes.c_uint64), ("max_span_samples", ctypes.c_uint64),
-        ("mode_ac", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("mode_ac", ctypes.c_int32), ("filter_dc", ctypes.c_int32),
     ]
 
 
@@ -211,18 +211,18 @@ class Demodulator:
     """One receiver stream: converter + demodulator + CRC tables + ICAO filter state.
 
     Parameters mirror the reference's flags: fmt = --iformat, nfix = --fix/--no-fix/--aggressive,
-    threshold = --preamble-threshold.
+    threshold = --preamble-threshold, modeac = --modeac, dcfilter = --dcfilter.
     """
 
     def __init__(self, fmt: str = "uc8", nfix: int = 1, threshold: int = 58,
                  block_samples: int = DEFAULT_BLOCK_SAMPLES, device: int = 0,
-                 max_span_samples: int = 0, startup_time_ms: int = 0, modeac: bool = False):
+                 max_span_samples: int = 0, startup_time_ms: int = 0, modeac: bool = False, dcfilter: bool = False):
         self._L = load()
         self.fmt = fmt
         self.bytes_per_sample = BYTES_PER_SAMPLE[fmt]
         self.block_samples = block_samples
         cfg = _Config(ABI_VERSION, device, FORMATS[fmt], nfix, threshold, block_samples, startup_time_ms, max_span_samples,
-                      1 if modeac else 0, 0)
+                      1 if modeac else 0, 1 if dcfilter else 0)
         h = ctypes.c_void_p()
         _check(self._L.b200_demod_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h

@@ -10,6 +10,7 @@
 // without a usable sm_100 device every entry point returns B200_ERR_CUDA.
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -167,7 +168,16 @@ struct ChunkSet {
 
 struct b200_demod {
     b200_demod_config cfg;
-    int bytes_per_sample = 2;
+    int bytes_per_sample = 2; // of the caller's IQ
+    // what K1a / K2 / the resolver see: the caller's format, or -- behind the DC-filter front end -- format 3,
+    // a stream of u16 magnitudes
+    uint32_t eff_format = 0;
+    int eff_bps = 2;
+    float dc_a = 0, dc_b = 1;           // init_converter, convert.c:476-488
+    DevBuf<float> d_dc_aI, d_dc_aQ, d_dc_state;
+    DevBuf<uint16_t> d_dc_mag;          // the DC-filtered magnitude stream of the span
+    DevBuf<uint8_t> d_dc_raw;           // host-buffer entry: the caller's IQ on the device
+    bool dc_sums_ready = false;         // d_span_fsums already holds the span's block sums
     int sm_count = 0;
     int scan_grid = 0, slice_grid = 0;
     size_t ac_hit_cap = 0; // grown when a chunk's Mode A/C hits did not fit
@@ -216,6 +226,7 @@ struct b200_demod {
         sets[0].release(); sets[1].release();
         d_span_fsums.release(); d_dbg_masks.release(); d_mag.release(); d_frames.release(); d_syn.release(); d_err.release(); d_bits.release();
         d_csum_u64.release(); d_csum_f64.release();
+        d_dc_aI.release(); d_dc_aQ.release(); d_dc_state.release(); d_dc_mag.release(); d_dc_raw.release();
         for (cudaEvent_t e : ev_chunk_h2d)
             cudaEventDestroy(e);
         if (ev_h2d_begin)
@@ -318,6 +329,16 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     if (d->cfg.max_span_samples == 0)
         d->cfg.max_span_samples = 64ull << 20;
     d->bytes_per_sample = (cfg->input_format == B200_INPUT_UC8) ? 2 : 4;
+    d->eff_format = (uint32_t) cfg->input_format;
+    d->eff_bps = d->bytes_per_sample;
+    if (cfg->filter_dc) {
+        // init DC block @ 1Hz (convert.c:476-480): float fields assigned from double expressions; the
+        // demodulator is the 2.4 MS/s one (Modes.sample_rate, readsb.c:141)
+        d->dc_b = (float) exp(-2.0 * M_PI * 1.0 / 2400000.0);
+        d->dc_a = (float) (1.0 - d->dc_b);
+        d->eff_format = 3;
+        d->eff_bps = 2;
+    }
     d->sm_count = prop.multiProcessorCount;
     memset(&d->timing, 0, sizeof(d->timing));
 
@@ -362,6 +383,8 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     CUDA_TRY(d->d_head.ensure((size_t) kHead * 4));
     CUDA_TRY(d->d_head_tmp.ensure((size_t) kHead * 4));
     CUDA_TRY(cudaMemsetAsync(d->d_head.p, 0, (size_t) kHead * 4, d->stream));
+    CUDA_TRY(d->d_dc_state.ensure(4));
+    CUDA_TRY(cudaMemsetAsync(d->d_dc_state.p, 0, 4 * sizeof(float), d->stream)); // z1_I = z1_Q = 0, convert.c:473-474
     CUDA_TRY(cudaStreamSynchronize(d->stream));
 
     // one persistent CTA per SM (the uc8 table takes most of an SM's shared memory)
@@ -381,6 +404,7 @@ extern "C" int b200_demod_reset(b200_demod *d) {
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     CUDA_TRY(cudaMemsetAsync(d->d_bitmap.p, 0, (1u << 24) / 8, d->stream));
     CUDA_TRY(cudaMemsetAsync(d->d_head.p, 0, (size_t) kHead * 4, d->stream));
+    CUDA_TRY(cudaMemsetAsync(d->d_dc_state.p, 0, 4 * sizeof(float), d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     d->head_valid = 0;
     d->first_sample = 0;
@@ -399,7 +423,7 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     a.iq = d_iq;
     a.head = d_head;
     a.head_valid = head_valid;
-    a.format = (uint32_t) d->cfg.input_format;
+    a.format = d->eff_format;
     a.nsamples = nsamples;
     a.threshold = d->cfg.preamble_threshold;
     a.block_samples = d->cfg.block_samples;
@@ -454,7 +478,7 @@ static int zero_chunk_outputs(b200_demod *, ChunkSet &c, uint64_t, cudaStream_t 
 
 // after a span: head <- last kHead samples of (head ++ span)
 static int carry_head(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, cudaStream_t s) {
-    const size_t bps = (size_t) d->bytes_per_sample;
+    const size_t bps = (size_t) d->eff_bps;
     if (nsamples >= (uint64_t) kHead) {
         CUDA_TRY(cudaMemcpyAsync(d->d_head.p, d_iq + (nsamples - kHead) * bps, kHead * bps, cudaMemcpyDeviceToDevice, s));
         d->head_valid = kHead;
@@ -483,7 +507,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     const size_t nblocks = (size_t) (n / B + (c.final_chunk ? 1 : 0));
 
     ScanArgs sa = make_scan_args(d, c, c.iq, c.head, n, c.head_valid, kCandSlab, kRecSlab, exact ? c.d_tile_off.p : nullptr);
-    const bool float_format = d->cfg.input_format != B200_INPUT_UC8;
+    const bool float_format = d->eff_format != B200_INPUT_UC8;
     if (float_format && n) {
         // mean_level / mean_power of the float converters are sequential float sums (convert.c:228,241-242):
         // K1a leaves them alone, float_block_sums_kernel walks every mag_buf's chain in order.  That kernel
@@ -653,7 +677,7 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     v.first_sample = d->first_sample + c.start;
     v.block_samples = d->cfg.block_samples;
     v.final_span = c.final_chunk;
-    v.format = (uint32_t) d->cfg.input_format;
+    v.format = d->eff_format; // != uc8: the block means are float sums divided in float
     v.ntiles = ntiles;
     v.tiles = c.h_tiles_out.p;
     v.dead = c.h_dead.p;
@@ -699,7 +723,7 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
 static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t flags, cudaStream_t exec, const void *host_src) {
     const bool final_span = (flags & B200_FLAG_FINAL) != 0;
     const uint32_t B = d->cfg.block_samples;
-    const size_t bps = (size_t) d->bytes_per_sample;
+    const size_t bps = (size_t) d->eff_bps;
     const double t_start = now_ms();
 
     // whole mag_bufs, and close to two tiles per resident K1a warp: a chunk is then two full waves
@@ -774,8 +798,8 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
     }
 
     // float formats, device-resident span: every mag_buf's sequential float sums in one launch up front
-    const bool span_sums = !host_src && d->cfg.input_format != B200_INPUT_UC8 && nsamples > 0;
-    if (span_sums) {
+    const bool span_sums = !host_src && d->eff_format != B200_INPUT_UC8 && nsamples > 0;
+    if (span_sums && !d->dc_sums_ready) {
         const uint32_t nb = (uint32_t) ((nsamples + B - 1) / B);
         CUDA_TRY(d->d_span_fsums.ensure(2 * (size_t) nb + 2));
         CUDA_TRY(launch_float_block_sums(d_iq, (uint32_t) d->cfg.input_format, nsamples, B, nb, d->d_span_fsums.p, exec));
@@ -852,12 +876,39 @@ static int check_span(b200_demod *d, const void *iq, uint64_t nsamples, uint32_t
     return B200_OK;
 }
 
+// --dcfilter: the span's IQ (on the device) -> DC-filtered u16 magnitudes + per-mag_buf float sums, then the
+// usual pipeline over the magnitude stream (format 3).  The filter state runs on from span to span.
+static int run_span_dc(b200_demod *d, const uint8_t *d_raw, uint64_t nsamples, uint32_t flags, cudaStream_t exec) {
+    const uint32_t B = d->cfg.block_samples;
+    const size_t padded = (size_t) ((nsamples + 1023) / 1024 * 1024 + 1024);
+    CUDA_TRY(d->d_dc_aI.ensure(padded));
+    CUDA_TRY(d->d_dc_aQ.ensure(padded));
+    CUDA_TRY(d->d_dc_mag.ensure((size_t) nsamples + 128));
+    const uint32_t nb = (uint32_t) ((nsamples + B - 1) / B);
+    CUDA_TRY(d->d_span_fsums.ensure(2 * (size_t) nb + 2));
+    CUDA_TRY(launch_dc_front_end(d_raw, (uint32_t) d->cfg.input_format, nsamples, B, d->dc_a, d->dc_b, d->d_dc_aI.p, d->d_dc_aQ.p,
+                                 d->d_dc_state.p, d->d_dc_mag.p, d->d_span_fsums.p, exec));
+    d->dc_sums_ready = true;
+    const int rc = run_span(d, reinterpret_cast<const uint8_t *>(d->d_dc_mag.p), nsamples, flags, exec, nullptr);
+    d->dc_sums_ready = false;
+    if (rc == B200_OK)
+        d->timing.scan_launches += nsamples ? 3 : 0;
+    return rc;
+}
+
 extern "C" int b200_demod_process(b200_demod *d, const void *iq, uint64_t nsamples, uint32_t flags) {
     int rc = check_span(d, iq, nsamples, flags);
     if (rc != B200_OK)
         return rc;
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     const size_t bytes = (size_t) nsamples * d->bytes_per_sample;
+    if (d->cfg.filter_dc) {
+        // the filter is one sequential chain over the span: nothing to overlap the copy with
+        CUDA_TRY(d->d_dc_raw.ensure(bytes + 256));
+        if (bytes)
+            CUDA_TRY(cudaMemcpyAsync(d->d_dc_raw.p, iq, bytes, cudaMemcpyHostToDevice, d->stream));
+        return run_span_dc(d, d->d_dc_raw.p, nsamples, flags, d->stream);
+    }
     CUDA_TRY(d->d_iq.ensure(bytes + 256));
     return run_span(d, d->d_iq.p, nsamples, flags, d->stream, nsamples ? iq : nullptr);
 }
@@ -870,6 +921,8 @@ extern "C" int b200_demod_process_device(b200_demod *d, const void *d_iq, uint64
         return fail(B200_ERR_ARG, "device span must be 16-byte aligned");
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
+    if (d->cfg.filter_dc)
+        return run_span_dc(d, (const uint8_t *) d_iq, nsamples, flags, s);
     return run_span(d, (const uint8_t *) d_iq, nsamples, flags, s, nullptr);
 }
 
@@ -917,6 +970,8 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
         return fail(B200_ERR_ARG, "device span must be 16-byte aligned");
     if (nsamples > d->cfg.max_span_samples)
         return fail(B200_ERR_CAPACITY, "span exceeds max_span_samples");
+    if (d->cfg.filter_dc)
+        return fail(B200_ERR_ARG, "the bare scan entry reads raw IQ: not available with filter_dc");
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
     ChunkSet &c = d->sets[0];
@@ -959,10 +1014,19 @@ extern "C" int b200_convert(b200_demod *d, const void *iq, uint32_t nsamples, ui
     CUDA_TRY(cudaMemsetAsync(d->d_csum_f64.p, 0, 2 * sizeof(double), s));
     if (bytes)
         CUDA_TRY(cudaMemcpyAsync(d->d_frames.p, iq, bytes, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(launch_convert(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, d->d_lut.p, d->d_mag.p, d->d_csum_u64.p,
-                            d->d_csum_f64.p, s));
-    if (d->cfg.input_format != B200_INPUT_UC8 && nsamples) // the float converters' sums in the reference's order
-        CUDA_TRY(launch_float_block_sums(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, (nsamples + 7u) & ~7u, 1, d->d_csum_f64.p, s));
+    if (d->cfg.filter_dc) {
+        // convert_*_generic (convert.c:113-213, 374-423): one call, the filter state carried to the next one
+        const size_t padded = ((size_t) nsamples + 1023) / 1024 * 1024 + 1024;
+        CUDA_TRY(d->d_dc_aI.ensure(padded));
+        CUDA_TRY(d->d_dc_aQ.ensure(padded));
+        CUDA_TRY(launch_dc_front_end(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, (nsamples + 7u) & ~7u, d->dc_a, d->dc_b,
+                                     d->d_dc_aI.p, d->d_dc_aQ.p, d->d_dc_state.p, d->d_mag.p, d->d_csum_f64.p, s));
+    } else {
+        CUDA_TRY(launch_convert(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, d->d_lut.p, d->d_mag.p, d->d_csum_u64.p,
+                                d->d_csum_f64.p, s));
+        if (d->cfg.input_format != B200_INPUT_UC8 && nsamples) // the float converters' sums in the reference's order
+            CUDA_TRY(launch_float_block_sums(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, (nsamples + 7u) & ~7u, 1, d->d_csum_f64.p, s));
+    }
     unsigned long long su[2] = {0, 0};
     double sf[2] = {0, 0};
     if (nsamples)
@@ -970,7 +1034,7 @@ extern "C" int b200_convert(b200_demod *d, const void *iq, uint32_t nsamples, ui
     CUDA_TRY(cudaMemcpyAsync(su, d->d_csum_u64.p, sizeof(su), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(sf, d->d_csum_f64.p, sizeof(sf), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (d->cfg.input_format == B200_INPUT_UC8) {
+    if (d->cfg.input_format == B200_INPUT_UC8 && !d->cfg.filter_dc) {
         if (mean_level)
             *mean_level = su[0] / 65536.0 / nsamples; // convert.c:105
         if (mean_power)
@@ -999,6 +1063,8 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
         return fail(B200_ERR_ARG, "null argument");
     if (nsamples > d->cfg.max_span_samples)
         return fail(B200_ERR_CAPACITY, "span exceeds max_span_samples");
+    if (d->cfg.filter_dc)
+        return fail(B200_ERR_ARG, "the debug scan reads raw IQ: not available with filter_dc");
     CUDA_TRY(cudaSetDevice(d->cfg.device));
     cudaStream_t s = d->stream;
     ChunkSet &c = d->sets[0];

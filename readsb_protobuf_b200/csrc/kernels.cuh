@@ -13,7 +13,7 @@ struct ScanArgs {
     const uint8_t *iq;    // new samples of the span, 16-byte aligned
     const uint8_t *head;  // kHead samples carried from the previous span, 16-byte aligned
     uint32_t head_valid;  // how many of them are real (0 at stream start: magnitude 0, fifo.c:47)
-    uint32_t format;      // B200_INPUT_*
+    uint32_t format;      // B200_INPUT_*, or 3 = the stream already holds u16 magnitudes (--dcfilter front end)
     uint64_t nsamples;    // new samples == scan positions of the span
     int32_t threshold;    // Modes.preambleThreshold
     uint32_t block_samples;
@@ -112,6 +112,11 @@ cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream);
 // leave them (sums[2k], sums[2k+1]); iq = the span's first new sample
 cudaError_t launch_float_block_sums(const uint8_t *iq, uint32_t format, uint64_t nsamples, uint32_t block_samples, uint32_t nblocks,
                                     double *sums, cudaStream_t stream);
+// --dcfilter front end (convert.c:113-213, 374-423): raw IQ -> DC-filtered u16 magnitudes (the stream K1a then
+// reads as format 3) and the converter's per-mag_buf float sums.  aI / aQ: scratch of nsamples floats rounded
+// up to whole batches of 1024 (+ 1024); state: the two filter states z1_I, z1_Q, carried from call to call
+cudaError_t launch_dc_front_end(const uint8_t *iq, uint32_t format, uint64_t nsamples, uint32_t block_samples, float dc_a, float dc_b,
+                                float *aI, float *aQ, float *state, uint16_t *mag_out, double *sums, cudaStream_t stream);
 // Mode A/C framing-pulse search over K1a's magnitudes (after K1a of the same chunk)
 cudaError_t launch_modeac(const ModeacArgs &a, cudaStream_t stream);
 

@@ -103,10 +103,7 @@ bool ifileOpen(void) {
     cfg.startup_time_ms = Modes.startup_time;
     cfg.max_span_samples = (uint64_t) SPAN_BLOCKS * MODES_MAG_BUF_SAMPLES;
     cfg.mode_ac = Modes.mode_ac ? 1 : 0; /* --modeac: the library also runs demodulate2400AC's search */
-    if (Modes.dc_filter) {
-        fprintf(stderr, "ifile: --dcfilter is not available on the GPU path\n");
-        return false;
-    }
+    cfg.filter_dc = Modes.dc_filter ? 1 : 0; /* --dcfilter: init_converter(..., Modes.dc_filter, ...), sdr_ifile.c:151 */
     if (b200_demod_create(&cfg, &ifile.demod) != B200_OK) {
         /* no CPU fallback: fail loudly, like a converter that cannot be initialised (sdr_ifile.c:155-159) */
         fprintf(stderr, "ifile: can't initialize the GPU demodulator: %s\n", b200_last_error());
@@ -322,15 +319,16 @@ static void convert_via_gpu(void *iq_data, uint16_t *mag_data, unsigned nsamples
 }
 
 iq_convert_fn init_converter(input_format_t format, double sample_rate, int filter_dc, struct converter_state **out_state) {
-    MODES_NOTUSED(sample_rate);
-    if (filter_dc) {
-        fprintf(stderr, "no suitable converter for format=%d dc=%d\n", format, filter_dc); /* convert.c:460-464 */
+    if (filter_dc && sample_rate != 2400000.0) {
+        /* the library's DC block is the 1 Hz one at the demodulator's 2.4 MS/s (convert.c:476-480) */
+        fprintf(stderr, "no suitable converter for format=%d dc=%d at %.0f samples/s\n", format, filter_dc, sample_rate);
         return NULL;
     }
     b200_demod_config cfg;
     memset(&cfg, 0, sizeof (cfg));
     cfg.abi_version = B200_ABI_VERSION;
     cfg.input_format = (int32_t) format;
+    cfg.filter_dc = filter_dc ? 1 : 0; /* convert_*_generic, convert.c:113-213, 374-423 */
     cfg.nfix_crc = 1;
     cfg.preamble_threshold = 58;
     *out_state = malloc(sizeof (struct converter_state));

@@ -42,4 +42,5 @@ def load_golden(name):
     return iq, DemodResult(z["msgs"], z["stats"][0], z["blocks"], iq.size // (2 if meta["fmt"] == "uc8" else 4)), meta
 
 
-GOLDEN_NAMES = ["uc8_fix1", "uc8_fix2_aggressive", "uc8_nofix_thr75", "uc8_whole_blocks", "sc16", "sc16q11", "kat_frame", "uc8_modeac", "uc8_df18", "uc8_all_df", "uc8_all_df_nofix"]
+GOLDEN_NAMES = ["uc8_fix1", "uc8_fix2_aggressive", "uc8_nofix_thr75", "uc8_whole_blocks", "sc16", "sc16q11", "kat_frame", "uc8_modeac", "uc8_df18", "uc8_all_df", "uc8_all_df_nofix",
+                "uc8_dcfilter", "sc16_dcfilter"]

@@ -46,6 +46,23 @@ FIXTURES = {
                 dict(nfix=1, threshold=58, block_samples=131072)),
 }
 
+DC_FIXTURES = {
+    "uc8_dcfilter": (synth.SynthConfig(seed=108, nsamples=120_000, fmt="uc8", frames_per_s=3000, frac_biterror=0.2,
+                                       modeac_per_s=3000), (9, -6)),
+    "sc16_dcfilter": (synth.SynthConfig(seed=109, nsamples=80_000, fmt="sc16", frames_per_s=3000, frac_biterror=0.2,
+                                        modeac_per_s=3000), (1500, -900)),
+}
+
+
+def add_dc_offset(iq: np.ndarray, fmt: str, di: int, dq: int) -> np.ndarray:
+    if fmt == "uc8":
+        v = iq.astype(np.int32).reshape(-1, 2) + [di, dq]
+        return np.clip(v, 0, 255).astype(np.uint8).reshape(-1)
+    full = 32767 if fmt == "sc16" else 2047
+    v = iq.view("<i2").astype(np.int32).reshape(-1, 2) + [di, dq]
+    return np.clip(v, -full - 1, full).astype("<i2").reshape(-1).view(np.uint8)
+
+
 # the one known-answer frame in the reference tree (comment at net_io.c:1645)
 KAT_FRAME_HEX = "8D4B969699155600E87406F5B69F"
 
@@ -183,6 +200,21 @@ def main(only=None):
         res = ref.run(iq, cfg.fmt, **flags)
         meta = dict(fmt=cfg.fmt, flags=flags, generator=cfg.__dict__, sha256=synth.sha256(iq), n_frames=len(frames),
                     source="oracle/_ref/ref_demod (unmodified reference objects)")
+        np.savez_compressed(HERE / f"{name}.npz", iq=iq, msgs=res.msgs, stats=np.array([res.stats]), blocks=res.blocks,
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        print(f"{name}: {len(frames)} frames, {len(res.msgs)} reference messages, {iq.nbytes} IQ bytes")
+
+    # --dcfilter (convert_*_generic, convert.c:113-213, 374-423): the same generator streams seen through a
+    # receiver with a DC offset on both rails, demodulated by the reference with its DC block on
+    for name, (cfg, offs) in DC_FIXTURES.items():
+        if only and name not in only:
+            continue
+        iq, frames = synth.generate(cfg)
+        iq = add_dc_offset(iq, cfg.fmt, *offs)
+        flags = dict(nfix=1, threshold=58, block_samples=32768, dcfilter=True, modeac=True)
+        res = ref.run(iq, cfg.fmt, **flags)
+        meta = dict(fmt=cfg.fmt, flags=flags, generator=cfg.__dict__, dc_offset=offs, sha256=synth.sha256(iq), n_frames=len(frames),
+                    source="oracle/_ref/ref_demod --dcfilter --modeac (unmodified reference objects)")
         np.savez_compressed(HERE / f"{name}.npz", iq=iq, msgs=res.msgs, stats=np.array([res.stats]), blocks=res.blocks,
                             meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
         print(f"{name}: {len(frames)} frames, {len(res.msgs)} reference messages, {iq.nbytes} IQ bytes")

@@ -151,6 +151,84 @@ def test_modeac_off_by_default_and_dense_hits():
     assert_parity(plain, port.run(iq, "uc8"), "uc8")
 
 
+def with_dc_offset(iq, fmt, di, dq):
+    """The same stream seen through a receiver with a DC offset on both rails (what --dcfilter is for)."""
+    if fmt == "uc8":
+        v = iq.astype(np.int32).reshape(-1, 2) + [di, dq]
+        return np.clip(v, 0, 255).astype(np.uint8).reshape(-1)
+    full = 32767 if fmt == "sc16" else 2047
+    v = iq.view("<i2").astype(np.int32).reshape(-1, 2) + [di, dq]
+    return np.clip(v, -full - 1, full).astype("<i2").reshape(-1).view(np.uint8)
+
+
+@pytest.mark.parametrize("fmt,di,dq", [("uc8", 9, -6), ("sc16", 1500, -900), ("sc16q11", -120, 75)])
+def test_dcfilter_matches_oracle(fmt, di, dq):
+    """--dcfilter: convert_*_generic (convert.c:113-213, 374-423).  The DC block is a float
+    recurrence over the whole stream; the library walks the same chain, so magnitudes, block means and the
+    message list are bit-exact, however the stream is cut into spans, with Mode A/C on top."""
+    cfg = synth.SynthConfig(seed=401, nsamples=1_800_000, fmt=fmt, frames_per_s=3000, frac_biterror=0.2, modeac_per_s=1500)
+    iq = with_dc_offset(synth.generate(cfg)[0], fmt, di, dq)
+    want = port.run(iq, fmt, dcfilter=True, modeac=True)
+    assert len(want.msgs) > 500
+    assert results.compare_results(want, port.run(iq, fmt, modeac=True)) != []  # the filter changes the outcome
+    assert_parity(run_gpu(iq, fmt, dcfilter=True, modeac=True), want, fmt)
+    for span in (131072, 131072 * 5):
+        assert_parity(run_gpu(iq, fmt, span_samples=span, dcfilter=True, modeac=True), want, fmt)
+    assert_parity(run_gpu(iq, fmt, dcfilter=True), port.run(iq, fmt, dcfilter=True), fmt)
+
+
+@pytest.mark.parametrize("n,block", [(0, 131072), (1, 131072), (5, 8), (1023, 256), (1024, 1024), (1025, 512), (40_001, 131072),
+                                     (262_144, 131072)])
+def test_dcfilter_ragged_lengths(n, block):
+    cfg = synth.SynthConfig(seed=410 + n % 7, nsamples=max(n, 1), frames_per_s=20000, noise_sigma=0.05)
+    iq = with_dc_offset(synth.generate(cfg)[0][: 2 * n], "uc8", 7, 3)
+    want = port.run(iq, "uc8", dcfilter=True, block_samples=block)
+    assert_parity(run_gpu(iq, "uc8", dcfilter=True, block_samples=block), want, "uc8")
+
+
+@pytest.mark.parametrize("fmt", ["uc8", "sc16", "sc16q11"])
+def test_dcfilter_converter_bit_exact(fmt):
+    """The iq_convert_fn boundary with filter_dc: magnitudes and means of consecutive calls (the filter
+    state runs on from call to call, struct converter_state convert.c:25-30)."""
+    rng = np.random.default_rng(19)
+    calls = [131072, 131072, 50_000, 1, 1030, 7]
+    n = sum(calls)
+    if fmt == "uc8":
+        iq = rng.integers(0, 256, 2 * n, dtype=np.uint8)
+        iq[:512] = np.repeat(np.array([0, 255, 127, 128], dtype=np.uint8), 128)
+    else:
+        full = 32767 if fmt == "sc16" else 2047
+        v = rng.integers(-full - 1, full + 1, 2 * n).astype("<i2")
+        v[:8] = [full, full, -full - 1, -full - 1, 0, 0, full, 0]
+        iq = v.view(np.uint8)
+    want_mag, want_means = port.convert_dc(iq, fmt, calls)
+    bps = 2 if fmt == "uc8" else 4
+    with api.Demodulator(fmt=fmt, dcfilter=True) as d:
+        at = 0
+        for c, (wl, wp) in zip(calls, want_means):
+            mag, ml, mp = d.convert(iq[at * bps: (at + c) * bps])
+            assert np.array_equal(mag, want_mag[at: at + c])
+            assert ml == wl and mp == wp
+            at += c
+        # a reset starts the filter from zero again (init_converter, convert.c:473-474)
+        d.reset()
+        mag, _, _ = d.convert(iq[: 1000 * bps])
+        assert np.array_equal(mag, want_mag[:1000])
+
+
+def test_dcfilter_device_resident_input():
+    import torch
+    cfg = synth.SynthConfig(seed=402, nsamples=1_000_000, fmt="sc16", frames_per_s=4000, frac_biterror=0.2)
+    iq = with_dc_offset(synth.generate(cfg)[0], "sc16", 800, 800)
+    want = port.run(iq, "sc16", dcfilter=True)
+    dev = torch.from_numpy(iq).cuda()
+    with api.Demodulator(fmt="sc16", dcfilter=True) as d:
+        r = d.process_device(dev.data_ptr(), cfg.nsamples, final=True, stream=torch.cuda.current_stream().cuda_stream)
+        st = d.stats().copy()
+    st["convert_cpu_s"] = st["demod_cpu_s"] = 0
+    assert_parity(results.DemodResult(r.msgs, st, r.blocks, cfg.nsamples), want, "sc16")
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_randomized_configurations(seed):
     """Random corners of the parameter space: format, repair depth, threshold, mag_buf size, stream
@@ -170,6 +248,9 @@ def test_randomized_configurations(seed):
     span = None if rng.integers(0, 2) else block * int(rng.integers(1, 6))
     got = run_gpu(iq, fmt, span_samples=span, modeac=modeac, **flags)
     assert_parity(got, want, fmt)
+    if seed % 3 == 0:  # the same corner behind the DC-filter front end
+        want = port.run(iq, fmt, modeac=modeac, dcfilter=True, **flags)
+        assert_parity(run_gpu(iq, fmt, span_samples=span, modeac=modeac, dcfilter=True, **flags), want, fmt)
 
 
 def test_icao_filter_flips_across_minutes():

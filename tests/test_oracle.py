@@ -108,6 +108,25 @@ def test_port_converter_matches_live_reference():
         assert np.array_equal(got, want)
 
 
+@pytest.mark.skipif(not ref.available(), reason="reference binary not built (no /root/reference here)")
+@pytest.mark.parametrize("fmt,seed", [("uc8", 41), ("sc16", 42), ("sc16q11", 43)])
+def test_port_dcfilter_matches_live_reference(fmt, seed):
+    """--dcfilter: the restated convert_*_generic against the reference's own, through
+    the whole path (messages, stats, block means) and magnitude by magnitude."""
+    cfg = synth.SynthConfig(seed=seed, nsamples=600_000, fmt=fmt, frames_per_s=3000, frac_biterror=0.2, modeac_per_s=1500,
+                            amp_max=1.3)
+    iq, _ = synth.generate(cfg)
+    for modeac in (False, True):
+        got = port.run(iq, fmt, dcfilter=True, modeac=modeac)
+        want = ref.run(iq, fmt, dcfilter=True, modeac=modeac)
+        assert len(want.msgs) > 300
+        assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
+    assert results.compare_results(got, port.run(iq, fmt, modeac=True), float_rtol=0.0, signal_atol=0.0) != []
+    calls = [131072] * (cfg.nsamples // 131072) + [cfg.nsamples % 131072]
+    mag, _ = port.convert_dc(iq, fmt, calls)
+    assert np.array_equal(mag, ref.magnitudes(iq, fmt, dcfilter=True))
+
+
 def test_generator_is_deterministic_and_chunk_invariant():
     cfg = synth.SynthConfig(seed=7, nsamples=300_000, frames_per_s=2000)
     frames = synth.plan(cfg)

@@ -1,6 +1,7 @@
 // Development aid: replays dumped resolver inputs (B200_DUMP_SPAN=dir) through the host resolver and
 // times it.  g++ -O2 -Iinclude -Ireadsb_protobuf_b200/csrc tools/resolver_bench.cc
 //     readsb_protobuf_b200/csrc/resolver.cc readsb_protobuf_b200/csrc/host_tables.cc -o /tmp/resolver_bench
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -49,7 +50,9 @@ int main(int argc, char **argv) {
     Resolver res(&crc, 0);
     std::vector<b200_message> msgs;
     std::vector<b200_block_info> blocks;
-    for (int rep = 0; rep < 20; ++rep) {
+    const int reps = getenv("RB_REPS") ? atoi(getenv("RB_REPS")) : 20;
+    std::vector<double> times;
+    for (int rep = 0; rep < reps; ++rep) {
         res.reset();
         msgs.clear();
         blocks.clear();
@@ -72,8 +75,12 @@ int main(int argc, char **argv) {
             res.resolve(v, msgs, blocks);
         }
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        printf("rep %d: %.3f ms, %zu msgs\n", rep, ms, msgs.size());
+        times.push_back(ms);
+        if (reps <= 50 || rep % 100 == 0)
+            printf("rep %d: %.3f ms, %zu msgs\n", rep, ms, msgs.size());
     }
+    std::sort(times.begin(), times.end());
+    printf("min %.3f ms, median %.3f ms over %d reps\n", times.front(), times[times.size() / 2], reps);
     // digest of everything the resolver produced (to compare two builds)
     auto fnv = [](const void *p, size_t n, uint64_t h) {
         const unsigned char *b = (const unsigned char *) p;
