@@ -57,7 +57,7 @@ typedef struct b200_demod_config {
     uint64_t startup_time_ms;    /* Modes.startup_time      (readsb.c:739) */
     uint64_t max_span_samples;   /* largest span one process call may carry; 0 = 64 Mi samples */
     int32_t mode_ac;             /* Modes.mode_ac (--modeac, readsb.c:831-833): also demodulate Mode A/C replies */
-    int32_t filter_dc;           /* Modes.dc_filter (--dcfilter, readsb.c:141,493): the convert_*_generic converters
+    int32_t filter_dc;           /* Modes.dc_filter (--dcfilter, readsb.c:486): the convert_*_generic converters
                                     (convert.c:113-213, 374-423) with their 1 Hz DC block at 2.4 MS/s */
 } b200_demod_config;
 

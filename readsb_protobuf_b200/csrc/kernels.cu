@@ -12,6 +12,9 @@
 //                              exact-slab retry of very dense chunks
 //   modeac_kernel              demodulate2400AC's framing-pulse search (demod_2400.c:522-683), --modeac only
 //   float_block_sums_kernel    sc16 / sc16q11 mean_level / mean_power in the reference's summation order
+//   dc_prepare / dc_chain /    --dcfilter: convert_*_generic (convert.c:113-213, 374-423), the one-pole DC block
+//   dc_magnitude_kernel        walked as the reference's own chain of float operations -> a u16 magnitude stream
+//                              that K1a reads as format 3
 //   convert_kernel             IQ -> u16 magnitudes in global memory (the iq_convert_fn boundary)
 //   crc_batch_kernel           CRC + diagnose for a batch of frames (the crc.h boundary)
 //

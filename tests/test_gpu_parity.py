@@ -452,8 +452,8 @@ def test_crc_batch_and_tables(nfix):
 # drop-in: the reference's own program on top of the shim
 # ------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("modeac", [False, True], ids=["modes", "modeac"])
-def test_reference_program_with_the_shim_prints_the_same_messages(modeac):
+@pytest.mark.parametrize("modeac,dcfilter", [(False, False), (True, False), (True, True)], ids=["modes", "modeac", "modeac-dcfilter"])
+def test_reference_program_with_the_shim_prints_the_same_messages(modeac, dcfilter):
     """oracle/_ref/readsb_b200 = readsb's main(), FIFO, CRC, field decoder and tracker objects linked
     with readsb_protobuf_b200/shim/readsb_b200_shim.c + libreadsb_b200.so instead of convert.o,
     demod_2400.o and sdr_ifile.o.  Its --raw --mlat output must equal the reference path's."""
@@ -468,8 +468,10 @@ def test_reference_program_with_the_shim_prints_the_same_messages(modeac):
     cfg = synth.SynthConfig(seed=91, nsamples=3_000_000, frames_per_s=3000, frac_biterror=0.2,
                             modeac_per_s=3000 if modeac else 0)
     iq, _ = synth.generate(cfg)
-    want = port.run(iq, "uc8", modeac=modeac)
-    extra = ["--modeac"] if modeac else []
+    if dcfilter:
+        iq = with_dc_offset(iq, "uc8", 5, -4)
+    want = port.run(iq, "uc8", modeac=modeac, dcfilter=dcfilter)
+    extra = (["--modeac"] if modeac else []) + (["--dcfilter"] if dcfilter else [])
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "in.bin")
         iq.tofile(path)
