@@ -441,6 +441,54 @@ int mo_convert_dc(int format, const void *iq, uint32_t n, mo_dc_state *st, uint1
     return 0;
 }
 
+void mo_sc16q11_table(int bits, uint16_t *table) {
+    /* init_sc16q11_lookup, convert.c:270-294 (USE_BITS = bits, LOSE_BITS = 11 - bits) */
+    const int lose = 11 - bits;
+    for (int i = 0; i < 2048; i += (1 << lose)) {
+        for (int q = 0; q < 2048; q += (1 << lose)) {
+            float fI = i / 2048.0, fQ = q / 2048.0; /* double division, rounded to float */
+            float magsq = fI * fI + fQ * fQ;
+            if (magsq > 1)
+                magsq = 1;
+            float m = sqrtf(magsq);
+            unsigned index = ((unsigned) (i >> lose) << bits) | (unsigned) (q >> lose);
+            table[index] = (uint16_t) (m * 65535.0f + 0.5f);
+        }
+    }
+}
+
+int mo_convert_sc16q11_table(int bits, const void *iq, uint32_t n, uint16_t *mag, double *mean_level, double *mean_power) {
+    /* convert_sc16q11_table, convert.c:296-328 */
+    if (bits < 1 || bits > 11)
+        return -1;
+    static uint16_t *table;
+    static int table_bits;
+    if (!table || table_bits != bits) {
+        free(table);
+        table = malloc(sizeof (uint16_t) << (2 * bits));
+        mo_sc16q11_table(bits, table);
+        table_bits = bits;
+    }
+    const uint8_t *in = iq;
+    const int lose = 11 - bits;
+    uint64_t sum_level = 0, sum_power = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        int16_t sI = (int16_t) ((uint16_t) in[4 * i] | ((uint16_t) in[4 * i + 1] << 8));
+        int16_t sQ = (int16_t) ((uint16_t) in[4 * i + 2] | ((uint16_t) in[4 * i + 3] << 8));
+        uint16_t I = abs(sI) & 2047; /* abs() of the promoted int: -32768 -> 32768 -> 0 */
+        uint16_t Q = abs(sQ) & 2047;
+        uint16_t m = table[((unsigned) (I >> lose) << bits) | (unsigned) (Q >> lose)];
+        mag[i] = m;
+        sum_level += m;
+        sum_power += (uint32_t) m * (uint32_t) m;
+    }
+    if (mean_level)
+        *mean_level = sum_level / 65536.0 / n;
+    if (mean_power)
+        *mean_power = sum_power / 65535.0 / 65535.0 / n;
+    return 0;
+}
+
 int mo_convert(int format, const void *iq, uint32_t n, uint16_t *mag, double *mean_level, double *mean_power) {
     /* converter choice: convert.c:425-444 with filter_dc == 0 */
     switch (format) {
@@ -953,6 +1001,9 @@ int mo_run(const mo_config *cfg, const void *iq, uint64_t nsamples, mo_result *r
         if (cfg->dcfilter) /* init_converter(..., Modes.dc_filter, ...), sdr_ifile.c:151 */
             mo_convert_dc(cfg->format, (const uint8_t *) iq + sampleCounter * bps, n, &dc, data + MO_OVERLAP,
                           &mean_level, &mean_power);
+        else if (cfg->format == MO_SC16Q11 && cfg->sc16q11_table_bits) /* converters_table order, convert.c:432-437 */
+            mo_convert_sc16q11_table(cfg->sc16q11_table_bits, (const uint8_t *) iq + sampleCounter * bps, n, data + MO_OVERLAP,
+                                     &mean_level, &mean_power);
         else
             mo_convert(cfg->format, (const uint8_t *) iq + sampleCounter * bps, n, data + MO_OVERLAP,
                        &mean_level, &mean_power);

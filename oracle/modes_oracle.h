@@ -94,6 +94,13 @@ void mo_dc_init(mo_dc_state *st, double sample_rate); /* init_converter, convert
 int mo_convert_dc(int format, const void *iq, uint32_t nsamples, mo_dc_state *st, uint16_t *mag,
                   double *mean_level, double *mean_power);
 
+/* convert.c:264-328, only in builds with -DSC16Q11_TABLE_BITS=bits (the armhf package: 8, debian/rules:19):
+ * sc16q11 through a 2^(2*bits)-entry magnitude table indexed by the top `bits` bits of |I| & 2047 and |Q| & 2047;
+ * integer sums like the uc8 converter.  bits in 1..11. */
+void mo_sc16q11_table(int bits, uint16_t *table /* 1 << (2 * bits) entries */);
+int mo_convert_sc16q11_table(int bits, const void *iq, uint32_t nsamples, uint16_t *mag,
+                             double *mean_level, double *mean_power);
+
 /* crc.c:67-82 */
 uint32_t mo_checksum(const uint8_t *msg, int bits);
 /* crc.c:42-65: syndrome of a single flipped bit, indexed from the start of a 112-bit frame */
@@ -120,6 +127,7 @@ typedef struct {
     uint32_t block_samples; /* samples per mag_buf (MO_BLOCK_SAMPLES) */
     int32_t modeac;        /* Modes.mode_ac: also run the Mode A/C demodulator on every block */
     int32_t dcfilter;      /* Modes.dc_filter (--dcfilter): the convert_*_generic converters */
+    int32_t sc16q11_table_bits; /* != 0: a reference built with -DSC16Q11_TABLE_BITS=N (sc16q11 without --dcfilter only) */
 } mo_config;
 
 typedef struct {

@@ -19,7 +19,7 @@ ERRORINFO_DTYPE = np.dtype([("syndrome", "<u4"), ("errors", "<i4"), ("bit", "i1"
 
 class _Config(ctypes.Structure):
     _fields_ = [("format", ctypes.c_int32), ("nfix", ctypes.c_int32), ("threshold", ctypes.c_int32),
-                ("block_samples", ctypes.c_uint32), ("modeac", ctypes.c_int32), ("dcfilter", ctypes.c_int32)]
+                ("block_samples", ctypes.c_uint32), ("modeac", ctypes.c_int32), ("dcfilter", ctypes.c_int32), ("sc16q11_table_bits", ctypes.c_int32)]
 
 
 class _Result(ctypes.Structure):
@@ -69,12 +69,13 @@ def lib():
 
 
 def run(iq: np.ndarray, fmt: str = "uc8", nfix: int = 1, threshold: int = 58,
-        block_samples: int = BLOCK_SAMPLES, modeac: bool = False, dcfilter: bool = False) -> DemodResult:
+        block_samples: int = BLOCK_SAMPLES, modeac: bool = False, dcfilter: bool = False,
+        table_bits: int = 0) -> DemodResult:
     """Demodulate a whole stream of raw IQ bytes with the CPU restatement."""
     iq = np.ascontiguousarray(iq).view(np.uint8).reshape(-1)
     bps = 2 if fmt == "uc8" else 4
     nsamples = iq.size // bps
-    cfg = _Config(FORMATS[fmt], nfix, threshold, block_samples, 1 if modeac else 0, 1 if dcfilter else 0)
+    cfg = _Config(FORMATS[fmt], nfix, threshold, block_samples, 1 if modeac else 0, 1 if dcfilter else 0, table_bits)
     res = _Result()
     rc = lib().mo_run(ctypes.byref(cfg), iq.ctypes.data, nsamples, ctypes.byref(res))
     if rc != 0:
@@ -109,6 +110,28 @@ def convert(iq: np.ndarray, fmt: str):
     ml, mp = ctypes.c_double(), ctypes.c_double()
     rc = lib().mo_convert(FORMATS[fmt], iq.ctypes.data, n, mag.ctypes.data, ctypes.byref(ml), ctypes.byref(mp))
     assert rc == 0
+    return mag, ml.value, mp.value
+
+
+def sc16q11_table(bits: int = 8) -> np.ndarray:
+    """init_sc16q11_lookup (convert.c:270-294) of a reference built with -DSC16Q11_TABLE_BITS=bits."""
+    t = np.empty(1 << (2 * bits), dtype=np.uint16)
+    lib().mo_sc16q11_table.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib().mo_sc16q11_table(bits, t.ctypes.data)
+    return t
+
+
+def convert_sc16q11_table(iq: np.ndarray, bits: int = 8):
+    """convert_sc16q11_table (convert.c:296-328): (mag, mean_level, mean_power) of one converter call."""
+    iq = np.ascontiguousarray(iq).view(np.uint8).reshape(-1)
+    n = iq.size // 4
+    mag = np.empty(n, dtype=np.uint16)
+    ml, mp = ctypes.c_double(), ctypes.c_double()
+    L = lib()
+    L.mo_convert_sc16q11_table.restype = ctypes.c_int
+    L.mo_convert_sc16q11_table.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
+                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    assert L.mo_convert_sc16q11_table(bits, iq.ctypes.data, n, mag.ctypes.data, ctypes.byref(ml), ctypes.byref(mp)) == 0
     return mag, ml.value, mp.value
 
 

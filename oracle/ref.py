@@ -29,10 +29,14 @@ def available() -> bool:
 
 def run_file(path, fmt: str = "uc8", nfix: int = 1, threshold: int = 58, block_samples: int | None = None,
              max_samples: int | None = None, repeat: int = 1, mag_out=None, modeac: bool = False,
-             dcfilter: bool = False) -> DemodResult:
+             dcfilter: bool = False, table_bits: int = 0) -> DemodResult:
     exe = binary()
     if exe is None:
         raise RuntimeError("oracle/_ref/ref_demod is not built and /root/reference is absent")
+    if table_bits:
+        # the reference as its armhf package builds it (-DSC16Q11_TABLE_BITS=8, debian/rules:19)
+        assert table_bits == 8, "oracle/Makefile builds the table variant for 8 bits only"
+        exe = exe.with_name("ref_demod_tb8")
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "ref.res")
         cmd = [str(exe), "--in", str(path), "--out", out, "--format", fmt, "--nfix", str(nfix),
@@ -58,13 +62,13 @@ def run(iq: np.ndarray, fmt: str = "uc8", **kw) -> DemodResult:
         return run_file(path, fmt, **kw)
 
 
-def magnitudes(iq: np.ndarray, fmt: str = "uc8", dcfilter: bool = False) -> np.ndarray:
+def magnitudes(iq: np.ndarray, fmt: str = "uc8", dcfilter: bool = False, table_bits: int = 0) -> np.ndarray:
     """The reference converter's u16 magnitudes for the whole stream."""
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "in.bin")
         mag = os.path.join(td, "mag.bin")
         np.ascontiguousarray(iq).view(np.uint8).tofile(path)
-        run_file(path, fmt, mag_out=mag, dcfilter=dcfilter)
+        run_file(path, fmt, mag_out=mag, dcfilter=dcfilter, table_bits=table_bits)
         return np.fromfile(mag, dtype=np.uint16)
 
 

@@ -47,7 +47,7 @@ class B200Error(RuntimeError):
         self.code = code
 
 
-ABI_VERSION = 2  # B200_ABI_VERSION
+ABI_VERSION = 3  # B200_ABI_VERSION
 
 
 class _Config(ctypes.Structure):
@@ -56,6 +56,7 @@ class _Config(ctypes.Structure):
         ("nfix_crc", ctypes.c_int32), ("preamble_threshold", ctypes.c_int32), ("block_samples", ctypes.c_uint32),
         ("startup_time_ms", ctypes.c_uint64), ("max_span_samples", ctypes.c_uint64),
         ("mode_ac", ctypes.c_int32), ("filter_dc", ctypes.c_int32),
+        ("sc16q11_table_bits", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -211,18 +212,20 @@ class Demodulator:
     """One receiver stream: converter + demodulator + CRC tables + ICAO filter state.
 
     Parameters mirror the reference's flags: fmt = --iformat, nfix = --fix/--no-fix/--aggressive,
-    threshold = --preamble-threshold, modeac = --modeac, dcfilter = --dcfilter.
+    threshold = --preamble-threshold, modeac = --modeac, dcfilter = --dcfilter; table_bits = the
+    SC16Q11_TABLE_BITS a reference build was compiled with (sc16q11 only; 0 = the float converter).
     """
 
     def __init__(self, fmt: str = "uc8", nfix: int = 1, threshold: int = 58,
                  block_samples: int = DEFAULT_BLOCK_SAMPLES, device: int = 0,
-                 max_span_samples: int = 0, startup_time_ms: int = 0, modeac: bool = False, dcfilter: bool = False):
+                 max_span_samples: int = 0, startup_time_ms: int = 0, modeac: bool = False, dcfilter: bool = False,
+                 table_bits: int = 0):
         self._L = load()
         self.fmt = fmt
         self.bytes_per_sample = BYTES_PER_SAMPLE[fmt]
         self.block_samples = block_samples
         cfg = _Config(ABI_VERSION, device, FORMATS[fmt], nfix, threshold, block_samples, startup_time_ms, max_span_samples,
-                      1 if modeac else 0, 1 if dcfilter else 0)
+                      1 if modeac else 0, 1 if dcfilter else 0, table_bits, 0)
         h = ctypes.c_void_p()
         _check(self._L.b200_demod_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h

@@ -191,7 +191,8 @@ struct b200_demod {
     std::vector<cudaEvent_t> ev_chunk_h2d;
 
     // tables
-    DevBuf<uint16_t> d_lut;
+    DevBuf<uint16_t> d_lut;     // uc8 table, plain + bank-swizzled copy
+    DevBuf<uint16_t> d_lut_q11; // format 4: the sc16q11 table (padded to 65536 entries), plain + swizzled
     DevBuf<ErrorInfo> d_tab_short, d_tab_long;
     DevBuf<uint32_t> d_bitmap;
     std::vector<uint16_t> h_lut;
@@ -221,7 +222,7 @@ struct b200_demod {
 
     ~b200_demod() {
         cudaSetDevice(cfg.device);
-        d_lut.release(); d_tab_short.release(); d_tab_long.release(); d_bitmap.release();
+        d_lut.release(); d_lut_q11.release(); d_tab_short.release(); d_tab_long.release(); d_bitmap.release();
         d_head.release(); d_head_tmp.release(); d_iq.release();
         sets[0].release(); sets[1].release();
         d_span_fsums.release(); d_dbg_masks.release(); d_mag.release(); d_frames.release(); d_syn.release(); d_err.release(); d_bits.release();
@@ -303,6 +304,8 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
         return fail(B200_ERR_ARG, "nfix_crc must be 0, 1 or 2");
     if (cfg->preamble_threshold < 1 || cfg->preamble_threshold > 6000)
         return fail(B200_ERR_ARG, "preamble_threshold out of range");
+    if (cfg->sc16q11_table_bits < 0 || cfg->sc16q11_table_bits > 8)
+        return fail(B200_ERR_ARG, "sc16q11_table_bits must be 0 (float path) or 1..8 (the table has to fit shared memory)");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -338,6 +341,8 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
         d->dc_a = (float) (1.0 - d->dc_b);
         d->eff_format = 3;
         d->eff_bps = 2;
+    } else if (cfg->input_format == B200_INPUT_SC16Q11 && cfg->sc16q11_table_bits) {
+        d->eff_format = 4; // converters_table order (convert.c:432-437): the table converter when it is compiled in
     }
     d->sm_count = prop.multiProcessorCount;
     memset(&d->timing, 0, sizeof(d->timing));
@@ -367,6 +372,19 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
         }
         CUDA_TRY(d->d_lut.ensure(2 * 65536));
         CUDA_TRY(cudaMemcpy(d->d_lut.p, both.data(), 2 * 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+
+    if (d->eff_format == 4) {
+        std::vector<uint16_t> table(65536, 0);
+        build_sc16q11_table(cfg->sc16q11_table_bits, table.data());
+        std::vector<uint32_t> both(65536);
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(table.data());
+        for (uint32_t i = 0; i < 32768; ++i) {
+            both[i] = words[i];
+            both[32768 + (i ^ ((i >> 7) & 31u))] = words[i];
+        }
+        CUDA_TRY(d->d_lut_q11.ensure(2 * 65536));
+        CUDA_TRY(cudaMemcpy(d->d_lut_q11.p, both.data(), 2 * 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
 
     const auto &ts = d->crc->short_table();
@@ -428,8 +446,9 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     a.threshold = d->cfg.preamble_threshold;
     a.block_samples = d->cfg.block_samples;
     a.ntiles = tiles_for(nsamples);
-    a.lut = d->d_lut.p;
-    a.lut_swz = d->d_lut.p + 65536;
+    a.lut = (d->eff_format == 4) ? d->d_lut_q11.p : d->d_lut.p;
+    a.lut_swz = a.lut + 65536;
+    a.table_bits = d->cfg.sc16q11_table_bits;
     a.tab_short = d->d_tab_short.p;
     a.tab_long = d->d_tab_long.p;
     a.n_short = (int32_t) d->crc->short_table().size();
@@ -507,7 +526,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     const size_t nblocks = (size_t) (n / B + (c.final_chunk ? 1 : 0));
 
     ScanArgs sa = make_scan_args(d, c, c.iq, c.head, n, c.head_valid, kCandSlab, kRecSlab, exact ? c.d_tile_off.p : nullptr);
-    const bool float_format = d->eff_format != B200_INPUT_UC8;
+    const bool float_format = d->eff_format != B200_INPUT_UC8 && d->eff_format != 4; // the table converters sum integers
     if (float_format && n) {
         // mean_level / mean_power of the float converters are sequential float sums (convert.c:228,241-242):
         // K1a leaves them alone, float_block_sums_kernel walks every mag_buf's chain in order.  That kernel
@@ -538,7 +557,8 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     ca.nsamples = n;
     ca.block_samples = B;
     ca.ntiles = ntiles;
-    ca.lut = d->d_lut.p;
+    ca.lut = sa.lut;
+    ca.table_bits = sa.table_bits;
     ca.tab_short = sa.tab_short;
     ca.tab_long = sa.tab_long;
     ca.n_short = sa.n_short;
@@ -677,7 +697,8 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     v.first_sample = d->first_sample + c.start;
     v.block_samples = d->cfg.block_samples;
     v.final_span = c.final_chunk;
-    v.format = d->eff_format; // != uc8: the block means are float sums divided in float
+    // the resolver only tells integer block sums (the table converters) from float ones
+    v.format = (d->eff_format == 4) ? (uint32_t) B200_INPUT_UC8 : d->eff_format;
     v.ntiles = ntiles;
     v.tiles = c.h_tiles_out.p;
     v.dead = c.h_dead.p;
@@ -798,7 +819,7 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
     }
 
     // float formats, device-resident span: every mag_buf's sequential float sums in one launch up front
-    const bool span_sums = !host_src && d->eff_format != B200_INPUT_UC8 && nsamples > 0;
+    const bool span_sums = !host_src && d->eff_format != B200_INPUT_UC8 && d->eff_format != 4 && nsamples > 0;
     if (span_sums && !d->dc_sums_ready) {
         const uint32_t nb = (uint32_t) ((nsamples + B - 1) / B);
         CUDA_TRY(d->d_span_fsums.ensure(2 * (size_t) nb + 2));
@@ -1022,9 +1043,9 @@ extern "C" int b200_convert(b200_demod *d, const void *iq, uint32_t nsamples, ui
         CUDA_TRY(launch_dc_front_end(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, (nsamples + 7u) & ~7u, d->dc_a, d->dc_b,
                                      d->d_dc_aI.p, d->d_dc_aQ.p, d->d_dc_state.p, d->d_mag.p, d->d_csum_f64.p, s));
     } else {
-        CUDA_TRY(launch_convert(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, d->d_lut.p, d->d_mag.p, d->d_csum_u64.p,
-                                d->d_csum_f64.p, s));
-        if (d->cfg.input_format != B200_INPUT_UC8 && nsamples) // the float converters' sums in the reference's order
+        CUDA_TRY(launch_convert(d->d_frames.p, d->eff_format, nsamples, d->eff_format == 4 ? d->d_lut_q11.p : d->d_lut.p,
+                                d->cfg.sc16q11_table_bits, d->d_mag.p, d->d_csum_u64.p, d->d_csum_f64.p, s));
+        if (d->eff_format != B200_INPUT_UC8 && d->eff_format != 4 && nsamples) // the float converters' sums in the reference's order
             CUDA_TRY(launch_float_block_sums(d->d_frames.p, (uint32_t) d->cfg.input_format, nsamples, (nsamples + 7u) & ~7u, 1, d->d_csum_f64.p, s));
     }
     unsigned long long su[2] = {0, 0};
@@ -1034,7 +1055,7 @@ extern "C" int b200_convert(b200_demod *d, const void *iq, uint32_t nsamples, ui
     CUDA_TRY(cudaMemcpyAsync(su, d->d_csum_u64.p, sizeof(su), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(sf, d->d_csum_f64.p, sizeof(sf), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (d->cfg.input_format == B200_INPUT_UC8 && !d->cfg.filter_dc) {
+    if (d->eff_format == B200_INPUT_UC8 || d->eff_format == 4) { // integer sums: convert.c:104-110, 321-327
         if (mean_level)
             *mean_level = su[0] / 65536.0 / nsamples; // convert.c:105
         if (mean_power)

@@ -181,4 +181,20 @@ void build_uc8_table(uint16_t *table) {
     }
 }
 
+void build_sc16q11_table(int bits, uint16_t *table) {
+    // convert.c:280-291 with USE_BITS = bits, LOSE_BITS = 11 - bits: a double division rounded to float,
+    // then float arithmetic as written there (no FMA contraction in this file)
+    const int lose = 11 - bits;
+    for (int i = 0; i < 2048; i += (1 << lose)) {
+        for (int q = 0; q < 2048; q += (1 << lose)) {
+            float fI = (float) (i / 2048.0), fQ = (float) (q / 2048.0);
+            float magsq = fI * fI + fQ * fQ;
+            if (magsq > 1)
+                magsq = 1;
+            float mag = sqrtf(magsq);
+            table[((unsigned) (i >> lose) << bits) | (unsigned) (q >> lose)] = (uint16_t) (mag * 65535.0f + 0.5f);
+        }
+    }
+}
+
 } // namespace b200

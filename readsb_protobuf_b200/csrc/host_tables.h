@@ -37,5 +37,7 @@ class CrcTables {
 
 // init_uc8_lookup (convert.c:35-61): table[I | Q << 8] for the little-endian u16 a uc8 sample is
 void build_uc8_table(uint16_t *table65536);
+// init_sc16q11_lookup (convert.c:270-294) of a build with -DSC16Q11_TABLE_BITS=bits: 1 << (2 * bits) entries
+void build_sc16q11_table(int bits, uint16_t *table);
 
 } // namespace b200

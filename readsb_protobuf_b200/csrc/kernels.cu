@@ -1,6 +1,7 @@
 // kernels.cu -- sm_100a kernels of the Mode S demodulator.
 //
-//   K1a scan_kernel            IQ -> magnitude -> per-block sums, preamble pre-check + three correlators for
+//   K1a scan_kernel            IQ -> magnitude (uc8 table, sc16 / sc16q11 float path, or format 4: the sc16q11 table
+//                              of a -DSC16Q11_TABLE_BITS build, convert.c:264-328) -> per-block sums, preamble pre-check + three correlators for
 //                              every scan position -> position-ordered candidate list per tile; the u16
 //                              magnitudes go to HBM for K1b / K2 / Mode A/C
 //                              replaces convert.c:63-111/215-253/332-370 and demod_2400.c:257-335
@@ -72,6 +73,13 @@ __device__ __forceinline__ uint32_t mag_sc16_word(uint32_t w, float inv_scale, f
     float fI = __fmul_rn((float) (int16_t) (w & 0xffff), inv_scale); // division by 2^k == exact scaling
     float fQ = __fmul_rn((float) (int16_t) (w >> 16), inv_scale);
     return mag_from_float(fI, fQ, magsq, mag);
+}
+
+// convert_sc16q11_table's table index of one sample (convert.c:312-314): I in the low half of the word
+__device__ __forceinline__ uint32_t sc16q11_table_index(uint32_t w, int bits) {
+    const uint32_t I = (uint32_t) abs((int) (int16_t) (w & 0xffffu)) & 2047u;
+    const uint32_t Q = (uint32_t) abs((int) (int16_t) (w >> 16)) & 2047u;
+    return ((I >> (11 - bits)) << bits) | (Q >> (11 - bits));
 }
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
@@ -295,6 +303,10 @@ struct Fmt<2> { // sc16q11
 };
 
 template <>
+struct Fmt<4> { // sc16q11 through the magnitude table of a -DSC16Q11_TABLE_BITS build (convert.c:264-328)
+    static constexpr int kBytes = 4, kUnitSamples = 4;
+};
+template <>
 struct Fmt<3> { // u16 magnitudes already converted (the --dcfilter front end, dc_* kernels below)
     static constexpr int kBytes = 2, kUnitSamples = 8;
 };
@@ -304,7 +316,7 @@ constexpr size_t kSmemWarp = kWarpBuf * sizeof(uint32_t);
 constexpr size_t kSmemTail = 0;
 
 size_t scan_smem_bytes(uint32_t format) {
-    return (format == 0 ? kSmemLut : 0) + kScanWarps * kSmemWarp + kSmemTail;
+    return ((format == 0 || format == 4) ? kSmemLut : 0) + kScanWarps * kSmemWarp + kSmemTail;
 }
 
 // Load the 16-byte unit holding samples [s, s + kUnitSamples) of the span (s relative to the first
@@ -397,6 +409,7 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
     constexpr int US = Fmt<FORMAT>::kUnitSamples, BPS = Fmt<FORMAT>::kBytes;
     constexpr int UNITS = kLanePos / US; // 16-byte units per lane per step
     const int lane = threadIdx.x & 31;
+    constexpr bool TABLE = (FORMAT == 0 || FORMAT == 4); // table converters: integer block sums (convert.c:104-110, 321-327)
     const float inv_scale = (FORMAT == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f);
     const long long n = (long long) a.nsamples;
     const long long B = (long long) a.block_samples;
@@ -425,7 +438,7 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
     auto flush_sums = [&]() { // rare (once per tile and per mag_buf boundary): kept out of the hot code
         if (FORMAT == 3)
             return;
-        if (FORMAT == 0)
+        if (TABLE)
             flush_sums_u64(a.block_sums_u64 + 2 * blk, sum_level, sum_power);
         else
             flush_sums_f64(a.block_sums_f64 ? a.block_sums_f64 + 2 * blk : nullptr, fsum_level, fsum_power);
@@ -467,6 +480,21 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                 for (int j = 0; j < 4; ++j) {
                     m[u * US + 2 * j] = s_lut[words[j] & 0xffffu];
                     m[u * US + 2 * j + 1] = s_lut[words[j] >> 16];
+                }
+            }
+        } else if (FORMAT == 4) {
+            // convert_sc16q11_table (convert.c:312-316): the top table_bits bits of |I| & 2047 and |Q| & 2047
+            // index the table (staged with the uc8 table's bank swizzle)
+            const int bits = (int) a.table_bits, lose = 11 - bits;
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u) {
+                const uint32_t words[4] = {pre[u].x, pre[u].y, pre[u].z, pre[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t I = (uint32_t) abs((int) (int16_t) (words[j] & 0xffffu)) & 2047u;
+                    const uint32_t Q = (uint32_t) abs((int) (int16_t) (words[j] >> 16)) & 2047u;
+                    const uint32_t idx = ((I >> lose) << bits) | (Q >> lose);
+                    m[(u * US + j) % kLanePos] = s_lut[idx ^ (((idx >> 8) & 31u) << 1)];
                 }
             }
         } else if (FORMAT == 3) {
@@ -534,7 +562,7 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                 if (own_hi <= next_bound) {
                     if (!EDGE || ls >= 0) { // head samples are not this span's (a lane never straddles 0: kHead % 16 == 8 is
                                             // handled below for the one lane that does)
-                        if (FORMAT == 0) {
+                        if (TABLE) {
                             uint32_t s32 = 0;
                             unsigned long long p64 = 0;
 #pragma unroll
@@ -559,7 +587,7 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
 #pragma unroll
                         for (int j = 0; j < kLanePos; ++j)
                             if (ls + j >= 0) {
-                                if (FORMAT == 0) {
+                                if (TABLE) {
                                     sum_level += m[j];
                                     sum_power += (unsigned long long) m[j] * m[j];
                                 } else {
@@ -576,9 +604,10 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                         const long long us = ls + u * US;
                         if (us >= 0 && us < n) {
                             const long long kb = us / B;
-                            if (FORMAT == 0)
+                            if (TABLE)
                                 unit_sums_u64(a.block_sums_u64, kb, make_uint4(m[u * US], m[u * US + 1], m[u * US + 2], m[u * US + 3]),
-                                              make_uint4(m[u * US + 4 % US], m[u * US + 5 % US], m[u * US + 6 % US], m[u * US + 7 % US]));
+                                              US == 8 ? make_uint4(m[u * US + 4 % US], m[u * US + 5 % US], m[u * US + 6 % US], m[u * US + 7 % US])
+                                                      : make_uint4(0, 0, 0, 0)); // a 16-byte unit of format 4 holds four samples
                             else
                                 unit_sums_f64(a.block_sums_f64, kb, make_float4(fmag[u * US], fmag[u * US + 1], fmag[u * US + 2], fmag[u * US + 3]),
                                               make_float4(fmagsq[u * US], fmagsq[u * US + 1], fmagsq[u * US + 2], fmagsq[u * US + 3]));
@@ -744,7 +773,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     // shared memory carve-up
     unsigned char *sp = smem_raw;
     const uint16_t *s_lut = reinterpret_cast<const uint16_t *>(sp);
-    if (FORMAT == 0)
+    if (FORMAT == 0 || FORMAT == 4)
         sp += kSmemLut;
     uint32_t *s_buf = reinterpret_cast<uint32_t *>(sp + (size_t) warp * kWarpBuf * sizeof(uint32_t));
     sp += (size_t) kScanWarps * kWarpBuf * sizeof(uint32_t);
@@ -752,7 +781,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     // one-time staging of the tables (the only block-wide barrier of the kernel).  The magnitude
     // table arrives pre-swizzled (32-bit word j of row Q at word j ^ (Q & 31)): all of a thread's
     // 16-byte loads are in flight at once, one round trip to L2 per CTA.
-    if (FORMAT == 0) {
+    if (FORMAT == 0 || FORMAT == 4) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.lut_swz);
         uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
         constexpr int kUnits = (int) (kSmemLut / 16);                      // 8192 sixteen-byte units
@@ -799,7 +828,7 @@ cudaError_t scan_configure() {
     e = cudaFuncSetAttribute(scan_kernel<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) scan_smem_bytes(F)); \
     if (e != cudaSuccess)                                                                                          \
         return e;
-    CFG(0, true) CFG(0, false) CFG(1, true) CFG(1, false) CFG(2, true) CFG(2, false) CFG(3, true) CFG(3, false)
+    CFG(0, true) CFG(0, false) CFG(1, true) CFG(1, false) CFG(2, true) CFG(2, false) CFG(3, true) CFG(3, false) CFG(4, true) CFG(4, false)
 #undef CFG
     return cudaSuccess;
 }
@@ -821,6 +850,7 @@ cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stre
         case 1: LAUNCH(1) break;
         case 2: LAUNCH(2) break;
         case 3: LAUNCH(3) break;
+        case 4: LAUNCH(4) break;
         default: return cudaErrorInvalidValue;
     }
 #undef LAUNCH
@@ -1209,6 +1239,8 @@ __device__ __forceinline__ uint32_t sample_mag(const ClassifyArgs &a, long long 
         return __ldg(&a.lut[idx]);
     }
     const uint32_t w = *reinterpret_cast<const uint32_t *>(base);
+    if (a.format == 4)
+        return __ldg(&a.lut[sc16q11_table_index(w, (int) a.table_bits)]);
     float magsq, mag;
     return mag_sc16_word(w, (a.format == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f), magsq, mag);
 }
@@ -1829,7 +1861,7 @@ __global__ void __launch_bounds__(64) float_block_sums_kernel(const uint8_t *__r
 
 cudaError_t launch_float_block_sums(const uint8_t *iq, uint32_t format, uint64_t nsamples, uint32_t block_samples, uint32_t nblocks,
                                     double *sums, cudaStream_t stream) {
-    if (nblocks == 0 || format == 0)
+    if (nblocks == 0 || format == 0 || format == 4)
         return cudaSuccess;
     float_block_sums_kernel<<<nblocks, 64, 0, stream>>>(iq, format, nsamples, block_samples, nblocks, sums);
     return cudaGetLastError();
@@ -1854,7 +1886,7 @@ __global__ void modeac_noise_kernel(const ModeacArgs a) {
     const unsigned long long B = a.block_samples, b0 = (unsigned long long) k * B;
     const unsigned nk = (unsigned) (a.nsamples > b0 ? (a.nsamples - b0 < B ? a.nsamples - b0 : B) : 0);
     double mean_level, mean_power;
-    if (a.format == 0) {
+    if (a.format == 0 || a.format == 4) {
         mean_level = __ddiv_rn(__ddiv_rn((double) a.sums_u64[2 * k], 65536.0), (double) nk); // sic: 65536
         mean_power = __ddiv_rn(__ddiv_rn(__ddiv_rn((double) a.sums_u64[2 * k + 1], 65535.0), 65535.0), (double) nk);
     } else {
@@ -2154,7 +2186,7 @@ cudaError_t launch_dc_front_end(const uint8_t *iq, uint32_t format, uint64_t nsa
 // ------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) convert_kernel(const uint8_t *__restrict__ iq, uint32_t format, uint32_t n,
-                                                       const uint16_t *__restrict__ lut, uint16_t *__restrict__ mag,
+                                                       const uint16_t *__restrict__ lut, int table_bits, uint16_t *__restrict__ mag,
                                                        unsigned long long *sums_u64, double *sums_f64) {
     unsigned long long sl = 0, sp = 0;
     double fl = 0, fp = 0;
@@ -2166,6 +2198,10 @@ __global__ void __launch_bounds__(256) convert_kernel(const uint8_t *__restrict_
             m = __ldg(&lut[idx]);
             sl += m;
             sp += (unsigned long long) m * m;
+        } else if (format == 4) {
+            m = __ldg(&lut[sc16q11_table_index(reinterpret_cast<const uint32_t *>(iq)[i], table_bits)]);
+            sl += m;
+            sp += (unsigned long long) m * m;
         } else {
             float magsq, fm;
             m = mag_sc16_word(reinterpret_cast<const uint32_t *>(iq)[i], inv_scale, magsq, fm);
@@ -2174,7 +2210,7 @@ __global__ void __launch_bounds__(256) convert_kernel(const uint8_t *__restrict_
         }
         mag[i] = (uint16_t) m;
     }
-    if (format == 0) {
+    if (format == 0 || format == 4) {
         sl = warp_sum_u64(sl);
         sp = warp_sum_u64(sp);
         if ((threadIdx.x & 31) == 0 && (sl | sp)) {
@@ -2191,14 +2227,14 @@ __global__ void __launch_bounds__(256) convert_kernel(const uint8_t *__restrict_
     }
 }
 
-cudaError_t launch_convert(const uint8_t *iq, uint32_t format, uint32_t nsamples, const uint16_t *lut, uint16_t *mag,
+cudaError_t launch_convert(const uint8_t *iq, uint32_t format, uint32_t nsamples, const uint16_t *lut, int table_bits, uint16_t *mag,
                            unsigned long long *sums_u64, double *sums_f64, cudaStream_t stream) {
     if (nsamples == 0)
         return cudaSuccess;
     int grid = (int) ((nsamples + 255) / 256);
     if (grid > 148 * 8)
         grid = 148 * 8;
-    convert_kernel<<<grid, 256, 0, stream>>>(iq, format, nsamples, lut, mag, sums_u64, sums_f64);
+    convert_kernel<<<grid, 256, 0, stream>>>(iq, format, nsamples, lut, table_bits, mag, sums_u64, sums_f64);
     return cudaGetLastError();
 }
 

@@ -13,14 +13,16 @@ struct ScanArgs {
     const uint8_t *iq;    // new samples of the span, 16-byte aligned
     const uint8_t *head;  // kHead samples carried from the previous span, 16-byte aligned
     uint32_t head_valid;  // how many of them are real (0 at stream start: magnitude 0, fifo.c:47)
-    uint32_t format;      // B200_INPUT_*, or 3 = the stream already holds u16 magnitudes (--dcfilter front end)
+    uint32_t format;      // B200_INPUT_*, 3 = the stream already holds u16 magnitudes (--dcfilter front end),
+                          // 4 = sc16q11 through the magnitude table of a -DSC16Q11_TABLE_BITS build
     uint64_t nsamples;    // new samples == scan positions of the span
     int32_t threshold;    // Modes.preambleThreshold
     uint32_t block_samples;
     uint32_t ntiles;
     // tables
-    const uint16_t *lut;  // uc8 magnitude table (65536 entries)
+    const uint16_t *lut;  // magnitude table of the format (65536 entries): uc8, or format 4's sc16q11 table
     const uint16_t *lut_swz; // the same table in K1's bank-swizzled shared-memory layout
+    int32_t table_bits;   // format 4: SC16Q11_TABLE_BITS (<= 8)
     const ErrorInfo *tab_short;
     const ErrorInfo *tab_long;
     int32_t n_short, n_long;
@@ -67,6 +69,7 @@ struct ClassifyArgs {
     uint32_t block_samples;
     uint32_t ntiles;
     const uint16_t *lut;
+    int32_t table_bits;
     const ErrorInfo *tab_short;
     const ErrorInfo *tab_long;
     int32_t n_short, n_long;
@@ -121,7 +124,7 @@ cudaError_t launch_dc_front_end(const uint8_t *iq, uint32_t format, uint64_t nsa
 cudaError_t launch_modeac(const ModeacArgs &a, cudaStream_t stream);
 
 // IQ -> u16 magnitudes materialised in global memory (+ sums into sums_u64[2] / sums_f64[2])
-cudaError_t launch_convert(const uint8_t *iq, uint32_t format, uint32_t nsamples, const uint16_t *lut,
+cudaError_t launch_convert(const uint8_t *iq, uint32_t format, uint32_t nsamples, const uint16_t *lut, int table_bits,
                            uint16_t *mag, unsigned long long *sums_u64, double *sums_f64, cudaStream_t stream);
 
 // frames14[n][14] -> syndrome, errors (-1 = uncorrectable), bits[n][2]

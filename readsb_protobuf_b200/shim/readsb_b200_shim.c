@@ -104,6 +104,9 @@ bool ifileOpen(void) {
     cfg.max_span_samples = (uint64_t) SPAN_BLOCKS * MODES_MAG_BUF_SAMPLES;
     cfg.mode_ac = Modes.mode_ac ? 1 : 0; /* --modeac: the library also runs demodulate2400AC's search */
     cfg.filter_dc = Modes.dc_filter ? 1 : 0; /* --dcfilter: init_converter(..., Modes.dc_filter, ...), sdr_ifile.c:151 */
+#ifdef SC16Q11_TABLE_BITS
+    cfg.sc16q11_table_bits = SC16Q11_TABLE_BITS; /* a table build (debian/rules:19): convert_sc16q11_table, convert.c:264-328 */
+#endif
     if (b200_demod_create(&cfg, &ifile.demod) != B200_OK) {
         /* no CPU fallback: fail loudly, like a converter that cannot be initialised (sdr_ifile.c:155-159) */
         fprintf(stderr, "ifile: can't initialize the GPU demodulator: %s\n", b200_last_error());
@@ -329,6 +332,9 @@ iq_convert_fn init_converter(input_format_t format, double sample_rate, int filt
     cfg.abi_version = B200_ABI_VERSION;
     cfg.input_format = (int32_t) format;
     cfg.filter_dc = filter_dc ? 1 : 0; /* convert_*_generic, convert.c:113-213, 374-423 */
+#ifdef SC16Q11_TABLE_BITS
+    cfg.sc16q11_table_bits = SC16Q11_TABLE_BITS;
+#endif
     cfg.nfix_crc = 1;
     cfg.preamble_threshold = 58;
     *out_state = malloc(sizeof (struct converter_state));

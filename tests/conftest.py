@@ -43,4 +43,4 @@ def load_golden(name):
 
 
 GOLDEN_NAMES = ["uc8_fix1", "uc8_fix2_aggressive", "uc8_nofix_thr75", "uc8_whole_blocks", "sc16", "sc16q11", "kat_frame", "uc8_modeac", "uc8_df18", "uc8_all_df", "uc8_all_df_nofix",
-                "uc8_dcfilter", "sc16_dcfilter"]
+                "uc8_dcfilter", "sc16_dcfilter", "sc16q11_table8"]

@@ -42,6 +42,10 @@ FIXTURES = {
     "uc8_modeac": (synth.SynthConfig(seed=107, nsamples=300_000, fmt="uc8", frames_per_s=1500, frac_biterror=0.2,
                                      modeac_per_s=4000),
                    dict(nfix=1, threshold=58, block_samples=131072, modeac=True)),
+    # the reference as its armhf package is built (-DSC16Q11_TABLE_BITS=8, debian/rules:19): convert_sc16q11_table
+    "sc16q11_table8": (synth.SynthConfig(seed=110, nsamples=100_000, fmt="sc16q11", frames_per_s=3000, frac_biterror=0.2,
+                                         modeac_per_s=2000, amp_max=1.3),
+                       dict(nfix=1, threshold=58, block_samples=32768, table_bits=8, modeac=True)),
     "sc16q11": (synth.SynthConfig(seed=106, nsamples=120_000, fmt="sc16q11", frames_per_s=3000, frac_biterror=0.2),
                 dict(nfix=1, threshold=58, block_samples=131072)),
 }

@@ -216,6 +216,34 @@ def test_dcfilter_converter_bit_exact(fmt):
         assert np.array_equal(mag, want_mag[:1000])
 
 
+@pytest.mark.parametrize("bits", [8, 7, 4])
+def test_sc16q11_table_converter_matches_oracle(bits):
+    """sc16q11 through the magnitude table of a -DSC16Q11_TABLE_BITS build
+    (convert_sc16q11_table, convert.c:264-328; the armhf package uses 8 bits): integer block sums,
+    table in K1a's shared memory like the uc8 one."""
+    cfg = synth.SynthConfig(seed=420 + bits, nsamples=1_500_000, fmt="sc16q11", frames_per_s=3000, frac_biterror=0.2,
+                            modeac_per_s=1500, amp_max=1.3)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "sc16q11", table_bits=bits, modeac=True)
+    assert len(want.msgs) > (500 if bits >= 7 else 0)
+    assert_parity(run_gpu(iq, "sc16q11", table_bits=bits, modeac=True), want, "sc16q11")
+    assert_parity(run_gpu(iq, "sc16q11", table_bits=bits, modeac=True, span_samples=131072 * 3), want, "sc16q11")
+    # --dcfilter picks the generic float converter in a table build too (converters_table, convert.c:432-437)
+    assert_parity(run_gpu(iq, "sc16q11", table_bits=bits, dcfilter=True), port.run(iq, "sc16q11", table_bits=bits, dcfilter=True),
+                  "sc16q11")
+    # the converter boundary: every table entry, the sign folds, -32768 and the & 2047 wrap
+    v = np.zeros((70_000, 2), dtype="<i2")
+    k = np.arange(65536)
+    v[:65536, 0] = (k >> 8) << 3
+    v[:65536, 1] = (k & 255) << 3
+    v[65536:65540] = [[-32768, 32767], [-2048, 2048], [-1, -2047], [4095, -4096]]
+    v[65540:] = np.random.default_rng(bits).integers(-32768, 32768, (70_000 - 65540, 2))
+    with api.Demodulator(fmt="sc16q11", table_bits=bits) as d:
+        mag, ml, mp = d.convert(v.reshape(-1).view(np.uint8))
+    wmag, wl, wp = port.convert_sc16q11_table(v.reshape(-1).view(np.uint8), bits)
+    assert np.array_equal(mag, wmag) and ml == wl and mp == wp
+
+
 def test_dcfilter_device_resident_input():
     import torch
     cfg = synth.SynthConfig(seed=402, nsamples=1_000_000, fmt="sc16", frames_per_s=4000, frac_biterror=0.2)

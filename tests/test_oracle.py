@@ -127,6 +127,30 @@ def test_port_dcfilter_matches_live_reference(fmt, seed):
     assert np.array_equal(mag, ref.magnitudes(iq, fmt, dcfilter=True))
 
 
+@pytest.mark.skipif(not ref.available(), reason="reference binary not built (no /root/reference here)")
+def test_port_sc16q11_table_matches_live_reference():
+    """convert_sc16q11_table (convert.c:264-328) against the reference built the way its
+    armhf package is (-DSC16Q11_TABLE_BITS=8, oracle/_ref/ref_demod_tb8): whole path and magnitudes."""
+    cfg = synth.SynthConfig(seed=44, nsamples=600_000, fmt="sc16q11", frames_per_s=3000, frac_biterror=0.2, modeac_per_s=1500,
+                            amp_max=1.3)
+    iq, _ = synth.generate(cfg)
+    for kw in (dict(), dict(modeac=True), dict(dcfilter=True)):  # --dcfilter picks the generic converter in that build too
+        got = port.run(iq, "sc16q11", table_bits=8, **kw)
+        want = ref.run(iq, "sc16q11", table_bits=8, **kw)
+        assert len(want.msgs) > 300
+        assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
+    assert results.compare_results(port.run(iq, "sc16q11", table_bits=8), port.run(iq, "sc16q11"), float_rtol=0.0, signal_atol=0.0) != []
+    mag = np.concatenate([port.convert_sc16q11_table(iq[o * 4: (o + 131072) * 4], 8)[0] for o in range(0, cfg.nsamples, 131072)])
+    assert np.array_equal(mag, ref.magnitudes(iq, "sc16q11", table_bits=8))
+    # the table itself: 0 at the origin, clamped to full scale beyond the unit circle, symmetric
+    t = port.sc16q11_table(8).reshape(256, 256)
+    assert t[0, 0] == 0 and t[255, 255] == 65535 and t[181, 181] == 65528 and t[182, 182] == 65535 and np.array_equal(t, t.T)
+    # other formats are untouched by the build flag
+    iq2, _ = synth.generate(synth.SynthConfig(seed=45, nsamples=200_000, fmt="sc16", frames_per_s=3000))
+    assert results.compare_results(port.run(iq2, "sc16", table_bits=8), ref.run(iq2, "sc16", table_bits=8), float_rtol=0.0,
+                                   signal_atol=0.0) == []
+
+
 def test_generator_is_deterministic_and_chunk_invariant():
     cfg = synth.SynthConfig(seed=7, nsamples=300_000, frames_per_s=2000)
     frames = synth.plan(cfg)
