@@ -134,9 +134,13 @@ struct ChunkSet {
     View<double> d_sums_f64, h_sums_f64;
     View<BlockDead> d_block_dead, h_block_dead;
     View<TileOut> d_tiles_out, h_tiles_out;
-    // K2 writes the live positions and records straight into pinned (device-mapped) host memory; the
+    // K2 leaves the live positions and records in device memory, tile by tile in the order its warps reserved
+    // them; order_live packs them into stream order straight into pinned (device-mapped) host memory.  The
     // (much longer) dead list stays in device memory and is downloaded behind the resolver's back
     PinnedBuf<uint32_t> h_dead;
+    DevBuf<LivePos> d_live;
+    DevBuf<LiveRec> d_liverecs;
+    DevBuf<uint2> d_live_base;
     PinnedBuf<LivePos> h_live;
     PinnedBuf<LiveRec> h_liverecs;
     // Mode A/C (only with cfg.mode_ac): per-block noise levels, unordered hit list in pinned host memory
@@ -155,7 +159,7 @@ struct ChunkSet {
     void release() {
         d_cand.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
         d_small.release(); h_small.release(); d_dead.release();
-        h_dead.release(); h_live.release(); h_liverecs.release(); d_ac_noise.release(); h_ac_hits.release();
+        h_dead.release(); h_live.release(); h_liverecs.release(); d_live.release(); d_liverecs.release(); d_live_base.release(); d_ac_noise.release(); h_ac_hits.release();
         for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists})
             if (*e) {
                 cudaEventDestroy(*e);
@@ -254,6 +258,9 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
     CUDA_TRY(c.h_dead.ensure(dead_cap));
     CUDA_TRY(c.h_live.ensure(live_cap));
     CUDA_TRY(c.h_liverecs.ensure(liverec_cap));
+    CUDA_TRY(c.d_live.ensure(c.h_live.cap));
+    CUDA_TRY(c.d_liverecs.ensure(c.h_liverecs.cap));
+    CUDA_TRY(c.d_live_base.ensure(ntiles + 1));
     CUDA_TRY(c.d_tiles.ensure(ntiles + 1));
     CUDA_TRY(c.d_magbuf.ensure(ntiles * (size_t) kTile + kMagSlack));
     CUDA_TRY(c.d_step_off.ensure((ntiles + 1) * (size_t) kScanSteps));
@@ -570,8 +577,8 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     ca.mag = c.d_magbuf.p;
     ca.max_cand_per_tile = exact ? 0xffffffffu : kCandSlab;
     ca.dead = c.d_dead.p;
-    ca.live = c.h_live.p;
-    ca.liverecs = c.h_liverecs.p;
+    ca.live = c.d_live.p;
+    ca.liverecs = c.d_liverecs.p;
     ca.tiles_out = c.d_tiles_out.p;
     ca.dead_cap = (uint32_t) std::min<size_t>(c.d_dead.cap, 0xffffffffu);
     ca.live_cap = (uint32_t) std::min<size_t>(c.h_live.cap, 0xffffffffu);
@@ -580,6 +587,10 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     ca.block_dead = c.d_block_dead.p;
     // K2 looks at K1's overflow flag itself and does nothing when K1 did not fit
     CUDA_TRY(launch_classify(ca, s));
+    // live positions / records in stream order, written into pinned host memory (posted writes over PCIe,
+    // done when the kernel is)
+    CUDA_TRY(launch_order_live(c.d_tiles_out.p, ntiles, c.d_counters.p, c.d_live_base.p, c.d_live.p, c.d_liverecs.p, c.h_live.p,
+                               c.h_liverecs.p, s));
     CUDA_TRY(cudaEventRecord(c.ev_k2, s));
     if (d->cfg.mode_ac && n) {
         // demodulate2400AC (readsb.c:831-833) over the same magnitudes
@@ -601,7 +612,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
             *launches += 2;
     }
     if (launches)
-        *launches += ntiles ? 3 : 0;
+        *launches += ntiles ? 5 : 0;
     CUDA_TRY(cudaMemcpyAsync(c.h_small.p, c.d_small.p, c.small_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(c.ev_small, s));
     c.small_d2h_bytes = sizeof(ScanCounters) + ntiles * sizeof(TileOut) +
@@ -683,8 +694,8 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
         t.classify_ms += ms;
     }
 
-    // K2 wrote the live positions and records straight into pinned host memory (posted writes over
-    // PCIe, done when the kernel is).  The dead list (4 B per noise candidate, only consulted where an
+    // order_live wrote the live positions and records straight into pinned host memory (posted writes
+    // over PCIe, done when the kernel is).  The dead list (4 B per noise candidate, only consulted where an
     // accepted frame skips ahead) is downloaded now, on its own stream, and waited for by the resolver
     // the first time it needs it.
     if (cnt.n_dead)
@@ -703,6 +714,7 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     v.tiles = c.h_tiles_out.p;
     v.dead = c.h_dead.p;
     v.live = c.h_live.p;
+    v.n_live = (uint32_t) cnt.n_live;
     v.liverecs = c.h_liverecs.p;
     v.block_dead = c.h_block_dead.p;
     v.block_sums_u64 = c.h_sums_u64.p;
@@ -718,7 +730,7 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
         cudaEventSynchronize(c.ev_lists);
         if (FILE *f = fopen(path, "wb")) {
             const uint64_t nblocks = n / v.block_samples + 2;
-            uint64_t hdr[12] = {n, v.first_sample, v.block_samples, v.final_span, v.format, v.ntiles, cnt.n_dead, cnt.n_live, cnt.n_liverec, nblocks, 0, 0};
+            uint64_t hdr[12] = {n, v.first_sample, v.block_samples, v.final_span, v.format, v.ntiles, cnt.n_dead, cnt.n_live, cnt.n_liverec, nblocks, 1 /* live lists in stream order */, 0};
             fwrite(hdr, sizeof(hdr), 1, f);
             fwrite(v.tiles, sizeof(TileOut), v.ntiles, f);
             fwrite(v.dead, sizeof(uint32_t), cnt.n_dead, f);

@@ -72,10 +72,10 @@ struct LivePos {
     uint32_t pos;       // scan position within the span
     uint32_t info;      // trymask[4:0] | nrec[10:8] | first live record (relative to the tile's liverec_off) [31:16]
     uint32_t dead_rank; // dead entries of the tile in front of this position (where a skip-ahead starts counting)
-    uint32_t pad;
+    uint32_t pad;       // 0 from K2; in the ordered list the host walks: index of the position's first record
 };
 
-// K2 -> host: a sliced frame of a live position.  48 bytes.
+// K2 -> host: a sliced frame of a live position.  40 bytes.
 struct LiveRec {
     uint32_t pos;
     uint32_t w0;    // as PhaseRec

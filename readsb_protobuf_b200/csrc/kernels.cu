@@ -11,6 +11,7 @@
 //   K2  classify_warp_kernel   address-set test, ordered dead / live lists, re-slice + signal power of the
 //       (classify_kernel)      survivors (demod_2400.c:387-399); the CTA-per-tile variant serves the
 //                              exact-slab retry of very dense chunks
+//   live_offsets / live_gather K2's per-tile live lists packed into stream order, straight into pinned host memory
 //   modeac_kernel              demodulate2400AC's framing-pulse search (demod_2400.c:522-683), --modeac only
 //   float_block_sums_kernel    sc16 / sc16q11 mean_level / mean_power in the reference's summation order
 //   dc_prepare / dc_chain /    --dcfilter: convert_*_generic (convert.c:113-213, 374-423), the one-pole DC block
@@ -1763,6 +1764,114 @@ cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream) {
     } else {
         classify_kernel<<<a.ntiles, kClassifyThreads, 0, stream>>>(a);
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// order_live: K2's per-tile live lists -> two flat arrays in stream order, in pinned host memory
+//
+// K2 reserves a tile's slice of the live-position and live-record lists with atomics, so the slices lie in
+// the order the warps got there.  The host walks the positions in stream order; handing it one
+// position-ordered array (and the records in the same order) turns that walk into two sequential reads:
+// live_offsets_kernel (one CTA) scans the tiles' counts, live_gather_kernel (a warp per tile) copies each
+// tile's slice to its place and rewrites a position's record index from tile-relative to absolute.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(1024) live_offsets_kernel(const TileOut *__restrict__ tiles_out, uint32_t ntiles,
+                                                             const ScanCounters *__restrict__ counters, uint2 *__restrict__ base) {
+    __shared__ uint32_t s_l[32], s_r[32];
+    __shared__ uint32_t s_carry[2];
+    if (counters->overflow) // the host re-runs the chunk with larger buffers
+        return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+        s_carry[0] = s_carry[1] = 0;
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < ntiles; t0 += 1024) {
+        const uint32_t t = t0 + tid;
+        uint32_t l = 0, r = 0;
+        if (t < ntiles) {
+            l = tiles_out[t].nlive;
+            r = tiles_out[t].nliverec;
+        }
+        uint32_t il = l, ir = r; // inclusive warp scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ul = __shfl_up_sync(0xffffffffu, il, o), ur = __shfl_up_sync(0xffffffffu, ir, o);
+            if (lane >= o) {
+                il += ul;
+                ir += ur;
+            }
+        }
+        if (lane == 31) {
+            s_l[warp] = il;
+            s_r[warp] = ir;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t wl = s_l[lane], wr = s_r[lane];
+            uint32_t xl = wl, xr = wr;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t ul = __shfl_up_sync(0xffffffffu, xl, o), ur = __shfl_up_sync(0xffffffffu, xr, o);
+                if (lane >= o) {
+                    xl += ul;
+                    xr += ur;
+                }
+            }
+            s_l[lane] = xl - wl; // exclusive prefix of the warps' totals
+            s_r[lane] = xr - wr;
+        }
+        __syncthreads();
+        const uint32_t cl = s_carry[0], cr = s_carry[1];
+        if (t < ntiles)
+            base[t] = make_uint2(cl + s_l[warp] + il - l, cr + s_r[warp] + ir - r);
+        __syncthreads();
+        if (tid == 1023) {
+            s_carry[0] = cl + s_l[31] + il;
+            s_carry[1] = cr + s_r[31] + ir;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) live_gather_kernel(const TileOut *__restrict__ tiles_out, uint32_t ntiles,
+                                                           const ScanCounters *__restrict__ counters, const uint2 *__restrict__ base,
+                                                           const LivePos *__restrict__ live, const LiveRec *__restrict__ recs,
+                                                           LivePos *__restrict__ live_out, LiveRec *__restrict__ recs_out) {
+    if (counters->overflow)
+        return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ntiles; t += warps) {
+        const TileOut to = tiles_out[t];
+        if (!to.nlive)
+            continue;
+        const uint2 b = base[t];
+        for (uint32_t i = lane; i < to.nlive; i += 32) {
+            LivePos lp = live[to.live_off + i];
+            lp.pad = b.y + (lp.info >> 16); // first record of the position, now an absolute index
+            live_out[b.x + i] = lp;
+        }
+        // records: whole 8-byte units (the struct holds a uint64_t, so every record starts on one)
+        static_assert(sizeof(LiveRec) % 8 == 0 && alignof(LiveRec) == 8, "LiveRec is copied in 8-byte units");
+        constexpr uint32_t kUnits = sizeof(LiveRec) / 8;
+        const uint2 *src = reinterpret_cast<const uint2 *>(recs + to.liverec_off);
+        uint2 *dst = reinterpret_cast<uint2 *>(recs_out + b.y);
+        for (uint32_t i = lane; i < kUnits * to.nliverec; i += 32)
+            dst[i] = src[i];
+    }
+}
+
+cudaError_t launch_order_live(const TileOut *tiles_out, uint32_t ntiles, const ScanCounters *counters, uint2 *base, const LivePos *live,
+                              const LiveRec *recs, LivePos *live_out, LiveRec *recs_out, cudaStream_t stream) {
+    if (ntiles == 0)
+        return cudaSuccess;
+    live_offsets_kernel<<<1, 1024, 0, stream>>>(tiles_out, ntiles, counters, base);
+    int grid = (int) ((ntiles + 7) / 8);
+    if (grid > 148 * 4)
+        grid = 148 * 4;
+    live_gather_kernel<<<grid, 256, 0, stream>>>(tiles_out, ntiles, counters, base, live, recs, live_out, recs_out);
     return cudaGetLastError();
 }
 

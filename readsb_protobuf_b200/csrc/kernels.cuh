@@ -111,6 +111,9 @@ cudaError_t slice_configure();
 cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
 cudaError_t launch_slice(const SliceArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream);
+// K2's per-tile live lists (device memory) -> position-ordered arrays (pinned host memory); base = ntiles scratch
+cudaError_t launch_order_live(const TileOut *tiles_out, uint32_t ntiles, const ScanCounters *counters, uint2 *base, const LivePos *live,
+                              const LiveRec *recs, LivePos *live_out, LiveRec *recs_out, cudaStream_t stream);
 // sc16 / sc16q11: per-mag_buf sum of mag and of magsq as the reference's sequential float accumulators
 // leave them (sums[2k], sums[2k+1]); iq = the span's first new sample
 cudaError_t launch_float_block_sums(const uint8_t *iq, uint32_t format, uint64_t nsamples, uint32_t block_samples, uint32_t nblocks,

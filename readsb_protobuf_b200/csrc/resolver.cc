@@ -352,76 +352,21 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
     const uint64_t nfull = n / B;
     const uint64_t nblocks = nfull + (v.final_span ? 1 : 0);
 
-    {
-        // room for every live position of the span: no reallocation (and no first-touch page faults after the
-        // first span of this size) inside the walk
-        size_t nlive = v.n_ac_hits;
-        for (uint32_t t = 0; t < v.ntiles; ++t)
-            nlive += v.tiles[t].nlive;
-        msgs.reserve(msgs.size() + nlive + 64);
-        skips_.clear();
-        skips_.reserve(nlive + 64);
-    }
+    // room for every live position of the span: no reallocation (and no first-touch page faults after the
+    // first span of this size) inside the walk
+    msgs.reserve(msgs.size() + v.n_live + v.n_ac_hits + 64);
+    skips_.clear();
+    skips_.reserve((size_t) v.n_live + 64);
     // what skip-ahead hides is un-counted after the walk: the dead list it needs may still be arriving
     std::vector<Skip> &skips = skips_;
     // Mode A/C hits in stream order (the kernel appends them as it finds them)
     if (v.n_ac_hits > 1)
         std::sort(v.ac_hits, v.ac_hits + v.n_ac_hits, [](const AcHit &a, const AcHit &b) { return a.q < b.q; });
     uint32_t ac_i = 0;
-    uint32_t tile = 0, live_i = 0; // cursor over live positions
-    // The lists were just written by DMA, so the first touch of a cache line misses the core's caches.
-    // Two cursors run ahead of the walk over the tiles that hold live positions: the far one
-    // prefetches the tile's live-position entries, the near one reads them (by then cached) and
-    // prefetches what the walk will touch: the records and the dead-list line where a skip starts.
-    uint32_t pf_far = 0, pf_near = 0;
-    int far_ahead = 0, near_ahead = 0;
-    auto prefetch_ahead = [&]() {
-        while (far_ahead < 24 && pf_far < v.ntiles) {
-            const TileOut &pt = v.tiles[pf_far++];
-            if (!pt.nlive)
-                continue;
-            ++far_ahead;
-            const char *a = reinterpret_cast<const char *>(v.live + pt.live_off);
-            for (size_t o = 0; o < pt.nlive * sizeof(LivePos); o += 64)
-                __builtin_prefetch(a + o);
-        }
-        while (near_ahead < 8 && pf_near < pf_far) {
-            const TileOut &pt = v.tiles[pf_near++];
-            if (!pt.nlive)
-                continue;
-            ++near_ahead;
-            const char *a = reinterpret_cast<const char *>(v.liverecs + pt.liverec_off);
-            for (size_t o = 0; o < pt.nliverec * sizeof(LiveRec); o += 64)
-                __builtin_prefetch(a + o);
-            const LivePos *lv = v.live + pt.live_off;
-            for (uint32_t i = 0; i < pt.nlive; i += 2)
-                __builtin_prefetch(v.dead + pt.dead_off + lv[i].dead_rank);
-        }
-    };
-    auto next_live = [&](const LivePos *&lp, const TileOut *&to) -> bool {
-        while (tile < v.ntiles) {
-            to = &v.tiles[tile];
-            if (live_i < to->nlive) {
-                lp = &v.live[to->live_off + live_i];
-                return true;
-            }
-            if (to->nlive) {
-                if (far_ahead > 0)
-                    --far_ahead;
-                if (near_ahead > 0)
-                    --near_ahead;
-            }
-            ++tile;
-            live_i = 0;
-            if (pf_near < tile)
-                pf_near = tile;
-            if (pf_far < pf_near)
-                pf_far = pf_near;
-            prefetch_ahead();
-        }
-        return false;
-    };
-    prefetch_ahead();
+    // The live positions and their records are two flat arrays in stream order, just written by the GPU: the
+    // walk is sequential in both, which the hardware prefetcher follows.
+    uint32_t live_i = 0;
+    const uint32_t n_live = v.n_live;
 
     for (uint64_t k = 0; k < nblocks; ++k) {
         const uint64_t b0 = k * B, b1 = std::min(n, b0 + B), nk = b1 - b0;
@@ -447,15 +392,14 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
         bool skipping = false;
         uint64_t skip_until = 0; // positions <= skip_until are skipped while `skipping`
 
-        const LivePos *lp;
-        const TileOut *to;
-        while (next_live(lp, to) && lp->pos < b1) {
+        while (live_i < n_live && v.live[live_i].pos < b1) {
+            const LivePos *lp = &v.live[live_i];
             const uint64_t p = lp->pos;
             ++live_i;
             if (skipping && p <= skip_until)
                 continue;
             const uint32_t trymask = lp->info & 31u, nrec = (lp->info >> 8) & 7u;
-            const LiveRec *recs = v.liverecs + to->liverec_off + (lp->info >> 16);
+            const LiveRec *recs = v.liverecs + lp->pad;
 
             // score_phase for every tried phase, in order (demod_2400.c:183-229, 306-330)
             int bestscore = -42, bestphase = -1;
@@ -580,8 +524,16 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
     if (v.dead_ready)
         v.dead_ready(v.dead_ctx); // also: the caller reuses the buffers once we return
     HiddenTotals hidden;
-    for (const Skip &sk : skips)
-        count_dead(v, sk.lo, sk.hi, sk.rank, hidden);
+    auto dead_line = [&](const Skip &sk) { // where the count of a skip starts reading
+        const uint32_t t = (uint32_t) ((sk.lo + kPosShift) / kTile);
+        return v.dead + v.tiles[t].dead_off + sk.rank;
+    };
+    constexpr size_t kAhead = 8;
+    for (size_t i = 0; i < skips.size(); ++i) {
+        if (i + kAhead < skips.size())
+            __builtin_prefetch(dead_line(skips[i + kAhead]));
+        count_dead(v, skips[i].lo, skips[i].hi, skips[i].rank, hidden);
+    }
     stats_.demod_preambles -= hidden.preambles;
     stats_.demod_rejected_bad -= hidden.bad;
     stats_.demod_rejected_unknown_icao -= hidden.unknown;

@@ -51,9 +51,12 @@ struct SpanView {
     bool final_span;
     uint32_t format;
     uint32_t ntiles;
-    const TileOut *tiles;
+    const TileOut *tiles;     // per tile: where its dead list is (the live_off / liverec_off fields are K2's scratch)
     const uint32_t *dead;
+    // live positions of the span in stream order and their records (order_live_kernel packed K2's per-tile
+    // lists): live[i].pad = index of the position's first record in liverecs
     const LivePos *live;
+    uint32_t n_live;
     const LiveRec *liverecs;
     const BlockDead *block_dead;               // [nblocks]
     const unsigned long long *block_sums_u64;  // [nblocks][2]

@@ -318,7 +318,7 @@ def test_device_resident_input_equals_host_input():
     st["convert_cpu_s"] = st["demod_cpu_s"] = 0
     got = results.DemodResult(r.msgs, st, r.blocks, cfg.nsamples)
     assert_parity(got, want, "uc8")
-    assert t["scan_launches"] == 3 and t["scan_ms"] > 0 and t["n_candidates"] > 0
+    assert t["scan_launches"] == 5 and t["scan_ms"] > 0 and t["n_candidates"] > 0
 
 
 @pytest.mark.skipif(not ref.available(), reason="prebuilt oracle/_ref not present")

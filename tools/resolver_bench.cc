@@ -45,6 +45,22 @@ int main(int argc, char **argv) {
         ok += fread(s.sf.data(), 8, s.sf.size(), f);
         fclose(f);
         (void) ok;
+        if (s.hdr[10] == 0) {
+            // dump of the per-tile layout K2 writes: pack it in tile order, as order_live_kernel does
+            std::vector<LivePos> live;
+            std::vector<LiveRec> recs;
+            for (const TileOut &to : s.tiles) {
+                for (uint32_t i = 0; i < to.nlive; ++i) {
+                    LivePos lp = s.live[to.live_off + i];
+                    lp.pad = (uint32_t) recs.size() + (lp.info >> 16);
+                    live.push_back(lp);
+                }
+                for (uint32_t i = 0; i < to.nliverec; ++i)
+                    recs.push_back(s.recs[to.liverec_off + i]);
+            }
+            s.live.swap(live);
+            s.recs.swap(recs);
+        }
     }
     CrcTables crc(1);
     Resolver res(&crc, 0);
@@ -68,6 +84,7 @@ int main(int argc, char **argv) {
             v.tiles = s.tiles.data();
             v.dead = s.dead.data();
             v.live = s.live.data();
+            v.n_live = (uint32_t) s.live.size();
             v.liverecs = s.recs.data();
             v.block_dead = s.bd.data();
             v.block_sums_u64 = s.su.data();
