@@ -401,24 +401,27 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             const uint32_t trymask = lp->info & 31u, nrec = (lp->info >> 8) & 7u;
             const LiveRec *recs = v.liverecs + lp->pad;
 
-            // score_phase for every tried phase, in order (demod_2400.c:183-229, 306-330)
+            // score_phase for every tried phase, in order (demod_2400.c:183-229, 306-330): every tried phase
+            // counts; one without a record scores -2, which only ever wins as the very first phase tried
+            // (a later phase must score strictly higher, and nothing scores below -2); the records are in
+            // phase order, so walking them alone gives the same pick as walking the five phases
+            for (int q = 0; q < 5; ++q)
+                stats_.demod_preamblePhase[q] += (trymask >> q) & 1u;
             int bestscore = -42, bestphase = -1;
             const LiveRec *best = nullptr;
-            uint32_t ri = 0;
-            for (int ph = 4; ph <= 8; ++ph) {
-                if (!((trymask >> (ph - 4)) & 1u))
-                    continue;
-                stats_.demod_preamblePhase[ph - 4]++;
-                int sc = -2;
-                const LiveRec *rec = nullptr;
-                if (ri < nrec && (int) ((recs[ri].w1 >> 24) & 15u) == ph) {
-                    rec = &recs[ri++];
-                    sc = score(*rec);
+            if (trymask) {
+                const int first = 4 + __builtin_ctz(trymask);
+                if (nrec == 0 || (int) ((recs[0].w1 >> 24) & 15u) != first) {
+                    bestscore = -2;
+                    bestphase = first;
                 }
-                if (sc > bestscore) {
-                    bestscore = sc;
-                    bestphase = ph;
-                    best = rec;
+                for (uint32_t ri = 0; ri < nrec; ++ri) {
+                    const int sc = score(recs[ri]);
+                    if (sc > bestscore) {
+                        bestscore = sc;
+                        bestphase = (int) ((recs[ri].w1 >> 24) & 15u);
+                        best = &recs[ri];
+                    }
                 }
             }
             stats_.demod_preambles++; // demod_2400.c:339
@@ -430,7 +433,8 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                 continue;
             }
 
-            b200_message mm;
+            msgs.emplace_back(); // built in place (room was reserved); taken back if the decoder rejects it
+            b200_message &mm = msgs.back();
             memset(&mm, 0, sizeof(mm));
             const uint64_t j = p - b0;
             mm.timestampMsg = sampleTimestamp + j * 5 + (8 + 56) * 12 + (uint64_t) bestphase; // demod_2400.c:358
@@ -445,6 +449,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                     stats_.demod_rejected_unknown_icao++;
                 else
                     stats_.demod_rejected_bad++;
+                msgs.pop_back();
                 continue;
             }
             stats_.demod_accepted[mm.correctedbits]++;
@@ -472,7 +477,6 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             stats_.messages_total++; // useModesMessage, mode_s.c:2149
             memset(mm.msg + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
             memset(mm.verbatim + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
-            msgs.push_back(mm);
         }
 
         // demodulate2400AC (readsb.c:831-833, demod_2400.c:522-708) runs after demodulate2400 on the same
