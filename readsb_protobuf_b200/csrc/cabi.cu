@@ -2,8 +2,8 @@
 //
 // A process call cuts the span into chunks of whole mag_bufs and runs them as a pipeline:
 //   copy stream : H2D of chunk i+1 ...................... (host-buffer entry only)
-//   exec stream : K1a scan -> K1b slice/CRC -> K2 classify (-> Mode A/C) -> one small download of chunk i+1
-//   list stream : dead list of chunk i D2H (K2 writes live positions / records into pinned host memory)
+//   exec stream : K1a scan -> K1b slice/CRC -> K2 classify -> order_live (-> Mode A/C) -> one small download of chunk i+1
+//   list stream : dead list of chunk i D2H (order_live writes live positions / records into pinned host memory)
 //   host        : order-dependent resolve (resolver.cc) of chunk i
 // Chunks are exact: K2 of chunk i only needs the address set of chunks <= i, which is what the ICAO
 // filter can hold when the host resolves chunk i.  There is no CPU implementation of the kernels;
