@@ -244,6 +244,13 @@ void b200_host_uc8_table(uint16_t *table65536);
 /* icao_filter.c:73-164 driven step by step: ops[i] = 0 add, 1 test, 2 expire(arg = now ms);
  * results[i] = test outcome (0/1), else 0 */
 int b200_host_filter_script(const uint8_t *ops, const uint64_t *args, uint32_t n, uint8_t *results);
+/* The order-dependent tail of demodulate2400 (demod_2400.c:236-428: best-phase pick, decode-time rejects, ICAO
+ * filter, skip-ahead, statistics) run on the host alone over recorded kernel outputs: `paths` = the files a
+ * process call wrote with B200_DUMP_SPAN=<dir> set (one per pipeline chunk), in stream order.  Lets the host
+ * logic be tested against the oracle without a GPU.  Returns B200_OK, or B200_ERR_ARG / B200_ERR_CAPACITY. */
+int b200_host_resolve_dumps(const char *const *paths, uint32_t npaths, int nfix_crc, b200_message *msgs, uint64_t msg_cap,
+                            uint64_t *n_msgs, b200_block_info *blocks, uint64_t block_cap, uint64_t *n_blocks,
+                            b200_demod_stats *stats);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "b200_demod_block_count", "b200_demod_blocks", "b200_demod_get_stats", "b200_demod_get_timing",
     "b200_scan_device", "b200_convert", "b200_uc8_table", "b200_debug_scan", "b200_crc_batch",
     "b200_error_table", "b200_abi_sizeof", "b200_host_checksum", "b200_host_error_table", "b200_host_uc8_table",
-    "b200_host_filter_script", "b200_demod_modeac_count", "b200_format_beast", "b200_format_raw",
+    "b200_host_filter_script", "b200_host_resolve_dumps", "b200_demod_modeac_count", "b200_format_beast", "b200_format_raw",
 )
 
 
@@ -138,6 +138,8 @@ def load():
     L.b200_host_uc8_table.argtypes = [vp]
     L.b200_host_filter_script.restype = i32
     L.b200_host_filter_script.argtypes = [vp, vp, u32, vp]
+    L.b200_host_resolve_dumps.restype = i32
+    L.b200_host_resolve_dumps.argtypes = [vp, u32, i32, vp, u64, vp, vp, u64, vp, vp]
     _lib = L
     return L
 
@@ -167,6 +169,28 @@ def host_filter_script(ops, args) -> np.ndarray:
     res = np.zeros(len(ops), dtype=np.uint8)
     _check(load().b200_host_filter_script(ops.ctypes.data, args.ctypes.data, len(ops), res.ctypes.data))
     return res
+
+
+def host_resolve_dumps(paths, nfix: int = 1) -> DemodResult:
+    """The host resolver alone over recorded kernel outputs (files written with B200_DUMP_SPAN set, one per
+    pipeline chunk, in stream order).  No GPU involved: this is how the CPU suite tests the host logic."""
+    L = load()
+    arr = (ctypes.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+    nm, nb = ctypes.c_uint64(), ctypes.c_uint64()
+    cap = 1 << 16
+    while True:
+        msgs = np.empty(cap, dtype=MSG_DTYPE)
+        blocks = np.empty(cap, dtype=BLOCK_DTYPE)
+        st = np.zeros(1, dtype=STATS_DTYPE)
+        rc = L.b200_host_resolve_dumps(arr, len(paths), nfix, msgs.ctypes.data, cap, ctypes.byref(nm), blocks.ctypes.data, cap,
+                                       ctypes.byref(nb), st.ctypes.data)
+        if rc == -4 and cap < (1 << 26):  # B200_ERR_CAPACITY
+            cap = max(int(nm.value), int(nb.value)) + 16
+            continue
+        _check(rc)
+        break
+    n = sum(int(np.fromfile(p, dtype=np.uint64, count=1)[0]) for p in paths)
+    return DemodResult(msgs[: int(nm.value)].copy(), st[0], blocks[: int(nb.value)].copy(), n)
 
 
 def _check(rc: int):

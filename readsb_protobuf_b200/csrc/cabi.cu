@@ -726,11 +726,11 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     if (const char *dump = getenv("B200_DUMP_SPAN")) {
         // development aid: write the resolver's inputs of this chunk to a file (tools/resolver_bench.cc)
         char path[512];
-        snprintf(path, sizeof(path), "%s/span_%llu.bin", dump, (unsigned long long) c.start);
+        snprintf(path, sizeof(path), "%s/span_%llu.bin", dump, (unsigned long long) v.first_sample); // stream position of the chunk
         cudaEventSynchronize(c.ev_lists);
         if (FILE *f = fopen(path, "wb")) {
             const uint64_t nblocks = n / v.block_samples + 2;
-            uint64_t hdr[12] = {n, v.first_sample, v.block_samples, v.final_span, v.format, v.ntiles, cnt.n_dead, cnt.n_live, cnt.n_liverec, nblocks, 1 /* live lists in stream order */, 0};
+            uint64_t hdr[12] = {n, v.first_sample, v.block_samples, v.final_span, v.format /* as the resolver sees it */, v.ntiles, cnt.n_dead, cnt.n_live, cnt.n_liverec, nblocks, 1 /* live lists in stream order */, 0};
             fwrite(hdr, sizeof(hdr), 1, f);
             fwrite(v.tiles, sizeof(TileOut), v.ntiles, f);
             fwrite(v.dead, sizeof(uint32_t), cnt.n_dead, f);
@@ -1229,6 +1229,76 @@ extern "C" int b200_host_error_table(int nfix, int bits, b200_errorinfo *out, in
 
 extern "C" void b200_host_uc8_table(uint16_t *table65536) {
     build_uc8_table(table65536);
+}
+
+extern "C" int b200_host_resolve_dumps(const char *const *paths, uint32_t npaths, int nfix_crc, b200_message *msgs, uint64_t msg_cap,
+                                       uint64_t *n_msgs, b200_block_info *blocks, uint64_t block_cap, uint64_t *n_blocks,
+                                       b200_demod_stats *stats) {
+    if (!paths || !n_msgs || !n_blocks || !stats || nfix_crc < 0 || nfix_crc > 2)
+        return fail(B200_ERR_ARG, "bad argument");
+    CrcTables crc(nfix_crc);
+    Resolver res(&crc, 0);
+    std::vector<b200_message> out_msgs;
+    std::vector<b200_block_info> out_blocks;
+    for (uint32_t i = 0; i < npaths; ++i) {
+        // the layout finish_chunk writes: 12-word header, tile outputs, dead list, live positions, live records,
+        // block dead counters, block sums (u64 and f64)
+        FILE *f = fopen(paths[i], "rb");
+        uint64_t hdr[12];
+        if (!f || fread(hdr, sizeof(hdr), 1, f) != 1) {
+            if (f)
+                fclose(f);
+            return fail(B200_ERR_ARG, "cannot read %s", paths[i]);
+        }
+        if (hdr[10] != 1) {
+            fclose(f);
+            return fail(B200_ERR_ARG, "%s holds per-tile live lists (a dump from before the ordered layout)", paths[i]);
+        }
+        std::vector<TileOut> tiles(hdr[5]);
+        std::vector<uint32_t> dead(hdr[6]);
+        std::vector<LivePos> live(hdr[7]);
+        std::vector<LiveRec> recs(hdr[8]);
+        std::vector<BlockDead> bd(hdr[9]);
+        std::vector<unsigned long long> su(2 * hdr[9]);
+        std::vector<double> sf(2 * hdr[9]);
+        size_t got = fread(tiles.data(), sizeof(TileOut), tiles.size(), f);
+        got += fread(dead.data(), sizeof(uint32_t), dead.size(), f);
+        got += fread(live.data(), sizeof(LivePos), live.size(), f);
+        got += fread(recs.data(), sizeof(LiveRec), recs.size(), f);
+        got += fread(bd.data(), sizeof(BlockDead), bd.size(), f);
+        got += fread(su.data(), sizeof(unsigned long long), su.size(), f);
+        got += fread(sf.data(), sizeof(double), sf.size(), f);
+        fclose(f);
+        if (got != tiles.size() + dead.size() + live.size() + recs.size() + bd.size() + su.size() + sf.size())
+            return fail(B200_ERR_ARG, "%s is truncated", paths[i]);
+        SpanView v;
+        v.nsamples = hdr[0];
+        v.first_sample = hdr[1];
+        v.block_samples = (uint32_t) hdr[2];
+        v.final_span = hdr[3] != 0;
+        v.format = (uint32_t) hdr[4];
+        v.ntiles = (uint32_t) hdr[5];
+        v.tiles = tiles.data();
+        v.dead = dead.data();
+        v.live = live.data();
+        v.n_live = (uint32_t) live.size();
+        v.liverecs = recs.data();
+        v.block_dead = bd.data();
+        v.block_sums_u64 = su.data();
+        v.block_sums_f64 = sf.data();
+        res.resolve(v, out_msgs, out_blocks);
+    }
+    *n_msgs = out_msgs.size();
+    *n_blocks = out_blocks.size();
+    *stats = res.stats();
+    stats->reserved[0] = (double) res.gpu_host_mismatches();
+    if (out_msgs.size() > msg_cap || out_blocks.size() > block_cap)
+        return fail(B200_ERR_CAPACITY, "%zu messages / %zu blocks do not fit the caller's arrays", out_msgs.size(), out_blocks.size());
+    if (msgs && !out_msgs.empty())
+        memcpy(msgs, out_msgs.data(), out_msgs.size() * sizeof(b200_message));
+    if (blocks && !out_blocks.empty())
+        memcpy(blocks, out_blocks.data(), out_blocks.size() * sizeof(b200_block_info));
+    return B200_OK;
 }
 
 extern "C" int b200_host_filter_script(const uint8_t *ops, const uint64_t *args, uint32_t n, uint8_t *results) {

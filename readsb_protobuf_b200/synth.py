@@ -133,6 +133,12 @@ def sha256(iq: np.ndarray) -> str:
     return hashlib.sha256(memoryview(np.ascontiguousarray(iq))).hexdigest()
 
 
+def resolver_fixture_config() -> SynthConfig:
+    """The small dense stream whose recorded kernel outputs (tests/golden/resolver_span_*.bin, written by
+    scripts/dump_spans.py fixture on a B200) let the CPU suite run the host resolver against the oracle."""
+    return SynthConfig(seed=77, nsamples=1_000_000, fmt="uc8", frames_per_s=3000.0, frac_biterror=0.3, n_icao=40)
+
+
 # BASELINE.json `configs`, by index (SURVEY.md section 8d table)
 def baseline_config(index: int, seed: int | None = None, seconds: float | None = None) -> SynthConfig:
     if index == 0:  # configs[0]: 1 s uc8 plumbing case

@@ -109,3 +109,26 @@ def test_output_writers_match_the_reference(verbatim):
     buf = np.full(101, 0xEE, dtype=np.uint8)
     assert L.b200_format_beast(m.ctypes.data, len(m), v, buf.ctypes.data, 100) == need
     assert buf[100] == 0xEE and bytes(buf[:100]) == z[f"beast_v{v}"].tobytes()[:100]
+
+
+def test_host_resolver_over_recorded_kernel_outputs():
+    """The order-dependent tail of demodulate2400 (best-phase pick, decode-time rejects, ICAO filter,
+    skip-ahead, statistics: resolver.cc) run on the CPU over what the kernels produced on a B200 for a small
+    seeded stream (tests/golden/resolver_span_*.bin, recorded by scripts/dump_spans.py fixture in two process
+    calls), against the oracle on the regenerated stream: messages, block means and every counter."""
+    from readsb_protobuf_b200 import synth
+    paths = sorted((ROOT / "tests" / "golden").glob("resolver_span_*.bin"), key=lambda p: int(p.stem.split("_")[-1]))
+    if not paths:
+        pytest.skip("no recorded kernel outputs (tests/golden/resolver_span_*.bin)")
+    cfg = synth.resolver_fixture_config()
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "uc8")
+    got = api.host_resolve_dumps(paths, nfix=1)
+    assert got.n_samples == cfg.nsamples and len(paths) == 2
+    assert int(got.stats["convert_cpu_s"]) == 0  # kernel-vs-host CRC disagreements
+    got.stats["convert_cpu_s"] = got.stats["demod_cpu_s"] = 0
+    assert len(want.msgs) > 500
+    assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
+    # cut differently, the files no longer describe the stream: the resolver must not silently agree
+    with pytest.raises(api.B200Error):
+        api.host_resolve_dumps([ROOT / "tests" / "golden" / "kat_frame.npz"])
