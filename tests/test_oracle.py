@@ -240,3 +240,33 @@ def test_port_writers_match_live_reference():
             wb, wr = ref.format_outputs(res, net_verbatim=verbatim, mlat=mlat)
             assert port.format_beast(res.msgs, verbatim) == wb
             assert port.format_raw(res.msgs, verbatim, mlat) == wr
+
+
+def test_dcfilter_and_table_converter_properties():
+    """Size-independent properties of the two converters added for SURVEY 8f rows 3 and 4 (oracle side; the
+    GPU tests require the library to reproduce the oracle bit for bit)."""
+    rng = np.random.default_rng(5)
+    # DC block: a constant input leaves a magnitude that decays monotonically (z creeps towards the input at
+    # 1 - exp(-2 pi / 2.4e6) per sample) and the state really is carried from call to call
+    n = 400_000
+    iq = np.tile(np.array([200, 90], dtype=np.uint8), n)
+    mag, means = port.convert_dc(iq, "uc8", calls=[n // 2, n // 2])
+    assert mag[0] > mag[n // 2] > mag[-1] > 0 and np.all(np.diff(mag.astype(np.int64)) <= 0)
+    assert means[0][0] > means[1][0] > 0
+    one_call, _ = port.convert_dc(iq, "uc8")
+    assert np.array_equal(mag, one_call)
+    # with the DC block off the same converter equals the plain float path for sc16 (dc_a = 0, dc_b = 1 there)
+    v = rng.integers(-32768, 32768, 2 * 5000).astype("<i2").view(np.uint8)
+    plain, _, _ = port.convert(v, "sc16")
+    filtered, _ = port.convert_dc(v, "sc16")
+    assert np.mean(plain != filtered) > 0.01  # the filter is on: it does change magnitudes ...
+    assert np.max(np.abs(plain.astype(np.int64) - filtered.astype(np.int64))) < 2000  # ... by the small DC estimate only
+    # table converter: depends on |I|, |Q| only, through their top bits; symmetric in I and Q
+    for bits in (8, 5):
+        k = 11 - bits
+        base = rng.integers(0, 2048, (3000, 2))
+        def mags(a):
+            return port.convert_sc16q11_table(a.astype("<i2").reshape(-1).view(np.uint8), bits)[0]
+        m0 = mags(base)
+        assert np.array_equal(m0, mags(-base)) and np.array_equal(m0, mags(base[:, ::-1]))
+        assert np.array_equal(m0, mags((base >> k) << k)) and np.array_equal(m0, mags(base + 2048 * 3))
