@@ -1254,6 +1254,22 @@ extern "C" int b200_host_resolve_dumps(const char *const *paths, uint32_t npaths
             fclose(f);
             return fail(B200_ERR_ARG, "%s holds per-tile live lists (a dump from before the ordered layout)", paths[i]);
         }
+        {
+            // the counts must describe this file, byte for byte, before anything is sized from them
+            fseek(f, 0, SEEK_END);
+            const unsigned long long fsize = (unsigned long long) ftell(f);
+            fseek(f, (long) sizeof(hdr), SEEK_SET);
+            const unsigned long long limit = fsize / 4 + 1; // no record is smaller than 4 bytes
+            bool sane = hdr[2] > 0 && hdr[4] <= 4;
+            for (int k = 5; k <= 9; ++k)
+                sane = sane && hdr[k] <= limit;
+            const unsigned long long want = sizeof(hdr) + hdr[5] * sizeof(TileOut) + hdr[6] * sizeof(uint32_t) + hdr[7] * sizeof(LivePos) +
+                                            hdr[8] * sizeof(LiveRec) + hdr[9] * (sizeof(BlockDead) + 2 * sizeof(unsigned long long) + 2 * sizeof(double));
+            if (!sane || want != fsize || hdr[5] != tiles_for(hdr[0])) {
+                fclose(f);
+                return fail(B200_ERR_ARG, "%s is not a span dump of this library version", paths[i]);
+            }
+        }
         std::vector<TileOut> tiles(hdr[5]);
         std::vector<uint32_t> dead(hdr[6]);
         std::vector<LivePos> live(hdr[7]);
@@ -1271,6 +1287,19 @@ extern "C" int b200_host_resolve_dumps(const char *const *paths, uint32_t npaths
         fclose(f);
         if (got != tiles.size() + dead.size() + live.size() + recs.size() + bd.size() + su.size() + sf.size())
             return fail(B200_ERR_ARG, "%s is truncated", paths[i]);
+        // every index the resolver follows must stay inside the arrays just read
+        bool ok = hdr[9] >= hdr[0] / hdr[2] + 1;
+        for (const TileOut &to : tiles)
+            ok = ok && (uint64_t) to.dead_off + to.ndead <= dead.size();
+        uint32_t prev_pos = 0;
+        for (const LivePos &lp : live) {
+            const uint64_t t = ((uint64_t) lp.pos + kPosShift) / kTile;
+            ok = ok && lp.pos < hdr[0] && lp.pos >= prev_pos && t < tiles.size() && (uint64_t) lp.pad + ((lp.info >> 8) & 7u) <= recs.size();
+            ok = ok && (t >= tiles.size() || lp.dead_rank <= tiles[t].ndead);
+            prev_pos = lp.pos;
+        }
+        if (!ok)
+            return fail(B200_ERR_ARG, "%s is inconsistent", paths[i]);
         SpanView v;
         v.nsamples = hdr[0];
         v.first_sample = hdr[1];
