@@ -146,6 +146,13 @@ const char *b200_last_error(void);
  * context until the next process call. */
 int b200_demod_process(b200_demod *d, const void *iq, uint64_t nsamples, uint32_t flags);
 
+/* Page-locked host memory for the sample buffers handed to b200_demod_process (replaces the malloc of ifileOpen's
+ * read buffer, sdr_ifile.c:142-146): the H2D copy of a pinned buffer runs at PCIe speed and overlaps the kernels,
+ * a pageable one is staged through the driver at a fraction of that.  NULL when no device is usable or the
+ * allocation fails (the caller may then fall back to malloc: any host pointer is accepted by process). */
+void *b200_host_alloc(size_t bytes);
+void b200_host_free(void *p);
+
 /* Same, with the span already resident in device memory (16-byte aligned), launched on
  * `cuda_stream` (a cudaStream_t passed as void*, NULL = the library's own stream). */
 int b200_demod_process_device(b200_demod *d, const void *d_iq, uint64_t nsamples, uint32_t flags,

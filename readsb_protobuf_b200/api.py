@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "b200_demod_block_count", "b200_demod_blocks", "b200_demod_get_stats", "b200_demod_get_timing",
     "b200_scan_device", "b200_convert", "b200_uc8_table", "b200_debug_scan", "b200_crc_batch",
     "b200_error_table", "b200_abi_sizeof", "b200_host_checksum", "b200_host_error_table", "b200_host_uc8_table",
-    "b200_host_filter_script", "b200_host_resolve_dumps", "b200_demod_modeac_count", "b200_format_beast", "b200_format_raw",
+    "b200_host_filter_script", "b200_host_resolve_dumps", "b200_host_alloc", "b200_host_free", "b200_demod_modeac_count", "b200_format_beast", "b200_format_raw",
 )
 
 

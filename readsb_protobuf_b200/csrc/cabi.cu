@@ -946,6 +946,20 @@ extern "C" int b200_demod_process(b200_demod *d, const void *iq, uint64_t nsampl
     return run_span(d, d->d_iq.p, nsamples, flags, d->stream, nsamples ? iq : nullptr);
 }
 
+extern "C" void *b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError(); // not sticky: the caller falls back to pageable memory
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void b200_host_free(void *p) {
+    if (p)
+        cudaFreeHost(p);
+}
+
 extern "C" int b200_demod_process_device(b200_demod *d, const void *d_iq, uint64_t nsamples, uint32_t flags, void *cuda_stream) {
     int rc = check_span(d, d_iq, nsamples, flags);
     if (rc != B200_OK)

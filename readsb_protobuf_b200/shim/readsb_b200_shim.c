@@ -37,6 +37,7 @@ static struct {
     unsigned bytes_per_sample;
     b200_demod *demod;
     char *span;
+    bool span_pinned; /* span came from b200_host_alloc */
 } ifile;
 
 /* one mag_buf's share of a resolved span, queued from the reader to the demodulator thread */
@@ -112,7 +113,12 @@ bool ifileOpen(void) {
         fprintf(stderr, "ifile: can't initialize the GPU demodulator: %s\n", b200_last_error());
         return false;
     }
-    ifile.span = malloc((size_t) SPAN_BLOCKS * MODES_MAG_BUF_SAMPLES * ifile.bytes_per_sample);
+    /* page-locked if possible: the span's H2D copy then runs at PCIe speed behind the kernels */
+    const size_t span_bytes = (size_t) SPAN_BLOCKS * MODES_MAG_BUF_SAMPLES * ifile.bytes_per_sample;
+    ifile.span = b200_host_alloc(span_bytes);
+    ifile.span_pinned = ifile.span != NULL;
+    if (!ifile.span)
+        ifile.span = malloc(span_bytes);
     return ifile.span != NULL;
 }
 
@@ -221,7 +227,10 @@ void ifileClose(void) {
         b200_demod_destroy(ifile.demod);
         ifile.demod = NULL;
     }
-    free(ifile.span);
+    if (ifile.span_pinned)
+        b200_host_free(ifile.span);
+    else
+        free(ifile.span);
     ifile.span = NULL;
     if (ifile.fd >= 0 && ifile.fd != STDIN_FILENO) {
         close(ifile.fd);
