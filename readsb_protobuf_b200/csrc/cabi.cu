@@ -3,7 +3,8 @@
 // A process call cuts the span into chunks of whole mag_bufs and runs them as a pipeline:
 //   copy stream : H2D of chunk i+1 ...................... (host-buffer entry only)
 //   exec stream : K1a scan -> K1b slice/CRC -> K2 classify -> order_live (-> Mode A/C) -> one small download of chunk i+1
-//   list stream : dead list of chunk i D2H (order_live writes live positions / records into pinned host memory)
+//                 (order_live writes the live positions, their records and what each would hide of the dead list
+//                 straight into pinned host memory; the dead list itself never leaves the device)
 //   host        : order-dependent resolve (resolver.cc) of chunk i
 // Chunks are exact: K2 of chunk i only needs the address set of chunks <= i, which is what the ICAO
 // filter can hold when the host resolves chunk i.  There is no CPU implementation of the kernels;
@@ -135,18 +136,19 @@ struct ChunkSet {
     View<BlockDead> d_block_dead, h_block_dead;
     View<TileOut> d_tiles_out, h_tiles_out;
     // K2 leaves the live positions and records in device memory, tile by tile in the order its warps reserved
-    // them; order_live packs them into stream order straight into pinned (device-mapped) host memory.  The
-    // (much longer) dead list stays in device memory and is downloaded behind the resolver's back
-    PinnedBuf<uint32_t> h_dead;
+    // them; order_live packs them into stream order straight into pinned (device-mapped) host memory, together
+    // with the dead-position counts a frame accepted at each live position would hide.  The (much longer) dead
+    // list itself stays in device memory.
     DevBuf<LivePos> d_live;
     DevBuf<LiveRec> d_liverecs;
     DevBuf<uint2> d_live_base;
     PinnedBuf<LivePos> h_live;
     PinnedBuf<LiveRec> h_liverecs;
+    PinnedBuf<LiveHidden> h_hidden;
     // Mode A/C (only with cfg.mode_ac): per-block noise levels, unordered hit list in pinned host memory
     DevBuf<uint32_t> d_ac_noise;
     PinnedBuf<AcHit> h_ac_hits;
-    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr, ev_lists = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_k1 = nullptr, ev_k1b = nullptr, ev_k2 = nullptr, ev_small = nullptr;
 
     // what is in flight
     uint64_t start = 0, nsamples = 0;
@@ -159,8 +161,8 @@ struct ChunkSet {
     void release() {
         d_cand.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
         d_small.release(); h_small.release(); d_dead.release();
-        h_dead.release(); h_live.release(); h_liverecs.release(); d_live.release(); d_liverecs.release(); d_live_base.release(); d_ac_noise.release(); h_ac_hits.release();
-        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_lists})
+        h_live.release(); h_liverecs.release(); h_hidden.release(); d_live.release(); d_liverecs.release(); d_live_base.release(); d_ac_noise.release(); h_ac_hits.release();
+        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small})
             if (*e) {
                 cudaEventDestroy(*e);
                 *e = nullptr;
@@ -190,7 +192,6 @@ struct b200_demod {
 
     cudaStream_t stream = nullptr;      // exec stream of the host-buffer entry
     cudaStream_t copy_stream = nullptr; // H2D
-    cudaStream_t list_stream = nullptr; // survivor lists D2H
     cudaEvent_t ev_h2d_begin = nullptr, ev_h2d_end = nullptr;
     std::vector<cudaEvent_t> ev_chunk_h2d;
 
@@ -238,7 +239,7 @@ struct b200_demod {
             cudaEventDestroy(ev_h2d_begin);
         if (ev_h2d_end)
             cudaEventDestroy(ev_h2d_end);
-        for (cudaStream_t s : {stream, copy_stream, list_stream})
+        for (cudaStream_t s : {stream, copy_stream})
             if (s)
                 cudaStreamDestroy(s);
     }
@@ -255,8 +256,8 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
     CUDA_TRY(c.d_cand.ensure(cand_total + 1));
     CUDA_TRY(c.d_recs.ensure(rec_total + 1));
     CUDA_TRY(c.d_dead.ensure(dead_cap));
-    CUDA_TRY(c.h_dead.ensure(dead_cap));
     CUDA_TRY(c.h_live.ensure(live_cap));
+    CUDA_TRY(c.h_hidden.ensure(c.h_live.cap));
     CUDA_TRY(c.h_liverecs.ensure(liverec_cap));
     CUDA_TRY(c.d_live.ensure(c.h_live.cap));
     CUDA_TRY(c.d_liverecs.ensure(c.h_liverecs.cap));
@@ -294,7 +295,6 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
         CUDA_TRY(cudaEventCreate(&c.ev_k1b));
         CUDA_TRY(cudaEventCreate(&c.ev_k2));
         CUDA_TRY(cudaEventCreate(&c.ev_small));
-        CUDA_TRY(cudaEventCreate(&c.ev_lists));
     }
     return B200_OK;
 }
@@ -359,10 +359,10 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
 
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&d->list_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_begin));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_end));
     CUDA_TRY(scan_configure());
+    CUDA_TRY(scan2_configure());
     CUDA_TRY(slice_configure());
     CUDA_TRY(upload_constants(d->crc->bit_syndromes()));
 
@@ -370,15 +370,18 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     build_uc8_table(d->h_lut.data());
     // second copy in the bank-swizzled shared-memory layout of K1 (32-bit word j of row Q at j ^ (Q & 31)),
     // so that every CTA stages the table with straight 16-byte copies
+    // ... and a third one in scan2_kernel's layout: entry i at i ^ ((i >> 5) & 0x38), i.e. 32-bit word j at
+    // j ^ ((j >> 5) & 0x1c)
     {
-        std::vector<uint32_t> both(65536);
+        std::vector<uint32_t> all(3 * 32768);
         const uint32_t *words = reinterpret_cast<const uint32_t *>(d->h_lut.data());
         for (uint32_t i = 0; i < 32768; ++i) {
-            both[i] = words[i];
-            both[32768 + (i ^ ((i >> 7) & 31u))] = words[i];
+            all[i] = words[i];
+            all[32768 + (i ^ ((i >> 7) & 31u))] = words[i];
+            all[65536 + (i ^ ((i >> 5) & 0x1cu))] = words[i];
         }
-        CUDA_TRY(d->d_lut.ensure(2 * 65536));
-        CUDA_TRY(cudaMemcpy(d->d_lut.p, both.data(), 2 * 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(d->d_lut.ensure(3 * 65536));
+        CUDA_TRY(cudaMemcpy(d->d_lut.p, all.data(), 3 * 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
 
     if (d->eff_format == 4) {
@@ -455,6 +458,8 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     a.ntiles = tiles_for(nsamples);
     a.lut = (d->eff_format == 4) ? d->d_lut_q11.p : d->d_lut.p;
     a.lut_swz = a.lut + 65536;
+    a.lut_swz2 = d->d_lut.p + 2 * 65536;
+    a.fast_lo = a.fast_hi = 0;
     a.table_bits = d->cfg.sc16q11_table_bits;
     a.tab_short = d->d_tab_short.p;
     a.tab_long = d->d_tab_long.p;
@@ -473,6 +478,10 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     a.block_sums_u64 = c.d_sums_u64.p;
     a.block_sums_f64 = c.d_sums_f64.p;
     a.dbg_masks = nullptr;
+    // the interior tiles of a uc8 span go through the register-window kernel (scan2.cu), the edge tiles (carried
+    // head, ragged tail) through scan_kernel
+    if (scan2_supports(a) && !getenv("B200_NO_SCAN2"))
+        scan2_tile_range(nsamples, a.fast_lo, a.fast_hi);
     return a;
 }
 
@@ -550,6 +559,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
             *launches += c.span_fsums ? 0 : 1;
     }
     CUDA_TRY(cudaEventRecord(c.ev_begin, s));
+    CUDA_TRY(launch_scan2(sa, 1, d->scan_grid, s));
     CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
     CUDA_TRY(cudaEventRecord(c.ev_k1, s));
     CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
@@ -589,8 +599,8 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     CUDA_TRY(launch_classify(ca, s));
     // live positions / records in stream order, written into pinned host memory (posted writes over PCIe,
     // done when the kernel is)
-    CUDA_TRY(launch_order_live(c.d_tiles_out.p, ntiles, c.d_counters.p, c.d_live_base.p, c.d_live.p, c.d_liverecs.p, c.h_live.p,
-                               c.h_liverecs.p, s));
+    CUDA_TRY(launch_order_live(c.d_tiles_out.p, ntiles, c.d_counters.p, c.d_live_base.p, c.d_live.p, c.d_liverecs.p, c.d_dead.p, n, B,
+                               c.h_live.p, c.h_liverecs.p, c.h_hidden.p, s));
     CUDA_TRY(cudaEventRecord(c.ev_k2, s));
     if (d->cfg.mode_ac && n) {
         // demodulate2400AC (readsb.c:831-833) over the same magnitudes
@@ -624,7 +634,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
 static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t *launches, b200_timing &t) {
     const uint64_t n = c.nsamples;
     const uint32_t ntiles = tiles_for(n);
-    size_t dead_cap = c.h_dead.cap, live_cap = c.h_live.cap, liverec_cap = c.h_liverecs.cap;
+    size_t dead_cap = c.d_dead.cap, live_cap = c.h_live.cap, liverec_cap = c.h_liverecs.cap;
 
     CUDA_TRY(cudaEventSynchronize(c.ev_small));
     ScanCounters cnt = *c.h_counters.p;
@@ -694,13 +704,8 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
         t.classify_ms += ms;
     }
 
-    // order_live wrote the live positions and records straight into pinned host memory (posted writes
-    // over PCIe, done when the kernel is).  The dead list (4 B per noise candidate, only consulted where an
-    // accepted frame skips ahead) is downloaded now, on its own stream, and waited for by the resolver
-    // the first time it needs it.
-    if (cnt.n_dead)
-        CUDA_TRY(cudaMemcpyAsync(c.h_dead.p, c.d_dead.p, (size_t) cnt.n_dead * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->list_stream));
-    CUDA_TRY(cudaEventRecord(c.ev_lists, d->list_stream));
+    // order_live wrote the live positions, their records and their hidden-dead counts straight into pinned host
+    // memory (posted writes over PCIe, done when the kernel is).
     // host: the order-dependent tail
     const double t_res0 = now_ms();
     SpanView v;
@@ -710,32 +715,27 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     v.final_span = c.final_chunk;
     // the resolver only tells integer block sums (the table converters) from float ones
     v.format = (d->eff_format == 4) ? (uint32_t) B200_INPUT_UC8 : d->eff_format;
-    v.ntiles = ntiles;
-    v.tiles = c.h_tiles_out.p;
-    v.dead = c.h_dead.p;
     v.live = c.h_live.p;
     v.n_live = (uint32_t) cnt.n_live;
     v.liverecs = c.h_liverecs.p;
+    v.hidden = c.h_hidden.p;
     v.block_dead = c.h_block_dead.p;
     v.block_sums_u64 = c.h_sums_u64.p;
     v.block_sums_f64 = c.h_sums_f64.p;
     v.ac_hits = d->cfg.mode_ac ? c.h_ac_hits.p : nullptr;
     v.n_ac_hits = d->cfg.mode_ac ? cnt.n_modeac_hits : 0;
-    v.dead_ready = [](void *ev) { cudaEventSynchronize((cudaEvent_t) ev); };
-    v.dead_ctx = c.ev_lists;
     if (const char *dump = getenv("B200_DUMP_SPAN")) {
-        // development aid: write the resolver's inputs of this chunk to a file (tools/resolver_bench.cc)
+        // development aid: write the resolver's inputs of this chunk to a file (tools/resolver_bench.cc,
+        // b200_host_resolve_dumps)
         char path[512];
         snprintf(path, sizeof(path), "%s/span_%llu.bin", dump, (unsigned long long) v.first_sample); // stream position of the chunk
-        cudaEventSynchronize(c.ev_lists);
         if (FILE *f = fopen(path, "wb")) {
             const uint64_t nblocks = n / v.block_samples + 2;
-            uint64_t hdr[12] = {n, v.first_sample, v.block_samples, v.final_span, v.format /* as the resolver sees it */, v.ntiles, cnt.n_dead, cnt.n_live, cnt.n_liverec, nblocks, 1 /* live lists in stream order */, 0};
+            uint64_t hdr[12] = {n, v.first_sample, v.block_samples, v.final_span, v.format /* as the resolver sees it */, 0, 0, cnt.n_live, cnt.n_liverec, nblocks, 2 /* layout version: live lists in stream order + hidden counts */, 0};
             fwrite(hdr, sizeof(hdr), 1, f);
-            fwrite(v.tiles, sizeof(TileOut), v.ntiles, f);
-            fwrite(v.dead, sizeof(uint32_t), cnt.n_dead, f);
             fwrite(v.live, sizeof(LivePos), cnt.n_live, f);
             fwrite(v.liverecs, sizeof(LiveRec), cnt.n_liverec, f);
+            fwrite(v.hidden, sizeof(LiveHidden), cnt.n_live, f);
             fwrite(v.block_dead, sizeof(BlockDead), nblocks, f);
             fwrite(v.block_sums_u64, sizeof(unsigned long long), 2 * nblocks, f);
             fwrite(v.block_sums_f64, sizeof(double), 2 * nblocks, f);
@@ -744,8 +744,7 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     }
     d->resolver->resolve(v, d->msgs, d->blocks);
     t.resolve_ms += (float) (now_ms() - t_res0);
-    t.d2h_bytes += c.small_d2h_bytes + (size_t) cnt.n_dead * sizeof(uint32_t) + (size_t) cnt.n_live * sizeof(LivePos) +
-                   (size_t) cnt.n_liverec * sizeof(LiveRec);
+    t.d2h_bytes += c.small_d2h_bytes + (size_t) cnt.n_live * (sizeof(LivePos) + sizeof(LiveHidden)) + (size_t) cnt.n_liverec * sizeof(LiveRec);
     t.n_candidates += cnt.n_cand;
     t.n_phase_records += cnt.n_rec;
     t.n_live += cnt.n_live;
@@ -857,7 +856,7 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
             CUDA_TRY(cudaStreamWaitEvent(exec, d->ev_chunk_h2d[i], 0));
         const uint32_t ntiles = tiles_for(c.nsamples);
         return issue_chunk(d, c, exec, false, (size_t) ntiles * kCandSlab, (size_t) ntiles * kRecSlab,
-                           std::max<size_t>(c.h_dead.cap, (size_t) (c.nsamples / 24 + 4096)),
+                           std::max<size_t>(c.d_dead.cap, (size_t) (c.nsamples / 24 + 4096)),
                            std::max<size_t>(c.h_live.cap, (size_t) (c.nsamples / 128 + 4096)),
                            std::max<size_t>(c.h_liverecs.cap, (size_t) (c.nsamples / 64 + 4096)), &launches);
     };
@@ -1023,7 +1022,7 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
     cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : d->stream;
     ChunkSet &c = d->sets[0];
     const size_t nt = tiles_for(nsamples);
-    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kCandSlab, nt * kRecSlab, std::max<size_t>(c.h_dead.cap, 4096),
+    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kCandSlab, nt * kRecSlab, std::max<size_t>(c.d_dead.cap, 4096),
                                   std::max<size_t>(c.h_live.cap, 4096), std::max<size_t>(c.h_liverecs.cap, 4096));
     if (rc != B200_OK)
         return rc;
@@ -1032,6 +1031,7 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
         return rc;
     ScanArgs sa = make_scan_args(d, c, (const uint8_t *) d_iq, d->d_head.p, nsamples, 0, kCandSlab, kRecSlab, nullptr);
     CUDA_TRY(cudaEventRecord(c.ev_begin, s));
+    CUDA_TRY(launch_scan2(sa, mode ? 1 : 0, d->scan_grid, s));
     CUDA_TRY(launch_scan(sa, mode ? 1 : 0, d->scan_grid, s));
     if (mode >= 2)
         CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
@@ -1120,7 +1120,7 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
     CUDA_TRY(d->d_dbg_masks.ensure((size_t) nsamples + 16));
     // slabs that can hold every position of a tile as a candidate with five records
     const size_t nt = tiles_for(nsamples);
-    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kTile, nt * kTile * 5, std::max<size_t>(c.h_dead.cap, 4096),
+    int rc = ensure_chunk_buffers(d, c, nsamples, nt * kTile, nt * kTile * 5, std::max<size_t>(c.d_dead.cap, 4096),
                                   std::max<size_t>(c.h_live.cap, 4096), std::max<size_t>(c.h_liverecs.cap, 4096));
     if (rc != B200_OK)
         return rc;
@@ -1132,6 +1132,7 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
     CUDA_TRY(cudaMemsetAsync(d->d_dbg_masks.p, 0, (size_t) nsamples + 16, s));
     ScanArgs sa = make_scan_args(d, c, d->d_iq.p, d->d_head.p, nsamples, 0, kTile, kTile * 5, nullptr);
     sa.dbg_masks = d->d_dbg_masks.p;
+    CUDA_TRY(launch_scan2(sa, 1, d->scan_grid, s));
     CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
     CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
     CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
@@ -1255,7 +1256,7 @@ extern "C" int b200_host_resolve_dumps(const char *const *paths, uint32_t npaths
     std::vector<b200_message> out_msgs;
     std::vector<b200_block_info> out_blocks;
     for (uint32_t i = 0; i < npaths; ++i) {
-        // the layout finish_chunk writes: 12-word header, tile outputs, dead list, live positions, live records,
+        // the layout finish_chunk writes: 12-word header, live positions, live records, hidden-dead counts,
         // block dead counters, block sums (u64 and f64)
         FILE *f = fopen(paths[i], "rb");
         uint64_t hdr[12];
@@ -1264,52 +1265,51 @@ extern "C" int b200_host_resolve_dumps(const char *const *paths, uint32_t npaths
                 fclose(f);
             return fail(B200_ERR_ARG, "cannot read %s", paths[i]);
         }
-        if (hdr[10] != 1) {
+        if (hdr[10] != 2) {
             fclose(f);
-            return fail(B200_ERR_ARG, "%s holds per-tile live lists (a dump from before the ordered layout)", paths[i]);
+            return fail(B200_ERR_ARG, "%s is a span dump of another library version (layout %llu, this one reads 2)", paths[i],
+                        (unsigned long long) hdr[10]);
         }
         {
             // the counts must describe this file, byte for byte, before anything is sized from them
-            fseek(f, 0, SEEK_END);
-            const unsigned long long fsize = (unsigned long long) ftell(f);
-            fseek(f, (long) sizeof(hdr), SEEK_SET);
+            long fsize_l = -1;
+            if (fseek(f, 0, SEEK_END) != 0 || (fsize_l = ftell(f)) < 0 || fseek(f, (long) sizeof(hdr), SEEK_SET) != 0) {
+                fclose(f);
+                return fail(B200_ERR_ARG, "cannot size %s", paths[i]);
+            }
+            const unsigned long long fsize = (unsigned long long) fsize_l;
             const unsigned long long limit = fsize / 4 + 1; // no record is smaller than 4 bytes
-            bool sane = hdr[2] > 0 && hdr[4] <= 4;
-            for (int k = 5; k <= 9; ++k)
+            // everything the resolver narrows to 32 bits must fit (a zero or 2^32 block size would divide by zero)
+            bool sane = hdr[2] > 0 && hdr[2] <= 0xffffffffull && hdr[0] <= 0xffffffffull && hdr[4] <= 4 && hdr[3] <= 1;
+            for (int k = 7; k <= 9; ++k)
                 sane = sane && hdr[k] <= limit;
-            const unsigned long long want = sizeof(hdr) + hdr[5] * sizeof(TileOut) + hdr[6] * sizeof(uint32_t) + hdr[7] * sizeof(LivePos) +
-                                            hdr[8] * sizeof(LiveRec) + hdr[9] * (sizeof(BlockDead) + 2 * sizeof(unsigned long long) + 2 * sizeof(double));
-            if (!sane || want != fsize || hdr[5] != tiles_for(hdr[0])) {
+            const unsigned long long want = sizeof(hdr) + hdr[7] * (sizeof(LivePos) + sizeof(LiveHidden)) + hdr[8] * sizeof(LiveRec) +
+                                            hdr[9] * (sizeof(BlockDead) + 2 * sizeof(unsigned long long) + 2 * sizeof(double));
+            if (!sane || want != fsize) {
                 fclose(f);
                 return fail(B200_ERR_ARG, "%s is not a span dump of this library version", paths[i]);
             }
         }
-        std::vector<TileOut> tiles(hdr[5]);
-        std::vector<uint32_t> dead(hdr[6]);
         std::vector<LivePos> live(hdr[7]);
         std::vector<LiveRec> recs(hdr[8]);
+        std::vector<LiveHidden> hidden(hdr[7]);
         std::vector<BlockDead> bd(hdr[9]);
         std::vector<unsigned long long> su(2 * hdr[9]);
         std::vector<double> sf(2 * hdr[9]);
-        size_t got = fread(tiles.data(), sizeof(TileOut), tiles.size(), f);
-        got += fread(dead.data(), sizeof(uint32_t), dead.size(), f);
-        got += fread(live.data(), sizeof(LivePos), live.size(), f);
+        size_t got = fread(live.data(), sizeof(LivePos), live.size(), f);
         got += fread(recs.data(), sizeof(LiveRec), recs.size(), f);
+        got += fread(hidden.data(), sizeof(LiveHidden), hidden.size(), f);
         got += fread(bd.data(), sizeof(BlockDead), bd.size(), f);
         got += fread(su.data(), sizeof(unsigned long long), su.size(), f);
         got += fread(sf.data(), sizeof(double), sf.size(), f);
         fclose(f);
-        if (got != tiles.size() + dead.size() + live.size() + recs.size() + bd.size() + su.size() + sf.size())
+        if (got != 2 * live.size() + recs.size() + bd.size() + su.size() + sf.size())
             return fail(B200_ERR_ARG, "%s is truncated", paths[i]);
         // every index the resolver follows must stay inside the arrays just read
         bool ok = hdr[9] >= hdr[0] / hdr[2] + 1;
-        for (const TileOut &to : tiles)
-            ok = ok && (uint64_t) to.dead_off + to.ndead <= dead.size();
         uint32_t prev_pos = 0;
         for (const LivePos &lp : live) {
-            const uint64_t t = ((uint64_t) lp.pos + kPosShift) / kTile;
-            ok = ok && lp.pos < hdr[0] && lp.pos >= prev_pos && t < tiles.size() && (uint64_t) lp.pad + ((lp.info >> 8) & 7u) <= recs.size();
-            ok = ok && (t >= tiles.size() || lp.dead_rank <= tiles[t].ndead);
+            ok = ok && lp.pos < hdr[0] && lp.pos >= prev_pos && (uint64_t) lp.pad + ((lp.info >> 8) & 7u) <= recs.size();
             prev_pos = lp.pos;
         }
         if (!ok)
@@ -1320,12 +1320,10 @@ extern "C" int b200_host_resolve_dumps(const char *const *paths, uint32_t npaths
         v.block_samples = (uint32_t) hdr[2];
         v.final_span = hdr[3] != 0;
         v.format = (uint32_t) hdr[4];
-        v.ntiles = (uint32_t) hdr[5];
-        v.tiles = tiles.data();
-        v.dead = dead.data();
         v.live = live.data();
         v.n_live = (uint32_t) live.size();
         v.liverecs = recs.data();
+        v.hidden = hidden.data();
         v.block_dead = bd.data();
         v.block_sums_u64 = su.data();
         v.block_sums_f64 = sf.data();

@@ -75,10 +75,19 @@ struct LivePos {
     uint32_t pad;       // 0 from K2; in the ordered list the host walks: index of the position's first record
 };
 
+// order_live -> host: what an accepted frame at a live position hides from the per-block dead totals -- the dead
+// positions in (pos, pos + 134] (a 56-bit frame) and in (pos, pos + 268] (a 112-bit frame), both cut at the last
+// position of the position's mag_buf (demod_2400.c:416: the for loop ends with the block).  Eight 16-bit counters
+// per case: lo = preambles | rejected_bad << 16 | rejected_unknown << 32 | phase[0] << 48, hi = phase[1..4].  32 bytes.
+struct LiveHidden {
+    uint64_t short_lo, short_hi;
+    uint64_t long_lo, long_hi;
+};
+
 // K2 -> host: a sliced frame of a live position.  40 bytes.
 struct LiveRec {
     uint32_t pos;
-    uint32_t w0;    // as PhaseRec
+    uint32_t w0;    // as PhaseRec, plus bit 31: the key is in the device-side address set S (outside it the ICAO filter says no)
     uint32_t w1;
     uint32_t errbits; // bit0[7:0] | bit1[15:8] (0xff = none)
     uint64_t power; // sum of m^2 over the frame's 134/268 samples (demod_2400.c:393-396)
@@ -109,8 +118,8 @@ struct ScanCounters {
     unsigned long long n_live;
     unsigned long long n_liverec;
     unsigned int overflow; // bit0 cand, bit1 rec, bit2 dead, bit3 live, bit4 liverec, bit5 Mode A/C hits
-    unsigned int next_tile; // K1a work queue
-    unsigned int reserved;
+    unsigned int next_tile; // K1a work queue (scan_kernel: the edge tiles, or every tile)
+    unsigned int next_tile2; // K1a work queue of scan2_kernel (the interior tiles)
     unsigned int n_modeac_hits;   // Mode A/C kernel
 };
 

@@ -809,6 +809,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
         if (lane == 0)
             tile = atomicAdd(&a.counters->next_tile, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.fast_lo) // tiles [fast_lo, fast_hi) belong to scan2_kernel
+            tile += a.fast_hi - a.fast_lo;
         if (tile >= a.ntiles)
             break;
         // interior tile: all 17 chunks are new samples of the span and all positions exist
@@ -837,7 +839,10 @@ cudaError_t scan_configure() {
 cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stream) {
     if (a.ntiles == 0)
         return cudaSuccess;
-    const int max_useful = (int) ((a.ntiles + kScanWarps - 1) / kScanWarps);
+    const uint32_t mine = a.ntiles - (a.fast_hi - a.fast_lo);
+    if (mine == 0)
+        return cudaSuccess;
+    const int max_useful = (int) ((mine + kScanWarps - 1) / kScanWarps);
     if (grid > max_useful)
         grid = max_useful;
     const size_t smem = scan_smem_bytes(a.format);
@@ -1478,7 +1483,7 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
         if (lane == 0) {
             LiveRec lr;
             lr.pos = pr.pos;
-            lr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
+            lr.w0 = syn | (fc.kind << 24) | (fc.errors << 28) | (bitmap_test(a.addr_bitmap, fc.key) ? 0x80000000u : 0u); // bit 31: key in S
             lr.w1 = fc.key | ((uint32_t) ph << 24);
             lr.errbits = (uint32_t) (uint8_t) fc.bit0 | ((uint32_t) (uint8_t) fc.bit1 << 8);
             lr.power = power;
@@ -1738,7 +1743,7 @@ __global__ void __launch_bounds__(kCwWarps * 32) classify_warp_kernel(const Clas
                 if (lane == 0) {
                     LiveRec lr;
                     lr.pos = pos;
-                    lr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
+                    lr.w0 = syn | (fc.kind << 24) | (fc.errors << 28) | (bitmap_test(a.addr_bitmap, fc.key) ? 0x80000000u : 0u); // bit 31: key in S
                     lr.w1 = fc.key | ((uint32_t) ph << 24);
                     lr.errbits = (uint32_t) (uint8_t) fc.bit0 | ((uint32_t) (uint8_t) fc.bit1 << 8);
                     lr.power = power;
@@ -1835,10 +1840,60 @@ __global__ void __launch_bounds__(1024) live_offsets_kernel(const TileOut *__res
     }
 }
 
+// What a frame accepted at live position `pos` hides from the per-block dead totals (LiveHidden): the dead
+// entries in (pos, pos + 134] and (pos, pos + 268], both cut at the last position of pos's mag_buf.  One walk
+// over the tile's ordered dead list from the position's rank (and into the following tiles when the frame
+// body crosses a tile boundary), a snapshot taken where the short body ends.
+__device__ __forceinline__ LiveHidden hidden_counts(const TileOut *__restrict__ tiles_out, uint32_t ntiles, const uint32_t *__restrict__ dead,
+                                                    uint32_t tile, uint32_t pos, uint32_t rank, uint64_t nsamples, uint32_t block_samples) {
+    const unsigned long long p = pos, B = block_samples;
+    unsigned long long b1 = (p / B + 1) * B;
+    if (b1 > nsamples)
+        b1 = nsamples;
+    const unsigned long long end_s = (p + 134 < b1 - 1) ? p + 134 : b1 - 1, end_l = (p + 268 < b1 - 1) ? p + 268 : b1 - 1;
+    unsigned long long lo = 0, hi = 0;
+    LiveHidden h;
+    h.short_lo = h.short_hi = 0;
+    bool snap = false;
+    if (end_l > p) {
+        const uint32_t t1 = (uint32_t) ((end_l + kPosShift) / kTile);
+        for (uint32_t t = tile; t <= t1 && t < ntiles; ++t) {
+            const TileOut to = tiles_out[t];
+            const long long base = (long long) t * kTile - kPosShift;
+            const uint32_t *it = dead + to.dead_off + (t == tile ? rank : 0u), *dend = dead + to.dead_off + to.ndead;
+            const long long last_l = (long long) end_l - base, last_s = (long long) end_s - base;
+            for (; it != dend; ++it) {
+                const uint32_t e = __ldg(it);
+                const long long pl = (long long) (e & 0x1fffu);
+                if (pl > last_l)
+                    break;
+                if (!snap && pl > last_s) {
+                    h.short_lo = lo;
+                    h.short_hi = hi;
+                    snap = true;
+                }
+                const uint32_t tm = (e >> 13) & 31u, unk = (e >> 18) & 1u;
+                lo += 1ull | ((unsigned long long) (unk ^ 1u) << 16) | ((unsigned long long) unk << 32) | ((unsigned long long) (tm & 1u) << 48);
+                hi += (unsigned long long) ((tm >> 1) & 1u) | ((unsigned long long) ((tm >> 2) & 1u) << 16) |
+                      ((unsigned long long) ((tm >> 3) & 1u) << 32) | ((unsigned long long) ((tm >> 4) & 1u) << 48);
+            }
+        }
+    }
+    if (!snap) {
+        h.short_lo = lo;
+        h.short_hi = hi;
+    }
+    h.long_lo = lo;
+    h.long_hi = hi;
+    return h;
+}
+
 __global__ void __launch_bounds__(256) live_gather_kernel(const TileOut *__restrict__ tiles_out, uint32_t ntiles,
                                                            const ScanCounters *__restrict__ counters, const uint2 *__restrict__ base,
                                                            const LivePos *__restrict__ live, const LiveRec *__restrict__ recs,
-                                                           LivePos *__restrict__ live_out, LiveRec *__restrict__ recs_out) {
+                                                           const uint32_t *__restrict__ dead, uint64_t nsamples, uint32_t block_samples,
+                                                           LivePos *__restrict__ live_out, LiveRec *__restrict__ recs_out,
+                                                           LiveHidden *__restrict__ hidden_out) {
     if (counters->overflow)
         return;
     const int lane = threadIdx.x & 31;
@@ -1850,8 +1905,12 @@ __global__ void __launch_bounds__(256) live_gather_kernel(const TileOut *__restr
         const uint2 b = base[t];
         for (uint32_t i = lane; i < to.nlive; i += 32) {
             LivePos lp = live[to.live_off + i];
+            const LiveHidden h = hidden_counts(tiles_out, ntiles, dead, t, lp.pos, lp.dead_rank, nsamples, block_samples);
             lp.pad = b.y + (lp.info >> 16); // first record of the position, now an absolute index
             live_out[b.x + i] = lp;
+            uint4 *ho = reinterpret_cast<uint4 *>(hidden_out + b.x + i);
+            ho[0] = make_uint4((uint32_t) h.short_lo, (uint32_t) (h.short_lo >> 32), (uint32_t) h.short_hi, (uint32_t) (h.short_hi >> 32));
+            ho[1] = make_uint4((uint32_t) h.long_lo, (uint32_t) (h.long_lo >> 32), (uint32_t) h.long_hi, (uint32_t) (h.long_hi >> 32));
         }
         // records: whole 8-byte units (the struct holds a uint64_t, so every record starts on one)
         static_assert(sizeof(LiveRec) % 8 == 0 && alignof(LiveRec) == 8, "LiveRec is copied in 8-byte units");
@@ -1864,14 +1923,16 @@ __global__ void __launch_bounds__(256) live_gather_kernel(const TileOut *__restr
 }
 
 cudaError_t launch_order_live(const TileOut *tiles_out, uint32_t ntiles, const ScanCounters *counters, uint2 *base, const LivePos *live,
-                              const LiveRec *recs, LivePos *live_out, LiveRec *recs_out, cudaStream_t stream) {
+                              const LiveRec *recs, const uint32_t *dead, uint64_t nsamples, uint32_t block_samples, LivePos *live_out,
+                              LiveRec *recs_out, LiveHidden *hidden_out, cudaStream_t stream) {
     if (ntiles == 0)
         return cudaSuccess;
     live_offsets_kernel<<<1, 1024, 0, stream>>>(tiles_out, ntiles, counters, base);
     int grid = (int) ((ntiles + 7) / 8);
     if (grid > 148 * 4)
         grid = 148 * 4;
-    live_gather_kernel<<<grid, 256, 0, stream>>>(tiles_out, ntiles, counters, base, live, recs, live_out, recs_out);
+    live_gather_kernel<<<grid, 256, 0, stream>>>(tiles_out, ntiles, counters, base, live, recs, dead, nsamples, block_samples, live_out,
+                                                 recs_out, hidden_out);
     return cudaGetLastError();
 }
 

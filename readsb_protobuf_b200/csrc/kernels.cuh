@@ -22,6 +22,8 @@ struct ScanArgs {
     // tables
     const uint16_t *lut;  // magnitude table of the format (65536 entries): uc8, or format 4's sc16q11 table
     const uint16_t *lut_swz; // the same table in K1's bank-swizzled shared-memory layout
+    const uint16_t *lut_swz2; // ... and in scan2_kernel's (entry i at i ^ ((i >> 5) & 0x38))
+    uint32_t fast_lo, fast_hi; // tiles [fast_lo, fast_hi) are scan2_kernel's: scan_kernel leaves them out
     int32_t table_bits;   // format 4: SC16Q11_TABLE_BITS (<= 8)
     const ErrorInfo *tab_short;
     const ErrorInfo *tab_long;
@@ -109,11 +111,18 @@ cudaError_t scan_configure();
 cudaError_t slice_configure();
 // mode 0: magnitude + preamble scan only (candidates counted); 1: + slice + CRC + records
 cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
+// scan2.cu: the register-window K1a for the interior tiles of a uc8 span (same outputs as scan_kernel)
+cudaError_t scan2_configure();
+bool scan2_supports(const ScanArgs &a);
+void scan2_tile_range(uint64_t nsamples, uint32_t &lo, uint32_t &hi);
+cudaError_t launch_scan2(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
 cudaError_t launch_slice(const SliceArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream);
-// K2's per-tile live lists (device memory) -> position-ordered arrays (pinned host memory); base = ntiles scratch
+// K2's per-tile live lists (device memory) -> position-ordered arrays (pinned host memory), plus per live position
+// what a frame accepted there hides of the dead list (which therefore never leaves the device); base = ntiles scratch
 cudaError_t launch_order_live(const TileOut *tiles_out, uint32_t ntiles, const ScanCounters *counters, uint2 *base, const LivePos *live,
-                              const LiveRec *recs, LivePos *live_out, LiveRec *recs_out, cudaStream_t stream);
+                              const LiveRec *recs, const uint32_t *dead, uint64_t nsamples, uint32_t block_samples, LivePos *live_out,
+                              LiveRec *recs_out, LiveHidden *hidden_out, cudaStream_t stream);
 // sc16 / sc16q11: per-mag_buf sum of mag and of magsq as the reference's sequential float accumulators
 // leave them (sums[2k], sums[2k+1]); iq = the span's first new sample
 cudaError_t launch_float_block_sums(const uint8_t *iq, uint32_t format, uint64_t nsamples, uint32_t block_samples, uint32_t nblocks,

@@ -2,7 +2,14 @@
 #include "resolver.h"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 
+#include <sched.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace b200 {
@@ -45,6 +52,13 @@ void IcaoFilter::reset() {
 }
 
 void IcaoFilter::add(uint32_t addr) {
+    // Already in the active table (the common case: the same aircraft again): both inserts below would find
+    // their entries and change nothing.  The shadow bitmap knows without walking the probe chains.
+    if (!dropped_ && addr < (1u << 24)) {
+        const std::vector<uint64_t> &bits = (active_ == a_) ? bits_a_ : bits_b_;
+        if ((bits[addr >> 6] >> (addr & 63u)) & 1ull)
+            return;
+    }
     // the address itself ...
     uint32_t h0 = hash(addr), h = h0;
     bool full = false;
@@ -139,8 +153,112 @@ void IcaoFilter::collect(std::vector<uint32_t> &out) const {
 }
 
 // ------------------------------------------------------------------------------------------
+// worker pool: the message-assembly half of the resolve runs on a few host threads
+// ------------------------------------------------------------------------------------------
+
+// A handful of threads parked on a condition variable; run() hands them (and the caller) slices of an index
+// range.  Only spans with thousands of accepted frames go through it: a sparse chunk is assembled inline.
+class WorkerPool {
+  public:
+    explicit WorkerPool(int nthreads) {
+        for (int i = 1; i < nthreads; ++i)
+            threads_.emplace_back([this, i] { loop(i); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            ++generation_;
+        }
+        cv_.notify_all();
+        for (std::thread &t : threads_)
+            t.join();
+    }
+    int size() const { return (int) threads_.size() + 1; }
+    // fn(worker, begin, end) over [0, n) in slices of `grain`; returns when every slice is done
+    void run(size_t n, size_t grain, const std::function<void(int, size_t, size_t)> &fn) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            n_ = n;
+            grain_ = grain;
+            next_.store(0, std::memory_order_relaxed);
+            pending_ = (int) threads_.size();
+            ++generation_;
+        }
+        cv_.notify_all();
+        work(0);
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void work(int worker) {
+        for (;;) {
+            const size_t b = next_.fetch_add(grain_, std::memory_order_relaxed);
+            if (b >= n_)
+                break;
+            (*fn_)(worker, b, std::min(n_, b + grain_));
+        }
+    }
+    void loop(int worker) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (stop_)
+                    return;
+            }
+            work(worker);
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0)
+                    done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, size_t, size_t)> *fn_ = nullptr;
+    size_t n_ = 0, grain_ = 1;
+    std::atomic<size_t> next_{0};
+    int pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
+static int resolver_threads() {
+    if (const char *e = getenv("B200_RESOLVER_THREADS")) {
+        const int n = atoi(e);
+        if (n >= 1)
+            return std::min(n, 64);
+    }
+    cpu_set_t set;
+    int cpus = 1;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0)
+        cpus = CPU_COUNT(&set);
+    // the caller's thread walks, the CUDA runtime has its own: leave them a core each
+    return std::max(1, std::min(8, cpus - 2));
+}
+
+// ------------------------------------------------------------------------------------------
 // scoring and the CRC-dependent part of decode
 // ------------------------------------------------------------------------------------------
+
+Resolver::Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), startup_(startup_time_ms), pool_(nullptr) {
+    const int n = resolver_threads();
+    if (n > 1)
+        pool_ = new WorkerPool(n);
+    reset();
+}
+
+Resolver::~Resolver() {
+    delete pool_;
+}
 
 void Resolver::reset() {
     filter_.reset();
@@ -151,34 +269,76 @@ void Resolver::reset() {
 }
 
 // scoreModesMessage (mode_s.c:311-409) for a frame K1 already classified
+// K2 marks a record whose address (key) is in the device-side set S of every address the filter could ever
+// hold (LiveRec::w0 bit 31).  Outside S the filter's answer is "no" whatever its state, and the host does not
+// have to touch its tables for the (random) addresses of the noise frames that share a live position.
+static inline bool may_be_known(const LiveRec &r) {
+    return (r.w0 >> 31) != 0;
+}
+
+// scoreModesMessage's values (mode_s.c:343-403) by [class][address known][repaired bits]: x / (errors + 1) spelled out,
+// so that the walk does no integer division.  Row kKindDF11 is the IID == 0 case; kDf11Iid is IID != 0.
+namespace {
+constexpr int kDf11Iid = 5;
+const int kScoreTable[6][2][4] = {
+    {{-2, -2, -2, -2}, {-2, -2, -2, -2}},                                      // kKindBad
+    {{-1, -1, -1, -1}, {1000, 1000, 1000, 1000}},                              // kKindAP
+    {{-2, -2, -2, -2}, {1000, 1000, 1000, 1000}},                              // kKindAPCommB
+    {{750 / 1, 750 / 2, 750 / 3, 750 / 4}, {1600 / 1, 1600 / 2, 1600 / 3, 1600 / 4}},   // kKindDF11, IID 0
+    {{1400 / 1, 1400 / 2, 1400 / 3, 1400 / 4}, {1800 / 1, 1800 / 2, 1800 / 3, 1800 / 4}}, // kKindES
+    {{-1, -1, -1, -1}, {1000 / 1, 1000 / 2, 1000 / 3, 1000 / 4}},              // kKindDF11, IID != 0
+};
+} // namespace
+
 int Resolver::score(const LiveRec &r) const {
     const uint32_t crc = r.w0 & 0xffffffu, kind = (r.w0 >> 24) & 7u, errors = (r.w0 >> 28) & 3u;
-    const uint32_t key = r.w1 & 0xffffffu;
-    switch (kind) {
-        case kKindAP: // mode_s.c:343
-            return filter_.test(crc) ? 1000 : -1;
-        case kKindAPCommB: // mode_s.c:393-403
-            return filter_.test(crc) ? 1000 : -2;
-        case kKindDF11: { // mode_s.c:364-374
-            const bool known = filter_.test(key);
-            if ((crc & 0x7fu) == 0)
-                return (known ? 1600 : 750) / (int) (errors + 1);
-            return known ? 1000 / (int) (errors + 1) : -1;
-        }
-        case kKindES: // mode_s.c:386-389
-            return (filter_.test(key) ? 1800 : 1400) / (int) (errors + 1);
-        default:
-            return -2;
-    }
+    const uint32_t key = r.w1 & 0xffffffu; // the address the filter is asked about: the syndrome for Address/Parity frames
+    const bool known = may_be_known(r) && filter_.test(key);
+    if (kind > kKindES)
+        return -2;
+    const uint32_t row = (kind == kKindDF11 && (crc & 0x7fu) != 0) ? (uint32_t) kDf11Iid : kind;
+    return kScoreTable[row][known ? 1 : 0][errors];
 }
 
 static inline uint32_t aa_field(const uint8_t *msg) { // getbits(msg, 9, 32)
     return ((uint32_t) msg[1] << 16) | ((uint32_t) msg[2] << 8) | (uint32_t) msg[3];
 }
 
-// The part of decodeModesMessage that can reject the frame or touches the filter
-// (mode_s.c:424-555, 560-562, 717-726).  CRC and repair are recomputed on the host from the
-// sliced bytes; a disagreement with the kernel's values is counted, never hidden.
+// The part of decodeModesMessage that can reject the frame or touches the filter (mode_s.c:445-555, 717-726),
+// decided from what the kernels recorded about the frame: its syndrome, class, repair (error count and bit
+// positions) and the address after repair (key).  Returns 0, or the reject code (-1 unknown ICAO, -2 bad).
+// An all-zero frame (mode_s.c:434) never gets a class record, so that test cannot fire here.
+int Resolver::admit(const LiveRec &r) {
+    const uint32_t crc = r.w0 & 0xffffffu, kind = (r.w0 >> 24) & 7u, errors = (r.w0 >> 28) & 3u;
+    const uint32_t key = r.w1 & 0xffffffu;
+    switch (kind) {
+        case kKindAP:      // DF0/4/5/16/24: mode_s.c:447-465
+        case kKindAPCommB: // DF20/21: mode_s.c:548-554
+            return (may_be_known(r) && filter_.test(key)) ? 0 : -1;
+        case kKindDF11: { // mode_s.c:467-506
+            if ((crc & 0xffff80u) && !(may_be_known(r) && filter_.test(key))) // a repaired all-call reply must come from a known aircraft
+                return -1;
+            if (!errors && (crc & 0x7fu) == 0)
+                filter_.add(key); // mode_s.c:717-726: a clean reply with IID 0
+            return 0;
+        }
+        case kKindES: { // DF17/18: mode_s.c:508-546
+            if (crc != 0) {
+                // a repair that touched the address field (frame bits 8..31) needs the new address to be known
+                const uint32_t b0 = r.errbits & 0xffu, b1 = (r.errbits >> 8) & 0xffu;
+                const bool touched = (errors >= 1 && b0 >= 8 && b0 <= 31) || (errors >= 2 && b1 >= 8 && b1 <= 31);
+                if (touched && !(may_be_known(r) && filter_.test(key)))
+                    return -1;
+            }
+            if (!errors && (r.msg[0] >> 3) == 17)
+                filter_.add(key); // a clean DF17 (not DF18)
+            return 0;
+        }
+        default:
+            return -2;
+    }
+}
+
 /* DF18: is the AA field something other than an ICAO address?  The extended-squitter decoder then
  * flags mm->addr with MODES_NON_ICAO_ADDRESS (1 << 24): by CF alone (mode_s.c:1379-1428), or for CF 2 / 3 /
  * 6 by the IMF bit of the ME field, whose position depends on the ME type (mode_s.c:806, 927, 966-968,
@@ -212,75 +372,93 @@ static int df18_non_icao(const uint8_t *msg) {
     return 0;
 }
 
-int Resolver::decode(const LiveRec &r, b200_message &mm) {
+// Everything else decodeModesMessage and demodulate2400 put into the message (demod_2400.c:353-399,
+// mode_s.c:424-562): pure functions of the winning record, the position and the block.  CRC and repair are
+// recomputed on the host from the sliced bytes; a disagreement with the kernel's values (the ones admit()
+// decided on) is counted, never hidden.
+uint32_t Resolver::build(const SpanView &v, const Accepted &a, b200_message &mm, double *signal_power_out) const {
+    memset(&mm, 0, sizeof(mm));
+    *signal_power_out = 0.0;
+    const uint64_t B = v.block_samples, b0 = (uint64_t) a.block * B;
+    const uint64_t sampleTimestamp = (uint64_t) ((double) (v.first_sample + b0) * 12e6 / 2400000.0); // sdr_ifile.c:187-190
+    const uint64_t sysTimestamp = sampleTimestamp / 12000U + startup_;
+    if (a.modeac) {
+        const AcHit h = v.ac_hits[a.index];
+        mm.timestampMsg = sampleTimestamp + (h.f1_clock + 87 * 14) / 5;                       // demod_2400.c:697, at F2
+        mm.sysTimestampMsg = sysTimestamp + (mm.timestampMsg - sampleTimestamp) / 12000U; // :700
+        mm.msgtype = 32;                                                                   // mode_ac.c:171
+        mm.msgbits = 16;
+        mm.msg[0] = mm.verbatim[0] = (uint8_t) (h.modeac >> 8);
+        mm.msg[1] = mm.verbatim[1] = (uint8_t) h.modeac;
+        mm.addr = (h.modeac & 0x0000FF7Fu) | (1u << 24); // mode_ac.c:180
+        return 0;
+    }
+    const LiveRec &r = v.liverecs[a.rec];
+    const uint64_t j = (uint64_t) v.live[a.index].pos - b0;
+    mm.timestampMsg = sampleTimestamp + j * 5 + (8 + 56) * 12 + (uint64_t) a.phase;       // demod_2400.c:358
+    mm.sysTimestampMsg = sysTimestamp + (mm.timestampMsg - sampleTimestamp) / 12000U; // :361
+    mm.score = a.score;
+    mm.bestphase = a.phase;
+
+    uint32_t bad = 0;
     memcpy(mm.msg, r.msg, 14);
     memcpy(mm.verbatim, r.msg, 14);
     uint8_t *msg = mm.msg;
-    static const uint8_t zeros[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (!memcmp(msg, zeros, 7))
-        return -2;
     mm.msgtype = msg[0] >> 3;
     mm.msgbits = (mm.msgtype & 0x10) ? 112 : 56;
     mm.crc = crc_->checksum(msg, mm.msgbits);
-    mm.correctedbits = 0;
-    mm.addr = 0;
     if (mm.crc != (r.w0 & 0xffffffu))
-        ++mismatches_;
-    uint32_t iid = 0;
-
+        ++bad;
+    const uint32_t kind = (r.w0 >> 24) & 7u, errors = (r.w0 >> 28) & 3u;
     switch (mm.msgtype) {
-        case 0: case 4: case 5: case 16:
-        case 24: case 25: case 26: case 27: case 28: case 29: case 30: case 31:
-            if (!filter_.test(mm.crc))
-                return -1;
-            mm.addr = mm.crc;
-            break;
-        case 11: {
-            iid = mm.crc & 0x7fu;
+        case 11:
             if (mm.crc & 0xffff80u) {
                 const ErrorInfo *ei = crc_->diagnose(mm.crc & 0xffff80u, mm.msgbits);
-                if (!ei || ei->errors > 1)
-                    return -2;
-                mm.correctedbits = (uint8_t) ei->errors;
-                CrcTables::fix(msg, ei);
-                if (!filter_.test(aa_field(msg)))
-                    return -1;
+                if (!ei || ei->errors > 1) {
+                    ++bad;
+                } else {
+                    mm.correctedbits = (uint8_t) ei->errors;
+                    CrcTables::fix(msg, ei);
+                }
             }
+            mm.addr = aa_field(msg);
+            if (kind != kKindDF11)
+                ++bad;
             break;
-        }
-        case 17: case 18: {
+        case 17: case 18:
             if (mm.crc != 0) {
                 const ErrorInfo *ei = crc_->diagnose(mm.crc, mm.msgbits);
-                if (!ei)
-                    return -2;
-                const uint32_t addr1 = aa_field(msg);
-                mm.correctedbits = (uint8_t) ei->errors;
-                CrcTables::fix(msg, ei);
-                const uint32_t addr2 = aa_field(msg);
-                if (addr1 != addr2 && !filter_.test(addr2))
-                    return -1;
+                if (!ei) {
+                    ++bad;
+                } else {
+                    mm.correctedbits = (uint8_t) ei->errors;
+                    CrcTables::fix(msg, ei);
+                }
             }
+            mm.addr = aa_field(msg);
+            if (kind != kKindES)
+                ++bad;
+            // decodeExtendedSquitter (mode_s.c:1373-1428) runs later in decodeModesMessage and may flag the address
+            if (mm.msgtype == 18 && df18_non_icao(mm.msg))
+                mm.addr |= 1u << 24;
             break;
-        }
-        case 20: case 21:
-            if (!filter_.test(mm.crc))
-                return -1;
+        default: // Address/Parity frames: the address is the syndrome (mode_s.c:465, 554)
             mm.addr = mm.crc;
+            if (kind != kKindAP && kind != kKindAPCommB)
+                ++bad;
             break;
-        default:
-            return -2;
     }
-    if (mm.msgtype == 11 || mm.msgtype == 17 || mm.msgtype == 18)
-        mm.addr = aa_field(msg);
-    if (((r.w0 >> 28) & 3u) != mm.correctedbits && mm.msgtype != 11)
-        ++mismatches_;
-    // the only place addresses enter the filter
-    if (!mm.correctedbits && (mm.msgtype == 17 || (mm.msgtype == 11 && iid == 0)))
-        filter_.add(mm.addr);
-    // decodeExtendedSquitter (mode_s.c:1373-1428) runs later in decodeModesMessage and may flag the address
-    if (mm.msgtype == 18 && df18_non_icao(mm.msg))
-        mm.addr |= 1u << 24;
-    return 0;
+    if (mm.correctedbits != errors || (mm.msgtype == 11 || mm.msgtype == 17 || mm.msgtype == 18 ? (mm.addr & 0xffffffu) != (r.w1 & 0xffffffu) : false))
+        ++bad;
+
+    // demod_2400.c:387-399
+    const int signal_len = a.long_frame ? 268 : 134;
+    const double signal_power = r.power / 65535.0 / 65535.0;
+    mm.signalLevel = signal_power / signal_len;
+    *signal_power_out = signal_power;
+    memset(mm.msg + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
+    memset(mm.verbatim + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
+    return bad;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -289,62 +467,37 @@ int Resolver::decode(const LiveRec &r, b200_message &mm) {
 
 namespace {
 
-// what skip-ahead hides, as eight 16-bit counters in two words (a frame body hides at most 268
-// positions): lo = preambles | bad << 16 | unknown << 32 | phase0 << 48, hi = phase1..phase4
-struct DeadCount {
-    uint64_t lo = 0, hi = 0;
-    uint32_t preambles() const { return (uint32_t) (lo & 0xffff); }
-    uint32_t bad() const { return (uint32_t) ((lo >> 16) & 0xffff); }
-    uint32_t unknown() const { return (uint32_t) ((lo >> 32) & 0xffff); }
-    uint32_t phase(int k) const { return (uint32_t) (k == 0 ? (lo >> 48) : (hi >> (16 * (k - 1)))) & 0xffff; }
-};
-
-struct DeadLut {
-    uint64_t lo[64], hi[64]; // indexed by trymask | unknown << 5
-    DeadLut() {
-        for (uint32_t i = 0; i < 64; ++i) {
-            const uint32_t tm = i & 31u, unk = i >> 5;
-            lo[i] = 1ull | ((uint64_t) (unk ? 0 : 1) << 16) | ((uint64_t) unk << 32) | ((uint64_t) (tm & 1u) << 48);
-            hi[i] = (uint64_t) ((tm >> 1) & 1u) | ((uint64_t) ((tm >> 2) & 1u) << 16) | ((uint64_t) ((tm >> 3) & 1u) << 32) |
-                    ((uint64_t) ((tm >> 4) & 1u) << 48);
-        }
-    }
-};
-const DeadLut kDeadLut;
-
-// dead positions in (lo, hi] that a skip-ahead hides (they are in the per-block totals K2 made);
-// `rank` = dead entries of lo's tile in front of lo (LivePos::dead_rank)
+// sums of LiveHidden packs (their 16-bit fields hold one frame body each)
 struct HiddenTotals {
-    uint32_t preambles = 0, bad = 0, unknown = 0, phase[5] = {0, 0, 0, 0, 0};
-};
-
-void count_dead(const SpanView &v, uint64_t lo, uint64_t hi, uint32_t rank, HiddenTotals &total) {
-    if (hi <= lo)
-        return;
-    // tile t covers positions [t*kTile - kPosShift, (t+1)*kTile - kPosShift)
-    const uint32_t t0 = (uint32_t) ((lo + kPosShift) / kTile), t1 = (uint32_t) ((hi + kPosShift) / kTile);
-    DeadCount dc; // one frame body: at most 268 entries, the 16-bit fields cannot overflow
-    for (uint32_t t = t0; t <= t1 && t < v.ntiles; ++t) {
-        const TileOut &to = v.tiles[t];
-        const uint32_t *d = v.dead + to.dead_off, *dend = d + to.ndead;
-        const int64_t base = (int64_t) t * kTile - kPosShift;
-        const uint32_t *it = (t == t0) ? d + rank : d;
-        const int64_t last = (int64_t) hi - base; // last tile-local index counted
-        for (; it != dend && (int64_t) (*it & 0x1fffu) <= last; ++it) {
-            const uint32_t key = (*it >> 13) & 63u; // trymask | unknown << 5
-            dc.lo += kDeadLut.lo[key];
-            dc.hi += kDeadLut.hi[key];
-        }
+    uint64_t preambles = 0, bad = 0, unknown = 0, phase[5] = {0, 0, 0, 0, 0};
+    void add(uint64_t lo, uint64_t hi) {
+        preambles += lo & 0xffff;
+        bad += (lo >> 16) & 0xffff;
+        unknown += (lo >> 32) & 0xffff;
+        phase[0] += lo >> 48;
+        phase[1] += hi & 0xffff;
+        phase[2] += (hi >> 16) & 0xffff;
+        phase[3] += (hi >> 32) & 0xffff;
+        phase[4] += hi >> 48;
     }
-    total.preambles += dc.preambles();
-    total.bad += dc.bad();
-    total.unknown += dc.unknown();
-    for (int k = 0; k < 5; ++k)
-        total.phase[k] += dc.phase(k);
-}
+    void add(const HiddenTotals &o) {
+        preambles += o.preambles;
+        bad += o.bad;
+        unknown += o.unknown;
+        for (int k = 0; k < 5; ++k)
+            phase[k] += o.phase[k];
+    }
+};
 
 } // namespace
 
+// Two halves.  The walk is the exact sequential loop of demodulate2400 over the live positions, reduced to
+// what depends on order: skip-ahead, the ICAO filter (scores, decode-time rejects, adds, the per-block
+// expiry), the statistics whose floating-point sums depend on order.  It touches 16 bytes per position and
+// the head of each record and leaves a 24-byte note per accepted frame.  The assembly of the messages from
+// those notes -- CRC recomputed and repaired on the host as a cross-check, timestamps, signal level, the
+// un-counting of dead positions a frame body hides -- is independent per frame and is shared out over the
+// worker pool when a span carries thousands of frames.
 void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::vector<b200_block_info> &blocks) {
     const uint64_t n = v.nsamples, B = v.block_samples;
     // ifileRun: full blocks, then (at end of stream) one short block, which is empty when the stream
@@ -352,13 +505,9 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
     const uint64_t nfull = n / B;
     const uint64_t nblocks = nfull + (v.final_span ? 1 : 0);
 
-    // room for every live position of the span: no reallocation (and no first-touch page faults after the
-    // first span of this size) inside the walk
-    msgs.reserve(msgs.size() + v.n_live + v.n_ac_hits + 64);
-    skips_.clear();
-    skips_.reserve((size_t) v.n_live + 64);
-    // what skip-ahead hides is un-counted after the walk: the dead list it needs may still be arriving
-    std::vector<Skip> &skips = skips_;
+    std::vector<Accepted> &acc = accepted_;
+    acc.clear();
+    acc.reserve((size_t) v.n_live + v.n_ac_hits + 64);
     // Mode A/C hits in stream order (the kernel appends them as it finds them)
     if (v.n_ac_hits > 1)
         std::sort(v.ac_hits, v.ac_hits + v.n_ac_hits, [](const AcHit &a, const AcHit &b) { return a.q < b.q; });
@@ -367,6 +516,8 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
     // walk is sequential in both, which the hardware prefetcher follows.
     uint32_t live_i = 0;
     const uint32_t n_live = v.n_live;
+    uint32_t tried[32]; // positions walked, by try mask: demod_preamblePhase (demod_2400.c:184) is added up at the end
+    memset(tried, 0, sizeof(tried));
 
     for (uint64_t k = 0; k < nblocks; ++k) {
         const uint64_t b0 = k * B, b1 = std::min(n, b0 + B), nk = b1 - b0;
@@ -395,7 +546,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
         while (live_i < n_live && v.live[live_i].pos < b1) {
             const LivePos *lp = &v.live[live_i];
             const uint64_t p = lp->pos;
-            ++live_i;
+            const uint32_t li = live_i++;
             if (skipping && p <= skip_until)
                 continue;
             const uint32_t trymask = lp->info & 31u, nrec = (lp->info >> 8) & 7u;
@@ -405,8 +556,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             // counts; one without a record scores -2, which only ever wins as the very first phase tried
             // (a later phase must score strictly higher, and nothing scores below -2); the records are in
             // phase order, so walking them alone gives the same pick as walking the five phases
-            for (int q = 0; q < 5; ++q)
-                stats_.demod_preamblePhase[q] += (trymask >> q) & 1u;
+            ++tried[trymask];
             int bestscore = -42, bestphase = -1;
             const LiveRec *best = nullptr;
             if (trymask) {
@@ -433,50 +583,45 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                 continue;
             }
 
-            msgs.emplace_back(); // built in place (room was reserved); taken back if the decoder rejects it
-            b200_message &mm = msgs.back();
-            memset(&mm, 0, sizeof(mm));
             const uint64_t j = p - b0;
-            mm.timestampMsg = sampleTimestamp + j * 5 + (8 + 56) * 12 + (uint64_t) bestphase; // demod_2400.c:358
-            mm.sysTimestampMsg = sysTimestamp + (mm.timestampMsg - sampleTimestamp) / 12000U; // :361
-            ifile_now_ = mm.sysTimestampMsg;                                                   // :364-366
-            mm.score = bestscore;
-            mm.bestphase = (uint8_t) bestphase;
+            const uint64_t timestampMsg = sampleTimestamp + j * 5 + (8 + 56) * 12 + (uint64_t) bestphase; // demod_2400.c:358
+            ifile_now_ = sysTimestamp + (timestampMsg - sampleTimestamp) / 12000U;                        // :361, 364-366
 
-            const int result = decode(*best, mm); // demod_2400.c:372
+            const int result = admit(*best); // demod_2400.c:372
             if (result < 0) {
                 if (result == -1)
                     stats_.demod_rejected_unknown_icao++;
                 else
                     stats_.demod_rejected_bad++;
-                msgs.pop_back();
                 continue;
             }
-            stats_.demod_accepted[mm.correctedbits]++;
+            stats_.demod_accepted[(best->w0 >> 28) & 3u]++;
             stats_.demod_bestPhase[bestphase - 4]++;
 
             // demod_2400.c:387-408
-            const int msglen = (best->msg[0] & 0x80) ? 112 : 56; // :350, from the uncorrected DF
-            const int signal_len = msglen * 12 / 5;
-            const uint64_t scaled = best->power;
-            const double signal_power = scaled / 65535.0 / 65535.0;
-            mm.signalLevel = signal_power / signal_len;
-            stats_.signal_power_sum += signal_power;
+            // (the floating-point side of :387-408 -- signal power and level, their running sum, peak and strong
+            // count -- is done with the assembly: the divisions are per frame, only the sum is ordered)
+            const bool long_frame = (best->msg[0] & 0x80) != 0; // :350, from the uncorrected DF
+            const int signal_len = long_frame ? 268 : 134;
             stats_.signal_power_count += (uint64_t) signal_len;
-            sum_scaled_signal_power += scaled;
-            if (mm.signalLevel > stats_.peak_signal_power)
-                stats_.peak_signal_power = mm.signalLevel;
-            if (mm.signalLevel > 0.50119)
-                stats_.strong_signal_count++;
+            sum_scaled_signal_power += best->power;
 
             // demod_2400.c:416: skip the frame body; the for loop ends at the block boundary
             skipping = true;
             skip_until = std::min<uint64_t>(p + (uint64_t) signal_len, b1 - 1);
-            skips.push_back({p, skip_until, lp->dead_rank});
 
             stats_.messages_total++; // useModesMessage, mode_s.c:2149
-            memset(mm.msg + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
-            memset(mm.verbatim + mm.msgbits / 8, 0, 14 - mm.msgbits / 8);
+            Accepted a;
+            a.index = li;
+            a.rec = (uint32_t) (best - v.liverecs);
+            a.score = bestscore;
+            a.block = (uint32_t) k;
+            a.phase = (uint8_t) bestphase;
+            a.modeac = 0;
+            a.long_frame = long_frame ? 1 : 0;
+            a.pad = 0;
+            a.pad2 = 0;
+            acc.push_back(a);
         }
 
         // demodulate2400AC (readsb.c:831-833, demod_2400.c:522-708) runs after demodulate2400 on the same
@@ -484,27 +629,23 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
         {
             uint64_t next_ok = 0; // first data index that may be examined again
             for (; ac_i < v.n_ac_hits && (uint64_t) v.ac_hits[ac_i].q < (k + 1) * B; ++ac_i) {
-                const AcHit h = v.ac_hits[ac_i];
-                const uint64_t f1 = (uint64_t) h.q - k * B;
+                const uint64_t f1 = (uint64_t) v.ac_hits[ac_i].q - k * B;
                 if (f1 < next_ok)
                     continue;
-                b200_message mm;
-                memset(&mm, 0, sizeof(mm));
-                mm.timestampMsg = sampleTimestamp + (h.f1_clock + 87 * 14) / 5;                           // :697, at F2
-                mm.sysTimestampMsg = sysTimestamp + (mm.timestampMsg - sampleTimestamp) / 12000U; // :700
-                mm.msgtype = 32;                                                                   // mode_ac.c:171
-                mm.msgbits = 16;
-                mm.msg[0] = mm.verbatim[0] = (uint8_t) (h.modeac >> 8);
-                mm.msg[1] = mm.verbatim[1] = (uint8_t) h.modeac;
-                mm.addr = (h.modeac & 0x0000FF7Fu) | (1u << 24);                                        // mode_ac.c:180
-                msgs.push_back(mm);
+                Accepted a;
+                memset(&a, 0, sizeof(a));
+                a.index = ac_i;
+                a.block = (uint32_t) k;
+                a.modeac = 1;
+                acc.push_back(a);
                 stats_.messages_total++; // useModesMessage, mode_s.c:2149
                 ++modeac_;
                 next_ok = f1 + 70; // f1_sample += 69, then the loop's ++
             }
         }
 
-        // positions no message can come from: K2's per-block totals minus what skip-ahead hid
+        // positions no message can come from: K2's per-block totals (what skip-ahead hid of them is taken
+        // out again below)
         if (nk) {
             const BlockDead &bd = v.block_dead[k];
             stats_.demod_preambles += bd.preambles;
@@ -523,26 +664,61 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
         filter_.expire(ifile_now_); // readsb.c:331
     }
 
-    // dead positions hidden by skip-ahead were counted in K2's per-block totals: take them out again
-    // (the counters are sums, so the order does not matter)
-    if (v.dead_ready)
-        v.dead_ready(v.dead_ctx); // also: the caller reuses the buffers once we return
-    HiddenTotals hidden;
-    auto dead_line = [&](const Skip &sk) { // where the count of a skip starts reading
-        const uint32_t t = (uint32_t) ((sk.lo + kPosShift) / kTile);
-        return v.dead + v.tiles[t].dead_off + sk.rank;
+    for (uint32_t mask = 1; mask < 32; ++mask)
+        for (int q = 0; q < 5; ++q)
+            if ((mask >> q) & 1u)
+                stats_.demod_preamblePhase[q] += tried[mask];
+
+    // ---- assembly: one message per note, in place ----
+    const size_t base = msgs.size(), count = acc.size();
+    msgs.resize(base + count);
+    b200_message *out = msgs.data() + base;
+    const int nworkers = pool_ ? pool_->size() : 1;
+    std::vector<HiddenTotals> hidden((size_t) nworkers);
+    std::vector<uint64_t> bad((size_t) nworkers, 0);
+    signal_power_.resize(count);
+    double *power = signal_power_.data();
+    auto assemble = [&](int worker, size_t lo, size_t hi) {
+        HiddenTotals &h = hidden[(size_t) worker];
+        uint64_t &nb = bad[(size_t) worker];
+        for (size_t i = lo; i < hi; ++i) {
+            const Accepted &a = acc[i];
+            nb += build(v, a, out[i], &power[i]);
+            if (!a.modeac) {
+                // dead positions the frame body hides were counted in K2's per-block totals
+                const LiveHidden &lh = v.hidden[a.index];
+                if (a.long_frame)
+                    h.add(lh.long_lo, lh.long_hi);
+                else
+                    h.add(lh.short_lo, lh.short_hi);
+            }
+        }
     };
-    constexpr size_t kAhead = 8;
-    for (size_t i = 0; i < skips.size(); ++i) {
-        if (i + kAhead < skips.size())
-            __builtin_prefetch(dead_line(skips[i + kAhead]));
-        count_dead(v, skips[i].lo, skips[i].hi, skips[i].rank, hidden);
+    if (pool_ && count >= 4096)
+        pool_->run(count, 1024, assemble);
+    else
+        assemble(0, 0, count);
+    // demod_2400.c:398-407 in message order: the running sum of doubles is the one thing here that depends on it
+    for (size_t i = 0; i < count; ++i) {
+        if (acc[i].modeac)
+            continue;
+        stats_.signal_power_sum += power[i];
+        const double level = out[i].signalLevel;
+        if (level > stats_.peak_signal_power)
+            stats_.peak_signal_power = level;
+        if (level > 0.50119)
+            stats_.strong_signal_count++;
     }
-    stats_.demod_preambles -= hidden.preambles;
-    stats_.demod_rejected_bad -= hidden.bad;
-    stats_.demod_rejected_unknown_icao -= hidden.unknown;
+    HiddenTotals total;
+    for (int w = 0; w < nworkers; ++w) {
+        total.add(hidden[(size_t) w]);
+        mismatches_ += bad[(size_t) w];
+    }
+    stats_.demod_preambles -= (uint32_t) total.preambles;
+    stats_.demod_rejected_bad -= (uint32_t) total.bad;
+    stats_.demod_rejected_unknown_icao -= (uint32_t) total.unknown;
     for (int q = 0; q < 5; ++q)
-        stats_.demod_preamblePhase[q] -= hidden.phase[q];
+        stats_.demod_preamblePhase[q] -= (uint32_t) total.phase[q];
 }
 
 } // namespace b200

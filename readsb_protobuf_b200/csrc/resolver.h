@@ -50,28 +50,27 @@ struct SpanView {
     uint32_t block_samples;
     bool final_span;
     uint32_t format;
-    uint32_t ntiles;
-    const TileOut *tiles;     // per tile: where its dead list is (the live_off / liverec_off fields are K2's scratch)
-    const uint32_t *dead;
-    // live positions of the span in stream order and their records (order_live_kernel packed K2's per-tile
-    // lists): live[i].pad = index of the position's first record in liverecs
+    // live positions of the span in stream order and their records (order_live packed K2's per-tile
+    // lists): live[i].pad = index of the position's first record in liverecs; hidden[i] = what a frame
+    // accepted at live[i] hides from the block's dead totals
     const LivePos *live;
     uint32_t n_live;
     const LiveRec *liverecs;
+    const LiveHidden *hidden;
     const BlockDead *block_dead;               // [nblocks]
     const unsigned long long *block_sums_u64;  // [nblocks][2]
     const double *block_sums_f64;              // [nblocks][2]
     // Mode A/C hits of the span, unordered; the resolver sorts them in place
     AcHit *ac_hits = nullptr;
     uint32_t n_ac_hits = 0;
-    // the dead list may still be arriving: called once, before its first use (nullptr = it is there)
-    void (*dead_ready)(void *ctx) = nullptr;
-    void *dead_ctx = nullptr;
 };
+
+class WorkerPool;
 
 class Resolver {
   public:
-    Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), startup_(startup_time_ms) { reset(); }
+    Resolver(const CrcTables *crc, uint64_t startup_time_ms);
+    ~Resolver();
     void reset();
     // Appends the span's messages and block infos; updates the running statistics.
     void resolve(const SpanView &v, std::vector<b200_message> &msgs, std::vector<b200_block_info> &blocks);
@@ -80,9 +79,21 @@ class Resolver {
     uint64_t gpu_host_mismatches() const { return mismatches_; }
     uint64_t modeac_count() const { return modeac_; } // Modes.stats_current.demod_modeac
 
+    // one accepted frame (or Mode A/C reply) of the sequential walk, materialised afterwards: 24 bytes
+    struct Accepted {
+        uint32_t index;  // live position (Mode S) or hit (Mode A/C) of the span
+        uint32_t rec;    // absolute index of the winning record
+        int32_t score;
+        uint32_t block;  // mag_buf of the span
+        uint8_t phase, modeac, long_frame, pad;
+        uint32_t pad2;
+    };
+
   private:
     int score(const LiveRec &r) const;
-    int decode(const LiveRec &r, b200_message &mm);
+    int admit(const LiveRec &r);                                    // the filter-dependent part of decodeModesMessage
+    // the rest of it; returns CRC disagreements, *signal_power = the frame's signal power (demod_2400.c:397)
+    uint32_t build(const SpanView &v, const Accepted &a, b200_message &mm, double *signal_power) const;
     const CrcTables *crc_;
     uint64_t startup_;
     IcaoFilter filter_;
@@ -90,11 +101,9 @@ class Resolver {
     uint64_t ifile_now_;
     uint64_t mismatches_;
     uint64_t modeac_;
-    struct Skip { // an accepted frame's skip-ahead: dead positions in (lo, hi] are un-counted afterwards
-        uint64_t lo, hi;
-        uint32_t rank;
-    };
-    std::vector<Skip> skips_;
+    std::vector<Accepted> accepted_;
+    std::vector<double> signal_power_;
+    WorkerPool *pool_;
 };
 
 } // namespace b200
