@@ -104,58 +104,84 @@ struct LaneSums {
     uint32_t g8_next;                // 8-sample group of the run at which the next mag_buf starts (>= 32: not in this run)
 };
 
-__device__ __noinline__ void lane_flush(unsigned long long *block_sums, LaneSums &s) {
+// by value, so that the caller's sums stay in registers
+__device__ __noinline__ void add_block_sums(unsigned long long *block_sums, uint32_t blk, unsigned long long level, unsigned long long power) {
+    if (level | power) {
+        atomicAdd(&block_sums[2 * (size_t) blk], level);
+        atomicAdd(&block_sums[2 * (size_t) blk + 1], power);
+    }
+}
+
+__device__ __forceinline__ void lane_flush(unsigned long long *block_sums, LaneSums &s) {
     s.level += s.level32;
     s.power += (unsigned long long) s.lo32 + ((unsigned long long) s.hi32 << 8);
     s.level32 = s.lo32 = s.hi32 = 0;
-    if (s.level | s.power) {
-        atomicAdd(&block_sums[2 * (size_t) s.blk], s.level);
-        atomicAdd(&block_sums[2 * (size_t) s.blk + 1], s.power);
-    }
+    add_block_sums(block_sums, s.blk, s.level, s.power);
     s.level = s.power = 0;
 }
 
-// One pair of samples enters the window (slots i0 = 2 * jj and i0 + 1 of the 32-slot ring), and the two scan
-// positions whose 19-sample windows end with it (window starts i0 - 18 and i0 - 17) are tested.
-// demod_2400.c:276-330 as sign tests, see scan_kernel: with Q/D/T folded into three-input adds,
-//   bn  = m5 + m8 + m16 + m17 + m18                        c = m1 - m2 + m3 + m4 + m9 + m12
-//   E0  = 32 c + 31 - thr bn     E45 = E0 - 32 (m10 - m11)     E67 = E0 + 32 (m10 - m11)
-//   E8  = E67 + 96 (m2 - m3) - 32 m9                            g = (m7 - m1) & (m14 - m12) & (m15 - m12)
-// a test passes when its E is non-negative, the pre-check when g is negative.
+// One pair of samples enters the window (slots s0 = 2 * JJ and s0 + 1 of the 32-slot rings), and the two scan
+// positions whose 19-sample windows end with it (window starts s0 - 18 and s0 - 17) are tested.
+// demod_2400.c:276-330 as sign tests (see scan_kernel), arranged so that what neighbouring positions share is
+// computed once, when the sample that completes it arrives:
+//   D[x] = m[x] - m[x+1]                      used as m2 - m3 of position x - 2 and as m10 - m11 of position x - 10
+//   F[x] = 32 (m[x+1] - m[x+2] + m[x+3] + m[x+4]) + 15
+//                                             the pulse pattern of one preamble half: position x uses F[x] + F[x+8]
+// and per position
+//   bn  = m5 + m8 + m16 + m17 + m18
+//   E0  = F[i] + F[i+8] + 1 - thr bn          (= 32 (m1 - m2 + m3 + m4 + m9 - m10 + m11 + m12) + 31 - thr bn)
+//   E45 = E0                                   phases 4, 5: common3456 - diff_10_11 >= ref_level
+//   E67 = E0 + 64 D[i+10]                      phases 6, 7: common3456 + diff_10_11
+//   E8  = E67 + 96 D[i+2] - 32 m9              phase 8:     sum_1_4 + 2 diff_2_3 + diff_10_11 + m12
+//   g   = (m7 - m1) & (m14 - m12) & (m15 - m12)
+// a test passes when its E is non-negative, the pre-check when g is negative.  Everything is exact int32:
+// |32 X| < 2^24 and thr * bn < 2^31 for thresholds up to 6000.
+struct Window {
+    int m[32], D[32], F[32];
+};
+
 template <int JJ>
-__device__ __forceinline__ void test_pair(const int (&m)[32], int nthr, uint32_t &s45, uint32_t &s67, uint32_t &s8, uint32_t &pm) {
+__device__ __forceinline__ void test_pair(Window &w, int nthr, uint32_t &s45, uint32_t &s67, uint32_t &s8, uint32_t &pm) {
+    constexpr int s0 = 2 * JJ + 64; // slot of the pair's first sample (before the & 31)
+#define M_(x) w.m[(x) & 31]
+#define D_(x) w.D[(x) & 31]
+#define F_(x) w.F[(x) & 31]
+    D_(s0 - 1) = M_(s0 - 1) - M_(s0);
+    D_(s0) = M_(s0) - M_(s0 + 1);
+    F_(s0 - 4) = (D_(s0 - 3) + M_(s0 - 1) + M_(s0)) * 32 + 15;
+    F_(s0 - 3) = (D_(s0 - 2) + M_(s0) + M_(s0 + 1)) * 32 + 15;
 #pragma unroll
     for (int odd = 0; odd < 2; ++odd) {
-        constexpr int kMask = 31;
-        const int b = 2 * JJ - 18 + odd + 64; // window start slot (before the & 31)
-#define M_(k) m[(b + (k)) & kMask]
-        const int bn = M_(5) + M_(8) + M_(16) + M_(17) + M_(18);
-        const int d2 = M_(2) - M_(3), d10 = M_(10) - M_(11);
-        const int c = M_(1) + M_(4) + M_(9) + M_(12) - d2;
-        const int E0 = nthr * bn + (c * 32 + 31);
-        const int E45 = d10 * -32 + E0;
-        const int E67 = d10 * 32 + E0;
-        const int E8 = M_(9) * -32 + (d2 * 96 + E67);
-        const int g = (M_(7) - M_(1)) & (M_(14) - M_(12)) & (M_(15) - M_(12));
-#undef M_
+        const int i = s0 - 18 + odd; // window start slot
+        const int bn = (M_(i + 5) + M_(i + 8) + M_(i + 16)) + (M_(i + 17) + M_(i + 18));
+        const int E45 = (nthr * bn + F_(i)) + F_(i + 8) + 1;
+        const int E67 = D_(i + 10) * 64 + E45;
+        const int E8 = M_(i + 9) * -32 + (D_(i + 2) * 96 + E67);
+        const int g = (M_(i + 7) - M_(i + 1)) & (M_(i + 14) - M_(i + 12)) & (M_(i + 15) - M_(i + 12));
         s45 = __funnelshift_l((uint32_t) E45, s45, 1);
         s67 = __funnelshift_l((uint32_t) E67, s67, 1);
         s8 = __funnelshift_l((uint32_t) E8, s8, 1);
         pm = __funnelshift_l((uint32_t) g, pm, 1);
     }
+#undef M_
+#undef D_
+#undef F_
 }
 
 struct TileMasks { // bit k of word w: lane-local position 32 w + k - 18 (words 0..8; bits 0..17 of word 0 are not this lane's)
     uint32_t b45[kBodies + 1], b67[kBodies + 1], b8[kBodies + 1];
 };
 
-template <bool SLICE>
+// ODD16: the runs start 16 bytes past a 32-byte boundary (the usual case: a tile starts kHead = 328 samples = 656
+// bytes before a multiple of 16 KiB).  The 256-bit loads then fetch the aligned blocks around the run and a body
+// takes the upper half of one block, a whole block and the lower half of a third -- register renaming, no shuffling.
+template <bool SLICE, bool ODD16>
 __device__ __forceinline__ void scan2_tile(const ScanArgs &a, WarpCand &cx, const uint32_t tile, const unsigned char *s_lut, uint32_t *s_apron) {
     const int lane = threadIdx.x & 31;
     const int nthr = -a.threshold;
     const long long c0 = (long long) tile * kTile - kHead; // first window-start sample of the tile (>= 0: interior)
     const long long s_run = c0 + (long long) lane * kRun;  // first sample of the lane's run
-    const uint8_t *gp = a.iq + s_run * 2;
+    const uint8_t *gp = a.iq + s_run * 2 - (ODD16 ? 16 : 0); // 32-byte aligned
     uint16_t *gm = a.mag + (size_t) tile * kTile + (size_t) lane * kRun;
 
     // ---- block sums bookkeeping ----
@@ -178,22 +204,43 @@ __device__ __forceinline__ void scan2_tile(const ScanArgs &a, WarpCand &cx, cons
         s_apron[31 * kApronWords + lane] = m0 | (m1 << 16);
     }
 
-    int m[32];
+    Window win;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-        m[i] = 0;
+        win.m[i] = win.D[i] = win.F[i] = 0;
     TileMasks tm;
 
-    uint32_t nxt[16]; // the next body's 32 samples, in flight
+    uint32_t nxt[16]; // the next body's two aligned 32-byte blocks, in flight
+    uint32_t carry[4] = {0, 0, 0, 0}; // ODD16: the upper half of the block the previous body ended in
+    if (ODD16) {
+        uint32_t first[8];
+        ldg256(first, gp);
+        gp += 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            carry[i] = first[4 + i];
+    }
     ldg256(*reinterpret_cast<uint32_t(*)[8]>(&nxt[0]), gp);
     ldg256(*reinterpret_cast<uint32_t(*)[8]>(&nxt[8]), gp + 32);
 
 #pragma unroll 1
     for (int body = 0; body < kBodies; ++body) {
         uint32_t cur[16];
+        if (ODD16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            cur[i] = nxt[i];
+            for (int i = 0; i < 4; ++i)
+                cur[i] = carry[i];
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+                cur[4 + i] = nxt[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                carry[i] = nxt[12 + i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                cur[i] = nxt[i];
+        }
         if (body + 1 < kBodies) {
             ldg256(*reinterpret_cast<uint32_t(*)[8]>(&nxt[0]), gp + (body + 1) * 64);
             ldg256(*reinterpret_cast<uint32_t(*)[8]>(&nxt[8]), gp + (body + 1) * 64 + 32);
@@ -219,9 +266,9 @@ __device__ __forceinline__ void scan2_tile(const ScanArgs &a, WarpCand &cx, cons
             const uint32_t bytes = __byte_perm(v, 0, 0x3120); // lo8(m0), lo8(m1), hi8(m0), hi8(m1)
             sums.lo32 = dp2a_lo_u(v, bytes, sums.lo32);
             sums.hi32 = dp2a_hi_u(v, bytes, sums.hi32);
-            m[(2 * JJ) & 31] = (int) m0;
-            m[(2 * JJ + 1) & 31] = (int) m1;
-            test_pair<JJ>(m, nthr, s45, s67, s8, pm);
+            win.m[(2 * JJ) & 31] = (int) m0;
+            win.m[(2 * JJ + 1) & 31] = (int) m1;
+            test_pair<JJ>(win, nthr, s45, s67, s8, pm);
         };
 #define STEP_(J) step(std::integral_constant<int, J>{});
         STEP_(0) STEP_(1) STEP_(2) STEP_(3) STEP_(4) STEP_(5) STEP_(6) STEP_(7)
@@ -258,9 +305,9 @@ __device__ __forceinline__ void scan2_tile(const ScanArgs &a, WarpCand &cx, cons
         uint32_t s45 = 0, s67 = 0, s8 = 0, pm = 0;
         auto step = [&](auto jj_c) {
             constexpr int JJ = decltype(jj_c)::value;
-            m[(2 * JJ) & 31] = (int) (V[JJ] & 0xffffu);
-            m[(2 * JJ + 1) & 31] = (int) (V[JJ] >> 16);
-            test_pair<JJ>(m, nthr, s45, s67, s8, pm);
+            win.m[(2 * JJ) & 31] = (int) (V[JJ] & 0xffffu);
+            win.m[(2 * JJ + 1) & 31] = (int) (V[JJ] >> 16);
+            test_pair<JJ>(win, nthr, s45, s67, s8, pm);
         };
 #define STEP_(J) step(std::integral_constant<int, J>{});
         STEP_(0) STEP_(1) STEP_(2) STEP_(3) STEP_(4) STEP_(5) STEP_(6) STEP_(7) STEP_(8)
@@ -357,7 +404,7 @@ __device__ __forceinline__ void scan2_tile(const ScanArgs &a, WarpCand &cx, cons
     cx.ncand_total += total;
 }
 
-template <bool SLICE>
+template <bool SLICE, bool ODD16>
 __global__ void __launch_bounds__(kScan2Threads, 1) scan2_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) unsigned char smem2[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -391,7 +438,7 @@ __global__ void __launch_bounds__(kScan2Threads, 1) scan2_kernel(const ScanArgs 
         const uint32_t tile = a.fast_lo + q;
         if (tile >= a.fast_hi)
             break;
-        scan2_tile<SLICE>(a, cx, tile, smem2, s_apron);
+        scan2_tile<SLICE, ODD16>(a, cx, tile, smem2, s_apron);
     }
     if (lane == 0 && cx.ncand_total) // one same-address atomic per warp, not per tile
         atomicAdd(&a.counters->n_cand, cx.ncand_total);
@@ -400,15 +447,19 @@ __global__ void __launch_bounds__(kScan2Threads, 1) scan2_kernel(const ScanArgs 
 } // namespace
 
 cudaError_t scan2_configure() {
-    cudaError_t e = cudaFuncSetAttribute(scan2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScan2Smem);
-    if (e != cudaSuccess)
+    cudaError_t e;
+#define CFG2(S, O)                                                                                                  \
+    e = cudaFuncSetAttribute(scan2_kernel<S, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScan2Smem);   \
+    if (e != cudaSuccess)                                                                                           \
         return e;
-    return cudaFuncSetAttribute(scan2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScan2Smem);
+    CFG2(true, true) CFG2(true, false) CFG2(false, true) CFG2(false, false)
+#undef CFG2
+    return cudaSuccess;
 }
 
 bool scan2_supports(const ScanArgs &a) {
     // uc8 through the table; thresholds for which 96 m + thr * 5 m stays inside 32 bits (any configured value does)
-    return a.format == 0 && a.block_samples % 8 == 0 && a.block_samples >= 8;
+    return a.format == 0 && a.block_samples % 8 == 0 && a.block_samples >= 8 && ((uintptr_t) a.iq & 15u) == 0;
 }
 
 void scan2_tile_range(uint64_t nsamples, uint32_t &lo, uint32_t &hi) {
@@ -430,10 +481,19 @@ cudaError_t launch_scan2(const ScanArgs &a, int mode, int grid, cudaStream_t str
     const int useful = (int) ((a.fast_hi - a.fast_lo + kScan2Warps - 1) / kScan2Warps);
     if (grid > useful)
         grid = useful;
-    if (mode)
-        scan2_kernel<true><<<grid, kScan2Threads, kScan2Smem, stream>>>(a);
-    else
-        scan2_kernel<false><<<grid, kScan2Threads, kScan2Smem, stream>>>(a);
+    // a run starts at iq + 2 * (tile * kTile - kHead + lane * 256): 16 or 0 bytes past a 32-byte boundary
+    const bool odd16 = (((uintptr_t) a.iq - 2 * (uintptr_t) kHead) & 31u) != 0;
+    if (mode) {
+        if (odd16)
+            scan2_kernel<true, true><<<grid, kScan2Threads, kScan2Smem, stream>>>(a);
+        else
+            scan2_kernel<true, false><<<grid, kScan2Threads, kScan2Smem, stream>>>(a);
+    } else {
+        if (odd16)
+            scan2_kernel<false, true><<<grid, kScan2Threads, kScan2Smem, stream>>>(a);
+        else
+            scan2_kernel<false, false><<<grid, kScan2Threads, kScan2Smem, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 
