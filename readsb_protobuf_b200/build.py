@@ -53,7 +53,7 @@ def cuda_sources():
 
 
 def cuda_headers():
-    return sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
+    return sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inl")) + sorted((ROOT / "include").glob("*.h"))
 
 
 def find_nvcc() -> str:

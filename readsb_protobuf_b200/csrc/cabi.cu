@@ -485,6 +485,13 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     return a;
 }
 
+// K1a: scan2_kernel when the span has interior uc8 tiles for it (it then takes the edge tiles along), else scan_kernel
+static cudaError_t launch_k1a(const ScanArgs &sa, int mode, int grid, cudaStream_t s) {
+    if (sa.fast_hi > sa.fast_lo)
+        return launch_scan2(sa, mode, grid, s);
+    return launch_scan(sa, mode, grid, s);
+}
+
 static SliceArgs make_slice_args(const ScanArgs &sa) {
     SliceArgs b;
     memset(&b, 0, sizeof(b));
@@ -559,8 +566,7 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
             *launches += c.span_fsums ? 0 : 1;
     }
     CUDA_TRY(cudaEventRecord(c.ev_begin, s));
-    CUDA_TRY(launch_scan2(sa, 1, d->scan_grid, s));
-    CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
+    CUDA_TRY(launch_k1a(sa, 1, d->scan_grid, s));
     CUDA_TRY(cudaEventRecord(c.ev_k1, s));
     CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
     CUDA_TRY(cudaEventRecord(c.ev_k1b, s));
@@ -760,7 +766,8 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
 
     // whole mag_bufs, and close to two tiles per resident K1a warp: a chunk is then two full waves
     // of the scan kernel instead of one full wave and a ragged one
-    const uint64_t two_waves = (uint64_t) 2 * d->scan_grid * kScanWarps * kTile - kTile; // tiles_for() adds one tile for the tail
+    const uint64_t k1a_warps = (uint64_t) k1a_warps_per_cta(d->eff_format);
+    const uint64_t two_waves = (uint64_t) 2 * d->scan_grid * k1a_warps * kTile - kTile; // tiles_for() adds one tile for the tail
     const uint64_t chunk_target = (d->sm_count > 0 && two_waves >= (16ull << 20) && two_waves <= (64ull << 20)) ? two_waves : kChunkTarget;
     const uint64_t chunk = std::max<uint64_t>(1, chunk_target / B) * B;
     // chunk i = [starts[i], starts[i + 1]), whole mag_bufs, as equal as possible (a short last chunk would run
@@ -780,7 +787,7 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
         const uint64_t nmain = std::max<uint64_t>(1, (main_blocks + main_big - 1) / main_big);
         uint64_t at = 0; // in mag_bufs
         // one wave of K1a = one tile per resident warp (tiles_for() adds a tile for the tail of a chunk)
-        const uint64_t wave = ((uint64_t) d->scan_grid * kScanWarps - 1) * kTile / B;
+        const uint64_t wave = ((uint64_t) d->scan_grid * k1a_warps - 1) * kTile / B;
         if (!ramp && wave > 0 && nb > 3 * wave) {
             // device-resident span: whole waves per chunk, so that only the last launch ends on a partial
             // wave -- one wave first (the host resolver starts early), then two at a time
@@ -1031,8 +1038,7 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
         return rc;
     ScanArgs sa = make_scan_args(d, c, (const uint8_t *) d_iq, d->d_head.p, nsamples, 0, kCandSlab, kRecSlab, nullptr);
     CUDA_TRY(cudaEventRecord(c.ev_begin, s));
-    CUDA_TRY(launch_scan2(sa, mode ? 1 : 0, d->scan_grid, s));
-    CUDA_TRY(launch_scan(sa, mode ? 1 : 0, d->scan_grid, s));
+    CUDA_TRY(launch_k1a(sa, mode ? 1 : 0, d->scan_grid, s));
     if (mode >= 2)
         CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
     CUDA_TRY(cudaEventRecord(c.ev_k1, s));
@@ -1132,8 +1138,7 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
     CUDA_TRY(cudaMemsetAsync(d->d_dbg_masks.p, 0, (size_t) nsamples + 16, s));
     ScanArgs sa = make_scan_args(d, c, d->d_iq.p, d->d_head.p, nsamples, 0, kTile, kTile * 5, nullptr);
     sa.dbg_masks = d->d_dbg_masks.p;
-    CUDA_TRY(launch_scan2(sa, 1, d->scan_grid, s));
-    CUDA_TRY(launch_scan(sa, 1, d->scan_grid, s));
+    CUDA_TRY(launch_k1a(sa, 1, d->scan_grid, s));
     CUDA_TRY(launch_slice(make_slice_args(sa), d->slice_grid, s));
     CUDA_TRY(cudaMemcpyAsync(c.h_counters.p, c.d_counters.p, sizeof(ScanCounters), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));

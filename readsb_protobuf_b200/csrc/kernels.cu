@@ -405,7 +405,13 @@ __device__ __forceinline__ uint32_t swizzle_pair(uint32_t w) {
     return w ^ ((w >> 7) & 0x003e003eu);
 }
 
-template <int FORMAT, bool SLICE, bool EDGE>
+// scan2_kernel's layout of the same table: entry i at i ^ ((i >> 5) & 0x38) (scan2.inl)
+__device__ __forceinline__ uint32_t swizzle_pair2(uint32_t w) {
+    return w ^ ((w >> 5) & 0x00380038u);
+}
+
+// SWZ: which shared-memory layout the uc8 table is staged in (1: scan_kernel's, 2: scan2_kernel's)
+template <int FORMAT, bool SLICE, bool EDGE, int SWZ = 1>
 __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, const uint32_t tile, const uint16_t *s_lut, uint32_t *s_buf) {
     constexpr int US = Fmt<FORMAT>::kUnitSamples, BPS = Fmt<FORMAT>::kBytes;
     constexpr int UNITS = kLanePos / US; // 16-byte units per lane per step
@@ -476,7 +482,8 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
         if (FORMAT == 0) {
 #pragma unroll
             for (int u = 0; u < UNITS; ++u) {
-                const uint32_t words[4] = {swizzle_pair(pre[u].x), swizzle_pair(pre[u].y), swizzle_pair(pre[u].z), swizzle_pair(pre[u].w)};
+                const uint32_t words[4] = {SWZ == 2 ? swizzle_pair2(pre[u].x) : swizzle_pair(pre[u].x), SWZ == 2 ? swizzle_pair2(pre[u].y) : swizzle_pair(pre[u].y),
+                                           SWZ == 2 ? swizzle_pair2(pre[u].z) : swizzle_pair(pre[u].z), SWZ == 2 ? swizzle_pair2(pre[u].w) : swizzle_pair(pre[u].w)};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     m[u * US + 2 * j] = s_lut[words[j] & 0xffffu];
@@ -862,6 +869,8 @@ cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stre
 #undef LAUNCH
     return cudaGetLastError();
 }
+
+#include "scan2.inl"
 
 // ------------------------------------------------------------------------------------------
 // K1b: slice kernel -- PPM slice + CRC class of every (candidate position, phase)

@@ -116,6 +116,8 @@ cudaError_t scan2_configure();
 bool scan2_supports(const ScanArgs &a);
 void scan2_tile_range(uint64_t nsamples, uint32_t &lo, uint32_t &hi);
 cudaError_t launch_scan2(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
+// resident K1a warps per CTA for a format (chunks are sized to whole waves of tiles)
+int k1a_warps_per_cta(uint32_t format);
 cudaError_t launch_slice(const SliceArgs &a, int grid, cudaStream_t stream);
 cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream);
 // K2's per-tile live lists (device memory) -> position-ordered arrays (pinned host memory), plus per live position

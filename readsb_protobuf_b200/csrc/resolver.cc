@@ -143,6 +143,40 @@ void IcaoFilter::expire(uint64_t now_ms) {
     next_flip_ = now_ms + 60000; // MODES_ICAO_FILTER_TTL, icao_filter.c:30
 }
 
+IcaoFilter::Snapshot IcaoFilter::snapshot() const {
+    Snapshot s;
+    s.seq_a = list_a_;
+    s.seq_b = list_b_;
+    s.a_active = active_ == a_;
+    s.next_flip = next_flip_;
+    return s;
+}
+
+void IcaoFilter::load(const Snapshot &s) {
+    reset();
+    active_ = a_;
+    for (uint32_t x : s.seq_a)
+        add(x);
+    active_ = b_;
+    for (uint32_t x : s.seq_b)
+        add(x);
+    active_ = s.a_active ? a_ : b_;
+    next_flip_ = s.next_flip;
+}
+
+bool IcaoFilter::same_members(const Snapshot &s) const {
+    if (s.a_active != (active_ == a_) || s.next_flip != next_flip_ || s.seq_a.size() != list_a_.size() || s.seq_b.size() != list_b_.size() ||
+        dropped_)
+        return false;
+    for (uint32_t x : s.seq_a)
+        if (!((bits_a_[x >> 6] >> (x & 63u)) & 1ull))
+            return false;
+    for (uint32_t x : s.seq_b)
+        if (!((bits_b_[x >> 6] >> (x & 63u)) & 1ull))
+            return false;
+    return true; // equal sizes, no duplicates within a sequence: the sets are equal
+}
+
 void IcaoFilter::collect(std::vector<uint32_t> &out) const {
     for (uint32_t i = 0; i < kSize; ++i) {
         if (a_[i] != kEmpty)
@@ -249,26 +283,6 @@ static int resolver_threads() {
 // scoring and the CRC-dependent part of decode
 // ------------------------------------------------------------------------------------------
 
-Resolver::Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), startup_(startup_time_ms), pool_(nullptr) {
-    const int n = resolver_threads();
-    if (n > 1)
-        pool_ = new WorkerPool(n);
-    reset();
-}
-
-Resolver::~Resolver() {
-    delete pool_;
-}
-
-void Resolver::reset() {
-    filter_.reset();
-    memset(&stats_, 0, sizeof(stats_));
-    ifile_now_ = 0;
-    mismatches_ = 0;
-    modeac_ = 0;
-}
-
-// scoreModesMessage (mode_s.c:311-409) for a frame K1 already classified
 // K2 marks a record whose address (key) is in the device-side set S of every address the filter could ever
 // hold (LiveRec::w0 bit 31).  Outside S the filter's answer is "no" whatever its state, and the host does not
 // have to touch its tables for the (random) addresses of the noise frames that share a live position.
@@ -290,7 +304,7 @@ const int kScoreTable[6][2][4] = {
 };
 } // namespace
 
-int Resolver::score(const LiveRec &r) const {
+int Resolver::score(const IcaoFilter &filter_, const LiveRec &r) {
     const uint32_t crc = r.w0 & 0xffffffu, kind = (r.w0 >> 24) & 7u, errors = (r.w0 >> 28) & 3u;
     const uint32_t key = r.w1 & 0xffffffu; // the address the filter is asked about: the syndrome for Address/Parity frames
     const bool known = may_be_known(r) && filter_.test(key);
@@ -308,7 +322,8 @@ static inline uint32_t aa_field(const uint8_t *msg) { // getbits(msg, 9, 32)
 // decided from what the kernels recorded about the frame: its syndrome, class, repair (error count and bit
 // positions) and the address after repair (key).  Returns 0, or the reject code (-1 unknown ICAO, -2 bad).
 // An all-zero frame (mode_s.c:434) never gets a class record, so that test cannot fire here.
-int Resolver::admit(const LiveRec &r) {
+int Resolver::admit(IcaoFilter &filter_, const LiveRec &r, uint32_t *added) {
+    *added = 0xffffffffu;
     const uint32_t crc = r.w0 & 0xffffffu, kind = (r.w0 >> 24) & 7u, errors = (r.w0 >> 28) & 3u;
     const uint32_t key = r.w1 & 0xffffffu;
     switch (kind) {
@@ -318,8 +333,10 @@ int Resolver::admit(const LiveRec &r) {
         case kKindDF11: { // mode_s.c:467-506
             if ((crc & 0xffff80u) && !(may_be_known(r) && filter_.test(key))) // a repaired all-call reply must come from a known aircraft
                 return -1;
-            if (!errors && (crc & 0x7fu) == 0)
+            if (!errors && (crc & 0x7fu) == 0) {
                 filter_.add(key); // mode_s.c:717-726: a clean reply with IID 0
+                *added = key;
+            }
             return 0;
         }
         case kKindES: { // DF17/18: mode_s.c:508-546
@@ -330,8 +347,10 @@ int Resolver::admit(const LiveRec &r) {
                 if (touched && !(may_be_known(r) && filter_.test(key)))
                     return -1;
             }
-            if (!errors && (r.msg[0] >> 3) == 17)
+            if (!errors && (r.msg[0] >> 3) == 17) {
                 filter_.add(key); // a clean DF17 (not DF18)
+                *added = key;
+            }
             return 0;
         }
         default:
@@ -491,54 +510,83 @@ struct HiddenTotals {
 
 } // namespace
 
-// Two halves.  The walk is the exact sequential loop of demodulate2400 over the live positions, reduced to
-// what depends on order: skip-ahead, the ICAO filter (scores, decode-time rejects, adds, the per-block
-// expiry), the statistics whose floating-point sums depend on order.  It touches 16 bytes per position and
-// the head of each record and leaves a 24-byte note per accepted frame.  The assembly of the messages from
-// those notes -- CRC recomputed and repaired on the host as a cross-check, timestamps, signal level, the
-// un-counting of dead positions a frame body hides -- is independent per frame and is shared out over the
-// worker pool when a span carries thousands of frames.
-void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::vector<b200_block_info> &blocks) {
+// ------------------------------------------------------------------------------------------
+// the walk over a run of mag_bufs
+// ------------------------------------------------------------------------------------------
+
+struct Resolver::Potential {
+    uint32_t addr, block;
+};
+
+// what a run of mag_bufs adds to the statistics: sums, so the runs can be walked side by side (the two
+// floating-point sums that depend on order are accumulated afterwards, in order, from per-block / per-frame terms)
+struct Resolver::WalkOut {
+    std::vector<Accepted> acc;
+    std::vector<Potential> adds;     // icaoFilterAdd calls of the run, in order (the caller's filter follows them)
+    std::vector<double> noise_terms; // per mag_buf: mean_power * n - sum_signal_power (demod_2400.c:423-426)
+    std::vector<uint64_t> now;       // per mag_buf: Modes.ifile_now when icaoFilterExpire runs (readsb.c:331)
+    uint32_t tried[32];              // positions walked, by try mask: demod_preamblePhase (demod_2400.c:184)
+    uint32_t preambles, rejected_bad, rejected_unknown, accepted[3], best_phase[5], messages;
+    uint64_t signal_power_count, modeac;
+    void clear() {
+        acc.clear();
+        adds.clear();
+        noise_terms.clear();
+        now.clear();
+        memset(tried, 0, sizeof(tried));
+        preambles = rejected_bad = rejected_unknown = messages = 0;
+        memset(accepted, 0, sizeof(accepted));
+        memset(best_phase, 0, sizeof(best_phase));
+        signal_power_count = modeac = 0;
+    }
+};
+
+// first live position at or after scan position `pos`
+static uint32_t first_live_at(const SpanView &v, uint64_t pos) {
+    uint32_t lo = 0, hi = v.n_live;
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if ((uint64_t) v.live[mid].pos < pos)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+static uint32_t first_hit_at(const SpanView &v, uint64_t q) {
+    uint32_t lo = 0, hi = v.n_ac_hits;
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if ((uint64_t) v.ac_hits[mid].q < q)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// The exact sequential loop of demodulate2400 over the live positions of mag_bufs [k0, k1), reduced to what
+// depends on order: skip-ahead, the ICAO filter `f` (scores, decode-time rejects, adds, the per-block expiry).
+// It touches 16 bytes per position and the head of each record and leaves a 24-byte note per accepted frame.
+void Resolver::walk(const SpanView &v, IcaoFilter &f, uint64_t k0, uint64_t k1, const std::vector<b200_block_info> &blocks, size_t block_base,
+                    WalkOut &out, bool log_adds) const {
     const uint64_t n = v.nsamples, B = v.block_samples;
-    // ifileRun: full blocks, then (at end of stream) one short block, which is empty when the stream
-    // length is a multiple of the block size (sdr_ifile.c:192-216)
-    const uint64_t nfull = n / B;
-    const uint64_t nblocks = nfull + (v.final_span ? 1 : 0);
-
-    std::vector<Accepted> &acc = accepted_;
-    acc.clear();
-    acc.reserve((size_t) v.n_live + v.n_ac_hits + 64);
-    // Mode A/C hits in stream order (the kernel appends them as it finds them)
-    if (v.n_ac_hits > 1)
-        std::sort(v.ac_hits, v.ac_hits + v.n_ac_hits, [](const AcHit &a, const AcHit &b) { return a.q < b.q; });
-    uint32_t ac_i = 0;
-    // The live positions and their records are two flat arrays in stream order, just written by the GPU: the
-    // walk is sequential in both, which the hardware prefetcher follows.
-    uint32_t live_i = 0;
+    out.clear();
+    uint32_t live_i = first_live_at(v, k0 * B);
+    uint32_t ac_i = first_hit_at(v, k0 * B);
     const uint32_t n_live = v.n_live;
-    uint32_t tried[32]; // positions walked, by try mask: demod_preamblePhase (demod_2400.c:184) is added up at the end
-    memset(tried, 0, sizeof(tried));
+    std::vector<Accepted> &acc = out.acc;
 
-    for (uint64_t k = 0; k < nblocks; ++k) {
+    for (uint64_t k = k0; k < k1; ++k) {
         const uint64_t b0 = k * B, b1 = std::min(n, b0 + B), nk = b1 - b0;
         const uint64_t sample_counter = v.first_sample + b0;
         // sdr_ifile.c:187-190
         const uint64_t sampleTimestamp = (uint64_t) ((double) sample_counter * 12e6 / 2400000.0);
         const uint64_t sysTimestamp = sampleTimestamp / 12000U + startup_;
+        const b200_block_info &bi = blocks[block_base + k];
 
-        // converter outputs of the block (convert.c:104-110 / 246-252)
-        b200_block_info bi;
-        if (v.format == B200_INPUT_UC8) {
-            const unsigned long long sl = v.block_sums_u64[2 * k], sp = v.block_sums_u64[2 * k + 1];
-            bi.mean_level = sl / 65536.0 / (unsigned) nk; // sic: 65536
-            bi.mean_power = sp / 65535.0 / 65535.0 / (unsigned) nk;
-        } else {
-            bi.mean_level = (double) ((float) v.block_sums_f64[2 * k] / (float) (unsigned) nk);
-            bi.mean_power = (double) ((float) v.block_sums_f64[2 * k + 1] / (float) (unsigned) nk);
-        }
-        blocks.push_back(bi);
-
-        ifile_now_ = sysTimestamp; // demod_2400.c:253-255
+        uint64_t ifile_now = sysTimestamp; // demod_2400.c:253-255
         uint64_t sum_scaled_signal_power = 0;
         bool skipping = false;
         uint64_t skip_until = 0; // positions <= skip_until are skipped while `skipping`
@@ -556,7 +604,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             // counts; one without a record scores -2, which only ever wins as the very first phase tried
             // (a later phase must score strictly higher, and nothing scores below -2); the records are in
             // phase order, so walking them alone gives the same pick as walking the five phases
-            ++tried[trymask];
+            ++out.tried[trymask];
             int bestscore = -42, bestphase = -1;
             const LiveRec *best = nullptr;
             if (trymask) {
@@ -566,7 +614,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                     bestphase = first;
                 }
                 for (uint32_t ri = 0; ri < nrec; ++ri) {
-                    const int sc = score(recs[ri]);
+                    const int sc = score(f, recs[ri]);
                     if (sc > bestscore) {
                         bestscore = sc;
                         bestphase = (int) ((recs[ri].w1 >> 24) & 15u);
@@ -574,43 +622,45 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                     }
                 }
             }
-            stats_.demod_preambles++; // demod_2400.c:339
-            if (bestscore < 0) {      // demod_2400.c:342-348
+            out.preambles++;     // demod_2400.c:339
+            if (bestscore < 0) { // demod_2400.c:342-348
                 if (bestscore == -1)
-                    stats_.demod_rejected_unknown_icao++;
+                    out.rejected_unknown++;
                 else
-                    stats_.demod_rejected_bad++;
+                    out.rejected_bad++;
                 continue;
             }
 
             const uint64_t j = p - b0;
             const uint64_t timestampMsg = sampleTimestamp + j * 5 + (8 + 56) * 12 + (uint64_t) bestphase; // demod_2400.c:358
-            ifile_now_ = sysTimestamp + (timestampMsg - sampleTimestamp) / 12000U;                        // :361, 364-366
+            ifile_now = sysTimestamp + (timestampMsg - sampleTimestamp) / 12000U;                         // :361, 364-366
 
-            const int result = admit(*best); // demod_2400.c:372
+            uint32_t added;
+            const int result = admit(f, *best, &added); // demod_2400.c:372
+            if (added != 0xffffffffu && log_adds)
+                out.adds.push_back({added, (uint32_t) k});
             if (result < 0) {
                 if (result == -1)
-                    stats_.demod_rejected_unknown_icao++;
+                    out.rejected_unknown++;
                 else
-                    stats_.demod_rejected_bad++;
+                    out.rejected_bad++;
                 continue;
             }
-            stats_.demod_accepted[(best->w0 >> 28) & 3u]++;
-            stats_.demod_bestPhase[bestphase - 4]++;
+            out.accepted[(best->w0 >> 28) & 3u]++;
+            out.best_phase[bestphase - 4]++;
 
-            // demod_2400.c:387-408
             // (the floating-point side of :387-408 -- signal power and level, their running sum, peak and strong
             // count -- is done with the assembly: the divisions are per frame, only the sum is ordered)
             const bool long_frame = (best->msg[0] & 0x80) != 0; // :350, from the uncorrected DF
             const int signal_len = long_frame ? 268 : 134;
-            stats_.signal_power_count += (uint64_t) signal_len;
+            out.signal_power_count += (uint64_t) signal_len;
             sum_scaled_signal_power += best->power;
 
             // demod_2400.c:416: skip the frame body; the for loop ends at the block boundary
             skipping = true;
             skip_until = std::min<uint64_t>(p + (uint64_t) signal_len, b1 - 1);
 
-            stats_.messages_total++; // useModesMessage, mode_s.c:2149
+            out.messages++; // useModesMessage, mode_s.c:2149
             Accepted a;
             a.index = li;
             a.rec = (uint32_t) (best - v.liverecs);
@@ -638,12 +688,243 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                 a.block = (uint32_t) k;
                 a.modeac = 1;
                 acc.push_back(a);
-                stats_.messages_total++; // useModesMessage, mode_s.c:2149
-                ++modeac_;
+                out.messages++; // useModesMessage, mode_s.c:2149
+                ++out.modeac;
                 next_ok = f1 + 70; // f1_sample += 69, then the loop's ++
             }
         }
 
+        // demod_2400.c:423-427
+        const double sum_signal_power = sum_scaled_signal_power / 65535.0 / 65535.0;
+        out.noise_terms.push_back(bi.mean_power * (uint32_t) nk - sum_signal_power);
+        out.now.push_back(ifile_now);
+        f.expire(ifile_now); // readsb.c:331
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// speculation: runs of mag_bufs walked side by side
+// ------------------------------------------------------------------------------------------
+
+// Only the ICAO filter couples one mag_buf to the next.  What it will hold when a later run of mag_bufs starts
+// can be predicted well: addresses enter it with clean DF17 / DF11-IID0 frames, which are accepted whatever the
+// filter holds unless an earlier frame's body hides them.  So: (0) every run lists its potential adds and a guess
+// of the filter clock at each block end; (1) the caller plays them through a copy of the filter and notes the
+// predicted state in front of every run; (2) the runs are walked side by side, each from its predicted state with
+// a filter of its own; (3) in order, a run's result stands if the state the previous run really left equals the
+// prediction -- the insertion sequences of both tables, the active table and the flip time -- and is walked
+// again from the true state otherwise.  The walk is a function of its input state, so the outcome is the
+// sequential one; a wrong guess only costs time.
+
+struct Resolver::Run {
+    WalkOut out;
+    IcaoFilter filter;              // the run's own filter: predicted state in, the state it leaves out
+    std::vector<Potential> adds;    // clean DF17 / DF11-IID0 frames of the run, in order
+    std::vector<uint64_t> now_guess; // per mag_buf: the filter clock at its end, guessed
+    IcaoFilter::Snapshot predicted; // the state the run was started from
+};
+
+Resolver::Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), startup_(startup_time_ms), pool_(nullptr) {
+    const int n = resolver_threads();
+    if (n > 1)
+        pool_ = new WorkerPool(n);
+    runs_.emplace_back(new Run());
+    // development / test knobs: when a span is worth walking as several runs
+    min_live_ = kParallelWalkMinLive;
+    min_blocks_per_run_ = 4;
+    if (const char *e = getenv("B200_RESOLVER_MIN_LIVE"))
+        min_live_ = (uint32_t) strtoul(e, nullptr, 10);
+    if (const char *e = getenv("B200_RESOLVER_MIN_BLOCKS"))
+        min_blocks_per_run_ = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+    reset();
+}
+
+Resolver::~Resolver() {
+    delete pool_;
+}
+
+void Resolver::reset() {
+    filter_.reset();
+    memset(&stats_, 0, sizeof(stats_));
+    ifile_now_ = 0;
+    mismatches_ = 0;
+    modeac_ = 0;
+}
+
+// scoreModesMessage (mode_s.c:311-409) for a frame K1 already classified
+
+
+void Resolver::prescan(const SpanView &v, uint64_t k0, uint64_t k1, std::vector<Potential> &adds, std::vector<uint64_t> &now_guess) const {
+    const uint64_t n = v.nsamples, B = v.block_samples;
+    adds.clear();
+    now_guess.assign((size_t) (k1 - k0), 0);
+    uint32_t li = first_live_at(v, k0 * B);
+    for (uint64_t k = k0; k < k1; ++k) {
+        const uint64_t b0 = k * B, b1 = std::min(n, b0 + B);
+        const uint64_t sampleTimestamp = (uint64_t) ((double) (v.first_sample + b0) * 12e6 / 2400000.0);
+        const uint64_t sysTimestamp = sampleTimestamp / 12000U + startup_;
+        uint64_t now = sysTimestamp;
+        for (; li < v.n_live && v.live[li].pos < b1; ++li) {
+            const LivePos &lp = v.live[li];
+            const uint32_t nrec = (lp.info >> 8) & 7u;
+            const LiveRec *recs = v.liverecs + lp.pad;
+            bool added = false;
+            for (uint32_t ri = 0; ri < nrec; ++ri) {
+                const LiveRec &r = recs[ri];
+                const uint32_t kind = (r.w0 >> 24) & 7u, crc = r.w0 & 0xffffffu;
+                const bool scores = kind == kKindES || (kind == kKindDF11 && (crc & 0x7fu) == 0); // >= 0 whatever the filter holds
+                if (scores) {
+                    const uint64_t ts = sampleTimestamp + ((uint64_t) lp.pos - b0) * 5 + (8 + 56) * 12 + ((r.w1 >> 24) & 15u);
+                    now = sysTimestamp + (ts - sampleTimestamp) / 12000U;
+                }
+                if (!added && crc == 0 && ((kind == kKindES && (r.msg[0] >> 3) == 17) || kind == kKindDF11)) {
+                    adds.push_back({r.w1 & 0xffffffu, (uint32_t) k});
+                    added = true;
+                }
+            }
+        }
+        now_guess[(size_t) (k - k0)] = now;
+    }
+}
+
+// Two halves.  The walk (above) is sequential in what it decides; runs of mag_bufs are walked side by side on
+// predicted filter states when a span carries enough live positions.  The assembly of the messages from the
+// walk's notes -- CRC recomputed and repaired on the host as a cross-check, timestamps, signal level, the
+// un-counting of dead positions a frame body hides -- is independent per frame and is shared out over the
+// worker pool as well.
+void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::vector<b200_block_info> &blocks) {
+    const uint64_t n = v.nsamples, B = v.block_samples;
+    // ifileRun: full blocks, then (at end of stream) one short block, which is empty when the stream
+    // length is a multiple of the block size (sdr_ifile.c:192-216)
+    const uint64_t nfull = n / B;
+    const uint64_t nblocks = nfull + (v.final_span ? 1 : 0);
+
+    // Mode A/C hits in stream order (the kernel appends them as it finds them)
+    if (v.n_ac_hits > 1)
+        std::sort(v.ac_hits, v.ac_hits + v.n_ac_hits, [](const AcHit &a, const AcHit &b) { return a.q < b.q; });
+
+    // converter outputs of every block (convert.c:104-110 / 246-252)
+    const size_t block_base = blocks.size();
+    for (uint64_t k = 0; k < nblocks; ++k) {
+        const uint64_t b0 = k * B, nk = std::min(n, b0 + B) - b0;
+        b200_block_info bi;
+        if (v.format == B200_INPUT_UC8) {
+            const unsigned long long sl = v.block_sums_u64[2 * k], sp = v.block_sums_u64[2 * k + 1];
+            bi.mean_level = sl / 65536.0 / (unsigned) nk; // sic: 65536
+            bi.mean_power = sp / 65535.0 / 65535.0 / (unsigned) nk;
+        } else {
+            bi.mean_level = (double) ((float) v.block_sums_f64[2 * k] / (float) (unsigned) nk);
+            bi.mean_power = (double) ((float) v.block_sums_f64[2 * k + 1] / (float) (unsigned) nk);
+        }
+        blocks.push_back(bi);
+    }
+
+    // ---- the walk: one run, or several side by side ----
+    const int nworkers = pool_ ? pool_->size() : 1;
+    int nruns = 1;
+    if (pool_ && v.n_live >= min_live_ && nblocks >= 2 * min_blocks_per_run_ && filter_.replayable())
+        nruns = (int) std::min<uint64_t>((uint64_t) nworkers, nblocks / min_blocks_per_run_);
+    if ((int) runs_.size() < std::max(nruns, 1)) {
+        runs_.resize((size_t) std::max(nruns, 1));
+        for (auto &r : runs_)
+            if (!r)
+                r.reset(new Run());
+    }
+    std::vector<uint64_t> cut((size_t) nruns + 1, nblocks); // run r walks mag_bufs [cut[r], cut[r + 1])
+    cut[0] = 0;
+    if (nruns > 1) {
+        // equal shares of the live positions, cut at mag_buf boundaries
+        for (int r = 1; r < nruns; ++r) {
+            const uint32_t li = (uint32_t) ((uint64_t) v.n_live * (uint64_t) r / (uint64_t) nruns);
+            uint64_t k = li < v.n_live ? (uint64_t) v.live[li].pos / B : nblocks;
+            cut[(size_t) r] = std::min<uint64_t>(std::max<uint64_t>(k, cut[(size_t) r - 1]), nblocks);
+        }
+    }
+    if (nruns == 1) {
+        walk(v, filter_, 0, nblocks, blocks, block_base, runs_[0]->out, false);
+    } else {
+        // (0) potential adds and filter-clock guesses of every run
+        pool_->run((size_t) nruns, 1, [&](int, size_t lo, size_t hi) {
+            for (size_t r = lo; r < hi; ++r)
+                prescan(v, cut[r], cut[r + 1], runs_[r]->adds, runs_[r]->now_guess);
+        });
+        // (1) the predicted state in front of every run
+        sim_.load(filter_.snapshot());
+        for (int r = 0; r < nruns; ++r) {
+            Run &run = *runs_[(size_t) r];
+            run.predicted = sim_.snapshot();
+            size_t ai = 0;
+            for (uint64_t k = cut[(size_t) r]; k < cut[(size_t) r + 1]; ++k) {
+                for (; ai < run.adds.size() && run.adds[ai].block == (uint32_t) k; ++ai)
+                    sim_.add(run.adds[ai].addr);
+                sim_.expire(run.now_guess[(size_t) (k - cut[(size_t) r])]);
+            }
+        }
+        // (2) every run from its predicted state
+        pool_->run((size_t) nruns, 1, [&](int, size_t lo, size_t hi) {
+            for (size_t r = lo; r < hi; ++r) {
+                Run &run = *runs_[r];
+                run.filter.load(run.predicted);
+                walk(v, run.filter, cut[r], cut[r + 1], blocks, block_base, run.out, true);
+            }
+        });
+        // (3) in order: a run's result stands if the filter it started from had the true members; otherwise the run
+        // is walked again from the true state.  The caller's own filter then follows the run's adds and expiries in
+        // their true order, so its tables are laid out slot for slot as the sequential walk would leave them.
+        for (int r = 0; r < nruns; ++r) {
+            Run &run = *runs_[(size_t) r];
+            if (!filter_.replayable()) {
+                // the filter outgrew what a copy reproduces safely: the rest of the span in one run, on the filter itself
+                ++respeculated_;
+                walk(v, filter_, cut[(size_t) r], nblocks, blocks, block_base, run.out, false);
+                nruns = r + 1;
+                break;
+            }
+            if (!filter_.same_members(run.predicted) || !run.filter.replayable()) {
+                ++respeculated_;
+                run.filter.load(filter_.snapshot());
+                walk(v, run.filter, cut[(size_t) r], cut[(size_t) r + 1], blocks, block_base, run.out, true);
+            }
+            size_t ai = 0;
+            for (uint64_t k = cut[(size_t) r]; k < cut[(size_t) r + 1]; ++k) {
+                for (; ai < run.out.adds.size() && run.out.adds[ai].block == (uint32_t) k; ++ai)
+                    filter_.add(run.out.adds[ai].addr);
+                filter_.expire(run.out.now[(size_t) (k - cut[(size_t) r])]);
+            }
+        }
+    }
+
+    // ---- merge the runs, in order ----
+    size_t count = 0;
+    for (int r = 0; r < nruns; ++r)
+        count += runs_[(size_t) r]->out.acc.size();
+    std::vector<Accepted> &acc = accepted_;
+    acc.clear();
+    acc.reserve(count);
+    for (int r = 0; r < nruns; ++r) {
+        const WalkOut &o = runs_[(size_t) r]->out;
+        acc.insert(acc.end(), o.acc.begin(), o.acc.end());
+        stats_.demod_preambles += o.preambles;
+        stats_.demod_rejected_bad += o.rejected_bad;
+        stats_.demod_rejected_unknown_icao += o.rejected_unknown;
+        for (int q = 0; q < 3; ++q)
+            stats_.demod_accepted[q] += o.accepted[q];
+        for (int q = 0; q < 5; ++q)
+            stats_.demod_bestPhase[q] += o.best_phase[q];
+        stats_.messages_total += o.messages;
+        stats_.signal_power_count += o.signal_power_count;
+        modeac_ += o.modeac;
+        for (uint32_t mask = 1; mask < 32; ++mask)
+            for (int q = 0; q < 5; ++q)
+                if ((mask >> q) & 1u)
+                    stats_.demod_preamblePhase[q] += o.tried[mask];
+        for (double t : o.noise_terms)
+            stats_.noise_power_sum += t; // in block order
+        if (!o.now.empty())
+            ifile_now_ = o.now.back();
+    }
+    for (uint64_t k = 0; k < nblocks; ++k) {
+        const uint64_t b0 = k * B, nk = std::min(n, b0 + B) - b0;
         // positions no message can come from: K2's per-block totals (what skip-ahead hid of them is taken
         // out again below)
         if (nk) {
@@ -654,26 +935,14 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             for (int q = 0; q < 5; ++q)
                 stats_.demod_preamblePhase[q] += bd.phase[q];
         }
-
-        // demod_2400.c:423-427
-        const double sum_signal_power = sum_scaled_signal_power / 65535.0 / 65535.0;
-        stats_.noise_power_sum += (bi.mean_power * (uint32_t) nk - sum_signal_power);
         stats_.noise_power_count += nk;
         stats_.samples_processed += kOverlap + nk; // readsb.c:835
-
-        filter_.expire(ifile_now_); // readsb.c:331
     }
 
-    for (uint32_t mask = 1; mask < 32; ++mask)
-        for (int q = 0; q < 5; ++q)
-            if ((mask >> q) & 1u)
-                stats_.demod_preamblePhase[q] += tried[mask];
-
     // ---- assembly: one message per note, in place ----
-    const size_t base = msgs.size(), count = acc.size();
+    const size_t base = msgs.size();
     msgs.resize(base + count);
     b200_message *out = msgs.data() + base;
-    const int nworkers = pool_ ? pool_->size() : 1;
     std::vector<HiddenTotals> hidden((size_t) nworkers);
     std::vector<uint64_t> bad((size_t) nworkers, 0);
     signal_power_.resize(count);

@@ -9,6 +9,7 @@
 
 #include <stdint.h>
 
+#include <memory>
 #include <vector>
 
 #include "device_types.h"
@@ -28,8 +29,28 @@ class IcaoFilter {
     // every address currently stored (for seeding the device-side address set)
     void collect(std::vector<uint32_t> &out) const;
 
+    // The filter as a value: the addresses each table received, in insertion order, which table is active and
+    // when it flips next.  Replaying the insertions into empty tables rebuilds them slot for slot (a table only
+    // receives addresses while it is the active one, from empty), which is how a copy is made (load) and how two
+    // filters are compared.  Valid while no insert was ever dropped by a full table (replayable()).
+    struct Snapshot {
+        std::vector<uint32_t> seq_a, seq_b;
+        bool a_active = true;
+        uint64_t next_flip = 0;
+        bool operator==(const Snapshot &o) const {
+            return a_active == o.a_active && next_flip == o.next_flip && seq_a == o.seq_a && seq_b == o.seq_b;
+        }
+    };
+    Snapshot snapshot() const;
+    void load(const Snapshot &s);
+    // same active table, same flip time, and the same SET of addresses in each table (whatever the insertion order):
+    // a filter loaded from `s` then answers every test, and takes every expiry, exactly as this one
+    bool same_members(const Snapshot &s) const;
+    bool replayable() const { return !dropped_ && list_a_.size() < kReplayMax && list_b_.size() < kReplayMax; }
+
   private:
     static constexpr uint32_t kSize = 8192, kEmpty = 0xffffffffu;
+    static constexpr size_t kReplayMax = 2048; // well inside what a table can take without ever filling up
     static uint32_t hash(uint32_t a);
     static bool probe(const uint32_t *t, uint32_t addr);
     bool test_tables(uint32_t addr) const;
@@ -89,9 +110,18 @@ class Resolver {
         uint32_t pad2;
     };
 
+    uint64_t respeculated_runs() const { return respeculated_; } // runs of mag_bufs walked twice (a wrong filter prediction)
+
   private:
-    int score(const LiveRec &r) const;
-    int admit(const LiveRec &r);                                    // the filter-dependent part of decodeModesMessage
+    struct WalkOut;
+    struct Potential;
+    struct Run;
+    static constexpr uint32_t kParallelWalkMinLive = 16384; // below this a span is walked in one run
+    static int score(const IcaoFilter &f, const LiveRec &r);
+    static int admit(IcaoFilter &f, const LiveRec &r, uint32_t *added); // the filter-dependent part of decodeModesMessage
+    void walk(const SpanView &v, IcaoFilter &f, uint64_t k0, uint64_t k1, const std::vector<b200_block_info> &blocks, size_t block_base,
+              WalkOut &out, bool log_adds) const;
+    void prescan(const SpanView &v, uint64_t k0, uint64_t k1, std::vector<Potential> &adds, std::vector<uint64_t> &now_guess) const;
     // the rest of it; returns CRC disagreements, *signal_power = the frame's signal power (demod_2400.c:397)
     uint32_t build(const SpanView &v, const Accepted &a, b200_message &mm, double *signal_power) const;
     const CrcTables *crc_;
@@ -103,6 +133,11 @@ class Resolver {
     uint64_t modeac_;
     std::vector<Accepted> accepted_;
     std::vector<double> signal_power_;
+    std::vector<std::unique_ptr<Run>> runs_; // one per run of mag_bufs walked side by side (runs_[0]: the whole span)
+    IcaoFilter sim_;                          // plays the potential adds through to predict the runs' start states
+    uint64_t respeculated_ = 0;
+    uint32_t min_live_;
+    uint64_t min_blocks_per_run_;
     WorkerPool *pool_;
 };
 

@@ -1,4 +1,4 @@
-// scan2.cu -- K1a for the interior uc8 tiles of a span: the register-window scan kernel.
+// scan2.inl -- K1a for uc8 spans: the register-window scan kernel (included by kernels.cu, after scan_kernel).
 //
 // Same job and same outputs as scan_kernel<0, *> (kernels.cu): IQ -> magnitude (convert.c:63-111), per-mag_buf
 // sums of mag and mag^2, the pre-check and the three preamble correlators of demod_2400.c:276-330 for every scan
@@ -29,28 +29,13 @@
 // into bits 3..5 of the index, which spreads the 16 x 16 codes receiver noise lives in evenly over the 32 banks
 // (measured 2.1 cycles per LDS.U16 against 4.0 for the r01 swizzle, tools/ubench.cu).
 //
-// Tiles that touch the start or the end of the span (carried head, ragged tail) stay with scan_kernel's EDGE path.
-
-#include "kernels.cuh"
-
-#include <cuda_runtime.h>
+// Tiles that touch the start or the end of the span (carried head, ragged tail: two or three per chunk) go through
+// scan_kernel's process_tile<.., EDGE> inside the same launch: warp 0 of a CTA owns the ring buffer that path needs
+// and picks them up once the interior tiles are handed out.
 
 #include <type_traits>
 
-namespace b200 {
-
 namespace {
-
-struct WarpCand {
-    unsigned long long ncand_total; // over the warp's tiles
-};
-
-__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 constexpr int kRun = kTile / 32;                 // scan positions (and owned samples) per lane and tile
 constexpr int kBodies = kRun / 32;               // loop bodies of 32 samples
@@ -58,7 +43,8 @@ constexpr int kScan2Warps = 16;                  // 128 registers per thread
 constexpr int kScan2Threads = kScan2Warps * 32;
 constexpr int kApronWords = 12;                  // per lane: 9 magnitude pairs (18 samples), padded to 48 bytes
 constexpr size_t kScan2Lut = 65536 * sizeof(uint16_t);
-constexpr size_t kScan2Smem = kScan2Lut + (size_t) kScan2Warps * 32 * kApronWords * sizeof(uint32_t);
+constexpr size_t kScan2Apron = (size_t) kScan2Warps * 32 * kApronWords * sizeof(uint32_t);
+constexpr size_t kScan2Smem = kScan2Lut + kScan2Apron + kSmemWarp; // + one ring buffer for the edge tiles
 
 __device__ __forceinline__ void ldg256(uint32_t (&w)[8], const uint8_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -176,7 +162,7 @@ struct TileMasks { // bit k of word w: lane-local position 32 w + k - 18 (words 
 // bytes before a multiple of 16 KiB).  The 256-bit loads then fetch the aligned blocks around the run and a body
 // takes the upper half of one block, a whole block and the lower half of a third -- register renaming, no shuffling.
 template <bool SLICE, bool ODD16>
-__device__ __forceinline__ void scan2_tile(const ScanArgs &a, WarpCand &cx, const uint32_t tile, const unsigned char *s_lut, uint32_t *s_apron) {
+__device__ __forceinline__ void scan2_tile(const ScanArgs &a, WarpCtx &cx, const uint32_t tile, const unsigned char *s_lut, uint32_t *s_apron) {
     const int lane = threadIdx.x & 31;
     const int nthr = -a.threshold;
     const long long c0 = (long long) tile * kTile - kHead; // first window-start sample of the tile (>= 0: interior)
@@ -428,7 +414,7 @@ __global__ void __launch_bounds__(kScan2Threads, 1) scan2_kernel(const ScanArgs 
     }
     __syncthreads();
 
-    WarpCand cx;
+    WarpCtx cx;
     cx.ncand_total = 0;
     for (;;) {
         uint32_t q = 0;
@@ -439,6 +425,21 @@ __global__ void __launch_bounds__(kScan2Threads, 1) scan2_kernel(const ScanArgs 
         if (tile >= a.fast_hi)
             break;
         scan2_tile<SLICE, ODD16>(a, cx, tile, smem2, s_apron);
+    }
+    if (warp == 0) {
+        // the edge tiles of the span: the generic path of scan_kernel, with this kernel's table layout
+        uint32_t *s_ring = reinterpret_cast<uint32_t *>(smem2 + kScan2Lut + kScan2Apron);
+        for (;;) {
+            uint32_t tile = 0;
+            if (lane == 0)
+                tile = atomicAdd(&a.counters->next_tile, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= a.fast_lo)
+                tile += a.fast_hi - a.fast_lo;
+            if (tile >= a.ntiles)
+                break;
+            process_tile<0, SLICE, true, 2>(a, cx, tile, reinterpret_cast<const uint16_t *>(smem2), s_ring);
+        }
     }
     if (lane == 0 && cx.ncand_total) // one same-address atomic per warp, not per tile
         atomicAdd(&a.counters->n_cand, cx.ncand_total);
@@ -475,6 +476,10 @@ void scan2_tile_range(uint64_t nsamples, uint32_t &lo, uint32_t &hi) {
     }
 }
 
+int k1a_warps_per_cta(uint32_t format) {
+    return format == 0 ? kScan2Warps : kScanWarps;
+}
+
 cudaError_t launch_scan2(const ScanArgs &a, int mode, int grid, cudaStream_t stream) {
     if (a.fast_hi <= a.fast_lo)
         return cudaSuccess;
@@ -496,5 +501,3 @@ cudaError_t launch_scan2(const ScanArgs &a, int mode, int grid, cudaStream_t str
     }
     return cudaGetLastError();
 }
-
-} // namespace b200

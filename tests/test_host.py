@@ -118,8 +118,7 @@ def test_host_resolver_over_recorded_kernel_outputs():
     calls), against the oracle on the regenerated stream: messages, block means and every counter."""
     from readsb_protobuf_b200 import synth
     paths = sorted((ROOT / "tests" / "golden").glob("resolver_span_*.bin"), key=lambda p: int(p.stem.split("_")[-1]))
-    if not paths:
-        pytest.skip("no recorded kernel outputs (tests/golden/resolver_span_*.bin)")
+    assert paths, "tests/golden/resolver_span_*.bin are part of the repository"
     cfg = synth.resolver_fixture_config()
     iq, _ = synth.generate(cfg)
     want = port.run(iq, "uc8")
@@ -132,3 +131,23 @@ def test_host_resolver_over_recorded_kernel_outputs():
     # cut differently, the files no longer describe the stream: the resolver must not silently agree
     with pytest.raises(api.B200Error):
         api.host_resolve_dumps([ROOT / "tests" / "golden" / "kat_frame.npz"])
+
+
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_host_resolver_runs_side_by_side(threads, monkeypatch):
+    """The same replay with the walk forced into several runs of mag_bufs per span, each started from a predicted
+    ICAO-filter state on its own thread and kept only if the prediction held (resolver.cc, 'speculation'): whatever
+    the number of threads and wherever the runs are cut, the result is the sequential one, bit for bit."""
+    from readsb_protobuf_b200 import synth
+    paths = sorted((ROOT / "tests" / "golden").glob("resolver_span_*.bin"), key=lambda p: int(p.stem.split("_")[-1]))
+    assert paths, "tests/golden/resolver_span_*.bin are part of the repository"
+    monkeypatch.setenv("B200_RESOLVER_THREADS", str(threads))
+    monkeypatch.setenv("B200_RESOLVER_MIN_LIVE", "0")
+    monkeypatch.setenv("B200_RESOLVER_MIN_BLOCKS", "1")
+    cfg = synth.resolver_fixture_config()
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "uc8")
+    got = api.host_resolve_dumps(paths, nfix=1)
+    assert int(got.stats["convert_cpu_s"]) == 0
+    got.stats["convert_cpu_s"] = got.stats["demod_cpu_s"] = 0
+    assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []

@@ -166,7 +166,7 @@ int main(int argc, char **argv) {
     h = fnv(blocks.data(), blocks.size() * sizeof(b200_block_info), h);
     const b200_demod_stats st = res.stats();
     h = fnv(&st, sizeof(st), h);
-    printf("digest %016llx  (%zu msgs, %zu blocks, mismatches %llu)\n", (unsigned long long) h, msgs.size(), blocks.size(),
-           (unsigned long long) res.gpu_host_mismatches());
+    printf("digest %016llx  (%zu msgs, %zu blocks, mismatches %llu, runs walked twice in the last pass %llu)\n", (unsigned long long) h,
+           msgs.size(), blocks.size(), (unsigned long long) res.gpu_host_mismatches(), (unsigned long long) res.respeculated_runs());
     return 0;
 }
