@@ -207,6 +207,7 @@ struct b200_demod {
     uint32_t head_valid = 0;
     uint64_t first_sample = 0;
     bool finished = false;
+    bool failed = false; // a process call failed half-way: the stream state is inconsistent until b200_demod_reset
 
     // span buffers
     DevBuf<uint8_t> d_iq;
@@ -221,7 +222,7 @@ struct b200_demod {
     DevBuf<double> d_csum_f64;
 
     // results of the last call
-    std::vector<b200_message> msgs;
+    MessageList msgs;
     std::vector<b200_block_info> blocks;
     b200_timing timing;
 
@@ -437,6 +438,7 @@ extern "C" int b200_demod_reset(b200_demod *d) {
     d->head_valid = 0;
     d->first_sample = 0;
     d->finished = false;
+    d->failed = false;
     d->resolver->reset();
     d->msgs.clear();
     d->blocks.clear();
@@ -748,7 +750,11 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
             fclose(f);
         }
     }
-    d->resolver->resolve(v, d->msgs, d->blocks);
+    try {
+        d->resolver->resolve(v, d->msgs, d->blocks);
+    } catch (const std::bad_alloc &) {
+        return fail(B200_ERR_NOMEM, "out of host memory while resolving a chunk");
+    }
     t.resolve_ms += (float) (now_ms() - t_res0);
     t.d2h_bytes += c.small_d2h_bytes + (size_t) cnt.n_live * (sizeof(LivePos) + sizeof(LiveHidden)) + (size_t) cnt.n_liverec * sizeof(LiveRec);
     t.n_candidates += cnt.n_cand;
@@ -758,7 +764,24 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
 }
 
 // The span is resident (or arriving, chunk by chunk, on the copy stream) at d_iq.
+static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t flags, cudaStream_t exec, const void *host_src);
+
+// A failure after the first chunk was issued leaves the resolver's filter and counters ahead of first_sample, the
+// head carry and the message list: quiesce the streams and refuse further spans until b200_demod_reset.
 static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t flags, cudaStream_t exec, const void *host_src) {
+    const int rc = run_span_impl(d, d_iq, nsamples, flags, exec, host_src);
+    if (rc != B200_OK) {
+        const std::string why = g_last_error; // keep the first error: the synchronisation below may add its own
+        cudaStreamSynchronize(exec);
+        cudaStreamSynchronize(d->copy_stream);
+        cudaGetLastError();
+        g_last_error = why;
+        d->failed = true;
+    }
+    return rc;
+}
+
+static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint32_t flags, cudaStream_t exec, const void *host_src) {
     const bool final_span = (flags & B200_FLAG_FINAL) != 0;
     const uint32_t B = d->cfg.block_samples;
     const size_t bps = (size_t) d->eff_bps;
@@ -905,6 +928,8 @@ static int check_span(b200_demod *d, const void *iq, uint64_t nsamples, uint32_t
         return fail(B200_ERR_ARG, "null context");
     if (!iq && nsamples)
         return fail(B200_ERR_ARG, "null sample buffer");
+    if (d->failed)
+        return fail(B200_ERR_STATE, "an earlier span failed half-way (%s); call b200_demod_reset", g_last_error.c_str());
     if (d->finished)
         return fail(B200_ERR_STATE, "the stream already ended (B200_FLAG_FINAL); call b200_demod_reset");
     if (nsamples > d->cfg.max_span_samples)
@@ -1258,7 +1283,7 @@ extern "C" int b200_host_resolve_dumps(const char *const *paths, uint32_t npaths
         return fail(B200_ERR_ARG, "bad argument");
     CrcTables crc(nfix_crc);
     Resolver res(&crc, 0);
-    std::vector<b200_message> out_msgs;
+    MessageList out_msgs;
     std::vector<b200_block_info> out_blocks;
     for (uint32_t i = 0; i < npaths; ++i) {
         // the layout finish_chunk writes: 12-word header, live positions, live records, hidden-dead counts,

@@ -6,13 +6,35 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <thread>
 
+#include <chrono>
+
 #include <sched.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 namespace b200 {
+
+MessageList::~MessageList() {
+    free(p_);
+}
+
+b200_message *MessageList::grow(size_t extra) {
+    if (n_ + extra > cap_) {
+        const size_t cap = std::max(n_ + extra, cap_ + cap_ / 2 + 1024);
+        b200_message *p = static_cast<b200_message *>(realloc(p_, cap * sizeof(b200_message)));
+        if (!p)
+            throw std::bad_alloc();
+        p_ = p;
+        cap_ = cap;
+    }
+    b200_message *first = p_ + n_;
+    n_ += extra;
+    return first;
+}
 
 // ------------------------------------------------------------------------------------------
 // ICAO filter (icao_filter.c)
@@ -209,13 +231,16 @@ class WorkerPool {
             t.join();
     }
     int size() const { return (int) threads_.size() + 1; }
-    // fn(worker, begin, end) over [0, n) in slices of `grain`; returns when every slice is done
-    void run(size_t n, size_t grain, const std::function<void(int, size_t, size_t)> &fn) {
+    // fn(worker, begin, end) over [0, n) in slices of `grain`; returns when every slice is done.
+    // fixed: item i always goes to worker i % size() (grain 1) -- a run of mag_bufs is then scanned, walked and
+    // assembled by the same thread, whose cache holds its records
+    void run(size_t n, size_t grain, const std::function<void(int, size_t, size_t)> &fn, bool fixed = false) {
         {
             std::lock_guard<std::mutex> g(m_);
             fn_ = &fn;
             n_ = n;
             grain_ = grain;
+            fixed_ = fixed;
             next_.store(0, std::memory_order_relaxed);
             pending_ = (int) threads_.size();
             ++generation_;
@@ -229,6 +254,11 @@ class WorkerPool {
 
   private:
     void work(int worker) {
+        if (fixed_) {
+            for (size_t i = (size_t) worker; i < n_; i += (size_t) size())
+                (*fn_)(worker, i, i + 1);
+            return;
+        }
         for (;;) {
             const size_t b = next_.fetch_add(grain_, std::memory_order_relaxed);
             if (b >= n_)
@@ -259,6 +289,7 @@ class WorkerPool {
     std::condition_variable cv_, done_;
     const std::function<void(int, size_t, size_t)> *fn_ = nullptr;
     size_t n_ = 0, grain_ = 1;
+    bool fixed_ = false;
     std::atomic<size_t> next_{0};
     int pending_ = 0;
     uint64_t generation_ = 0;
@@ -275,8 +306,8 @@ static int resolver_threads() {
     int cpus = 1;
     if (sched_getaffinity(0, sizeof(set), &set) == 0)
         cpus = CPU_COUNT(&set);
-    // the caller's thread walks, the CUDA runtime has its own: leave them a core each
-    return std::max(1, std::min(8, cpus - 2));
+    // the CUDA runtime has threads of its own: leave them two of the cores this process may run on
+    return std::max(1, std::min(16, cpus - 2));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -661,6 +692,7 @@ void Resolver::walk(const SpanView &v, IcaoFilter &f, uint64_t k0, uint64_t k1, 
             skip_until = std::min<uint64_t>(p + (uint64_t) signal_len, b1 - 1);
 
             out.messages++; // useModesMessage, mode_s.c:2149
+            __builtin_prefetch(&v.hidden[li]); // the assembly reads it
             Accepted a;
             a.index = li;
             a.rec = (uint32_t) (best - v.liverecs);
@@ -740,7 +772,18 @@ Resolver::Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), 
 }
 
 Resolver::~Resolver() {
+    if (getenv("B200_RESOLVER_TRACE"))
+        fprintf(stderr,
+                "resolver: %llu spans, %llu as several runs (%llu runs, %llu walked twice); ms: prescan %.2f predict %.2f walk %.2f "
+                "validate %.2f merge %.2f assemble %.2f ordered sums %.2f\n",
+                (unsigned long long) trace_.spans, (unsigned long long) trace_.parallel_spans, (unsigned long long) trace_.runs,
+                (unsigned long long) trace_.rewalks, trace_.ms[0], trace_.ms[1], trace_.ms[2], trace_.ms[3], trace_.ms[4], trace_.ms[5], trace_.ms[6]);
     delete pool_;
+}
+
+static inline double trace_now() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
 void Resolver::reset() {
@@ -792,7 +835,7 @@ void Resolver::prescan(const SpanView &v, uint64_t k0, uint64_t k1, std::vector<
 // walk's notes -- CRC recomputed and repaired on the host as a cross-check, timestamps, signal level, the
 // un-counting of dead positions a frame body hides -- is independent per frame and is shared out over the
 // worker pool as well.
-void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::vector<b200_block_info> &blocks) {
+void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_block_info> &blocks) {
     const uint64_t n = v.nsamples, B = v.block_samples;
     // ifileRun: full blocks, then (at end of stream) one short block, which is empty when the stream
     // length is a multiple of the block size (sdr_ifile.c:192-216)
@@ -840,14 +883,25 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             cut[(size_t) r] = std::min<uint64_t>(std::max<uint64_t>(k, cut[(size_t) r - 1]), nblocks);
         }
     }
+    ++trace_.spans;
+    double t_mark = trace_now();
+    auto lap = [&](int phase) {
+        const double t = trace_now();
+        trace_.ms[phase] += t - t_mark;
+        t_mark = t;
+    };
     if (nruns == 1) {
         walk(v, filter_, 0, nblocks, blocks, block_base, runs_[0]->out, false);
+        lap(2);
     } else {
+        ++trace_.parallel_spans;
+        trace_.runs += (uint64_t) nruns;
         // (0) potential adds and filter-clock guesses of every run
         pool_->run((size_t) nruns, 1, [&](int, size_t lo, size_t hi) {
             for (size_t r = lo; r < hi; ++r)
                 prescan(v, cut[r], cut[r + 1], runs_[r]->adds, runs_[r]->now_guess);
-        });
+        }, true);
+        lap(0);
         // (1) the predicted state in front of every run
         sim_.load(filter_.snapshot());
         for (int r = 0; r < nruns; ++r) {
@@ -860,6 +914,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                 sim_.expire(run.now_guess[(size_t) (k - cut[(size_t) r])]);
             }
         }
+        lap(1);
         // (2) every run from its predicted state
         pool_->run((size_t) nruns, 1, [&](int, size_t lo, size_t hi) {
             for (size_t r = lo; r < hi; ++r) {
@@ -867,7 +922,8 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                 run.filter.load(run.predicted);
                 walk(v, run.filter, cut[r], cut[r + 1], blocks, block_base, run.out, true);
             }
-        });
+        }, true);
+        lap(2);
         // (3) in order: a run's result stands if the filter it started from had the true members; otherwise the run
         // is walked again from the true state.  The caller's own filter then follows the run's adds and expiries in
         // their true order, so its tables are laid out slot for slot as the sequential walk would leave them.
@@ -882,6 +938,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             }
             if (!filter_.same_members(run.predicted) || !run.filter.replayable()) {
                 ++respeculated_;
+                ++trace_.rewalks;
                 run.filter.load(filter_.snapshot());
                 walk(v, run.filter, cut[(size_t) r], cut[(size_t) r + 1], blocks, block_base, run.out, true);
             }
@@ -892,18 +949,70 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
                 filter_.expire(run.out.now[(size_t) (k - cut[(size_t) r])]);
             }
         }
+        lap(3);
     }
 
-    // ---- merge the runs, in order ----
-    size_t count = 0;
+    // ---- assembly: one message per note, in place; every run by the thread that walked it ----
+    std::vector<size_t> first((size_t) nruns + 1, 0); // run r's messages are msgs[base + first[r] ...)
     for (int r = 0; r < nruns; ++r)
-        count += runs_[(size_t) r]->out.acc.size();
-    std::vector<Accepted> &acc = accepted_;
-    acc.clear();
-    acc.reserve(count);
+        first[(size_t) r + 1] = first[(size_t) r] + runs_[(size_t) r]->out.acc.size();
+    const size_t count = first[(size_t) nruns];
+    b200_message *out = msgs.grow(count);
+    std::vector<HiddenTotals> hidden((size_t) nruns);
+    std::vector<uint64_t> bad((size_t) nruns, 0);
+    if (count > signal_power_cap_) {
+        signal_power_cap_ = count + count / 2 + 1024;
+        signal_power_.reset(new double[signal_power_cap_]);
+    }
+    double *power = signal_power_.get();
+    std::atomic<int> turn{0}; // whose frames the ordered statistics take next
+    auto assemble = [&](int, size_t rlo, size_t rhi) {
+        for (size_t r = rlo; r < rhi; ++r) {
+            const std::vector<Accepted> &acc = runs_[r]->out.acc;
+            HiddenTotals h; // thread-local until the run is done: the runs' slots share cache lines
+            uint64_t nbad = 0;
+            b200_message *o = out + first[r];
+            double *pw = power + first[r];
+            for (size_t i = 0; i < acc.size(); ++i) {
+                const Accepted &a = acc[i];
+                nbad += build(v, a, o[i], &pw[i]);
+                if (!a.modeac) {
+                    // dead positions the frame body hides were counted in K2's per-block totals
+                    const LiveHidden &lh = v.hidden[a.index];
+                    if (a.long_frame)
+                        h.add(lh.long_lo, lh.long_hi);
+                    else
+                        h.add(lh.short_lo, lh.short_hi);
+                }
+            }
+            hidden[r] = h;
+            bad[r] = nbad;
+            // demod_2400.c:398-407 in message order: the running sum of doubles is the one thing here that depends on
+            // it, so the runs take turns, each adding its own (cache-warm) terms
+            while (turn.load(std::memory_order_acquire) != (int) r) {
+            }
+            for (size_t i = 0; i < acc.size(); ++i) {
+                if (acc[i].modeac)
+                    continue;
+                stats_.signal_power_sum += pw[i];
+                const double level = o[i].signalLevel;
+                if (level > stats_.peak_signal_power)
+                    stats_.peak_signal_power = level;
+                if (level > 0.50119)
+                    stats_.strong_signal_count++;
+            }
+            turn.store((int) r + 1, std::memory_order_release);
+        }
+    };
+    if (nruns > 1)
+        pool_->run((size_t) nruns, 1, assemble, true);
+    else
+        assemble(0, 0, 1);
+    lap(5);
+
+    // ---- the runs' counters, in order ----
     for (int r = 0; r < nruns; ++r) {
         const WalkOut &o = runs_[(size_t) r]->out;
-        acc.insert(acc.end(), o.acc.begin(), o.acc.end());
         stats_.demod_preambles += o.preambles;
         stats_.demod_rejected_bad += o.rejected_bad;
         stats_.demod_rejected_unknown_icao += o.rejected_unknown;
@@ -922,6 +1031,7 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
             stats_.noise_power_sum += t; // in block order
         if (!o.now.empty())
             ifile_now_ = o.now.back();
+        mismatches_ += bad[(size_t) r];
     }
     for (uint64_t k = 0; k < nblocks; ++k) {
         const uint64_t b0 = k * B, nk = std::min(n, b0 + B) - b0;
@@ -938,56 +1048,15 @@ void Resolver::resolve(const SpanView &v, std::vector<b200_message> &msgs, std::
         stats_.noise_power_count += nk;
         stats_.samples_processed += kOverlap + nk; // readsb.c:835
     }
-
-    // ---- assembly: one message per note, in place ----
-    const size_t base = msgs.size();
-    msgs.resize(base + count);
-    b200_message *out = msgs.data() + base;
-    std::vector<HiddenTotals> hidden((size_t) nworkers);
-    std::vector<uint64_t> bad((size_t) nworkers, 0);
-    signal_power_.resize(count);
-    double *power = signal_power_.data();
-    auto assemble = [&](int worker, size_t lo, size_t hi) {
-        HiddenTotals &h = hidden[(size_t) worker];
-        uint64_t &nb = bad[(size_t) worker];
-        for (size_t i = lo; i < hi; ++i) {
-            const Accepted &a = acc[i];
-            nb += build(v, a, out[i], &power[i]);
-            if (!a.modeac) {
-                // dead positions the frame body hides were counted in K2's per-block totals
-                const LiveHidden &lh = v.hidden[a.index];
-                if (a.long_frame)
-                    h.add(lh.long_lo, lh.long_hi);
-                else
-                    h.add(lh.short_lo, lh.short_hi);
-            }
-        }
-    };
-    if (pool_ && count >= 4096)
-        pool_->run(count, 1024, assemble);
-    else
-        assemble(0, 0, count);
-    // demod_2400.c:398-407 in message order: the running sum of doubles is the one thing here that depends on it
-    for (size_t i = 0; i < count; ++i) {
-        if (acc[i].modeac)
-            continue;
-        stats_.signal_power_sum += power[i];
-        const double level = out[i].signalLevel;
-        if (level > stats_.peak_signal_power)
-            stats_.peak_signal_power = level;
-        if (level > 0.50119)
-            stats_.strong_signal_count++;
-    }
     HiddenTotals total;
-    for (int w = 0; w < nworkers; ++w) {
-        total.add(hidden[(size_t) w]);
-        mismatches_ += bad[(size_t) w];
-    }
+    for (int r = 0; r < nruns; ++r)
+        total.add(hidden[(size_t) r]);
     stats_.demod_preambles -= (uint32_t) total.preambles;
     stats_.demod_rejected_bad -= (uint32_t) total.bad;
     stats_.demod_rejected_unknown_icao -= (uint32_t) total.unknown;
     for (int q = 0; q < 5; ++q)
         stats_.demod_preamblePhase[q] -= (uint32_t) total.phase[q];
+    lap(6);
 }
 
 } // namespace b200

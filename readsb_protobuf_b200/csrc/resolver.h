@@ -65,6 +65,27 @@ class IcaoFilter {
     bool dropped_;
 };
 
+// The messages of a process call: a growable array that never zero-fills.  (std::vector::resize would write every
+// new element on the caller's core just before the workers fill them in from theirs.)
+class MessageList {
+  public:
+    MessageList() = default;
+    MessageList(const MessageList &) = delete;
+    MessageList &operator=(const MessageList &) = delete;
+    ~MessageList();
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    const b200_message *data() const { return p_; }
+    b200_message *data() { return p_; }
+    const b200_message &operator[](size_t i) const { return p_[i]; }
+    void clear() { n_ = 0; }
+    b200_message *grow(size_t extra); // room for `extra` more; returns the first of them, contents unspecified
+
+  private:
+    b200_message *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
+
 struct SpanView {
     uint64_t nsamples;        // new samples == scan positions of the span
     uint64_t first_sample;    // stream sample index of the span's first new sample
@@ -94,7 +115,7 @@ class Resolver {
     ~Resolver();
     void reset();
     // Appends the span's messages and block infos; updates the running statistics.
-    void resolve(const SpanView &v, std::vector<b200_message> &msgs, std::vector<b200_block_info> &blocks);
+    void resolve(const SpanView &v, MessageList &msgs, std::vector<b200_block_info> &blocks);
     const b200_demod_stats &stats() const { return stats_; }
     const IcaoFilter &filter() const { return filter_; }
     uint64_t gpu_host_mismatches() const { return mismatches_; }
@@ -132,10 +153,15 @@ class Resolver {
     uint64_t mismatches_;
     uint64_t modeac_;
     std::vector<Accepted> accepted_;
-    std::vector<double> signal_power_;
+    std::unique_ptr<double[]> signal_power_; // per accepted frame of the span; never zero-filled
+    size_t signal_power_cap_ = 0;
     std::vector<std::unique_ptr<Run>> runs_; // one per run of mag_bufs walked side by side (runs_[0]: the whole span)
     IcaoFilter sim_;                          // plays the potential adds through to predict the runs' start states
     uint64_t respeculated_ = 0;
+    struct Trace { // B200_RESOLVER_TRACE: where the time of resolve() goes, printed when the resolver is destroyed
+        uint64_t spans = 0, parallel_spans = 0, runs = 0, rewalks = 0;
+        double ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    } trace_;
     uint32_t min_live_;
     uint64_t min_blocks_per_run_;
     WorkerPool *pool_;

@@ -13,8 +13,12 @@
  *   demodulate2400                      demod_2400.c:236-428: hands the block's already resolved
  *       frames to readsb's decodeModesMessage() / useModesMessage() and adds the block's counters
  *       to Modes.stats_current
- *   init_converter / cleanup_converter  convert.c:446-499: a converter for callers that want the
- *       raw magnitudes (other SDR front-ends, Mode A/C); forwards to b200_convert()
+ *   init_converter / cleanup_converter  convert.c:446-499: iq_convert_fn over b200_convert() for callers that
+ *       want the magnitudes of a block themselves (oneoff/convert_benchmark.c style)
+ *
+ * Scope: --device-type ifile only (the north star's boundary).  demodulate2400() here replays what ifileRun
+ * resolved; with any other SDR front-end nothing would feed it, so init_converter() -- the first thing every
+ * live front-end calls (sdr_rtlsdr.c:321-325, sdr_bladerf.c, sdr_plutosdr.c) -- refuses them loudly.
  *
  * The reference's fifo_enqueue() loses buffers when more than one is queued (it never advances
  * fifo_tail, fifo.c:192-197), so the reader hands blocks over one at a time and waits until
@@ -28,6 +32,8 @@
 #include "readsb_b200.h"
 
 #define SPAN_BLOCKS 256 /* mag_bufs per GPU call: 14 s of samples */
+#define FIRST_SPAN_BLOCKS 1 /* the first call carries one mag_buf: the main loop gets a block before its 100 ms FIFO
+                               time-out runs backgroundTasks() -> icaoFilterExpire() on an empty stream (readsb.c:797-835) */
 
 static struct {
     const char *filename;
@@ -143,11 +149,15 @@ void ifileRun(void) {
     b200_demod_stats before, after;
     memset(&before, 0, sizeof (before));
 
+    bool failed = false, first = true;
     while (!Modes.exit && !eof) {
-        size_t bytes = read_fully(ifile.fd, ifile.span, (size_t) SPAN_BLOCKS * MODES_MAG_BUF_SAMPLES * ifile.bytes_per_sample, &eof);
+        const size_t span_blocks = first ? FIRST_SPAN_BLOCKS : SPAN_BLOCKS;
+        first = false;
+        size_t bytes = read_fully(ifile.fd, ifile.span, span_blocks * MODES_MAG_BUF_SAMPLES * ifile.bytes_per_sample, &eof);
         uint64_t nsamples = bytes / ifile.bytes_per_sample;
         if (b200_demod_process(ifile.demod, ifile.span, nsamples, eof ? B200_FLAG_FINAL : 0) != B200_OK) {
             fprintf(stderr, "ifile: GPU demodulation failed: %s\n", b200_last_error());
+            failed = true;
             break;
         }
         const b200_message *msgs = b200_demod_messages(ifile.demod);
@@ -219,7 +229,8 @@ void ifileRun(void) {
         before = after;
     }
     fifo_drain();
-    Modes.exit = 1; /* sdr_ifile.c:234-236 */
+    /* sdr_ifile.c:234-236; a stream cut short by a GPU failure is not a normal exit (readsb.c:867: "Abnormal exit") */
+    Modes.exit = failed ? 2 : 1;
 }
 
 void ifileClose(void) {
@@ -265,8 +276,21 @@ void demodulate2400(struct mag_buf *mag) {
         mm.score = m->score;
         unsigned char raw[MODES_LONG_MSG_BYTES];
         memcpy(raw, m->verbatim, MODES_LONG_MSG_BYTES);
-        /* readsb's filter copy sees the same adds and flips as the library's, so this cannot reject */
-        if (decodeModesMessage(&mm, raw) < 0) {
+        /* The library's resolver decided with its own copy of the ICAO filter, fed in stream order and expired once
+         * per mag_buf; that decision is authoritative.  readsb's copy (icao_filter.c) sees the same adds through
+         * decodeModesMessage, but the main loop may expire it at a different block (backgroundTasks() also runs on
+         * FIFO time-outs), so it can lag by one table generation: if it does not know the address yet, tell it. */
+        int rc = decodeModesMessage(&mm, raw);
+        if (rc < 0) {
+            icaoFilterAdd(m->addr & 0xffffffu);
+            memcpy(raw, m->verbatim, MODES_LONG_MSG_BYTES);
+            mm = zeroMessage;
+            mm.timestampMsg = m->timestampMsg;
+            mm.sysTimestampMsg = m->sysTimestampMsg;
+            mm.score = m->score;
+            rc = decodeModesMessage(&mm, raw);
+        }
+        if (rc < 0) {
             fprintf(stderr, "readsb_b200_shim: decodeModesMessage disagrees with the GPU path at %012llx\n",
                     (unsigned long long) m->timestampMsg);
             continue;
@@ -326,11 +350,22 @@ struct converter_state {
 
 static void convert_via_gpu(void *iq_data, uint16_t *mag_data, unsigned nsamples, struct converter_state *state,
         double *out_mean_level, double *out_mean_power) {
-    if (b200_convert(state->demod, iq_data, nsamples, mag_data, out_mean_level, out_mean_power) != B200_OK)
+    if (b200_convert(state->demod, iq_data, nsamples, mag_data, out_mean_level, out_mean_power) != B200_OK) {
+        /* iq_convert_fn cannot fail (convert.h:33-38): say so and hand back silence rather than stale memory */
         fprintf(stderr, "convert: %s\n", b200_last_error());
+        memset(mag_data, 0, (size_t) nsamples * sizeof (uint16_t));
+        if (out_mean_level) *out_mean_level = 0;
+        if (out_mean_power) *out_mean_power = 0;
+    }
 }
 
 iq_convert_fn init_converter(input_format_t format, double sample_rate, int filter_dc, struct converter_state **out_state) {
+    if (Modes.sdr_type != SDR_IFILE && Modes.sdr_type != SDR_NONE) {
+        /* a live front-end: its mag_bufs would reach demodulate2400() above, which only replays what ifileRun resolved */
+        fprintf(stderr, "readsb_b200_shim: this build demodulates --device-type ifile only; "
+                "SDR type %d would decode nothing (feed live blocks through b200_demod_process, INTEGRATION.md)\n", (int) Modes.sdr_type);
+        return NULL;
+    }
     if (filter_dc && sample_rate != 2400000.0) {
         /* the library's DC block is the 1 Hz one at the demodulator's 2.4 MS/s (convert.c:476-480) */
         fprintf(stderr, "no suitable converter for format=%d dc=%d at %.0f samples/s\n", format, filter_dc, sample_rate);

@@ -515,6 +515,31 @@ def test_crc_batch_and_tables(nfix):
 # drop-in: the reference's own program on top of the shim
 # ------------------------------------------------------------------------------------------
 
+def test_reference_program_with_the_shim_across_filter_flips():
+    """The drop-in binary over 130 s of stream: two ICAO-filter generations pass, readsb's own copy of the filter
+    (expired by its main loop) must never make it drop a frame the library accepted; output equals the oracle's."""
+    import os
+    import subprocess
+    import tempfile
+    from readsb_protobuf_b200 import build
+    exe = build.ORACLE / "_ref" / "readsb_b200"
+    assert exe.exists(), "oracle/_ref/readsb_b200 is missing on the GPU box (built by __graft_entry__.build() where /root/reference exists)"
+    cfg = synth.SynthConfig(seed=93, nsamples=int(130 * 2.4e6), frames_per_s=400, frac_biterror=0.2, n_icao=60)
+    iq, _ = synth.generate(cfg)
+    want = port.run(iq, "uc8")
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "in.bin")
+        iq.tofile(path)
+        out = subprocess.run([str(exe), "--device-type", "ifile", "--ifile", path, "--preamble-threshold", "58", "--raw", "--mlat"],
+                             capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("@")]
+    expect = ["@%012X%s;" % (int(m["timestampMsg"]), bytes(m["msg"][: m["msgbits"] // 8]).hex()) for m in want.msgs]
+    assert len(expect) > 20000
+    assert lines == expect
+    assert "disagrees" not in out.stderr
+
+
 @pytest.mark.parametrize("modeac,dcfilter", [(False, False), (True, False), (True, True)], ids=["modes", "modeac", "modeac-dcfilter"])
 def test_reference_program_with_the_shim_prints_the_same_messages(modeac, dcfilter):
     """oracle/_ref/readsb_b200 = readsb's main(), FIFO, CRC, field decoder and tracker objects linked

@@ -122,7 +122,7 @@ int main(int argc, char **argv) {
     }
     CrcTables crc(1);
     Resolver res(&crc, 0);
-    std::vector<b200_message> msgs;
+    MessageList msgs;
     std::vector<b200_block_info> blocks;
     const int reps = getenv("RB_REPS") ? atoi(getenv("RB_REPS")) : 20;
     std::vector<double> times;
