@@ -19,7 +19,8 @@ GPU.  A step is one pass of the hot path over that stream.
   cpu_baseline  the unmodified reference (oracle/_ref/ref_demod) on one host core, bounded sample
 
   other_configs  the remaining BASELINE configs, each with value / e2e / msgs_per_s / per-stage ms:
-            N=1: configs[2] (60 s sc16 and sc16q11, seed 3) and configs[3] (600 s dense uc8, seed 4);
+            N=1: configs[2] (60 s sc16 and sc16q11, seed 3), configs[3] (600 s dense uc8, seed 4) and eight
+            --dcfilter receiver streams side by side on the one GPU;
             N>1: configs[4] (one 600 s dense uc8 file per GPU, seeds 10..)
   sustained the configs[1] device-resident step repeated for >= 1.5 s with nvidia-smi clock sampling
             at 5 Hz (the K-step timed region itself lasts tens of milliseconds)
@@ -293,11 +294,12 @@ class StreamBench:
 
     def step_device(self):
         self.demod.reset()
-        return self.demod.process_device(self.dev.data_ptr(), self.nsamples, final=True, stream=self.sptr)
+        # copy=False: the decoded messages are in host memory the library owns (a view, not a second copy into numpy)
+        return self.demod.process_device(self.dev.data_ptr(), self.nsamples, final=True, stream=self.sptr, copy=False)
 
     def step_host(self):
         self.demod.reset()
-        return self.demod.process_ptr(self.host.data_ptr(), self.nsamples, final=True)
+        return self.demod.process_ptr(self.host.data_ptr(), self.nsamples, final=True, copy=False)
 
     def close(self):
         self.demod.close()
@@ -471,10 +473,48 @@ def run_ours(args):
         b.close()
         return out
 
+    def run_dcfilter_streams(nstreams=8, seconds=10.0):
+        """--dcfilter (convert_*_generic, convert.c:113-213): the DC block is one sequential chain per receiver stream
+        (a single warp walks it), so one stream leaves the GPU idle; several receivers side by side -- one context and
+        one host thread each, as a multi-receiver host would run them -- fill it."""
+        from readsb_protobuf_b200 import api
+        n = int(seconds * SAMPLE_RATE)
+        ctxs = []
+        for i in range(nstreams):
+            c = synth.SynthConfig(seed=40 + i + 100 * rank, nsamples=n, frames_per_s=500.0)
+            iq, _ = synth.generate(c)
+            dev = torch.from_numpy(iq).cuda()
+            ctxs.append((api.Demodulator(fmt="uc8", nfix=1, threshold=58, device=local_rank, max_span_samples=n + (1 << 20), dcfilter=True), dev))
+        nmsg = [0] * nstreams
+
+        def one(i):
+            d, dev = ctxs[i]
+            d.reset()
+            nmsg[i] = len(d.process_device(dev.data_ptr(), n, final=True, copy=False).msgs)
+
+        def all_streams(k):
+            ths = [threading.Thread(target=one, args=(i,)) for i in range(k)]
+            t0 = time.perf_counter()
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+
+        all_streams(nstreams)  # warm-up (allocations)
+        t1 = min(all_streams(1) for _ in range(2))
+        tn = min(all_streams(nstreams) for _ in range(2))
+        for d, _ in ctxs:
+            d.close()
+        return {"workload": f"{nstreams} receiver streams of {seconds:.0f} s uc8 with --dcfilter on one GPU, one context and host thread each",
+                "one_stream_value": n / t1 / 1e6, "value": nstreams * n / tn / 1e6, "unit": UNIT, "streams": nstreams,
+                "seconds_wall": tn, "decoded_msgs": int(sum(nmsg)), "timing": "host wall clock around the process calls (device-resident input)"}
+
     others = {}
     want = args.other_configs
     if want == "auto":
-        want = "2,3" if world == 1 else "4"
+        want = "2,3,dc" if world == 1 else "4"
     try:
         for tok in [t for t in want.split(",") if t and t != "none"]:
             if tok == "2":
@@ -482,6 +522,8 @@ def run_ours(args):
                 others["configs[2] sc16q11"] = run_config("configs[2]: 60 s sc16q11, ~200 frames/s, seed 3", 2, "sc16q11", 5, 3)
             elif tok == "3":
                 others["configs[3]"] = run_config("configs[3]: 600 s dense uc8, 5000 frames/s, 20 % one-bit errors, seed 4", 3, "uc8", 3, 3)
+            elif tok == "dc":
+                others["dcfilter x8 streams"] = run_dcfilter_streams()
             elif tok == "4":
                 others["configs[4]"] = run_config(f"configs[4]: {world} independent 600 s dense uc8 files, one per GPU, seeds 10..{9 + world}",
                                                   4, "uc8", 3, 3)
@@ -559,7 +601,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=WORKLOAD_SECONDS, help=argparse.SUPPRESS)
     ap.add_argument("--other-configs", default="auto",
-                    help="auto (N=1: configs[2] and [3]; N>1: configs[4]), none, or a list such as 2,3")
+                    help="auto (N=1: configs[2], configs[3] and the --dcfilter multi-stream case; N>1: configs[4]), none, or a list such as 2,3,dc")
     ap.add_argument("--sustain", type=float, default=1.5, help="seconds of back-to-back steps for the clock record")
     args = ap.parse_args()
     if args.impl == "reference":

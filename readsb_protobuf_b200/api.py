@@ -275,7 +275,14 @@ class Demodulator:
         _check(self._L.b200_demod_reset(self._h))
 
     # ---- the hot path ----
-    def _collect(self) -> SpanResult:
+    def _collect(self, copy: bool = True) -> SpanResult:
+        if not copy:
+            # the messages stay where the library put them (host memory it owns, b200_demod_messages): a view, valid
+            # until the next process call -- a benchmark loop should not time a 68-byte-per-message memmove into numpy
+            n = int(self._L.b200_demod_message_count(self._h))
+            msgs = np.ctypeslib.as_array(ctypes.cast(self._L.b200_demod_messages(self._h), ctypes.POINTER(ctypes.c_uint8)),
+                                         shape=(n * MSG_DTYPE.itemsize,)).view(MSG_DTYPE) if n else np.empty(0, dtype=MSG_DTYPE)
+            return SpanResult(msgs, np.empty(0, dtype=BLOCK_DTYPE), self.timing())
         n = int(self._L.b200_demod_message_count(self._h))
         msgs = np.empty(n, dtype=MSG_DTYPE)
         if n:
@@ -293,14 +300,14 @@ class Demodulator:
         _check(self._L.b200_demod_process(self._h, b.ctypes.data, n, FLAG_FINAL if final else 0))
         return self._collect()
 
-    def process_ptr(self, host_ptr: int, nsamples: int, final: bool = True) -> SpanResult:
+    def process_ptr(self, host_ptr: int, nsamples: int, final: bool = True, copy: bool = True) -> SpanResult:
         _check(self._L.b200_demod_process(self._h, host_ptr, nsamples, FLAG_FINAL if final else 0))
-        return self._collect()
+        return self._collect(copy)
 
-    def process_device(self, dev_ptr: int, nsamples: int, final: bool = True, stream: int = 0) -> SpanResult:
+    def process_device(self, dev_ptr: int, nsamples: int, final: bool = True, stream: int = 0, copy: bool = True) -> SpanResult:
         """Demodulate a span already resident in device memory (e.g. a torch uint8 tensor's data_ptr())."""
         _check(self._L.b200_demod_process_device(self._h, dev_ptr, nsamples, FLAG_FINAL if final else 0, stream))
-        return self._collect()
+        return self._collect(copy)
 
     def stats(self) -> np.ndarray:
         s = np.zeros(1, dtype=STATS_DTYPE)

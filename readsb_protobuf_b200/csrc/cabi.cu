@@ -821,6 +821,11 @@ static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, 
                 at += 2 * wave;
             }
             starts.push_back(at * B);
+            // ... and a short last chunk (half a wave at most): nothing overlaps the host's resolve of the last
+            // chunk, so it should be little work
+            const uint64_t rest = nb - at, tail = std::min<uint64_t>(rest / 4, std::max<uint64_t>(1, wave / 2));
+            if (tail >= 1 && rest > tail)
+                starts.push_back((nb - tail) * B);
         } else {
             for (uint64_t i = 0; i < nmain; ++i) {
                 starts.push_back(std::min(nsamples, at * B));

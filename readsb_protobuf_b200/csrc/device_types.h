@@ -43,12 +43,15 @@ enum : uint32_t {
     kKindES = 4,      // DF17/18, syndrome clean or repairable
 };
 
-// K1 -> K2: one per (candidate position, phase) whose class is not kKindBad.  16 bytes.
+// K1b -> K2: one per (candidate position, phase) whose class is not kKindBad, with the frame as sliced: K2 only
+// has to add the signal power of the ones that stay live.  32 bytes.
 struct PhaseRec {
-    uint32_t pos;  // scan position within the span
-    uint32_t w0;   // crc[23:0] | kind[26:24] | errors[29:28]
-    uint32_t w1;   // key[23:0] (address the score depends on) | phase[27:24]
-    uint32_t pad;
+    uint32_t pos;     // scan position within the span
+    uint32_t w0;      // crc[23:0] | kind[26:24] | errors[29:28]
+    uint32_t w1;      // key[23:0] (address the score depends on) | phase[27:24]
+    uint32_t errbits; // bit0[7:0] | bit1[15:8]: the frame bits the syndrome table would repair (0xff = none)
+    uint8_t msg[14];  // the frame as sliced, MSB first; bytes past a short frame are 0
+    uint8_t pad[2];
 };
 
 // K1 per tile: where the tile's candidate entries and class records are, and how many

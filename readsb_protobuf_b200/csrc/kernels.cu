@@ -1143,12 +1143,12 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_kernel(const SliceArgs
                 FrameClass fc;
                 fc.kind = kKindBad;
                 uint32_t syn = 0, item = 0, df = 0, aa = 0;
+                uint32_t w[5] = {0, 0, 0, 0, 0}; // the frame's bits (bit b of the frame = bit b % 32 of w[b / 32])
                 if (lane < nb) {
                     const bool is_long = lane < nlb;
                     const int ng = is_long ? kGroupsLong : kGroupsShort;
                     const uint32_t *gs = s_gsyn + (is_long ? 0 : kGroupsLong * 32);
                     const uint32_t *bw = reinterpret_cast<const uint32_t *>(s_bits + lane * kFrameBytes);
-                    uint32_t w[5] = {0, 0, 0, 0, 0};
 #pragma unroll
                     for (int kw = 0; kw < 6; ++kw) {
                         const uint32_t four = bw[kw];
@@ -1186,12 +1186,13 @@ __global__ void __launch_bounds__(kSliceThreads, 1) slice_kernel(const SliceArgs
                     if (has) {
                         const uint32_t slot = base + __popc(mask & below);
                         if (slot < rec_cap) {
-                            PhaseRec pr;
-                            pr.pos = (uint32_t) (p0 + (item & 1023u));
-                            pr.w0 = syn | (fc.kind << 24) | (fc.errors << 28);
-                            pr.w1 = fc.key | (((item >> 10) + 4u) << 24);
-                            pr.pad = 0;
-                            *reinterpret_cast<uint4 *>(&recs[slot]) = *reinterpret_cast<const uint4 *>(&pr);
+                            // the frame's bytes, MSB first (frame bit b = bit b % 32 of w[b / 32])
+                            const uint32_t m0 = __byte_perm(__brev(w[0]), 0, 0x0123), m1 = __byte_perm(__brev(w[1]), 0, 0x0123),
+                                           m2 = __byte_perm(__brev(w[2]), 0, 0x0123), m3 = __byte_perm(__brev(w[3]), 0, 0x0123) & 0xffffu;
+                            uint4 *dst = reinterpret_cast<uint4 *>(&recs[slot]);
+                            dst[0] = make_uint4((uint32_t) (p0 + (item & 1023u)), syn | (fc.kind << 24) | (fc.errors << 28),
+                                                fc.key | (((item >> 10) + 4u) << 24), (uint32_t) (uint8_t) fc.bit0 | ((uint32_t) (uint8_t) fc.bit1 << 8));
+                            dst[1] = make_uint4(m0, m1, m2, m3);
                         }
                         // mode_s.c:717-726: only a clean DF17, or a clean DF11 with IID 0, can ever be added to
                         // the ICAO filter; remember every such address of the stream
@@ -1452,57 +1453,38 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
         return;
     __syncthreads();
 
-    // ---- pass 4: class records of live positions: re-slice the frame, signal power ----
+    // ---- pass 4: class records of live positions -> live records: the frame as K1b sliced it + its signal power ----
     // a live position owns consecutive output slots, one per recorded phase in phase order
     for (uint32_t r = warp; r < td.nrec; r += kClassifyThreads / 32) {
-        const PhaseRec pr = a.recs[td.rec_off + r];
-        const uint32_t c = find_cand(cand, td.ncand, (uint32_t) ((long long) pr.pos - p0));
+        const uint4 *src = reinterpret_cast<const uint4 *>(&a.recs[td.rec_off + r]);
+        const uint4 ra = src[0]; // pos, w0, w1, errbits
+        const uint32_t c = find_cand(cand, td.ncand, (uint32_t) ((long long) ra.x - p0));
         if (!(s_flags[c] & 1u))
             continue;
-        const int ph = (int) ((pr.w1 >> 24) & 15u);
+        const uint4 rm = src[1]; // the frame's bytes
+        const int ph = (int) ((ra.z >> 24) & 15u);
         const uint32_t rank = (uint32_t) __popc((uint32_t) s_nb[c] & ((1u << (ph - 4)) - 1u));
         const uint32_t slot = liverec_off + s_slot[c] + rank;
 
-        // magnitudes the frame touches: window position pos -> samples pos - kOverlap ...
-        uint16_t *fm = s_frame[warp];
-        const long long s_first = (long long) pr.pos - kOverlap;
-        for (int x = lane; x < kFrameSamples; x += 32)
-            fm[x] = (uint16_t) sample_mag(a, s_first + x);
-        __syncwarp();
-
-        uint32_t w[4], syn;
-        // DF from the first five bits decides the length (demod_2400.c:193-205)
-        uint32_t df = 0;
-        for (int b = 0; b < 5; ++b)
-            df = (df << 1) | (slice_bit(fm, ph, b, s_coef) ? 1u : 0u);
-        const int nbits = (df & 0x10u) ? 112 : 56;
-        warp_slice_frame(fm, ph, nbits, s_coef, s_syn, w, syn);
-
-        // demod_2400.c:387-396: sum of m^2 over msglen*12/5 samples from m[19]
-        const int signal_len = nbits * 12 / 5;
+        // demod_2400.c:387-396: sum of m^2 over msglen*12/5 samples from m[19]; K1a's magnitudes: window position
+        // pos starts at magnitude index pos + kPosShift
+        const int signal_len = (rm.x & 0x80u) ? 268 : 134;
+        const uint16_t *fm = a.mag + (size_t) ra.x + kPosShift + 19;
         unsigned long long power = 0;
         for (int k = lane; k < signal_len; k += 32) {
-            unsigned long long v = fm[19 + k];
+            const unsigned long long v = fm[k];
             power += v * v;
         }
         power = warp_sum_u64(power);
-
-        const FrameClass fc = classify_frame(df, __brev(w[0]) & 0xffffffu, syn, (w[0] | w[1] | w[2] | w[3]) == 0,
-                                             a.tab_short, a.n_short, a.tab_long, a.n_long);
         if (lane == 0) {
-            LiveRec lr;
-            lr.pos = pr.pos;
-            lr.w0 = syn | (fc.kind << 24) | (fc.errors << 28) | (bitmap_test(a.addr_bitmap, fc.key) ? 0x80000000u : 0u); // bit 31: key in S
-            lr.w1 = fc.key | ((uint32_t) ph << 24);
-            lr.errbits = (uint32_t) (uint8_t) fc.bit0 | ((uint32_t) (uint8_t) fc.bit1 << 8);
-            lr.power = power;
-#pragma unroll
-            for (int k = 0; k < 14; ++k)
-                lr.msg[k] = (uint8_t) ((__brev(w[k >> 2]) >> (24 - 8 * (k & 3))) & 0xffu);
-            lr.pad[0] = lr.pad[1] = 0;
-            a.liverecs[slot] = lr;
+            const uint32_t w0 = ra.y | (bitmap_test(a.addr_bitmap, ra.z & 0xffffffu) ? 0x80000000u : 0u); // bit 31: key in S
+            uint2 *dst = reinterpret_cast<uint2 *>(&a.liverecs[slot]);
+            dst[0] = make_uint2(ra.x, w0);
+            dst[1] = make_uint2(ra.z, ra.w);
+            dst[2] = make_uint2((uint32_t) power, (uint32_t) (power >> 32));
+            dst[3] = make_uint2(rm.x, rm.y);
+            dst[4] = make_uint2(rm.z, rm.w & 0xffffu);
         }
-        __syncwarp();
     }
 }
 
@@ -1704,64 +1686,74 @@ __global__ void __launch_bounds__(kCwWarps * 32) classify_warp_kernel(const Clas
             continue;
         __syncwarp();
 
-        // ---- pass 4: class records of live positions: re-slice the frame, signal power ----
-        // a live position owns consecutive output slots, one per recorded phase in phase order
+        // ---- pass 4: class records of live positions -> live records: the frame as K1b sliced it + its signal power ----
+        // a live position owns consecutive output slots, one per recorded phase in phase order.  Four records at a
+        // time, eight lanes each: demod_2400.c:387-396, the sum of m^2 over msglen * 12 / 5 samples from m[19].
         for (uint32_t rb = 0; rb < td.nrec; rb += 32) {
             const uint32_t r = rb + lane;
-            PhaseRec pr;
-            pr.pos = pr.w0 = pr.w1 = pr.pad = 0;
-            uint32_t c = 0;
+            uint4 ra = make_uint4(0, 0, 0, 0), rm = make_uint4(0, 0, 0, 0);
+            uint32_t out = 0;
             bool mine = false;
             if (r < td.nrec) {
-                pr = a.recs[td.rec_off + r];
-                c = find_cand_smem(cand, ncand, (uint32_t) ((long long) pr.pos - p0));
+                const uint4 *src = reinterpret_cast<const uint4 *>(&a.recs[td.rec_off + r]);
+                ra = src[0]; // pos, w0, w1, errbits
+                const uint32_t c = find_cand_smem(cand, ncand, (uint32_t) ((long long) ra.x - p0));
                 mine = flags[c] & 1u;
+                if (mine) {
+                    rm = src[1]; // the frame's bytes
+                    const uint32_t ph = (ra.z >> 24) & 15u;
+                    out = liverec_off + slot[c] + (uint32_t) __popc((uint32_t) nbs[c] & ((1u << (ph - 4)) - 1u));
+                }
             }
             uint32_t todo = __ballot_sync(0xffffffffu, mine);
+            unsigned long long my_power = 0;
             while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t pos = __shfl_sync(0xffffffffu, pr.pos, src);
-                const uint32_t w1 = __shfl_sync(0xffffffffu, pr.w1, src);
-                const uint32_t cc = __shfl_sync(0xffffffffu, c, src);
-                const int ph = (int) ((w1 >> 24) & 15u);
-                const uint32_t rank = (uint32_t) __popc((uint32_t) nbs[cc] & ((1u << (ph - 4)) - 1u));
-                const uint32_t out = liverec_off + slot[cc] + rank;
-                // K1a's magnitudes: window position pos starts at magnitude index pos + kPosShift
-                const uint16_t *fm = a.mag + (size_t) pos + kPosShift;
-
-                uint32_t w[4], syn;
-                // DF from the first five bits decides the length (demod_2400.c:193-205)
-                uint32_t df = 0;
-                for (int b = 0; b < 5; ++b)
-                    df = (df << 1) | (slice_bit(fm, ph, b, s_coef) ? 1u : 0u);
-                const int nbits = (df & 0x10u) ? 112 : 56;
-                warp_slice_frame(fm, ph, nbits, s_coef, s_syn, w, syn);
-
-                // demod_2400.c:387-396: sum of m^2 over msglen*12/5 samples from m[19]
-                const int signal_len = nbits * 12 / 5;
-                unsigned long long power = 0;
-                for (int k = lane; k < signal_len; k += 32) {
-                    const unsigned long long v = fm[19 + k];
-                    power += v * v;
-                }
-                power = warp_sum_u64(power);
-
-                const FrameClass fc = classify_frame(df, __brev(w[0]) & 0xffffffu, syn, (w[0] | w[1] | w[2] | w[3]) == 0,
-                                                     a.tab_short, a.n_short, a.tab_long, a.n_long);
-                if (lane == 0) {
-                    LiveRec lr;
-                    lr.pos = pos;
-                    lr.w0 = syn | (fc.kind << 24) | (fc.errors << 28) | (bitmap_test(a.addr_bitmap, fc.key) ? 0x80000000u : 0u); // bit 31: key in S
-                    lr.w1 = fc.key | ((uint32_t) ph << 24);
-                    lr.errbits = (uint32_t) (uint8_t) fc.bit0 | ((uint32_t) (uint8_t) fc.bit1 << 8);
-                    lr.power = power;
+                // group g = lane / 8 takes the g-th record still to do (if there is one)
+                const int g = lane >> 3, sub = lane & 7;
+                uint32_t t = todo;
+                int src = -1;
 #pragma unroll
-                    for (int k = 0; k < 14; ++k)
-                        lr.msg[k] = (uint8_t) ((__brev(w[k >> 2]) >> (24 - 8 * (k & 3))) & 0xffu);
-                    lr.pad[0] = lr.pad[1] = 0;
-                    a.liverecs[out] = lr;
+                for (int k = 0; k < 4; ++k) {
+                    const int s0 = t ? __ffs(t) - 1 : -1;
+                    if (k == g)
+                        src = s0;
+                    t &= t - 1;
                 }
+                todo = t;
+                const int from = src < 0 ? 0 : src;
+                const uint32_t pos = __shfl_sync(0xffffffffu, ra.x, from);
+                const uint32_t first = __shfl_sync(0xffffffffu, rm.x, from); // msg[0..3]: the DF bit 0x80 of msg[0] decides the length
+                unsigned long long power = 0;
+                if (src >= 0) {
+                    const int signal_len = (first & 0x80u) ? 268 : 134;
+                    // K1a's magnitudes: window position pos starts at magnitude index pos + kPosShift
+                    const uint16_t *fm = a.mag + (size_t) pos + kPosShift + 19;
+                    for (int k = sub; k < signal_len; k += 8) {
+                        const unsigned long long v = fm[k];
+                        power += v * v;
+                    }
+                }
+                power += __shfl_xor_sync(0xffffffffu, power, 4);
+                power += __shfl_xor_sync(0xffffffffu, power, 2);
+                power += __shfl_xor_sync(0xffffffffu, power, 1);
+                // hand the sums back to the lanes that own the records
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int owner = __shfl_sync(0xffffffffu, src, 8 * k);
+                    const unsigned long long pk = __shfl_sync(0xffffffffu, power, 8 * k);
+                    if (owner == lane)
+                        my_power = pk;
+                }
+            }
+            if (mine) {
+                // LiveRec: pos, w0 (+ bit 31: the key is in S), w1, errbits, power, msg[14]
+                const uint32_t w0 = ra.y | (bitmap_test(a.addr_bitmap, ra.z & 0xffffffu) ? 0x80000000u : 0u);
+                uint2 *dst = reinterpret_cast<uint2 *>(&a.liverecs[out]);
+                dst[0] = make_uint2(ra.x, w0);
+                dst[1] = make_uint2(ra.z, ra.w);
+                dst[2] = make_uint2((uint32_t) my_power, (uint32_t) (my_power >> 32));
+                dst[3] = make_uint2(rm.x, rm.y);
+                dst[4] = make_uint2(rm.z, rm.w & 0xffffu);
             }
         }
     }

@@ -31,7 +31,7 @@
 //
 // Tiles that touch the start or the end of the span (carried head, ragged tail: two or three per chunk) go through
 // scan_kernel's process_tile<.., EDGE> inside the same launch: warp 0 of a CTA owns the ring buffer that path needs
-// and picks them up once the interior tiles are handed out.
+// and takes them before it joins the interior queue.
 
 #include <type_traits>
 
@@ -416,18 +416,10 @@ __global__ void __launch_bounds__(kScan2Threads, 1) scan2_kernel(const ScanArgs 
 
     WarpCtx cx;
     cx.ncand_total = 0;
-    for (;;) {
-        uint32_t q = 0;
-        if (lane == 0)
-            q = atomicAdd(&a.counters->next_tile2, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        const uint32_t tile = a.fast_lo + q;
-        if (tile >= a.fast_hi)
-            break;
-        scan2_tile<SLICE, ODD16>(a, cx, tile, smem2, s_apron);
-    }
     if (warp == 0) {
-        // the edge tiles of the span: the generic path of scan_kernel, with this kernel's table layout
+        // The edge tiles of the span first (the generic path of scan_kernel, with this kernel's table layout): they
+        // take two to three times as long as an interior tile, and handed out last they would be the tail of the
+        // launch.  The warps that take them simply come to the interior queue later.
         uint32_t *s_ring = reinterpret_cast<uint32_t *>(smem2 + kScan2Lut + kScan2Apron);
         for (;;) {
             uint32_t tile = 0;
@@ -440,6 +432,16 @@ __global__ void __launch_bounds__(kScan2Threads, 1) scan2_kernel(const ScanArgs 
                 break;
             process_tile<0, SLICE, true, 2>(a, cx, tile, reinterpret_cast<const uint16_t *>(smem2), s_ring);
         }
+    }
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0)
+            q = atomicAdd(&a.counters->next_tile2, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        const uint32_t tile = a.fast_lo + q;
+        if (tile >= a.fast_hi)
+            break;
+        scan2_tile<SLICE, ODD16>(a, cx, tile, smem2, s_apron);
     }
     if (lane == 0 && cx.ncand_total) // one same-address atomic per warp, not per tile
         atomicAdd(&a.counters->n_cand, cx.ncand_total);

@@ -7,7 +7,8 @@ from readsb_protobuf_b200 import api, synth
 
 seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 fmt = sys.argv[2] if len(sys.argv) > 2 else "uc8"
-cfg = synth.baseline_config(1, seconds=seconds)
+dense = len(sys.argv) > 3 and sys.argv[3] == "dense"  # the configs[3] traffic (5000 frames/s, 20 % one-bit errors)
+cfg = synth.baseline_config(3 if dense else 1, seconds=seconds)
 if fmt != "uc8":
     cfg = synth.SynthConfig(seed=3, nsamples=cfg.nsamples, fmt=fmt, frames_per_s=200.0)
 iq, _ = synth.generate(cfg)
