@@ -59,9 +59,10 @@ typedef struct b200_demod_config {
     int32_t mode_ac;             /* Modes.mode_ac (--modeac, readsb.c:831-833): also demodulate Mode A/C replies */
     int32_t filter_dc;           /* Modes.dc_filter (--dcfilter, readsb.c:486): the convert_*_generic converters
                                     (convert.c:113-213, 374-423) with their 1 Hz DC block at 2.4 MS/s */
-    int32_t sc16q11_table_bits;  /* 0, or the SC16Q11_TABLE_BITS (1..8) the reference was built with: sc16q11 input then
+    int32_t sc16q11_table_bits;  /* 0, or the SC16Q11_TABLE_BITS (1..11) the reference was built with: sc16q11 input then
                                     goes through convert_sc16q11_table (convert.c:264-328; the armhf package uses 8,
-                                    debian/rules:19) instead of the float path, unless filter_dc picks the generic one */
+                                    debian/rules:19; oneoff/convert_benchmark.c also times 9..11) instead of the float
+                                    path, unless filter_dc picks the generic one */
     int32_t reserved;
 } b200_demod_config;
 

@@ -34,9 +34,10 @@ def run_file(path, fmt: str = "uc8", nfix: int = 1, threshold: int = 58, block_s
     if exe is None:
         raise RuntimeError("oracle/_ref/ref_demod is not built and /root/reference is absent")
     if table_bits:
-        # the reference as its armhf package builds it (-DSC16Q11_TABLE_BITS=8, debian/rules:19)
-        assert table_bits == 8, "oracle/Makefile builds the table variant for 8 bits only"
-        exe = exe.with_name("ref_demod_tb8")
+        # the reference as its armhf package builds it (-DSC16Q11_TABLE_BITS=8, debian/rules:19), or with the larger
+        # tables of its oneoff/convert_benchmark.c (9, 10, 11 bits)
+        assert table_bits in (8, 9, 10, 11), "oracle/Makefile builds the table variants for 8..11 bits"
+        exe = exe.with_name(f"ref_demod_tb{table_bits}")
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "ref.res")
         cmd = [str(exe), "--in", str(path), "--out", out, "--format", fmt, "--nfix", str(nfix),

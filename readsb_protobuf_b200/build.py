@@ -104,7 +104,7 @@ def ensure_ref() -> Path | None:
     if have_reference_sources():
         netfmt = ORACLE / "_ref" / "ref_netfmt"
         deps = [ORACLE / "ref_harness.c", ORACLE / "ref_netfmt.c", ORACLE / "ref_shim" / "stubs.c", ORACLE / "Makefile"]
-        if not _newer(binary, deps) or not _newer(netfmt, deps):
+        if not _newer(binary, deps) or not _newer(netfmt, deps) or not _newer(ORACLE / "_ref" / "ref_demod_tb11", deps):
             _run(["make", "-C", ORACLE, "ref", "CC=gcc", f"REF={REFERENCE}"])
     return binary if binary.exists() else None
 

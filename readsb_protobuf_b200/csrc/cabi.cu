@@ -312,8 +312,8 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
         return fail(B200_ERR_ARG, "nfix_crc must be 0, 1 or 2");
     if (cfg->preamble_threshold < 1 || cfg->preamble_threshold > 6000)
         return fail(B200_ERR_ARG, "preamble_threshold out of range");
-    if (cfg->sc16q11_table_bits < 0 || cfg->sc16q11_table_bits > 8)
-        return fail(B200_ERR_ARG, "sc16q11_table_bits must be 0 (float path) or 1..8 (the table has to fit shared memory)");
+    if (cfg->sc16q11_table_bits < 0 || cfg->sc16q11_table_bits > 11)
+        return fail(B200_ERR_ARG, "sc16q11_table_bits must be 0 (float path) or 1..11 (SC16Q11_TABLE_BITS, convert.c:264-268)");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -364,6 +364,7 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_end));
     CUDA_TRY(scan_configure());
     CUDA_TRY(scan2_configure());
+    CUDA_TRY(scan3_configure());
     CUDA_TRY(slice_configure());
     CUDA_TRY(upload_constants(d->crc->bit_syndromes()));
 
@@ -386,16 +387,25 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
     }
 
     if (d->eff_format == 4) {
-        std::vector<uint16_t> table(65536, 0);
-        build_sc16q11_table(cfg->sc16q11_table_bits, table.data());
-        std::vector<uint32_t> both(65536);
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(table.data());
-        for (uint32_t i = 0; i < 32768; ++i) {
-            both[i] = words[i];
-            both[32768 + (i ^ ((i >> 7) & 31u))] = words[i];
+        // up to 8 bits the table (<= 65536 entries) takes the uc8 table's place in K1a's shared memory, staged from
+        // its swizzled copy; with 9..11 bits (512 KiB .. 8 MiB) it stays in global memory and is read through L2
+        const int bits = cfg->sc16q11_table_bits;
+        const size_t entries = std::max<size_t>(65536, (size_t) 1 << (2 * bits));
+        std::vector<uint16_t> table(entries, 0);
+        build_sc16q11_table(bits, table.data());
+        if (bits <= 8) {
+            std::vector<uint32_t> both(65536);
+            const uint32_t *words = reinterpret_cast<const uint32_t *>(table.data());
+            for (uint32_t i = 0; i < 32768; ++i) {
+                both[i] = words[i];
+                both[32768 + (i ^ ((i >> 7) & 31u))] = words[i];
+            }
+            CUDA_TRY(d->d_lut_q11.ensure(2 * 65536));
+            CUDA_TRY(cudaMemcpy(d->d_lut_q11.p, both.data(), 2 * 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        } else {
+            CUDA_TRY(d->d_lut_q11.ensure(entries));
+            CUDA_TRY(cudaMemcpy(d->d_lut_q11.p, table.data(), entries * sizeof(uint16_t), cudaMemcpyHostToDevice));
         }
-        CUDA_TRY(d->d_lut_q11.ensure(2 * 65536));
-        CUDA_TRY(cudaMemcpy(d->d_lut_q11.p, both.data(), 2 * 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
 
     const auto &ts = d->crc->short_table();
@@ -459,7 +469,7 @@ static ScanArgs make_scan_args(b200_demod *d, ChunkSet &c, const uint8_t *d_iq, 
     a.block_samples = d->cfg.block_samples;
     a.ntiles = tiles_for(nsamples);
     a.lut = (d->eff_format == 4) ? d->d_lut_q11.p : d->d_lut.p;
-    a.lut_swz = a.lut + 65536;
+    a.lut_swz = (d->eff_format == 4 && d->cfg.sc16q11_table_bits > 8) ? a.lut : a.lut + 65536; // no staged copy of a big table
     a.lut_swz2 = d->d_lut.p + 2 * 65536;
     a.fast_lo = a.fast_hi = 0;
     a.table_bits = d->cfg.sc16q11_table_bits;

@@ -240,39 +240,6 @@ __device__ __forceinline__ int frame_bytes_for_df(uint32_t df) {
     return 0;
 }
 
-// One PPM bit decision (demod_2400.c:73-177 in closed form): frame bit b of a candidate whose
-// preamble window starts at m[0], tried at phase try_phase, sits t = try_phase + 12*b fifths of a
-// sample after m[19]; correlator t%5 over the four samples from m[19 + t/5].
-__device__ __forceinline__ bool slice_bit(const uint16_t *m, int try_phase, int b, const int (*coef)[4]) {
-    int t = try_phase + 12 * b;
-    int s = t / 5;
-    int r = t - 5 * s;
-    const uint16_t *p = m + 19 + s;
-    int v = coef[r][0] * (int) p[0] + coef[r][1] * (int) p[1] + coef[r][2] * (int) p[2] + coef[r][3] * (int) p[3];
-    return v > 0;
-}
-
-// Warp-cooperative slice of a whole frame: lane l decides bits l, l+32, l+64, l+96; the ballots
-// are the packed message (bit b of the frame = bit b%32 of w[b/32]).  Also returns the CRC
-// syndrome (crc.c:67-82, by linearity the XOR of the single-bit syndromes of the set bits).
-__device__ __forceinline__ void warp_slice_frame(const uint16_t *m, int try_phase, int nbits, const int (*coef)[4],
-                                                 const uint32_t *s_syn, uint32_t w[4], uint32_t &syndrome) {
-    const int lane = threadIdx.x & 31;
-    const int off = 112 - nbits; // crc.c:143: short frames use the tail of the 112-bit syndrome list
-    uint32_t x = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int b = lane + 32 * k;
-        bool bit = false;
-        if (b < nbits)
-            bit = slice_bit(m, try_phase, b, coef);
-        w[k] = __ballot_sync(0xffffffffu, bit);
-        if (bit)
-            x ^= s_syn[b + off];
-    }
-    syndrome = __reduce_xor_sync(0xffffffffu, x);
-}
-
 // ------------------------------------------------------------------------------------------
 // K1: scan kernel -- warp-autonomous streaming
 //
@@ -502,7 +469,9 @@ __device__ __forceinline__ void process_tile(const ScanArgs &a, WarpCtx &cx, con
                     const uint32_t I = (uint32_t) abs((int) (int16_t) (words[j] & 0xffffu)) & 2047u;
                     const uint32_t Q = (uint32_t) abs((int) (int16_t) (words[j] >> 16)) & 2047u;
                     const uint32_t idx = ((I >> lose) << bits) | (Q >> lose);
-                    m[(u * US + j) % kLanePos] = s_lut[idx ^ (((idx >> 8) & 31u) << 1)];
+                    // up to 8 bits the table is in shared memory (the uc8 table's slot and swizzle); the larger ones
+                    // (9..11 bits: 512 KiB .. 8 MiB) are read through L2
+                    m[(u * US + j) % kLanePos] = bits <= 8 ? (uint32_t) s_lut[idx ^ (((idx >> 8) & 31u) << 1)] : (uint32_t) __ldg(&a.lut[idx]);
                 }
             }
         } else if (FORMAT == 3) {
@@ -789,7 +758,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const ScanArgs a)
     // one-time staging of the tables (the only block-wide barrier of the kernel).  The magnitude
     // table arrives pre-swizzled (32-bit word j of row Q at word j ^ (Q & 31)): all of a thread's
     // 16-byte loads are in flight at once, one round trip to L2 per CTA.
-    if (FORMAT == 0 || FORMAT == 4) {
+    if (FORMAT == 0 || (FORMAT == 4 && a.table_bits <= 8)) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.lut_swz);
         uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
         constexpr int kUnits = (int) (kSmemLut / 16);                      // 8192 sixteen-byte units
@@ -871,6 +840,7 @@ cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stre
 }
 
 #include "scan2.inl"
+#include "scan3.inl"
 
 // ------------------------------------------------------------------------------------------
 // K1b: slice kernel -- PPM slice + CRC class of every (candidate position, phase)
@@ -1226,7 +1196,6 @@ cudaError_t launch_slice(const SliceArgs &a, int grid, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 
 constexpr int kClassifyThreads = 256;
-constexpr int kFrameSamples = 296; // samples a frame's slice + power can touch: m[0..290]
 
 __device__ __forceinline__ bool bitmap_test(const uint32_t *__restrict__ bm, uint32_t addr) {
     return (__ldg(&bm[(addr & 0xffffffu) >> 5]) >> (addr & 31u)) & 1u;
@@ -1240,25 +1209,6 @@ __device__ __forceinline__ bool record_is_live(uint32_t w0, uint32_t w1, const u
     if (kind == kKindDF11 && (w0 & 0x7fu) == 0)
         return true; // IID 0 scores 750/375 even for an unknown address
     return bitmap_test(bm, w1 & 0xffffffu);
-}
-
-// magnitude of span sample s (relative to the first new sample), 0 outside the stream
-__device__ __forceinline__ uint32_t sample_mag(const ClassifyArgs &a, long long s) {
-    if (s < -(long long) a.head_valid || s >= (long long) a.nsamples)
-        return 0;
-    const int bps = (a.format == 0 || a.format == 3) ? 2 : 4;
-    const uint8_t *base = (s < 0) ? a.head + (s + kHead) * bps : a.iq + s * bps;
-    if (a.format == 3) // the stream holds magnitudes
-        return (uint32_t) base[0] | ((uint32_t) base[1] << 8);
-    if (a.format == 0) {
-        const uint32_t idx = (uint32_t) base[0] | ((uint32_t) base[1] << 8);
-        return __ldg(&a.lut[idx]);
-    }
-    const uint32_t w = *reinterpret_cast<const uint32_t *>(base);
-    if (a.format == 4)
-        return __ldg(&a.lut[sc16q11_table_index(w, (int) a.table_bits)]);
-    float magsq, mag;
-    return mag_sc16_word(w, (a.format == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f), magsq, mag);
 }
 
 // index of the candidate entry of tile-local position pl (the entries are in position order)
@@ -1280,9 +1230,6 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
     __shared__ __align__(16) uint8_t s_nb[kTile];    // which phases own a class record
     __shared__ uint16_t s_slot[kTile];               // first live-record slot of a live candidate
     __shared__ int s_warp[40];
-    __shared__ uint32_t s_syn[112];
-    __shared__ int s_coef[5][4];
-    __shared__ __align__(16) uint16_t s_frame[kClassifyThreads / 32][kFrameSamples];
     __shared__ uint32_t s_bd[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1301,10 +1248,6 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
         return;
     }
 
-    if (tid < 112)
-        s_syn[tid] = c_bit_syndrome[tid];
-    if (tid < 20)
-        (&s_coef[0][0])[tid] = (&c_slice_coef[0][0])[tid];
     if (tid < 8)
         s_bd[tid] = 0;
     for (uint32_t i = tid; i < (td.ncand + 3) / 4; i += kClassifyThreads) {
@@ -1515,15 +1458,8 @@ __global__ void __launch_bounds__(kCwWarps * 32) classify_warp_kernel(const Clas
     __shared__ uint32_t s_flagw[kCwWarps][kCwCap / 4]; // per candidate byte: live[0] | has a -1 phase[1]
     __shared__ uint32_t s_nbw[kCwWarps][kCwCap / 4];   // per candidate byte: which phases own a class record
     __shared__ uint16_t s_slot[kCwWarps][kCwCap];      // first live-record slot of a live candidate
-    __shared__ uint32_t s_syn[112];
-    __shared__ int s_coef[5][4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 112)
-        s_syn[tid] = c_bit_syndrome[tid];
-    if (tid < 20)
-        (&s_coef[0][0])[tid] = (&c_slice_coef[0][0])[tid];
-    __syncthreads(); // the only block-wide barrier
     if (a.counters->overflow & 3u)
         return; // K1 ran out of room: the host places the slabs exactly and runs the span again
 

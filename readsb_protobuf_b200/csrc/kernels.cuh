@@ -113,6 +113,7 @@ cudaError_t slice_configure();
 cudaError_t launch_scan(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
 // scan2.cu: the register-window K1a for the interior tiles of a uc8 span (same outputs as scan_kernel)
 cudaError_t scan2_configure();
+cudaError_t scan3_configure();
 bool scan2_supports(const ScanArgs &a);
 void scan2_tile_range(uint64_t nsamples, uint32_t &lo, uint32_t &hi);
 cudaError_t launch_scan2(const ScanArgs &a, int mode, int grid, cudaStream_t stream);

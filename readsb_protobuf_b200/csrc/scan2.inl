@@ -33,13 +33,16 @@
 // scan_kernel's process_tile<.., EDGE> inside the same launch: warp 0 of a CTA owns the ring buffer that path needs
 // and takes them before it joins the interior queue.
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <type_traits>
 
 namespace {
 
 constexpr int kRun = kTile / 32;                 // scan positions (and owned samples) per lane and tile
 constexpr int kBodies = kRun / 32;               // loop bodies of 32 samples
-constexpr int kScan2Warps = 16;                  // 128 registers per thread
+constexpr int kScan2Warps = 16;                  // 128 registers per thread (20 warps at 96 registers spill and measure 7 % slower)
 constexpr int kScan2Threads = kScan2Warps * 32;
 constexpr int kApronWords = 12;                  // per lane: 9 magnitude pairs (18 samples), padded to 48 bytes
 constexpr size_t kScan2Lut = 65536 * sizeof(uint16_t);
@@ -478,13 +481,29 @@ void scan2_tile_range(uint64_t nsamples, uint32_t &lo, uint32_t &hi) {
     }
 }
 
+// scan3.inl: the packed-FP32 edition.  Bit-identical output (it runs the whole GPU suite when selected) and 25 % fewer
+// instructions, but measured slower on the B200 (scan only: 0.177 of the HBM roofline against 0.266): its loop body
+// is 23.6 KB of SASS, which the instruction caches do not hold for 12 unsynchronised warps (ncu: top stall
+// no_instruction, issue slots 42 % busy), and its 168 registers leave 12 warps per SM.  Kept selectable
+// (B200_K1A=scan3) as the measured alternative; scan2_kernel is the product path.
+cudaError_t launch_scan3(const ScanArgs &a, int mode, int grid, cudaStream_t stream);
+bool scan3_supports(const ScanArgs &a);
+int scan3_warps_per_cta();
+
+static bool use_scan3() {
+    static const bool on = getenv("B200_K1A") && !strcmp(getenv("B200_K1A"), "scan3"); // development switch
+    return on;
+}
+
 int k1a_warps_per_cta(uint32_t format) {
-    return format == 0 ? kScan2Warps : kScanWarps;
+    return format == 0 ? (use_scan3() ? scan3_warps_per_cta() : kScan2Warps) : kScanWarps;
 }
 
 cudaError_t launch_scan2(const ScanArgs &a, int mode, int grid, cudaStream_t stream) {
     if (a.fast_hi <= a.fast_lo)
         return cudaSuccess;
+    if (use_scan3() && scan3_supports(a))
+        return launch_scan3(a, mode, grid, stream);
     const int useful = (int) ((a.fast_hi - a.fast_lo + kScan2Warps - 1) / kScan2Warps);
     if (grid > useful)
         grid = useful;

@@ -145,6 +145,10 @@ def test_port_sc16q11_table_matches_live_reference():
     # the table itself: 0 at the origin, clamped to full scale beyond the unit circle, symmetric
     t = port.sc16q11_table(8).reshape(256, 256)
     assert t[0, 0] == 0 and t[255, 255] == 65535 and t[181, 181] == 65528 and t[182, 182] == 65535 and np.array_equal(t, t.T)
+    # the larger tables of the reference's oneoff/convert_benchmark.c (oracle/_ref/ref_demod_tb9 .. tb11)
+    for bits in (9, 10, 11):
+        assert results.compare_results(port.run(iq, "sc16q11", table_bits=bits), ref.run(iq, "sc16q11", table_bits=bits),
+                                       float_rtol=0.0, signal_atol=0.0) == []
     # other formats are untouched by the build flag
     iq2, _ = synth.generate(synth.SynthConfig(seed=45, nsamples=200_000, fmt="sc16", frames_per_s=3000))
     assert results.compare_results(port.run(iq2, "sc16", table_bits=8), ref.run(iq2, "sc16", table_bits=8), float_rtol=0.0,
