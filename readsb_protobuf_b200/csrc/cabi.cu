@@ -22,6 +22,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "device_types.h"
@@ -105,6 +106,33 @@ double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
+
+// development aid (B200_SPAN_TRACE=1): host-side time marks of a span's chunk pipeline, printed when the span ends
+struct SpanTrace {
+    bool on;
+    double t0;
+    std::vector<std::pair<const char *, double>> marks;
+    SpanTrace() : on(getenv("B200_SPAN_TRACE") != nullptr), t0(0) {}
+    void begin() {
+        if (on) {
+            marks.clear();
+            t0 = now_ms();
+        }
+    }
+    void mark(const char *what) {
+        if (on)
+            marks.emplace_back(what, now_ms() - t0);
+    }
+    void print(uint64_t nsamples) {
+        if (!on)
+            return;
+        fprintf(stderr, "span of %llu samples:", (unsigned long long) nsamples);
+        for (auto &m : marks)
+            fprintf(stderr, " %s@%.3f", m.first, m.second);
+        fprintf(stderr, "\n");
+    }
+};
+static thread_local SpanTrace g_trace;
 
 // a typed window into a larger allocation (not owning)
 template <typename T>
@@ -211,7 +239,11 @@ struct b200_demod {
 
     // span buffers
     DevBuf<uint8_t> d_iq;
-    ChunkSet sets[2];
+    // chunks in flight: the host issues up to kSets chunks ahead of the one it is resolving, so that in a span of a
+    // few chunks every launch is queued while the GPU works on the first one and the host's part of the pipeline is
+    // the resolver alone
+    static constexpr int kSets = 6;
+    ChunkSet sets[kSets];
     DevBuf<uint8_t> d_dbg_masks;
     DevBuf<double> d_span_fsums; // float formats: [mag_bufs of the span][2]
     DevBuf<uint16_t> d_mag;
@@ -230,7 +262,8 @@ struct b200_demod {
         cudaSetDevice(cfg.device);
         d_lut.release(); d_lut_q11.release(); d_tab_short.release(); d_tab_long.release(); d_bitmap.release();
         d_head.release(); d_head_tmp.release(); d_iq.release();
-        sets[0].release(); sets[1].release();
+        for (ChunkSet &c : sets)
+            c.release();
         d_span_fsums.release(); d_dbg_masks.release(); d_mag.release(); d_frames.release(); d_syn.release(); d_err.release(); d_bits.release();
         d_csum_u64.release(); d_csum_f64.release();
         d_dc_aI.release(); d_dc_aQ.release(); d_dc_state.release(); d_dc_mag.release(); d_dc_raw.release();
@@ -654,7 +687,9 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     const uint32_t ntiles = tiles_for(n);
     size_t dead_cap = c.d_dead.cap, live_cap = c.h_live.cap, liverec_cap = c.h_liverecs.cap;
 
+    g_trace.mark("wait");
     CUDA_TRY(cudaEventSynchronize(c.ev_small));
+    g_trace.mark("ready");
     ScanCounters cnt = *c.h_counters.p;
     {
         float ms = 0;
@@ -706,7 +741,7 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
             live_cap = std::max<size_t>(live_cap, (size_t) cnt.n_live + 4096);
             liverec_cap = std::max<size_t>(liverec_cap, (size_t) cnt.n_liverec + 4096);
         }
-        // the other chunk set may still be running on `exec`; this one is idle, so re-issuing is safe
+        // later chunks may be queued or running on `exec`; this set is idle, so re-issuing it (behind them) is safe
         int rc = issue_chunk(d, c, exec, exact, cand_total, rec_total, dead_cap, live_cap, liverec_cap, launches);
         if (rc != B200_OK)
             return rc;
@@ -766,6 +801,7 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
         return fail(B200_ERR_NOMEM, "out of host memory while resolving a chunk");
     }
     t.resolve_ms += (float) (now_ms() - t_res0);
+    g_trace.mark("resolved");
     t.d2h_bytes += c.small_d2h_bytes + (size_t) cnt.n_live * (sizeof(LivePos) + sizeof(LiveHidden)) + (size_t) cnt.n_liverec * sizeof(LiveRec);
     t.n_candidates += cnt.n_cand;
     t.n_phase_records += cnt.n_rec;
@@ -823,17 +859,28 @@ static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, 
         const uint64_t wave = ((uint64_t) d->scan_grid * k1a_warps - 1) * kTile / B;
         if (!ramp && wave > 0 && nb > 3 * wave) {
             // device-resident span: whole waves per chunk, so that only the last launch ends on a partial
-            // wave -- one wave first (the host resolver starts early), then two at a time
+            // wave -- one wave first (the host resolver starts early), then three at a time (every chunk costs
+            // about 25 us of launch gaps and of order_live's fixed latency; B200_CHUNK_WAVES, measured 2 -> 3:
+            // 1.15 -> 1.06 ms for the 144 M-sample stream)
+            static const uint64_t per_chunk = [] {
+                const char *e = getenv("B200_CHUNK_WAVES");
+                const long v = e ? atol(e) : 3;
+                return (uint64_t) (v >= 1 && v <= 16 ? v : 3);
+            }();
             starts.push_back(0);
             at = wave;
-            while (nb - at > 3 * wave) {
+            while (nb - at > (per_chunk + 1) * wave) {
                 starts.push_back(at * B);
-                at += 2 * wave;
+                at += per_chunk * wave;
             }
             starts.push_back(at * B);
-            // ... and a short last chunk (half a wave at most): nothing overlaps the host's resolve of the last
+            // ... and a short last chunk (a wave at most): nothing overlaps the host's resolve of the last
             // chunk, so it should be little work
-            const uint64_t rest = nb - at, tail = std::min<uint64_t>(rest / 4, std::max<uint64_t>(1, wave / 2));
+            static const uint64_t tail_div = [] {
+                const char *e = getenv("B200_CHUNK_TAIL_DIV");
+                return (uint64_t) (e ? atol(e) : 4);
+            }();
+            const uint64_t rest = nb - at, tail = tail_div ? std::min<uint64_t>(rest / tail_div, wave) : 0;
             if (tail >= 1 && rest > tail)
                 starts.push_back((nb - tail) * B);
         } else {
@@ -884,7 +931,7 @@ static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, 
     }
 
     auto setup = [&](uint64_t i) -> int {
-        ChunkSet &c = d->sets[i & 1];
+        ChunkSet &c = d->sets[i % b200_demod::kSets];
         c.start = starts[i];
         c.nsamples = starts[i + 1] - starts[i];
         c.final_chunk = final_span && (i + 1 == nchunks);
@@ -906,16 +953,18 @@ static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, 
                            std::max<size_t>(c.h_liverecs.cap, (size_t) (c.nsamples / 64 + 4096)), &launches);
     };
 
-    int rc = setup(0);
-    if (rc != B200_OK)
-        return rc;
+    g_trace.begin();
+    int rc = B200_OK;
+    uint64_t issued = 0;
     for (uint64_t i = 0; i < nchunks; ++i) {
-        if (i + 1 < nchunks) {
-            rc = setup(i + 1); // the GPU works on chunk i+1 while the host resolves chunk i
+        // the GPU works through chunks i .. i + kSets - 1 while the host resolves chunk i
+        for (; issued < nchunks && issued < i + b200_demod::kSets; ++issued) {
+            rc = setup(issued);
             if (rc != B200_OK)
                 return rc;
+            g_trace.mark("issued");
         }
-        rc = finish_chunk(d, d->sets[i & 1], exec, &launches, t);
+        rc = finish_chunk(d, d->sets[i % b200_demod::kSets], exec, &launches, t);
         if (rc != B200_OK)
             return rc;
     }
@@ -923,6 +972,8 @@ static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, 
     if (rc != B200_OK)
         return rc;
     CUDA_TRY(cudaStreamSynchronize(exec));
+    g_trace.mark("end");
+    g_trace.print(nsamples);
 
     d->first_sample += nsamples;
     if (final_span)

@@ -1884,23 +1884,27 @@ cudaError_t launch_order_live(const TileOut *tiles_out, uint32_t ntiles, const S
 // on a side stream next to K1a.
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(64) float_block_sums_kernel(const uint8_t *__restrict__ iq, uint32_t format, uint64_t nsamples,
+__global__ void __launch_bounds__(96) float_block_sums_kernel(const uint8_t *__restrict__ iq, uint32_t format, uint64_t nsamples,
                                                                uint32_t block_samples, uint32_t nblocks, double *__restrict__ sums) {
-    // one CTA of two warps per mag_buf: warp 0 converts the next batch of 128 samples into the other half
-    // of a double buffer while lanes 0 and 1 of warp 1 walk the two chains over the current one
-    __shared__ __align__(16) float s_val[2][2][128]; // [buffer][0 = mag, 1 = magsq][sample]
+    // one CTA of three warps per mag_buf: warps 0 and 1 convert the next batch of 256 samples (half each) into
+    // the other half of a double buffer while lanes 0 and 1 of warp 2 walk the two chains over the current one.
+    // The chains are the floor (one dependent FADD per sample, 4 cycles each); two converter warps keep the
+    // conversion (an IEEE square root per sample) well under that, so a batch costs the chain plus one barrier.
+    constexpr int kBatch = 256;
+    __shared__ __align__(16) float s_val[2][2][kBatch]; // [buffer][0 = mag, 1 = magsq][sample]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t k = blockIdx.x;
     const uint64_t b0 = (uint64_t) k * block_samples;
     const uint64_t nk = nsamples > b0 ? (nsamples - b0 < block_samples ? nsamples - b0 : block_samples) : 0;
     const float inv_scale = (format == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f);
     const uint32_t *src = reinterpret_cast<const uint32_t *>(iq) + b0; // one 32-bit word per sample
+    const int mine4 = 128 * (warp & 1) + 4 * lane;                     // a converter lane's 4 samples of a batch
 
     // 4 samples per lane (block_samples % 8 == 0 and 16-byte aligned spans: whole uint4s except in the
     // stream's ragged last batch)
     auto load = [&](uint64_t base) {
         uint4 v = make_uint4(0, 0, 0, 0);
-        const uint64_t s0 = base + 4 * (uint64_t) lane;
+        const uint64_t s0 = base + (uint64_t) mine4;
         if (s0 + 4 <= nk) {
             v = ldg_stream(reinterpret_cast<const uint4 *>(src + s0));
         } else if (s0 < nk) {
@@ -1918,42 +1922,45 @@ __global__ void __launch_bounds__(64) float_block_sums_kernel(const uint8_t *__r
         mag_sc16_word(v.y, inv_scale, sq[1], mg[1]);
         mag_sc16_word(v.z, inv_scale, sq[2], mg[2]);
         mag_sc16_word(v.w, inv_scale, sq[3], mg[3]);
-        *reinterpret_cast<float4 *>(&s_val[buf][0][4 * lane]) = make_float4(mg[0], mg[1], mg[2], mg[3]);
-        *reinterpret_cast<float4 *>(&s_val[buf][1][4 * lane]) = make_float4(sq[0], sq[1], sq[2], sq[3]);
+        *reinterpret_cast<float4 *>(&s_val[buf][0][mine4]) = make_float4(mg[0], mg[1], mg[2], mg[3]);
+        *reinterpret_cast<float4 *>(&s_val[buf][1][mine4]) = make_float4(sq[0], sq[1], sq[2], sq[3]);
     };
 
-    const uint64_t nbatches = (nk + 127) / 128;
+    const uint64_t nbatches = (nk + kBatch - 1) / kBatch;
     uint4 ahead[3] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}; // batches b+1 .. b+3 in flight
-    if (warp == 0 && nbatches) {
+    if (warp < 2 && nbatches) {
         put(0, load(0));
-        ahead[0] = load(128);
-        ahead[1] = load(256);
-        ahead[2] = load(384);
+        ahead[0] = load(kBatch);
+        ahead[1] = load(2 * kBatch);
+        ahead[2] = load(3 * kBatch);
     }
-    float acc = 0.0f; // warp 1, lane 0: sum_level, lane 1: sum_power
+    float acc = 0.0f; // warp 2, lane 0: sum_level, lane 1: sum_power
     __syncthreads();
     for (uint64_t b = 0; b < nbatches; ++b) {
-        if (warp == 0) {
+        if (warp < 2) {
             if (b + 1 < nbatches) {
                 put((int) ((b + 1) & 1), ahead[0]);
                 ahead[0] = ahead[1];
                 ahead[1] = ahead[2];
-                ahead[2] = load((b + 4) * 128);
+                ahead[2] = load((b + 4) * kBatch);
             }
         } else if (lane < 2) {
             const float *mine = s_val[b & 1][lane];
-            const uint64_t left = nk - b * 128;
-            if (left >= 128) {
-                float4 r[32]; // all loads first: they do not depend on the chain
+            const uint64_t left = nk - b * kBatch;
+            if (left >= kBatch) {
+#pragma unroll 1
+                for (int h = 0; h < kBatch / 128; ++h) {
+                    float4 r[32]; // all loads first: they do not depend on the chain
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    r[i] = reinterpret_cast<const float4 *>(mine)[i];
+                    for (int i = 0; i < 32; ++i)
+                        r[i] = reinterpret_cast<const float4 *>(mine + 128 * h)[i];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    acc = __fadd_rn(acc, r[i].x);
-                    acc = __fadd_rn(acc, r[i].y);
-                    acc = __fadd_rn(acc, r[i].z);
-                    acc = __fadd_rn(acc, r[i].w);
+                    for (int i = 0; i < 32; ++i) {
+                        acc = __fadd_rn(acc, r[i].x);
+                        acc = __fadd_rn(acc, r[i].y);
+                        acc = __fadd_rn(acc, r[i].z);
+                        acc = __fadd_rn(acc, r[i].w);
+                    }
                 }
             } else {
                 for (int i = 0; i < (int) left; ++i)
@@ -1962,7 +1969,7 @@ __global__ void __launch_bounds__(64) float_block_sums_kernel(const uint8_t *__r
         }
         __syncthreads();
     }
-    if (warp == 1 && lane < 2)
+    if (warp == 2 && lane < 2)
         sums[2 * k + lane] = (double) acc; // exactly the float the reference divides by nsamples
 }
 
@@ -1970,7 +1977,7 @@ cudaError_t launch_float_block_sums(const uint8_t *iq, uint32_t format, uint64_t
                                     double *sums, cudaStream_t stream) {
     if (nblocks == 0 || format == 0 || format == 4)
         return cudaSuccess;
-    float_block_sums_kernel<<<nblocks, 64, 0, stream>>>(iq, format, nsamples, block_samples, nblocks, sums);
+    float_block_sums_kernel<<<nblocks, 96, 0, stream>>>(iq, format, nsamples, block_samples, nblocks, sums);
     return cudaGetLastError();
 }
 

@@ -128,9 +128,71 @@ bool IcaoFilter::probe(const uint32_t *t, uint32_t addr) {
 }
 
 bool IcaoFilter::test(uint32_t addr) const {
-    if (!dropped_ && addr < (1u << 24))
+    if (!dropped_ && addr < (1u << 24)) {
+        if (track_) {
+            uint64_t &w = probed_[addr >> 6];
+            const uint64_t bit = 1ull << (addr & 63u);
+            if (!(w & bit)) {
+                w |= bit;
+                probed_list_.push_back(addr);
+            }
+        }
         return ((bits_a_[addr >> 6] | bits_b_[addr >> 6]) >> (addr & 63u)) & 1ull;
+    }
     return test_tables(addr);
+}
+
+void IcaoFilter::track_probes(bool on) {
+    for (uint32_t x : probed_list_)
+        probed_[x >> 6] = 0;
+    probed_list_.clear();
+    if (on && probed_.empty())
+        probed_.assign((1u << 24) / 64, 0);
+    track_ = on;
+}
+
+bool IcaoFilter::differs_only_unprobed(const Snapshot &s, const IcaoFilter &walked, uint64_t last_now) const {
+    if (dropped_ || walked.dropped_ || !walked.track_)
+        return false;
+    if (scratch_.empty())
+        scratch_.assign((1u << 24) / 64, 0);
+    auto bit = [](const std::vector<uint64_t> &b, uint32_t x) { return (b[x >> 6] >> (x & 63u)) & 1ull; };
+    // Can a table flip while the run is walked, on either clock?  If not, test() only ever sees the union of the two
+    // tables, and neither which of them is active nor when it flips next has any say in the run.
+    const bool may_flip = last_now >= std::min(s.next_flip, next_flip_);
+    if (may_flip && (s.a_active != (active_ == a_) || s.next_flip != next_flip_))
+        return false;
+    bool ok = true;
+    for (int pass = 0; pass < (may_flip ? 2 : 1) && ok; ++pass) {
+        // pass 0: table a (or the union), pass 1: table b
+        const std::vector<uint32_t> *theirs[2] = {may_flip ? (pass ? &s.seq_b : &s.seq_a) : &s.seq_a, may_flip ? nullptr : &s.seq_b};
+        const std::vector<uint32_t> *mine[2] = {may_flip ? (pass ? &list_b_ : &list_a_) : &list_a_, may_flip ? nullptr : &list_b_};
+        // in s but not here
+        for (const std::vector<uint32_t> *l : theirs)
+            if (l)
+                for (uint32_t x : *l) {
+                    const bool here = may_flip ? bit(pass ? bits_b_ : bits_a_, x) : (bit(bits_a_, x) || bit(bits_b_, x));
+                    if (!here && walked.probed(x))
+                        ok = false;
+                }
+        // here but not in s
+        for (const std::vector<uint32_t> *l : theirs)
+            if (l)
+                for (uint32_t x : *l)
+                    scratch_[x >> 6] |= 1ull << (x & 63u);
+        for (const std::vector<uint32_t> *l : mine)
+            if (l && ok)
+                for (uint32_t x : *l)
+                    if (walked.probed(x) && !bit(scratch_, x)) {
+                        ok = false;
+                        break;
+                    }
+        for (const std::vector<uint32_t> *l : theirs)
+            if (l)
+                for (uint32_t x : *l)
+                    scratch_[x >> 6] = 0;
+    }
+    return ok;
 }
 
 bool IcaoFilter::test_tables(uint32_t addr) const {
@@ -176,6 +238,8 @@ IcaoFilter::Snapshot IcaoFilter::snapshot() const {
 
 void IcaoFilter::load(const Snapshot &s) {
     reset();
+    const bool tracking = track_;
+    track_probes(false); // forget the last walk's probes; the inserts below are not probes
     active_ = a_;
     for (uint32_t x : s.seq_a)
         add(x);
@@ -184,6 +248,7 @@ void IcaoFilter::load(const Snapshot &s) {
         add(x);
     active_ = s.a_active ? a_ : b_;
     next_flip_ = s.next_flip;
+    track_ = tracking;
 }
 
 bool IcaoFilter::same_members(const Snapshot &s) const {
@@ -224,7 +289,7 @@ class WorkerPool {
         {
             std::lock_guard<std::mutex> g(m_);
             stop_ = true;
-            ++generation_;
+            generation_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         for (std::thread &t : threads_)
@@ -233,26 +298,45 @@ class WorkerPool {
     int size() const { return (int) threads_.size() + 1; }
     // fn(worker, begin, end) over [0, n) in slices of `grain`; returns when every slice is done.
     // fixed: item i always goes to worker i % size() (grain 1) -- a run of mag_bufs is then scanned, walked and
-    // assembled by the same thread, whose cache holds its records
+    // assembled by the same thread, whose cache holds its records.
+    // The phases of one resolve() follow each other within microseconds and the resolves of a stream within a few
+    // hundred, so a worker that has finished its share keeps polling the generation counter for kSpinUs before it
+    // goes to sleep on the condition variable (a futex wake-up costs 30-60 us, as much as a whole phase of a sparse
+    // chunk); the caller polls for completion, it has nothing else to do.
     void run(size_t n, size_t grain, const std::function<void(int, size_t, size_t)> &fn, bool fixed = false) {
+        fn_ = &fn;
+        n_ = n;
+        grain_ = grain;
+        fixed_ = fixed;
+        next_.store(0, std::memory_order_relaxed);
+        pending_.store((int) threads_.size(), std::memory_order_relaxed);
+        bool wake;
         {
-            std::lock_guard<std::mutex> g(m_);
-            fn_ = &fn;
-            n_ = n;
-            grain_ = grain;
-            fixed_ = fixed;
-            next_.store(0, std::memory_order_relaxed);
-            pending_ = (int) threads_.size();
-            ++generation_;
+            std::lock_guard<std::mutex> g(m_); // a worker between its last poll and its sleep sees the new generation
+            generation_.fetch_add(1, std::memory_order_release);
+            wake = sleepers_ > 0;
         }
-        cv_.notify_all();
+        if (wake)
+            cv_.notify_all();
         work(0);
-        std::unique_lock<std::mutex> g(m_);
-        done_.wait(g, [this] { return pending_ == 0; });
+        for (uint32_t spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins) {
+            if (spins < 4096)
+                cpu_relax();
+            else
+                std::this_thread::yield(); // fewer cores than threads: let the workers run
+        }
         fn_ = nullptr;
     }
 
   private:
+    static constexpr double kSpinUs = 250.0;
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#elif defined(__aarch64__)
+        asm volatile("yield");
+#endif
+    }
     void work(int worker) {
         if (fixed_) {
             for (size_t i = (size_t) worker; i < n_; i += (size_t) size())
@@ -269,30 +353,42 @@ class WorkerPool {
     void loop(int worker) {
         uint64_t seen = 0;
         for (;;) {
-            {
+            // poll first ...
+            const auto t0 = std::chrono::steady_clock::now();
+            bool got = false;
+            for (uint32_t spins = 0;; ++spins) {
+                if (generation_.load(std::memory_order_acquire) != seen) {
+                    got = true;
+                    break;
+                }
+                cpu_relax();
+                if ((spins & 63u) == 63u &&
+                    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() > kSpinUs)
+                    break;
+            }
+            if (!got) { // ... then sleep
                 std::unique_lock<std::mutex> g(m_);
-                cv_.wait(g, [&] { return generation_ != seen; });
-                seen = generation_;
-                if (stop_)
-                    return;
+                ++sleepers_;
+                cv_.wait(g, [&] { return generation_.load(std::memory_order_acquire) != seen; });
+                --sleepers_;
             }
+            seen = generation_.load(std::memory_order_acquire);
+            if (stop_)
+                return;
             work(worker);
-            {
-                std::lock_guard<std::mutex> g(m_);
-                if (--pending_ == 0)
-                    done_.notify_one();
-            }
+            pending_.fetch_sub(1, std::memory_order_release);
         }
     }
     std::vector<std::thread> threads_;
     std::mutex m_;
-    std::condition_variable cv_, done_;
+    std::condition_variable cv_;
     const std::function<void(int, size_t, size_t)> *fn_ = nullptr;
     size_t n_ = 0, grain_ = 1;
     bool fixed_ = false;
     std::atomic<size_t> next_{0};
-    int pending_ = 0;
-    uint64_t generation_ = 0;
+    std::atomic<int> pending_{0};
+    std::atomic<uint64_t> generation_{0};
+    int sleepers_ = 0;
     bool stop_ = false;
 };
 
@@ -766,6 +862,10 @@ Resolver::Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), 
     min_blocks_per_run_ = 4;
     if (const char *e = getenv("B200_RESOLVER_MIN_LIVE"))
         min_live_ = (uint32_t) strtoul(e, nullptr, 10);
+    if (const char *e = getenv("B200_RESOLVER_ABSOLVE"))
+        absolve_ = atoi(e) != 0;
+    if (const char *e = getenv("B200_RESOLVER_MIN_LIVE_PER_RUN"))
+        min_live_per_run_ = std::max<uint32_t>(1, (uint32_t) strtoul(e, nullptr, 10));
     if (const char *e = getenv("B200_RESOLVER_MIN_BLOCKS"))
         min_blocks_per_run_ = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
     reset();
@@ -774,10 +874,10 @@ Resolver::Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), 
 Resolver::~Resolver() {
     if (getenv("B200_RESOLVER_TRACE"))
         fprintf(stderr,
-                "resolver: %llu spans, %llu as several runs (%llu runs, %llu walked twice); ms: prescan %.2f predict %.2f walk %.2f "
+                "resolver: %llu spans, %llu as several runs (%llu runs, %llu walked twice, %llu kept although the filter prediction was off); ms: prescan %.2f predict %.2f walk %.2f "
                 "validate %.2f merge %.2f assemble %.2f ordered sums %.2f\n",
                 (unsigned long long) trace_.spans, (unsigned long long) trace_.parallel_spans, (unsigned long long) trace_.runs,
-                (unsigned long long) trace_.rewalks, trace_.ms[0], trace_.ms[1], trace_.ms[2], trace_.ms[3], trace_.ms[4], trace_.ms[5], trace_.ms[6]);
+                (unsigned long long) trace_.rewalks, (unsigned long long) trace_.absolved, trace_.ms[0], trace_.ms[1], trace_.ms[2], trace_.ms[3], trace_.ms[4], trace_.ms[5], trace_.ms[6]);
     delete pool_;
 }
 
@@ -866,7 +966,7 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
     const int nworkers = pool_ ? pool_->size() : 1;
     int nruns = 1;
     if (pool_ && v.n_live >= min_live_ && nblocks >= 2 * min_blocks_per_run_ && filter_.replayable())
-        nruns = (int) std::min<uint64_t>((uint64_t) nworkers, nblocks / min_blocks_per_run_);
+        nruns = (int) std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t) nworkers, nblocks / min_blocks_per_run_, (uint64_t) v.n_live / min_live_per_run_}));
     if ((int) runs_.size() < std::max(nruns, 1)) {
         runs_.resize((size_t) std::max(nruns, 1));
         for (auto &r : runs_)
@@ -919,6 +1019,7 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
         pool_->run((size_t) nruns, 1, [&](int, size_t lo, size_t hi) {
             for (size_t r = lo; r < hi; ++r) {
                 Run &run = *runs_[r];
+                run.filter.track_probes(absolve_);
                 run.filter.load(run.predicted);
                 walk(v, run.filter, cut[r], cut[r + 1], blocks, block_base, run.out, true);
             }
@@ -936,7 +1037,10 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
                 nruns = r + 1;
                 break;
             }
-            if (!filter_.same_members(run.predicted) || !run.filter.replayable()) {
+            if (!run.filter.replayable() ||
+                (!filter_.same_members(run.predicted) &&
+                 !(absolve_ && filter_.differs_only_unprobed(run.predicted, run.filter, run.out.now.empty() ? 0 : *std::max_element(run.out.now.begin(), run.out.now.end())) &&
+                   ++trace_.absolved))) {
                 ++respeculated_;
                 ++trace_.rewalks;
                 run.filter.load(filter_.snapshot());

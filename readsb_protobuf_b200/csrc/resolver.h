@@ -46,6 +46,17 @@ class IcaoFilter {
     // same active table, same flip time, and the same SET of addresses in each table (whatever the insertion order):
     // a filter loaded from `s` then answers every test, and takes every expiry, exactly as this one
     bool same_members(const Snapshot &s) const;
+    // Probe tracking (for a filter a run of mag_bufs is walked on speculatively): remember every address test() was
+    // asked about since the last load().  differs_only_unprobed(s, walked, last_now): the answers `walked` got on its
+    // way from state `s` are the answers it would have got from this filter's (the true) state, because
+    //  * the two differ only in addresses the run never asked about (the difference between two filters only shrinks
+    //    while the same inserts and flips are applied to both), and
+    //  * either they flip at the same times, or the run's clock never reached a flip of either (last_now = the
+    //    latest filter clock of the run) -- then test() only ever saw the union of the two tables, and which table
+    //    is active or when it flips next had no say.
+    // The run's result then stands although its start state was predicted wrong.
+    void track_probes(bool on);
+    bool differs_only_unprobed(const Snapshot &s, const IcaoFilter &walked, uint64_t last_now) const;
     bool replayable() const { return !dropped_ && list_a_.size() < kReplayMax && list_b_.size() < kReplayMax; }
 
   private:
@@ -63,6 +74,11 @@ class IcaoFilter {
     std::vector<uint64_t> bits_a_, bits_b_;
     std::vector<uint32_t> list_a_, list_b_;
     bool dropped_;
+    bool track_ = false;
+    mutable std::vector<uint64_t> probed_;      // one bit per 24-bit address, allocated when tracking is first switched on
+    mutable std::vector<uint64_t> scratch_;     // differs_only_unprobed's marks
+    mutable std::vector<uint32_t> probed_list_; // the addresses whose bit is set (to clear them again)
+    bool probed(uint32_t addr) const { return !probed_.empty() && ((probed_[addr >> 6] >> (addr & 63u)) & 1ull); }
 };
 
 // The messages of a process call: a growable array that never zero-fills.  (std::vector::resize would write every
@@ -137,7 +153,7 @@ class Resolver {
     struct WalkOut;
     struct Potential;
     struct Run;
-    static constexpr uint32_t kParallelWalkMinLive = 16384; // below this a span is walked in one run
+    static constexpr uint32_t kParallelWalkMinLive = 2048; // below this a span is walked in one run
     static int score(const IcaoFilter &f, const LiveRec &r);
     static int admit(IcaoFilter &f, const LiveRec &r, uint32_t *added); // the filter-dependent part of decodeModesMessage
     void walk(const SpanView &v, IcaoFilter &f, uint64_t k0, uint64_t k1, const std::vector<b200_block_info> &blocks, size_t block_base,
@@ -159,10 +175,12 @@ class Resolver {
     IcaoFilter sim_;                          // plays the potential adds through to predict the runs' start states
     uint64_t respeculated_ = 0;
     struct Trace { // B200_RESOLVER_TRACE: where the time of resolve() goes, printed when the resolver is destroyed
-        uint64_t spans = 0, parallel_spans = 0, runs = 0, rewalks = 0;
+        uint64_t spans = 0, parallel_spans = 0, runs = 0, rewalks = 0, absolved = 0;
         double ms[7] = {0, 0, 0, 0, 0, 0, 0};
     } trace_;
     uint32_t min_live_;
+    bool absolve_ = true; // keep a run whose start state was predicted wrong only in addresses it never asked about
+    uint32_t min_live_per_run_ = 512; // a run shorter than this costs more in hand-over than it saves
     uint64_t min_blocks_per_run_;
     WorkerPool *pool_;
 };
