@@ -881,6 +881,8 @@ Resolver::~Resolver() {
     delete pool_;
 }
 
+static std::atomic<int> g_resolving{0}; // resolve() calls in progress in this process
+
 static inline double trace_now() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -963,7 +965,15 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
     }
 
     // ---- the walk: one run, or several side by side ----
-    const int nworkers = pool_ ? pool_->size() : 1;
+    // Several demodulators of one process (receiver streams on one GPU, a thread each) share the host's cores:
+    // a resolve takes its share of the pool, not all of it.
+    struct Busy {
+        std::atomic<int> &n;
+        int now;
+        explicit Busy(std::atomic<int> &c) : n(c), now(c.fetch_add(1, std::memory_order_relaxed) + 1) {}
+        ~Busy() { n.fetch_sub(1, std::memory_order_relaxed); }
+    } busy(g_resolving);
+    const int nworkers = pool_ ? std::max(1, pool_->size() / busy.now) : 1;
     int nruns = 1;
     if (pool_ && v.n_live >= min_live_ && nblocks >= 2 * min_blocks_per_run_ && filter_.replayable())
         nruns = (int) std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t) nworkers, nblocks / min_blocks_per_run_, (uint64_t) v.n_live / min_live_per_run_}));
