@@ -975,7 +975,8 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
     } busy(g_resolving);
     const int nworkers = pool_ ? std::max(1, pool_->size() / busy.now) : 1;
     int nruns = 1;
-    if (pool_ && v.n_live >= min_live_ && nblocks >= 2 * min_blocks_per_run_ && filter_.replayable())
+    // (walking side by side is about twice the work of one walk -- prescan, prediction, check: not worth it on two threads)
+    if (pool_ && nworkers >= 3 && v.n_live >= min_live_ && nblocks >= 2 * min_blocks_per_run_ && filter_.replayable())
         nruns = (int) std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t) nworkers, nblocks / min_blocks_per_run_, (uint64_t) v.n_live / min_live_per_run_}));
     if ((int) runs_.size() < std::max(nruns, 1)) {
         runs_.resize((size_t) std::max(nruns, 1));
@@ -1066,28 +1067,48 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
         lap(3);
     }
 
-    // ---- assembly: one message per note, in place; every run by the thread that walked it ----
-    std::vector<size_t> first((size_t) nruns + 1, 0); // run r's messages are msgs[base + first[r] ...)
-    for (int r = 0; r < nruns; ++r)
-        first[(size_t) r + 1] = first[(size_t) r] + runs_[(size_t) r]->out.acc.size();
-    const size_t count = first[(size_t) nruns];
+    // ---- assembly: one message per note, in place; every run by the thread that walked it.  A span walked in one
+    // run is cut into one slice of its notes per worker instead. ----
+    struct Slice {
+        const Accepted *acc;
+        size_t n, first; // its messages are msgs[base + first ...)
+    };
+    std::vector<Slice> slices;
+    size_t count = 0;
+    if (nruns == 1 && nworkers > 1 && runs_[0]->out.acc.size() >= 2 * (size_t) kMinNotesPerSlice) {
+        const std::vector<Accepted> &acc = runs_[0]->out.acc;
+        const size_t ns = std::min<size_t>((size_t) nworkers, acc.size() / kMinNotesPerSlice);
+        for (size_t i = 0; i < ns; ++i) {
+            const size_t lo = acc.size() * i / ns, hi = acc.size() * (i + 1) / ns;
+            slices.push_back({acc.data() + lo, hi - lo, lo});
+        }
+        count = acc.size();
+    } else {
+        for (int r = 0; r < nruns; ++r) {
+            const std::vector<Accepted> &acc = runs_[(size_t) r]->out.acc;
+            slices.push_back({acc.data(), acc.size(), count});
+            count += acc.size();
+        }
+    }
+    const size_t nslices = slices.size();
     b200_message *out = msgs.grow(count);
-    std::vector<HiddenTotals> hidden((size_t) nruns);
-    std::vector<uint64_t> bad((size_t) nruns, 0);
+    std::vector<HiddenTotals> hidden(nslices);
+    std::vector<uint64_t> bad(nslices, 0);
     if (count > signal_power_cap_) {
         signal_power_cap_ = count + count / 2 + 1024;
         signal_power_.reset(new double[signal_power_cap_]);
     }
     double *power = signal_power_.get();
     std::atomic<int> turn{0}; // whose frames the ordered statistics take next
-    auto assemble = [&](int, size_t rlo, size_t rhi) {
-        for (size_t r = rlo; r < rhi; ++r) {
-            const std::vector<Accepted> &acc = runs_[r]->out.acc;
-            HiddenTotals h; // thread-local until the run is done: the runs' slots share cache lines
+    auto assemble = [&](int, size_t lo, size_t hi) {
+        for (size_t r = lo; r < hi; ++r) {
+            const Accepted *acc = slices[r].acc;
+            const size_t na = slices[r].n;
+            HiddenTotals h; // thread-local until the slice is done: the slices' slots share cache lines
             uint64_t nbad = 0;
-            b200_message *o = out + first[r];
-            double *pw = power + first[r];
-            for (size_t i = 0; i < acc.size(); ++i) {
+            b200_message *o = out + slices[r].first;
+            double *pw = power + slices[r].first;
+            for (size_t i = 0; i < na; ++i) {
                 const Accepted &a = acc[i];
                 nbad += build(v, a, o[i], &pw[i]);
                 if (!a.modeac) {
@@ -1102,10 +1123,10 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
             hidden[r] = h;
             bad[r] = nbad;
             // demod_2400.c:398-407 in message order: the running sum of doubles is the one thing here that depends on
-            // it, so the runs take turns, each adding its own (cache-warm) terms
+            // it, so the slices take turns, each adding its own (cache-warm) terms
             while (turn.load(std::memory_order_acquire) != (int) r) {
             }
-            for (size_t i = 0; i < acc.size(); ++i) {
+            for (size_t i = 0; i < na; ++i) {
                 if (acc[i].modeac)
                     continue;
                 stats_.signal_power_sum += pw[i];
@@ -1118,9 +1139,9 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
             turn.store((int) r + 1, std::memory_order_release);
         }
     };
-    if (nruns > 1)
-        pool_->run((size_t) nruns, 1, assemble, true);
-    else
+    if (nslices > 1)
+        pool_->run(nslices, 1, assemble, true);
+    else if (nslices == 1)
         assemble(0, 0, 1);
     lap(5);
 
@@ -1145,8 +1166,9 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
             stats_.noise_power_sum += t; // in block order
         if (!o.now.empty())
             ifile_now_ = o.now.back();
-        mismatches_ += bad[(size_t) r];
     }
+    for (uint64_t b : bad)
+        mismatches_ += b;
     for (uint64_t k = 0; k < nblocks; ++k) {
         const uint64_t b0 = k * B, nk = std::min(n, b0 + B) - b0;
         // positions no message can come from: K2's per-block totals (what skip-ahead hid of them is taken
@@ -1163,8 +1185,8 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
         stats_.samples_processed += kOverlap + nk; // readsb.c:835
     }
     HiddenTotals total;
-    for (int r = 0; r < nruns; ++r)
-        total.add(hidden[(size_t) r]);
+    for (const HiddenTotals &h : hidden)
+        total.add(h);
     stats_.demod_preambles -= (uint32_t) total.preambles;
     stats_.demod_rejected_bad -= (uint32_t) total.bad;
     stats_.demod_rejected_unknown_icao -= (uint32_t) total.unknown;

@@ -180,6 +180,7 @@ class Resolver {
     } trace_;
     uint32_t min_live_;
     bool absolve_ = true; // keep a run whose start state was predicted wrong only in addresses it never asked about
+    static constexpr size_t kMinNotesPerSlice = 256; // messages a worker assembles at least, when one run's notes are shared out
     uint32_t min_live_per_run_ = 512; // a run shorter than this costs more in hand-over than it saves
     uint64_t min_blocks_per_run_;
     WorkerPool *pool_;
