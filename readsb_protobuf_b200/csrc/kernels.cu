@@ -70,9 +70,15 @@ __device__ __forceinline__ uint32_t mag_from_float(float fI, float fQ, float &ma
 }
 
 __device__ __forceinline__ uint32_t mag_sc16_word(uint32_t w, float inv_scale, float &magsq, float &mag) {
-    // little-endian int16 pair: I in the low half (convert.c:231-232)
-    float fI = __fmul_rn((float) (int16_t) (w & 0xffff), inv_scale); // division by 2^k == exact scaling
-    float fQ = __fmul_rn((float) (int16_t) (w >> 16), inv_scale);
+    // little-endian int16 pair: I in the low half (convert.c:231-232).  (float) v / 2^k without the quarter-rate
+    // I2F: 0x4b40_0000 + v is the float 1.5 * 2^23 + v (|v| < 2^22), and (1.5 * 2^23 + v) * 2^-k - 1.5 * 2^(23-k)
+    // is exact in one FMA (a power-of-two product, a representable difference).
+    int vI, vQ; // the sign-extended halves: prmt's selector bit 3 replicates the byte's sign (__byte_perm masks it off)
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(vI) : "r"(w));
+    asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(vQ) : "r"(w));
+    const float bias = __fmul_rn(-12582912.0f, inv_scale);
+    float fI = __fmaf_rn(__int_as_float(0x4b400000 + vI), inv_scale, bias);
+    float fQ = __fmaf_rn(__int_as_float(0x4b400000 + vQ), inv_scale, bias);
     return mag_from_float(fI, fQ, magsq, mag);
 }
 
@@ -1878,33 +1884,40 @@ cudaError_t launch_order_live(const TileOut *tiles_out, uint32_t ntiles, const S
 //
 // convert_sc16_nodc / convert_sc16q11_nodc add mag and magsq of every sample to two float
 // accumulators in stream order (convert.c:228,241-242 / 345,358-359).  Float addition is not
-// associative, so the only way to the same bits is the same order: per mag_buf one warp converts 128
-// samples at a time in parallel (4 per lane) and two lanes of a second warp walk the chains in order.
-// 131072 dependent adds at 4 cycles each = 0.27 ms per mag_buf at best, all mag_bufs in parallel,
-// on a side stream next to K1a.
+// associative -- but while the running sum S stays inside one binade [2^k, 2^(k+1)) every step
+// S <- RN(S + x) moves it by a whole number of its (fixed) ulps u = 2^(k-23):
+//     RN(S + x) = S + RN_u(x),   RN_u(x) = x rounded to the nearest multiple of u,
+// unless x falls exactly half-way between two multiples (the tie then goes to the even neighbour of
+// S + x, which depends on S).  RN_u(x) does not depend on S, so a batch of samples is rounded in
+// parallel -- the hardware does it: bits(x + 2^k) - bits(2^k) is RN_u(x) / u when x < 2^k -- the
+// batch's counts are added up as integers, and S moves by their total (an integer add on the float's
+// bits).  A batch that holds a tie, or that would carry S into the next binade, or that starts below
+// S = 4 (x <= 1 < 2^k must hold), is added one sample after the other instead; that happens about ten
+// times per mag_buf and sum (one per binade S passes through, plus the first batch).
+// One CTA of four warps per mag_buf, 512 samples per batch, two barriers per batch (the batch's
+// total has to be in S before the next batch knows its binade).
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(96) float_block_sums_kernel(const uint8_t *__restrict__ iq, uint32_t format, uint64_t nsamples,
-                                                               uint32_t block_samples, uint32_t nblocks, double *__restrict__ sums) {
-    // one CTA of three warps per mag_buf: warps 0 and 1 convert the next batch of 256 samples (half each) into
-    // the other half of a double buffer while lanes 0 and 1 of warp 2 walk the two chains over the current one.
-    // The chains are the floor (one dependent FADD per sample, 4 cycles each); two converter warps keep the
-    // conversion (an IEEE square root per sample) well under that, so a batch costs the chain plus one barrier.
-    constexpr int kBatch = 256;
-    __shared__ __align__(16) float s_val[2][2][kBatch]; // [buffer][0 = mag, 1 = magsq][sample]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+constexpr int kSumBatch = 512;
+
+__global__ void __launch_bounds__(128) float_block_sums_kernel(const uint8_t *__restrict__ iq, uint32_t format, uint64_t nsamples,
+                                                                uint32_t block_samples, uint32_t nblocks, double *__restrict__ sums) {
+    __shared__ __align__(16) float s_val[2][kSumBatch]; // [0 = mag, 1 = magsq][sample]: read only by the sequential fall-back
+    __shared__ uint32_t s_part[2][4];                   // [sum][warp]: the warp's total of RN_u(x) / u
+    __shared__ uint32_t s_tie[2][4];                    // [sum][warp]: a tie in the warp's share
+    __shared__ uint32_t s_S[2];                         // the two running sums (float bits)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t k = blockIdx.x;
     const uint64_t b0 = (uint64_t) k * block_samples;
     const uint64_t nk = nsamples > b0 ? (nsamples - b0 < block_samples ? nsamples - b0 : block_samples) : 0;
     const float inv_scale = (format == 1) ? (1.0f / 32768.0f) : (1.0f / 2048.0f);
     const uint32_t *src = reinterpret_cast<const uint32_t *>(iq) + b0; // one 32-bit word per sample
-    const int mine4 = 128 * (warp & 1) + 4 * lane;                     // a converter lane's 4 samples of a batch
 
-    // 4 samples per lane (block_samples % 8 == 0 and 16-byte aligned spans: whole uint4s except in the
-    // stream's ragged last batch)
+    // 4 samples per thread (block_samples % 8 == 0 and 16-byte aligned spans: whole uint4s except in the stream's
+    // ragged last batch); a sample past the end reads as zero IQ = magnitude +0, which changes no sum
     auto load = [&](uint64_t base) {
         uint4 v = make_uint4(0, 0, 0, 0);
-        const uint64_t s0 = base + (uint64_t) mine4;
+        const uint64_t s0 = base + 4 * (uint64_t) tid;
         if (s0 + 4 <= nk) {
             v = ldg_stream(reinterpret_cast<const uint4 *>(src + s0));
         } else if (s0 < nk) {
@@ -1916,68 +1929,87 @@ __global__ void __launch_bounds__(96) float_block_sums_kernel(const uint8_t *__r
         }
         return v;
     };
-    auto put = [&](int buf, uint4 v) {
-        float mg[4], sq[4];
-        mag_sc16_word(v.x, inv_scale, sq[0], mg[0]);
-        mag_sc16_word(v.y, inv_scale, sq[1], mg[1]);
-        mag_sc16_word(v.z, inv_scale, sq[2], mg[2]);
-        mag_sc16_word(v.w, inv_scale, sq[3], mg[3]);
-        *reinterpret_cast<float4 *>(&s_val[buf][0][mine4]) = make_float4(mg[0], mg[1], mg[2], mg[3]);
-        *reinterpret_cast<float4 *>(&s_val[buf][1][mine4]) = make_float4(sq[0], sq[1], sq[2], sq[3]);
-    };
 
-    const uint64_t nbatches = (nk + kBatch - 1) / kBatch;
-    uint4 ahead[3] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}; // batches b+1 .. b+3 in flight
-    if (warp < 2 && nbatches) {
-        put(0, load(0));
-        ahead[0] = load(kBatch);
-        ahead[1] = load(2 * kBatch);
-        ahead[2] = load(3 * kBatch);
-    }
-    float acc = 0.0f; // warp 2, lane 0: sum_level, lane 1: sum_power
+    const uint64_t nbatches = (nk + kSumBatch - 1) / kSumBatch;
+    uint4 ahead[3] = {load(0), load(kSumBatch), load(2 * kSumBatch)};
+    if (tid < 2)
+        s_S[tid] = 0; // +0.0f
     __syncthreads();
     for (uint64_t b = 0; b < nbatches; ++b) {
-        if (warp < 2) {
-            if (b + 1 < nbatches) {
-                put((int) ((b + 1) & 1), ahead[0]);
-                ahead[0] = ahead[1];
-                ahead[1] = ahead[2];
-                ahead[2] = load((b + 4) * kBatch);
+        const uint4 v = ahead[0];
+        ahead[0] = ahead[1];
+        ahead[1] = ahead[2];
+        ahead[2] = load((b + 3) * kSumBatch);
+        float x[2][4];
+        mag_sc16_word(v.x, inv_scale, x[1][0], x[0][0]);
+        mag_sc16_word(v.y, inv_scale, x[1][1], x[0][1]);
+        mag_sc16_word(v.z, inv_scale, x[1][2], x[0][2]);
+        mag_sc16_word(v.w, inv_scale, x[1][3], x[0][3]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<float4 *>(&s_val[q][4 * tid]) = make_float4(x[q][0], x[q][1], x[q][2], x[q][3]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t Sb = s_S[q];
+            const uint32_t Mb = Sb & 0x7f800000u;                  // 2^k
+            const float M = __uint_as_float(Mb);
+            const float half_u = __uint_as_float(Mb - (24u << 23)); // 2^(k-24); garbage below S = 4, where the batch is redone anyway
+            uint32_t acc = 0;
+            bool tie = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float z = __fadd_rn(x[q][j], M);                       // M + RN_u(x)
+                acc += __float_as_uint(z) - Mb;                              // RN_u(x) / u
+                const float err = __fsub_rn(x[q][j], __fsub_rn(z, M));       // x - RN_u(x), exact
+                tie |= fabsf(err) == half_u;
             }
-        } else if (lane < 2) {
-            const float *mine = s_val[b & 1][lane];
-            const uint64_t left = nk - b * kBatch;
-            if (left >= kBatch) {
+            const uint32_t total = __reduce_add_sync(0xffffffffu, acc);
+            const bool any_tie = __any_sync(0xffffffffu, tie);
+            if (lane == 0) {
+                s_part[q][warp] = total;
+                s_tie[q][warp] = any_tie ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        if (lane == 0 && warp < 2) { // thread 0 owns the level sum, thread 32 the power sum
+            const int q = warp;
+            const uint32_t Sb = s_S[q];
+            const uint32_t T = s_part[q][0] + s_part[q][1] + s_part[q][2] + s_part[q][3];
+            const bool tie = (s_tie[q][0] | s_tie[q][1] | s_tie[q][2] | s_tie[q][3]) != 0;
+            // x <= 1 (convert.c:236-237 clamps magsq), so below 2^21 counts per sample and 2^30 per batch once S >= 4
+            if (Sb >= 0x40800000u /* 4.0f */ && !tie && (Sb & 0x007fffffu) + T < (1u << 23)) {
+                s_S[q] = Sb + T;
+            } else {
+                float accf = __uint_as_float(Sb);
+                const float4 *vals = reinterpret_cast<const float4 *>(s_val[q]);
 #pragma unroll 1
-                for (int h = 0; h < kBatch / 128; ++h) {
+                for (int h = 0; h < kSumBatch / 128; ++h) {
                     float4 r[32]; // all loads first: they do not depend on the chain
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        r[i] = reinterpret_cast<const float4 *>(mine + 128 * h)[i];
+                        r[i] = vals[32 * h + i];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        acc = __fadd_rn(acc, r[i].x);
-                        acc = __fadd_rn(acc, r[i].y);
-                        acc = __fadd_rn(acc, r[i].z);
-                        acc = __fadd_rn(acc, r[i].w);
+                        accf = __fadd_rn(accf, r[i].x);
+                        accf = __fadd_rn(accf, r[i].y);
+                        accf = __fadd_rn(accf, r[i].z);
+                        accf = __fadd_rn(accf, r[i].w);
                     }
                 }
-            } else {
-                for (int i = 0; i < (int) left; ++i)
-                    acc = __fadd_rn(acc, mine[i]);
+                s_S[q] = __float_as_uint(accf);
             }
         }
         __syncthreads();
     }
-    if (warp == 2 && lane < 2)
-        sums[2 * k + lane] = (double) acc; // exactly the float the reference divides by nsamples
+    if (tid < 2)
+        sums[2 * k + tid] = (double) __uint_as_float(s_S[tid]); // exactly the float the reference divides by nsamples
 }
 
 cudaError_t launch_float_block_sums(const uint8_t *iq, uint32_t format, uint64_t nsamples, uint32_t block_samples, uint32_t nblocks,
                                     double *sums, cudaStream_t stream) {
     if (nblocks == 0 || format == 0 || format == 4)
         return cudaSuccess;
-    float_block_sums_kernel<<<nblocks, 96, 0, stream>>>(iq, format, nsamples, block_samples, nblocks, sums);
+    float_block_sums_kernel<<<nblocks, 128, 0, stream>>>(iq, format, nsamples, block_samples, nblocks, sums);
     return cudaGetLastError();
 }
 

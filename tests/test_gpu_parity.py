@@ -105,6 +105,46 @@ def test_span_split_is_invisible():
         assert_parity(run_gpu(iq, "sc16q11", span_samples=span, modeac=True), want, "sc16q11")
 
 
+@pytest.mark.parametrize("fmt", ["sc16", "sc16q11"])
+@pytest.mark.parametrize("kind", ["ties", "constant", "silence_then_full_scale", "random_few_bits"])
+def test_float_block_sums_on_inputs_built_to_break_them(fmt, kind):
+    """The float converters' sequential sums (convert.c:228,241-242) are reproduced batch-parallel
+    (float_block_sums_kernel: whole batches rounded to the running sum's ulp at once); the batches it has to
+    walk one by one are those with a tie -- a sample exactly half-way between two ulps of the sum -- and those
+    that carry the sum into the next binade.  These inputs are made of them."""
+    rng = np.random.default_rng(5)
+    n = 3 * 131072 + 4001
+    scale = 32768 if fmt == "sc16" else 2048
+    I = np.zeros(n, dtype=np.int64)
+    Q = np.zeros(n, dtype=np.int64)
+    if kind == "ties":
+        # Q = 0: mag = |I| / scale exactly, an odd multiple of 1 / scale -- once the level sum is in the binade whose
+        # half-ulp is 1 / scale every sample is a tie (sc16: [512, 1024), reached after ~8 K samples of mag 0.06)
+        I = (2 * rng.integers(scale // 40, scale // 12, size=n) + 1) * rng.choice([-1, 1], size=n)
+    elif kind == "constant":
+        I[:] = scale // 8 + 1
+        Q[:] = -(scale // 16)
+    elif kind == "silence_then_full_scale":
+        I[n // 3:] = scale - 1  # sums stay 0 for a block, then cross a binade every few batches
+        Q[n // 3:] = -(scale - 1)
+        I[2 * n // 3:] = 3
+        Q[2 * n // 3:] = 0
+    else:
+        I = rng.integers(-8, 9, size=n) * (scale // 64)
+        Q = rng.integers(-8, 9, size=n) * (scale // 64)
+    iq = np.empty(2 * n, dtype="<i2")
+    iq[0::2] = I
+    iq[1::2] = Q
+    iq = iq.view(np.uint8)
+    want = port.run(iq, fmt)
+    got = run_gpu(iq, fmt)
+    assert_parity(got, want, fmt)
+    assert np.array_equal(got.blocks["mean_level"], want.blocks["mean_level"])
+    assert np.array_equal(got.blocks["mean_power"], want.blocks["mean_power"])
+    # one mag_buf per call (the host-buffer path runs the kernel per chunk)
+    assert_parity(run_gpu(iq, fmt, span_samples=131072), want, fmt)
+
+
 @pytest.mark.parametrize("seed,nsamples,block", [(311, 1_000_000, 131072), (312, 600_001, 50000), (313, 4 * 131072, 131072)])
 def test_modeac_matches_oracle(seed, nsamples, block):
     """--modeac (demodulate2400AC, demod_2400.c:522-708): a block's Mode A/C replies follow its Mode S
