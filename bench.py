@@ -567,12 +567,12 @@ def run_ours(args):
                                  "messages_total": int(merged_headline["messages_total"]),
                                  "samples_processed": int(merged_headline["samples_processed"]),
                                  "peak_signal_power": float(merged_headline["peak_signal_power"])}},
-            "roofline": {"bound": "hbm", "kernel": "scan_kernel<uc8> (K1a: IQ -> magnitude + preamble scan + candidates)",
+            "roofline": {"bound": "hbm", "kernel": "scan2_kernel (K1a, uc8: IQ -> magnitude + preamble scan + candidates + u16 magnitudes)",
                          "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/k1_traffic.json: DRAM bytes per algorithmic byte of the ncu-captured launch x this run's bytes per launch", "peak_source": peak_src,
                          "launches_per_step": int(n_chunks), "algorithmic_bytes_per_launch": nbytes // max(int(n_chunks), 1),
                          "kernel_ms_per_launch": k1_mean / max(int(n_chunks), 1), "kernel_ms_per_step": k1_mean,
-                         "scan_only": {"kernel": "scan_kernel<uc8, scan only> (magnitude + preamble scan)",
+                         "scan_only": {"kernel": "scan2_kernel, scan only (magnitude + preamble scan; no candidate list, no magnitude store)",
                                        "kernel_ms": so_mean, "achieved": nbytes / (so_mean * 1e-3) / 1e9,
                                        "frac": nbytes / (so_mean * 1e-3) / 1e9 / peak},
                          "k1a_whole_span_ms": sf_mean,
@@ -581,7 +581,7 @@ def run_ours(args):
                              "K1b slice_kernel (PPM slice + CRC class of every candidate phase; reads the u16 magnitudes, 2 B/sample)":
                                  {"ms_per_step": k1b_mean, "whole_span_ms": k1b_alone,
                                   "achieved": nbytes / (k1b_mean * 1e-3) / 1e9, "frac": nbytes / (k1b_mean * 1e-3) / 1e9 / peak},
-                             "K2 classify_warp_kernel (address-set test, dead/live lists, survivors re-sliced; touches candidates only)":
+                             "K2 classify_warp_kernel + order_live (address-set test, dead/live lists, live records and hidden counts into pinned host memory; touches candidates only)":
                                  {"ms_per_step": k2_mean}}},
             "cpu_baseline": cpu,
             "other_configs": others,

@@ -1,6 +1,8 @@
 // kernels.cu -- sm_100a kernels of the Mode S demodulator.
 //
-//   K1a scan_kernel            IQ -> magnitude (uc8 table, sc16 / sc16q11 float path, or format 4: the sc16q11 table
+//   K1a scan2_kernel (uc8,     IQ -> magnitude (uc8 table, sc16 / sc16q11 float path, or format 4: the sc16q11 table
+//       scan2.inl) /
+//       scan_kernel (others)
 //                              of a -DSC16Q11_TABLE_BITS build, convert.c:264-328) -> per-block sums, preamble pre-check + three correlators for
 //                              every scan position -> position-ordered candidate list per tile; the u16
 //                              magnitudes go to HBM for K1b / K2 / Mode A/C
@@ -8,10 +10,11 @@
 //   K1b slice_kernel           PPM slice of every (candidate, phase), CRC-24 syndrome, error-table lookup ->
 //                              class records; replaces demod_2400.c:98-229, crc.c:67-82,389-412 and the
 //                              filter-independent half of mode_s.c:311-409
-//   K2  classify_warp_kernel   address-set test, ordered dead / live lists, re-slice + signal power of the
-//       (classify_kernel)      survivors (demod_2400.c:387-399); the CTA-per-tile variant serves the
-//                              exact-slab retry of very dense chunks
-//   live_offsets / live_gather K2's per-tile live lists packed into stream order, straight into pinned host memory
+//   K2  classify_warp_kernel   address-set test, ordered dead / live lists, live records (K1b's record, frame
+//       (classify_kernel)      bytes included) + signal power of the survivors (demod_2400.c:387-399); the
+//                              CTA-per-tile variant serves the exact-slab retry of very dense chunks
+//   live_offsets / live_gather K2's per-tile live lists packed into stream order, straight into pinned host memory,
+//                              with the dead positions a frame accepted at each live position would hide
 //   modeac_kernel              demodulate2400AC's framing-pulse search (demod_2400.c:522-683), --modeac only
 //   float_block_sums_kernel    sc16 / sc16q11 mean_level / mean_power in the reference's summation order
 //   dc_prepare / dc_chain /    --dcfilter: convert_*_generic (convert.c:113-213, 374-423), the one-pole DC block
@@ -1440,8 +1443,8 @@ __global__ void __launch_bounds__(kClassifyThreads) classify_kernel(const Classi
 // ------------------------------------------------------------------------------------------
 // K2, warp-per-tile variant: the same passes as classify_kernel with no block-wide barrier, for the
 // normal case of fixed per-tile slabs (at most kCwCap candidates per tile).  A warp keeps the tile's
-// candidate entries and per-candidate flags in its own shared memory; survivors are re-sliced
-// straight from K1a's magnitude array.
+// candidate entries and per-candidate flags in its own shared memory; a survivor's record is K1b's
+// (frame bytes included), its signal power comes straight from K1a's magnitude array.
 // ------------------------------------------------------------------------------------------
 
 constexpr int kCwWarps = 8;
