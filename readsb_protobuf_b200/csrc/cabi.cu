@@ -170,9 +170,15 @@ struct ChunkSet {
     DevBuf<LivePos> d_live;
     DevBuf<LiveRec> d_liverecs;
     DevBuf<uint2> d_live_base;
-    PinnedBuf<LivePos> h_live;
-    PinnedBuf<LiveRec> h_liverecs;
-    PinnedBuf<LiveHidden> h_hidden;
+    // order_live's output, packed [n_live LivePos | n_live LiveHidden | n_liverec LiveRec] in device memory; the copy
+    // engine brings exactly those bytes to the pinned mirror once the host has read the chunk's counters (the SMs'
+    // own posted writes over PCIe cost the GPU 20-55 us per chunk; the DMA runs under the next chunk's kernels)
+    DevBuf<uint8_t> d_packed;
+    PinnedBuf<uint8_t> h_packed;
+    size_t live_cap = 0, liverec_cap = 0;
+    cudaEvent_t ev_packed = nullptr;
+    bool packed_issued = false;
+    bool in_flight = false; // issued, not yet resolved
     // Mode A/C (only with cfg.mode_ac): per-block noise levels, unordered hit list in pinned host memory
     DevBuf<uint32_t> d_ac_noise;
     PinnedBuf<AcHit> h_ac_hits;
@@ -189,8 +195,8 @@ struct ChunkSet {
     void release() {
         d_cand.release(); d_tile_off.release(); d_recs.release(); d_tiles.release(); d_magbuf.release(); d_step_off.release();
         d_small.release(); h_small.release(); d_dead.release();
-        h_live.release(); h_liverecs.release(); h_hidden.release(); d_live.release(); d_liverecs.release(); d_live_base.release(); d_ac_noise.release(); h_ac_hits.release();
-        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small})
+        h_packed.release(); d_packed.release(); live_cap = liverec_cap = 0; d_live.release(); d_liverecs.release(); d_live_base.release(); d_ac_noise.release(); h_ac_hits.release();
+        for (cudaEvent_t *e : {&ev_begin, &ev_k1, &ev_k1b, &ev_k2, &ev_small, &ev_packed})
             if (*e) {
                 cudaEventDestroy(*e);
                 *e = nullptr;
@@ -220,6 +226,7 @@ struct b200_demod {
 
     cudaStream_t stream = nullptr;      // exec stream of the host-buffer entry
     cudaStream_t copy_stream = nullptr; // H2D
+    cudaStream_t d2h_stream = nullptr;  // the chunks' packed live data
     cudaEvent_t ev_h2d_begin = nullptr, ev_h2d_end = nullptr;
     std::vector<cudaEvent_t> ev_chunk_h2d;
 
@@ -273,7 +280,7 @@ struct b200_demod {
             cudaEventDestroy(ev_h2d_begin);
         if (ev_h2d_end)
             cudaEventDestroy(ev_h2d_end);
-        for (cudaStream_t s : {stream, copy_stream})
+        for (cudaStream_t s : {stream, copy_stream, d2h_stream})
             if (s)
                 cudaStreamDestroy(s);
     }
@@ -290,11 +297,15 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
     CUDA_TRY(c.d_cand.ensure(cand_total + 1));
     CUDA_TRY(c.d_recs.ensure(rec_total + 1));
     CUDA_TRY(c.d_dead.ensure(dead_cap));
-    CUDA_TRY(c.h_live.ensure(live_cap));
-    CUDA_TRY(c.h_hidden.ensure(c.h_live.cap));
-    CUDA_TRY(c.h_liverecs.ensure(liverec_cap));
-    CUDA_TRY(c.d_live.ensure(c.h_live.cap));
-    CUDA_TRY(c.d_liverecs.ensure(c.h_liverecs.cap));
+    c.live_cap = std::max(c.live_cap, live_cap);
+    c.liverec_cap = std::max(c.liverec_cap, liverec_cap);
+    {
+        const size_t bytes = c.live_cap * (sizeof(LivePos) + sizeof(LiveHidden)) + c.liverec_cap * sizeof(LiveRec) + 64;
+        CUDA_TRY(c.d_packed.ensure(bytes));
+        CUDA_TRY(c.h_packed.ensure(bytes));
+    }
+    CUDA_TRY(c.d_live.ensure(c.live_cap));
+    CUDA_TRY(c.d_liverecs.ensure(c.liverec_cap));
     CUDA_TRY(c.d_live_base.ensure(ntiles + 1));
     CUDA_TRY(c.d_tiles.ensure(ntiles + 1));
     CUDA_TRY(c.d_magbuf.ensure(ntiles * (size_t) kTile + kMagSlack));
@@ -329,6 +340,7 @@ static int ensure_chunk_buffers(b200_demod *d, ChunkSet &c, uint64_t nsamples, s
         CUDA_TRY(cudaEventCreate(&c.ev_k1b));
         CUDA_TRY(cudaEventCreate(&c.ev_k2));
         CUDA_TRY(cudaEventCreate(&c.ev_small));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.ev_packed, cudaEventDisableTiming));
     }
     return B200_OK;
 }
@@ -393,6 +405,7 @@ extern "C" int b200_demod_create(const b200_demod_config *cfg, b200_demod **out)
 
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_begin));
     CUDA_TRY(cudaEventCreate(&d->ev_h2d_end));
     CUDA_TRY(scan_configure());
@@ -642,16 +655,17 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     ca.liverecs = c.d_liverecs.p;
     ca.tiles_out = c.d_tiles_out.p;
     ca.dead_cap = (uint32_t) std::min<size_t>(c.d_dead.cap, 0xffffffffu);
-    ca.live_cap = (uint32_t) std::min<size_t>(c.h_live.cap, 0xffffffffu);
-    ca.liverec_cap = (uint32_t) std::min<size_t>(c.h_liverecs.cap, 0xffffffffu);
+    ca.live_cap = (uint32_t) std::min<size_t>(c.live_cap, 0xffffffffu);
+    ca.liverec_cap = (uint32_t) std::min<size_t>(c.liverec_cap, 0xffffffffu);
     ca.counters = c.d_counters.p;
     ca.block_dead = c.d_block_dead.p;
     // K2 looks at K1's overflow flag itself and does nothing when K1 did not fit
     CUDA_TRY(launch_classify(ca, s));
-    // live positions / records in stream order, written into pinned host memory (posted writes over PCIe,
-    // done when the kernel is)
+    // live positions / hidden counts / records in stream order, packed back to back in device memory
     CUDA_TRY(launch_order_live(c.d_tiles_out.p, ntiles, c.d_counters.p, c.d_live_base.p, c.d_live.p, c.d_liverecs.p, c.d_dead.p, n, B,
-                               c.h_live.p, c.h_liverecs.p, c.h_hidden.p, s));
+                               c.d_packed.p, s));
+    c.packed_issued = false;
+    c.in_flight = true;
     CUDA_TRY(cudaEventRecord(c.ev_k2, s));
     if (d->cfg.mode_ac && n) {
         // demodulate2400AC (readsb.c:831-833) over the same magnitudes
@@ -681,11 +695,23 @@ static int issue_chunk(b200_demod *d, ChunkSet &c, cudaStream_t s, bool exact, s
     return B200_OK;
 }
 
+// the chunk's packed live data -> its pinned mirror, on the download stream (the chunk's kernels are known to be through)
+static int download_packed(b200_demod *d, ChunkSet &c, const ScanCounters &cnt) {
+    if (c.packed_issued)
+        return B200_OK;
+    const size_t bytes = (size_t) cnt.n_live * (sizeof(LivePos) + sizeof(LiveHidden)) + (size_t) cnt.n_liverec * sizeof(LiveRec);
+    if (bytes)
+        CUDA_TRY(cudaMemcpyAsync(c.h_packed.p, c.d_packed.p, bytes, cudaMemcpyDeviceToHost, d->d2h_stream));
+    CUDA_TRY(cudaEventRecord(c.ev_packed, d->d2h_stream));
+    c.packed_issued = true;
+    return B200_OK;
+}
+
 // wait for a chunk's kernels, fetch its survivors, resolve it on the host
 static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t *launches, b200_timing &t) {
     const uint64_t n = c.nsamples;
     const uint32_t ntiles = tiles_for(n);
-    size_t dead_cap = c.d_dead.cap, live_cap = c.h_live.cap, liverec_cap = c.h_liverecs.cap;
+    size_t dead_cap = c.d_dead.cap, live_cap = c.live_cap, liverec_cap = c.liverec_cap;
 
     g_trace.mark("wait");
     CUDA_TRY(cudaEventSynchronize(c.ev_small));
@@ -757,8 +783,34 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
         t.classify_ms += ms;
     }
 
-    // order_live wrote the live positions, their records and their hidden-dead counts straight into pinned host
-    // memory (posted writes over PCIe, done when the kernel is).
+    // order_live packed the live positions, their hidden-dead counts and their records in device memory: bring
+    // exactly those bytes over (copy engine), and -- while waiting -- do the same for the chunks behind this one
+    // whose kernels are already through, so that their bytes are there when their turn comes
+    {
+        const int rc = download_packed(d, c, cnt);
+        if (rc != B200_OK)
+            return rc;
+    }
+    static const int lookahead = [] {
+        const char *e = getenv("B200_D2H_LOOKAHEAD");
+        const int v = e ? atoi(e) : 1; // one chunk ahead hides the DMA; five at once (50 MB on a dense stream) slow the resolver's own memory traffic by 10 %
+        return v < 0 ? 0 : (v > b200_demod::kSets - 1 ? b200_demod::kSets - 1 : v);
+    }();
+    for (int ahead = 1; ahead <= lookahead; ++ahead) {
+        ChunkSet &nx = d->sets[(size_t) ((&c - d->sets) + ahead) % b200_demod::kSets];
+        if (!nx.in_flight || nx.packed_issued || cudaEventQuery(nx.ev_small) != cudaSuccess)
+            continue;
+        const ScanCounters nc = *nx.h_counters.p;
+        if (!nc.overflow) {
+            const int rc = download_packed(d, nx, nc);
+            if (rc != B200_OK)
+                return rc;
+        }
+    }
+    cudaGetLastError(); // cudaEventQuery's cudaErrorNotReady is not an error
+    g_trace.mark("d2h");
+    CUDA_TRY(cudaEventSynchronize(c.ev_packed));
+    c.in_flight = false;
     // host: the order-dependent tail
     const double t_res0 = now_ms();
     SpanView v;
@@ -768,10 +820,10 @@ static int finish_chunk(b200_demod *d, ChunkSet &c, cudaStream_t exec, uint32_t 
     v.final_span = c.final_chunk;
     // the resolver only tells integer block sums (the table converters) from float ones
     v.format = (d->eff_format == 4) ? (uint32_t) B200_INPUT_UC8 : d->eff_format;
-    v.live = c.h_live.p;
+    v.live = reinterpret_cast<const LivePos *>(c.h_packed.p);
     v.n_live = (uint32_t) cnt.n_live;
-    v.liverecs = c.h_liverecs.p;
-    v.hidden = c.h_hidden.p;
+    v.hidden = reinterpret_cast<const LiveHidden *>(c.h_packed.p + (size_t) cnt.n_live * sizeof(LivePos));
+    v.liverecs = reinterpret_cast<const LiveRec *>(c.h_packed.p + (size_t) cnt.n_live * (sizeof(LivePos) + sizeof(LiveHidden)));
     v.block_dead = c.h_block_dead.p;
     v.block_sums_u64 = c.h_sums_u64.p;
     v.block_sums_f64 = c.h_sums_f64.p;
@@ -820,6 +872,9 @@ static int run_span(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, uint3
         const std::string why = g_last_error; // keep the first error: the synchronisation below may add its own
         cudaStreamSynchronize(exec);
         cudaStreamSynchronize(d->copy_stream);
+        cudaStreamSynchronize(d->d2h_stream);
+        for (ChunkSet &c : d->sets)
+            c.in_flight = false;
         cudaGetLastError();
         g_last_error = why;
         d->failed = true;
@@ -949,8 +1004,8 @@ static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, 
         const uint32_t ntiles = tiles_for(c.nsamples);
         return issue_chunk(d, c, exec, false, (size_t) ntiles * kCandSlab, (size_t) ntiles * kRecSlab,
                            std::max<size_t>(c.d_dead.cap, (size_t) (c.nsamples / 24 + 4096)),
-                           std::max<size_t>(c.h_live.cap, (size_t) (c.nsamples / 128 + 4096)),
-                           std::max<size_t>(c.h_liverecs.cap, (size_t) (c.nsamples / 64 + 4096)), &launches);
+                           std::max<size_t>(c.live_cap, (size_t) (c.nsamples / 128 + 4096)),
+                           std::max<size_t>(c.liverec_cap, (size_t) (c.nsamples / 64 + 4096)), &launches);
     };
 
     g_trace.begin();
@@ -1121,7 +1176,7 @@ extern "C" int b200_scan_device(b200_demod *d, const void *d_iq, uint64_t nsampl
     ChunkSet &c = d->sets[0];
     const size_t nt = tiles_for(nsamples);
     int rc = ensure_chunk_buffers(d, c, nsamples, nt * kCandSlab, nt * kRecSlab, std::max<size_t>(c.d_dead.cap, 4096),
-                                  std::max<size_t>(c.h_live.cap, 4096), std::max<size_t>(c.h_liverecs.cap, 4096));
+                                  std::max<size_t>(c.live_cap, 4096), std::max<size_t>(c.liverec_cap, 4096));
     if (rc != B200_OK)
         return rc;
     rc = zero_chunk_outputs(d, c, nsamples, s);
@@ -1218,7 +1273,7 @@ extern "C" int b200_debug_scan(b200_demod *d, const void *iq, uint64_t nsamples,
     // slabs that can hold every position of a tile as a candidate with five records
     const size_t nt = tiles_for(nsamples);
     int rc = ensure_chunk_buffers(d, c, nsamples, nt * kTile, nt * kTile * 5, std::max<size_t>(c.d_dead.cap, 4096),
-                                  std::max<size_t>(c.h_live.cap, 4096), std::max<size_t>(c.h_liverecs.cap, 4096));
+                                  std::max<size_t>(c.live_cap, 4096), std::max<size_t>(c.liverec_cap, 4096));
     if (rc != B200_OK)
         return rc;
     rc = zero_chunk_outputs(d, c, nsamples, s);

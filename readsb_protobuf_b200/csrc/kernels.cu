@@ -1838,10 +1838,14 @@ __global__ void __launch_bounds__(256) live_gather_kernel(const TileOut *__restr
                                                            const ScanCounters *__restrict__ counters, const uint2 *__restrict__ base,
                                                            const LivePos *__restrict__ live, const LiveRec *__restrict__ recs,
                                                            const uint32_t *__restrict__ dead, uint64_t nsamples, uint32_t block_samples,
-                                                           LivePos *__restrict__ live_out, LiveRec *__restrict__ recs_out,
-                                                           LiveHidden *__restrict__ hidden_out) {
+                                                           uint8_t *__restrict__ packed) {
     if (counters->overflow)
         return;
+    // [n_live LivePos | n_live LiveHidden | n_liverec LiveRec], back to back: one download of exactly these bytes
+    const size_t n_live_total = (size_t) counters->n_live;
+    LivePos *__restrict__ live_out = reinterpret_cast<LivePos *>(packed);
+    LiveHidden *__restrict__ hidden_out = reinterpret_cast<LiveHidden *>(packed + n_live_total * sizeof(LivePos));
+    LiveRec *__restrict__ recs_out = reinterpret_cast<LiveRec *>(packed + n_live_total * (sizeof(LivePos) + sizeof(LiveHidden)));
     const int lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ntiles; t += warps) {
@@ -1869,16 +1873,15 @@ __global__ void __launch_bounds__(256) live_gather_kernel(const TileOut *__restr
 }
 
 cudaError_t launch_order_live(const TileOut *tiles_out, uint32_t ntiles, const ScanCounters *counters, uint2 *base, const LivePos *live,
-                              const LiveRec *recs, const uint32_t *dead, uint64_t nsamples, uint32_t block_samples, LivePos *live_out,
-                              LiveRec *recs_out, LiveHidden *hidden_out, cudaStream_t stream) {
+                              const LiveRec *recs, const uint32_t *dead, uint64_t nsamples, uint32_t block_samples, uint8_t *packed,
+                              cudaStream_t stream) {
     if (ntiles == 0)
         return cudaSuccess;
     live_offsets_kernel<<<1, 1024, 0, stream>>>(tiles_out, ntiles, counters, base);
     int grid = (int) ((ntiles + 7) / 8);
     if (grid > 148 * 4)
         grid = 148 * 4;
-    live_gather_kernel<<<grid, 256, 0, stream>>>(tiles_out, ntiles, counters, base, live, recs, dead, nsamples, block_samples, live_out,
-                                                 recs_out, hidden_out);
+    live_gather_kernel<<<grid, 256, 0, stream>>>(tiles_out, ntiles, counters, base, live, recs, dead, nsamples, block_samples, packed);
     return cudaGetLastError();
 }
 

@@ -124,8 +124,8 @@ cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream);
 // K2's per-tile live lists (device memory) -> position-ordered arrays (pinned host memory), plus per live position
 // what a frame accepted there hides of the dead list (which therefore never leaves the device); base = ntiles scratch
 cudaError_t launch_order_live(const TileOut *tiles_out, uint32_t ntiles, const ScanCounters *counters, uint2 *base, const LivePos *live,
-                              const LiveRec *recs, const uint32_t *dead, uint64_t nsamples, uint32_t block_samples, LivePos *live_out,
-                              LiveRec *recs_out, LiveHidden *hidden_out, cudaStream_t stream);
+                              const LiveRec *recs, const uint32_t *dead, uint64_t nsamples, uint32_t block_samples, uint8_t *packed,
+                              cudaStream_t stream);
 // sc16 / sc16q11: per-mag_buf sum of mag and of magsq as the reference's sequential float accumulators
 // leave them (sums[2k], sums[2k+1]); iq = the span's first new sample
 cudaError_t launch_float_block_sums(const uint8_t *iq, uint32_t format, uint64_t nsamples, uint32_t block_samples, uint32_t nblocks,

@@ -134,7 +134,7 @@ def test_host_resolver_over_recorded_kernel_outputs():
 
 
 @pytest.mark.parametrize("threads", [2, 3, 8])
-def test_host_resolver_runs_side_by_side(threads, monkeypatch):
+def test_host_resolver_runs_side_by_side(threads, monkeypatch, capfd):
     """The same replay with the walk forced into several runs of mag_bufs per span, each started from a predicted
     ICAO-filter state on its own thread and kept only if the prediction held (resolver.cc, 'speculation'): whatever
     the number of threads and wherever the runs are cut, the result is the sequential one, bit for bit."""
@@ -144,6 +144,8 @@ def test_host_resolver_runs_side_by_side(threads, monkeypatch):
     monkeypatch.setenv("B200_RESOLVER_THREADS", str(threads))
     monkeypatch.setenv("B200_RESOLVER_MIN_LIVE", "0")
     monkeypatch.setenv("B200_RESOLVER_MIN_BLOCKS", "1")
+    monkeypatch.setenv("B200_RESOLVER_MIN_LIVE_PER_RUN", "1")
+    monkeypatch.setenv("B200_RESOLVER_TRACE", "1")
     cfg = synth.resolver_fixture_config()
     iq, _ = synth.generate(cfg)
     want = port.run(iq, "uc8")
@@ -151,3 +153,11 @@ def test_host_resolver_runs_side_by_side(threads, monkeypatch):
     assert int(got.stats["convert_cpu_s"]) == 0
     got.stats["convert_cpu_s"] = got.stats["demod_cpu_s"] = 0
     assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == []
+    # ... and the walk really was split (two workers walk in one run by design: side by side costs twice the work)
+    import re
+    m = re.search(r"resolver: (\d+) spans, (\d+) as several runs \((\d+) runs", capfd.readouterr().err)
+    assert m, "B200_RESOLVER_TRACE prints the resolver's run counts when it is destroyed"
+    if threads >= 3:
+        assert int(m.group(2)) == int(m.group(1)) > 0 and int(m.group(3)) > int(m.group(1))
+    else:
+        assert int(m.group(2)) == 0
