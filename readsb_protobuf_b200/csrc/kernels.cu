@@ -1719,7 +1719,7 @@ cudaError_t launch_classify(const ClassifyArgs &a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------
-// order_live: K2's per-tile live lists -> two flat arrays in stream order, in pinned host memory
+// order_live: K2's per-tile live lists -> flat arrays in stream order, packed in device memory (cabi.cu DMAs them)
 //
 // K2 reserves a tile's slice of the live-position and live-record lists with atomics, so the slices lie in
 // the order the warps got there.  The host walks the positions in stream order; handing it one
