@@ -912,7 +912,7 @@ static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, 
         uint64_t at = 0; // in mag_bufs
         // one wave of K1a = one tile per resident warp (tiles_for() adds a tile for the tail of a chunk)
         const uint64_t wave = ((uint64_t) d->scan_grid * k1a_warps - 1) * kTile / B;
-        if (!ramp && wave > 0 && nb > 3 * wave) {
+        if (!ramp && wave > 0 && nb > 4 * wave) {
             // device-resident span: whole waves per chunk, so that only the last launch ends on a partial
             // wave -- one wave first (the host resolver starts early), then three at a time (every chunk costs
             // about 25 us of launch gaps and of order_live's fixed latency; B200_CHUNK_WAVES, measured 2 -> 3:
@@ -922,18 +922,24 @@ static int run_span_impl(b200_demod *d, const uint8_t *d_iq, uint64_t nsamples, 
                 const long v = e ? atol(e) : 3;
                 return (uint64_t) (v >= 1 && v <= 16 ? v : 3);
             }();
+            static const uint64_t first_waves = [] {
+                const char *e = getenv("B200_CHUNK_FIRST_WAVES");
+                const long v = e ? atol(e) : 1;
+                return (uint64_t) (v >= 1 && v <= 16 ? v : 1);
+            }();
             starts.push_back(0);
-            at = wave;
+            at = first_waves * wave;
             while (nb - at > (per_chunk + 1) * wave) {
                 starts.push_back(at * B);
                 at += per_chunk * wave;
             }
             starts.push_back(at * B);
-            // ... and a short last chunk (a wave at most): nothing overlaps the host's resolve of the last
-            // chunk, so it should be little work
+            // ... and optionally a short last chunk (B200_CHUNK_TAIL_DIV: rest / div, a wave at most).  Nothing
+            // overlaps the host's resolve of the last chunk, which argued for a small one while the resolver was one
+            // thread; now a separate tail costs more in launches and a ragged K1a wave than it hides (measured).
             static const uint64_t tail_div = [] {
                 const char *e = getenv("B200_CHUNK_TAIL_DIV");
-                return (uint64_t) (e ? atol(e) : 4);
+                return (uint64_t) (e ? atol(e) : 0);
             }();
             const uint64_t rest = nb - at, tail = tail_div ? std::min<uint64_t>(rest / tail_div, wave) : 0;
             if (tail >= 1 && rest > tail)
