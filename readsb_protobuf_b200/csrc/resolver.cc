@@ -98,6 +98,8 @@ void IcaoFilter::add(uint32_t addr) {
     if (active_[h] == kEmpty) {
         active_[h] = addr;
         if (addr < (1u << 24)) {
+            if (!(((bits_a_[addr >> 6] | bits_b_[addr >> 6]) >> (addr & 63u)) & 1ull))
+                ++new_members_; // in neither table before: test(addr) changes its answer
             std::vector<uint64_t> &bits = (active_ == a_) ? bits_a_ : bits_b_;
             bits[addr >> 6] |= 1ull << (addr & 63u);
             ((active_ == a_) ? list_a_ : list_b_).push_back(addr);
@@ -864,6 +866,11 @@ Resolver::Resolver(const CrcTables *crc, uint64_t startup_time_ms) : crc_(crc), 
     min_blocks_per_run_ = 4;
     if (const char *e = getenv("B200_RESOLVER_MIN_LIVE"))
         min_live_ = (uint32_t) strtoul(e, nullptr, 10);
+    if (const char *e = getenv("B200_RESOLVER_PREDICT")) {
+        optimistic_ = strcmp(e, "prescan") != 0;
+        if (!strcmp(e, "always-optimistic")) // test knob: never mind how much the population moves
+            optimistic_max_new_ = 0xffffffffu;
+    }
     if (const char *e = getenv("B200_RESOLVER_ABSOLVE"))
         absolve_ = atoi(e) != 0;
     if (const char *e = getenv("B200_RESOLVER_MIN_LIVE_PER_RUN"))
@@ -896,6 +903,8 @@ void Resolver::reset() {
     ifile_now_ = 0;
     mismatches_ = 0;
     modeac_ = 0;
+    recent_new_members_ = 0xffffffffu; // a new stream: nothing is known about its aircraft yet
+    filter_.take_new_members();
 }
 
 // scoreModesMessage (mode_s.c:311-409) for a frame K1 already classified
@@ -978,7 +987,8 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
     const int nworkers = pool_ ? std::max(1, pool_->size() / busy.now) : 1;
     int nruns = 1;
     // (walking side by side is about twice the work of one walk -- prescan, prediction, check: not worth it on two threads)
-    if (pool_ && nworkers >= 3 && v.n_live >= min_live_ && nblocks >= 2 * min_blocks_per_run_ && filter_.replayable())
+    const bool optimistic = optimistic_ && recent_new_members_ <= optimistic_max_new_;
+    if (pool_ && nworkers >= (optimistic ? 2 : 3) && v.n_live >= min_live_ && nblocks >= 2 * min_blocks_per_run_ && filter_.replayable())
         nruns = (int) std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t) nworkers, nblocks / min_blocks_per_run_, (uint64_t) v.n_live / min_live_per_run_}));
     if ((int) runs_.size() < std::max(nruns, 1)) {
         runs_.resize((size_t) std::max(nruns, 1));
@@ -997,6 +1007,7 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
         }
     }
     ++trace_.spans;
+    bool force_prescan = false; // speculation from the true state kept failing on this span
     double t_mark = trace_now();
     auto lap = [&](int phase) {
         const double t = trace_now();
@@ -1009,6 +1020,68 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
     } else {
         ++trace_.parallel_spans;
         trace_.runs += (uint64_t) nruns;
+      if (optimistic) {
+        // Every run starts from the TRUE state in front of the first not yet confirmed run: an aircraft population
+        // changes slowly, so the addresses the later runs ask about are almost always answered the same by that
+        // state as by the one they would really meet (re-inserts of known aircraft change tables, not answers).
+        // The runs are then confirmed in order -- same members, or a difference the run never asked about and no
+        // flip inside it (differs_only_unprobed) -- while the caller's filter follows their inserts and expiries in
+        // true order.  The first run that cannot be confirmed (a new aircraft it asked about, a table flip in front
+        // of it) becomes the first run of the next round, started from the then-true state.  No prescan, no
+        // prediction pass; a round confirms at least its first run.
+        int base = 0, rounds = 0;
+        while (base < nruns) {
+            if (!filter_.replayable() || rounds >= kMaxRounds) {
+                // the filter outgrew what a copy reproduces safely, or speculation keeps failing on this span: the
+                // rest in one run, on the filter itself (and the next span predicts its start states again)
+
+                ++respeculated_;
+                walk(v, filter_, cut[(size_t) base], nblocks, blocks, block_base, runs_[(size_t) base]->out, false);
+                nruns = base + 1;
+                force_prescan = rounds >= kMaxRounds;
+                break;
+            }
+            ++rounds;
+            const IcaoFilter::Snapshot snap = filter_.snapshot();
+            pool_->run((size_t) (nruns - base), 1, [&](int, size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i) {
+                    const size_t r = (size_t) base + i;
+                    Run &run = *runs_[r];
+                    run.predicted = snap;
+                    run.filter.track_probes(true);
+                    run.filter.load(snap);
+                    walk(v, run.filter, cut[r], cut[r + 1], blocks, block_base, run.out, true);
+                }
+            }, true);
+            lap(2);
+            int r = base;
+            for (; r < nruns; ++r) {
+                Run &run = *runs_[(size_t) r];
+                if (r > base) {
+                    if (!filter_.replayable() || !run.filter.replayable())
+                        break;
+                    if (!filter_.same_members(run.predicted)) {
+                        const uint64_t last_now = run.out.now.empty() ? 0 : *std::max_element(run.out.now.begin(), run.out.now.end());
+                        if (!filter_.differs_only_unprobed(run.predicted, run.filter, last_now))
+                            break;
+                        ++trace_.absolved;
+                    }
+                }
+                size_t ai = 0;
+                for (uint64_t k = cut[(size_t) r]; k < cut[(size_t) r + 1]; ++k) {
+                    for (; ai < run.out.adds.size() && run.out.adds[ai].block == (uint32_t) k; ++ai)
+                        filter_.add(run.out.adds[ai].addr);
+                    filter_.expire(run.out.now[(size_t) (k - cut[(size_t) r])]);
+                }
+            }
+            lap(3);
+            if (r < nruns) {
+                trace_.rewalks += (uint64_t) (nruns - r);
+                respeculated_ += (uint64_t) (nruns - r);
+            }
+            base = r;
+        }
+      } else {
         // (0) potential adds and filter-clock guesses of every run
         pool_->run((size_t) nruns, 1, [&](int, size_t lo, size_t hi) {
             for (size_t r = lo; r < hi; ++r)
@@ -1067,7 +1140,13 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
             }
         }
         lap(3);
+      }
     }
+
+    // how much the aircraft population moved in this span decides how the next one is speculated
+    recent_new_members_ = filter_.take_new_members();
+    if (force_prescan)
+        recent_new_members_ = 0xffffffffu;
 
     // ---- assembly: one message per note, in place; every run by the thread that walked it.  A span walked in one
     // run is cut into one slice of its notes per worker instead. ----

@@ -57,6 +57,12 @@ class IcaoFilter {
     // The run's result then stands although its start state was predicted wrong.
     void track_probes(bool on);
     bool differs_only_unprobed(const Snapshot &s, const IcaoFilter &walked, uint64_t last_now) const;
+    // inserts since the last call that made test() change its answer (the address was in neither table)
+    uint32_t take_new_members() {
+        const uint32_t n = new_members_;
+        new_members_ = 0;
+        return n;
+    }
     bool replayable() const { return !dropped_ && list_a_.size() < kReplayMax && list_b_.size() < kReplayMax; }
 
   private:
@@ -74,6 +80,7 @@ class IcaoFilter {
     std::vector<uint64_t> bits_a_, bits_b_;
     std::vector<uint32_t> list_a_, list_b_;
     bool dropped_;
+    uint32_t new_members_ = 0;
     bool track_ = false;
     mutable std::vector<uint64_t> probed_;      // one bit per 24-bit address, allocated when tracking is first switched on
     mutable std::vector<uint64_t> scratch_;     // differs_only_unprobed's marks
@@ -179,6 +186,12 @@ class Resolver {
         double ms[7] = {0, 0, 0, 0, 0, 0, 0};
     } trace_;
     uint32_t min_live_;
+    bool optimistic_ = true;        // runs start from the true state in front of the round (B200_RESOLVER_PREDICT=prescan: the predicted one)
+    // new filter members of the previous span: while the population moves (a stream's first seconds) the runs'
+    // start states are predicted from a prescan; once it is stable they all start from the true state
+    uint32_t recent_new_members_ = 0xffffffffu;
+    uint32_t optimistic_max_new_ = 2;
+    static constexpr int kMaxRounds = 3;
     bool absolve_ = true; // keep a run whose start state was predicted wrong only in addresses it never asked about
     static constexpr size_t kMinNotesPerSlice = 256; // messages a worker assembles at least, when one run's notes are shared out
     uint32_t min_live_per_run_ = 512; // a run shorter than this costs more in hand-over than it saves
