@@ -1043,13 +1043,32 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
             }
             ++rounds;
             const IcaoFilter::Snapshot snap = filter_.snapshot();
+            // A table flip is the one change of state that can be seen coming: it happens after the first mag_buf whose
+            // clock reaches next_flip (icao_filter.c:150-164), and a mag_buf's clock lies within its 54.6 ms.  Runs
+            // that start behind that mag_buf start from the flipped state: the inactive table emptied and made active.
+            // (Its next_flip is a guess, which the confirmation tolerates as long as the run ends before either clock
+            // flips again -- 60 s on.)
+            uint64_t flip_block = nblocks;
+            for (uint64_t k = cut[(size_t) base]; k < nblocks; ++k) {
+                const uint64_t end_ts = (uint64_t) ((double) (v.first_sample + std::min(n, (k + 1) * B)) * 12e6 / 2400000.0) / 12000U + startup_;
+                if (end_ts >= snap.next_flip) {
+                    flip_block = k;
+                    break;
+                }
+            }
+            IcaoFilter::Snapshot flipped = snap;
+            if (flip_block < nblocks) {
+                (flipped.a_active ? flipped.seq_b : flipped.seq_a).clear();
+                flipped.a_active = !flipped.a_active;
+                flipped.next_flip = (uint64_t) ((double) (v.first_sample + std::min(n, (flip_block + 1) * B)) * 12e6 / 2400000.0) / 12000U + startup_ + 60000;
+            }
             pool_->run((size_t) (nruns - base), 1, [&](int, size_t lo, size_t hi) {
                 for (size_t i = lo; i < hi; ++i) {
                     const size_t r = (size_t) base + i;
                     Run &run = *runs_[r];
-                    run.predicted = snap;
+                    run.predicted = (cut[r] > flip_block) ? flipped : snap;
                     run.filter.track_probes(true);
-                    run.filter.load(snap);
+                    run.filter.load(run.predicted);
                     walk(v, run.filter, cut[r], cut[r + 1], blocks, block_base, run.out, true);
                 }
             }, true);
