@@ -165,3 +165,21 @@ def test_host_resolver_runs_side_by_side(threads, predict, monkeypatch, capfd):
         # ("always-optimistic": every run starts from the true state in front of its round although the fixture is the
         # beginning of a stream, where every aircraft is new -- rounds, re-speculation and the one-run fall-back all run)
         assert int(m.group(2)) >= 1 and int(m.group(3)) > int(m.group(2))
+
+
+def test_filter_speculation_rule_is_sound(tmp_path):
+    """tests/cpp/test_icao_filter.cc: whenever IcaoFilter::same_members / differs_only_unprobed keep a speculatively
+    walked run, replaying the run on the true filter state gives the same answer to every test() -- checked on
+    thousands of random filter histories and runs (inserts, flips on different clocks, probes inside and outside the
+    difference).  The resolver's parallel walk (resolver.cc) is exact because of this rule."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    assert gxx, "g++ is part of this image"
+    exe = tmp_path / "test_icao_filter"
+    csrc = ROOT / "readsb_protobuf_b200" / "csrc"
+    subprocess.run([gxx, "-std=c++17", "-O1", "-I", str(ROOT / "include"), "-I", str(csrc), str(ROOT / "tests" / "cpp" / "test_icao_filter.cc"),
+                    str(csrc / "resolver.cc"), str(csrc / "host_tables.cc"), "-lpthread", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe), "4000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "kept by the probe rule" in r.stdout
