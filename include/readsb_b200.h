@@ -115,7 +115,7 @@ typedef struct b200_timing {
     float h2d_ms;      /* host -> device copy of the span (0 for device-resident input) */
     float scan_ms;     /* K1a: magnitude + preamble scan (+ candidate list, magnitudes for K1b) */
     float classify_ms; /* K2: address-set test, live records and signal power of survivors; + packing the live lists (and their hidden-dead counts) into stream order */
-    float d2h_ms;      /* 0 since ABI 2: the kernels write survivors into pinned host memory, nothing is waited for */
+    float d2h_ms;      /* 0 since ABI 2: the survivors' download (one DMA per chunk of exactly the live data) runs under the next chunk's kernels */
     float resolve_ms;  /* host: order-dependent resolve (wall clock) */
     float total_ms;    /* wall clock of the whole call */
     uint64_t n_candidates;   /* scan positions with a non-empty try mask */

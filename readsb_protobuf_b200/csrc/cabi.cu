@@ -1,11 +1,13 @@
 // cabi.cu -- the C ABI of include/readsb_b200.h: context, device buffers, launch sequence.
 //
 // A process call cuts the span into chunks of whole mag_bufs and runs them as a pipeline:
-//   copy stream : H2D of chunk i+1 ...................... (host-buffer entry only)
-//   exec stream : K1a scan -> K1b slice/CRC -> K2 classify -> order_live (-> Mode A/C) -> one small download of chunk i+1
-//                 (order_live writes the live positions, their records and what each would hide of the dead list
-//                 straight into pinned host memory; the dead list itself never leaves the device)
-//   host        : order-dependent resolve (resolver.cc) of chunk i
+//   copy stream : H2D of chunks i+1 ... .................. (host-buffer entry only; all copies queued up front)
+//   exec stream : [K1a scan -> K1b slice/CRC -> K2 classify -> order_live (-> Mode A/C) -> one small download]
+//                 of chunks i .. i+5 (six ChunkSets: the host issues that far ahead of the chunk it resolves)
+//                 (order_live packs the live positions, what each would hide of the dead list and their records in
+//                 stream order in device memory; the dead list itself never leaves the device)
+//   d2h stream  : one DMA of exactly the packed bytes of chunk i (and of chunk i+1 when its kernels are through)
+//   host        : order-dependent resolve (resolver.cc: speculative, on a pool of host threads) of chunk i
 // Chunks are exact: K2 of chunk i only needs the address set of chunks <= i, which is what the ICAO
 // filter can hold when the host resolves chunk i.  There is no CPU implementation of the kernels;
 // without a usable sm_100 device every entry point returns B200_ERR_CUDA.
@@ -164,9 +166,8 @@ struct ChunkSet {
     View<BlockDead> d_block_dead, h_block_dead;
     View<TileOut> d_tiles_out, h_tiles_out;
     // K2 leaves the live positions and records in device memory, tile by tile in the order its warps reserved
-    // them; order_live packs them into stream order straight into pinned (device-mapped) host memory, together
-    // with the dead-position counts a frame accepted at each live position would hide.  The (much longer) dead
-    // list itself stays in device memory.
+    // them; order_live packs them into stream order (d_packed below), together with the dead-position counts a
+    // frame accepted at each live position would hide.  The (much longer) dead list itself stays in device memory.
     DevBuf<LivePos> d_live;
     DevBuf<LiveRec> d_liverecs;
     DevBuf<uint2> d_live_base;
