@@ -281,6 +281,14 @@ void IcaoFilter::collect(std::vector<uint32_t> &out) const {
 
 // A handful of threads parked on a condition variable; run() hands them (and the caller) slices of an index
 // range.  Only spans with thousands of accepted frames go through it: a sparse chunk is assembled inline.
+static inline void spin_pause() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield");
+#endif
+}
+
 class WorkerPool {
   public:
     explicit WorkerPool(int nthreads) {
@@ -1224,7 +1232,11 @@ void Resolver::resolve(const SpanView &v, MessageList &msgs, std::vector<b200_bl
             bad[r] = nbad;
             // demod_2400.c:398-407 in message order: the running sum of doubles is the one thing here that depends on
             // it, so the slices take turns, each adding its own (cache-warm) terms
-            while (turn.load(std::memory_order_acquire) != (int) r) {
+            for (uint32_t spins = 0; turn.load(std::memory_order_acquire) != (int) r; ++spins) {
+                if (spins < 2048)
+                    spin_pause();
+                else
+                    std::this_thread::yield(); // the slice before this one may sit on a core that was taken away
             }
             for (size_t i = 0; i < na; ++i) {
                 if (acc[i].modeac)

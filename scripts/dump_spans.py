@@ -18,7 +18,7 @@ fixture = len(sys.argv) > 1 and sys.argv[1] == "fixture"
 dense = len(sys.argv) > 1 and sys.argv[1] == "dense"   # 20 s of the configs[3] stream -> gpurun_out/spans_dense/
 out = "gpurun_out/resolver_fixture" if fixture else ("gpurun_out/spans_dense" if dense else "gpurun_out/spans")
 os.makedirs(out, exist_ok=True)
-cfg = synth.resolver_fixture_config() if fixture else (synth.baseline_config(3, seconds=20.0) if dense else synth.baseline_config(1, seconds=60.0))
+cfg = synth.resolver_fixture_config() if fixture else (synth.baseline_config(3, seconds=float(os.environ.get("DUMP_SECONDS", "20"))) if dense else synth.baseline_config(1, seconds=60.0))
 iq, _ = synth.generate(cfg)
 dev = torch.from_numpy(iq).cuda()
 d = api.Demodulator(fmt="uc8", max_span_samples=cfg.nsamples + (1 << 20))
