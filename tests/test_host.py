@@ -183,3 +183,89 @@ def test_filter_speculation_rule_is_sound(tmp_path):
     r = subprocess.run([str(exe), "4000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "kept by the probe rule" in r.stdout
+
+
+def _synthetic_span_dumps(tmp_path, n_aircraft, seed):
+    """Resolver inputs written by hand in the layout B200_DUMP_SPAN produces (cabi.cu, layout 2): three spans of 400
+    mag_bufs (65 s of stream: the start-up flip of the ICAO filter and the one a minute later), a live position every
+    ~6000 samples carrying one frame: a clean DF17 of one of `n_aircraft` addresses (an insert into the filter), or a DF4
+    reply whose address -- the CRC residue -- is one of them (accepted only while the filter knows it)."""
+    rng = np.random.default_rng(seed)
+    B, blocks_per_span = 131072, 400
+    pool = rng.choice(np.arange(0x100000, 0xf00000), size=n_aircraft, replace=False).astype(np.uint32)
+    live_dt = np.dtype([("pos", "<u4"), ("info", "<u4"), ("dead_rank", "<u4"), ("pad", "<u4")])
+    rec_dt = np.dtype([("pos", "<u4"), ("w0", "<u4"), ("w1", "<u4"), ("errbits", "<u4"), ("power", "<u8"), ("msg", "u1", (14,)), ("pad", "u1", (2,))])
+    assert live_dt.itemsize == 16 and rec_dt.itemsize == 40
+    paths = []
+    for span in range(3):
+        n = B * blocks_per_span
+        pos = np.arange(500, n - 700, 6000, dtype=np.int64) + rng.integers(0, 4000, size=len(np.arange(500, n - 700, 6000)))
+        pos = np.unique(pos).astype(np.uint32)
+        k = len(pos)
+        live = np.zeros(k, dtype=live_dt)
+        recs = np.zeros(k, dtype=rec_dt)
+        live["pos"] = pos
+        live["pad"] = np.arange(k, dtype=np.uint32)
+        addr = pool[rng.integers(0, n_aircraft, size=k)]
+        is_es = rng.random(k) < 0.7
+        phase = rng.integers(4, 9, size=k).astype(np.uint32)
+        live["info"] = (1 << (phase - 4)).astype(np.uint32) | (1 << 8)  # try mask: that phase; one record
+        for i in range(k):
+            a = int(addr[i])
+            if is_es[i]:
+                body = bytes([0x8D, a >> 16, (a >> 8) & 255, a & 255]) + rng.integers(0, 256, size=7, dtype=np.uint8).tobytes()
+                crc = port.checksum(body + b"\0\0\0")  # parity that makes the frame's syndrome 0
+                msg = body + bytes([crc >> 16, (crc >> 8) & 255, crc & 255])
+                assert port.checksum(msg) == 0
+                recs["w0"][i] = 0 | (4 << 24) | (1 << 31)  # crc 0, kKindES, no repair, key in S
+                recs["w1"][i] = a | (int(phase[i]) << 24)
+            else:
+                body = bytes([0x20]) + rng.integers(0, 256, size=3, dtype=np.uint8).tobytes()  # DF4
+                crc = port.checksum(body + b"\0\0\0")
+                ap = crc ^ a  # Address/Parity: the residue is the address
+                msg = body + bytes([ap >> 16, (ap >> 8) & 255, ap & 255])
+                assert port.checksum(msg) == a
+                recs["w0"][i] = a | (1 << 24) | (1 << 31)  # crc = the address, kKindAP, key in S
+                recs["w1"][i] = a | (int(phase[i]) << 24)
+            recs["msg"][i, : len(msg)] = np.frombuffer(msg, dtype=np.uint8)
+        recs["pos"] = pos
+        recs["errbits"] = 0xFFFF
+        recs["power"] = rng.integers(1 << 20, 1 << 34, size=k).astype(np.uint64)
+        nblocks = blocks_per_span + 2
+        hdr = np.array([n, span * n, B, 1 if span == 2 else 0, 0, 0, 0, k, k, nblocks, 2, 0], dtype=np.uint64)
+        path = tmp_path / f"span_{span}.bin"
+        with open(path, "wb") as f:
+            f.write(hdr.tobytes())
+            f.write(live.tobytes())
+            f.write(recs.tobytes())
+            f.write(np.zeros(4 * k, dtype=np.uint64).tobytes())           # hidden-dead counts: none
+            f.write(np.zeros(8 * nblocks, dtype=np.uint32).tobytes())     # block dead counters
+            sums = rng.integers(1 << 30, 1 << 34, size=2 * nblocks).astype(np.uint64)
+            sums[2 * blocks_per_span:] = 0  # the empty last mag_buf of a stream of whole blocks (0 / 0 = NaN, as in the reference)
+            f.write(sums.tobytes())  # integer block sums
+            f.write(np.zeros(2 * nblocks, dtype=np.float64).tobytes())
+        paths.append(path)
+    return paths
+
+
+@pytest.mark.parametrize("n_aircraft", [300, 3000, 12000])
+def test_host_resolver_side_by_side_with_large_populations(n_aircraft, tmp_path, monkeypatch):
+    """The walk in several runs against the walk in one, on hand-made resolver inputs with more aircraft than the
+    fixtures have: 300 (the filter stays small), 3000 (its insert lists outgrow what a copy reproduces, so speculation
+    has to hand over to the one-run walk in the middle of a span) and 12000 (its 8192-entry tables fill up and drop
+    inserts, icao_filter.c:78-81).  Same messages, same counters, whatever the mode and the number of threads."""
+    paths = _synthetic_span_dumps(tmp_path, n_aircraft, seed=n_aircraft)
+    monkeypatch.setenv("B200_RESOLVER_THREADS", "1")
+    want = api.host_resolve_dumps(paths, nfix=1)
+    assert int(want.stats["convert_cpu_s"]) == 0  # no kernel-vs-host CRC disagreement: the frames are well formed
+    n_es = int(np.sum(want.msgs["msgtype"] == 17))
+    n_ap = int(np.sum(want.msgs["msgtype"] == 4))
+    assert n_es > 15000 and n_ap > 0 and int(want.stats["demod_rejected_unknown_icao"]) > 0, (n_es, n_ap)
+    for predict in ("optimistic", "always-optimistic", "prescan"):
+        for threads in (2, 5, 8):
+            monkeypatch.setenv("B200_RESOLVER_THREADS", str(threads))
+            monkeypatch.setenv("B200_RESOLVER_PREDICT", predict)
+            monkeypatch.setenv("B200_RESOLVER_MIN_LIVE", "0")
+            got = api.host_resolve_dumps(paths, nfix=1)
+            got.stats["convert_cpu_s"] = want.stats["convert_cpu_s"]
+            assert results.compare_results(got, want, float_rtol=0.0, signal_atol=0.0) == [], (predict, threads)
