@@ -22,7 +22,7 @@ GPU.  A step is one pass of the hot path over that stream.
             N=1: configs[2] (60 s sc16 and sc16q11, seed 3), configs[3] (600 s dense uc8, seed 4) and eight
             --dcfilter receiver streams side by side on the one GPU;
             N>1: configs[4] (one 600 s dense uc8 file per GPU, seeds 10..)
-  sustained the configs[1] device-resident step repeated for >= 1.5 s with nvidia-smi clock sampling
+  sustained the configs[1] device-resident step repeated for >= 3 s with nvidia-smi clock sampling
             at 5 Hz (the K-step timed region itself lasts tens of milliseconds)
 
 --impl reference times the reference's own CPU path (oracle/_ref/ref_demod, else the C port)
@@ -411,7 +411,7 @@ def run_ours(args):
                            and np.array_equal(mm, torch.stack(gm).max(0).values.cpu().numpy()))
     merged_headline = merged_holder.get("stats")
 
-    # sustained: the same device-resident step back to back for >= 1.5 s, so that the clock record holds
+    # sustained: the same device-resident step back to back for >= 3 s (--sustain), so that the clock record holds
     # more than a handful of samples under load
     barrier()
     sus_steps, sus_t0 = 0, time.perf_counter()
@@ -602,7 +602,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=WORKLOAD_SECONDS, help=argparse.SUPPRESS)
     ap.add_argument("--other-configs", default="auto",
                     help="auto (N=1: configs[2], configs[3] and the --dcfilter multi-stream case; N>1: configs[4]), none, or a list such as 2,3,dc")
-    ap.add_argument("--sustain", type=float, default=1.5, help="seconds of back-to-back steps for the clock record")
+    ap.add_argument("--sustain", type=float, default=3.0, help="seconds of back-to-back steps for the clock record")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
